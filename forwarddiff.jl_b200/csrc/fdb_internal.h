@@ -1,0 +1,116 @@
+// fdb_internal.h -- context / array objects behind the opaque handles of fdb200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/fdb200.h"
+
+struct fdb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    bool async = false;
+    bool nansafe = false;
+    bool lane_sharing = true;   // see fdb_sweep.cu (SHARE)
+    int sm_count = 148;
+    int64_t launches = 0;
+    // reusable device scratch (block partials of reductions, staging of host entry points)
+    double* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // pinned host staging for the *_host entry points
+    double* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    std::string err;
+};
+
+struct fdb_array {
+    fdb_ctx* ctx = nullptr;
+    double* data = nullptr;
+    int64_t n = 0;     // elements
+    int64_t ld = 0;    // plane stride in doubles
+    int N = 0;         // chunk size (0 for level 0)
+    int level = 0;     // 0 plain, 1 Dual, 2 nested Dual
+    bool owned = true;
+    int planes() const { return level == 0 ? 1 : (level == 1 ? N + 1 : (N + 1) * (N + 1)); }
+};
+
+namespace fdb {
+
+extern thread_local std::string g_init_error;
+
+inline int fail(fdb_ctx* ctx, int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
+inline int fail(fdb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_init_error = buf;
+    return code;
+}
+
+#define FDB_CUDA(ctx, expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fdb::fail(ctx, e__ == cudaErrorMemoryAllocation ? FDB_ERR_OOM : FDB_ERR_CUDA,   \
+                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// after a kernel launch: check the launch, count it, and drain the stream unless async
+inline int finish(fdb_ctx* ctx, int nlaunch, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
+    ctx->launches += nlaunch;
+    if (!ctx->async) {
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    return FDB_OK;
+}
+
+int ensure_scratch(fdb_ctx* ctx, size_t bytes);
+int ensure_pinned(fdb_ctx* ctx, size_t bytes);
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// host mirror of the reference's chunk bookkeeping (src/gradient.jl:121-125)
+struct Plan {
+    int64_t xlen, remainder, lastchunksize, lastchunkindex, middle_hi, nchunks;
+};
+inline Plan make_plan(int64_t xlen, int64_t N) {
+    Plan p;
+    p.xlen = xlen;
+    p.remainder = xlen % N;
+    p.lastchunksize = p.remainder == 0 ? N : p.remainder;
+    p.lastchunkindex = xlen - p.lastchunksize + 1;
+    p.middle_hi = (xlen - p.lastchunksize) / N;
+    p.nchunks = p.middle_hi + 1;
+    return p;
+}
+
+// dispatch a run-time chunk size to a compile-time one (N = 1..12, src/prelude.jl:12 `@nif 12`)
+#define FDB_DISPATCH_N(N_, ...)                                        \
+    switch (N_) {                                                      \
+        case 1: { constexpr int NN = 1; __VA_ARGS__; } break;          \
+        case 2: { constexpr int NN = 2; __VA_ARGS__; } break;          \
+        case 3: { constexpr int NN = 3; __VA_ARGS__; } break;          \
+        case 4: { constexpr int NN = 4; __VA_ARGS__; } break;          \
+        case 5: { constexpr int NN = 5; __VA_ARGS__; } break;          \
+        case 6: { constexpr int NN = 6; __VA_ARGS__; } break;          \
+        case 7: { constexpr int NN = 7; __VA_ARGS__; } break;          \
+        case 8: { constexpr int NN = 8; __VA_ARGS__; } break;          \
+        case 9: { constexpr int NN = 9; __VA_ARGS__; } break;          \
+        case 10: { constexpr int NN = 10; __VA_ARGS__; } break;        \
+        case 11: { constexpr int NN = 11; __VA_ARGS__; } break;        \
+        case 12: { constexpr int NN = 12; __VA_ARGS__; } break;        \
+        default: return fdb::fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", (int)(N_)); \
+    }
+#define FDB_DISPATCH_NS(ns_, ...)                                     \
+    if (ns_) { constexpr bool NS = true; __VA_ARGS__; } else { constexpr bool NS = false; __VA_ARGS__; }
+
+}  // namespace fdb

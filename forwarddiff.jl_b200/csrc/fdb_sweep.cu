@@ -1,0 +1,227 @@
+// fdb_sweep.cu -- the batched chunk-mode gradient: replaces the chunk loop of
+// src/gradient.jl:114-159 (chunk_mode_gradient!) and vector mode (:97-108).
+//
+// Reference per chunk c:  seed!(xdual, x, i, seeds) -> ydual = f(xdual) ->
+// extract_gradient_chunk!(result, ydual, i, N) -> seed_zero_partials!(xdual, x, i).
+// Here ALL requested chunks run in one launch: blockIdx.x is the chunk, the seeded
+// Dual of element e is built in registers from (e, chunk start) instead of being
+// read from a materialised xdual (SeedLoader), the N partials of every
+// intermediate stay in registers, the reduction uses warp shuffles plus a
+// shared-memory tree, and thread 0 of the block stores the chunk's partials
+// straight into the gradient slice (fused extraction).  x (8n bytes) is the only
+// global input and stays L2-resident across chunks.
+//
+// Work per launch is identical to the reference: every chunk evaluates every term
+// of f with N-wide partials; nothing is skipped for elements outside the seeded
+// window.  The kernel is therefore bound by FP64 issue, not HBM.
+#include "fdb_internal.h"
+#include "fdb_targets.cuh"
+
+namespace fdb {
+
+// SHARE = lane sharing.  A term whose inputs all lie outside the seeded window sees
+// Duals with N identical (zero) partial lanes, so its N partial lanes are N copies of
+// one IEEE computation.  With SHARE the kernel evaluates such terms on Dual{1}
+// (value + one representative partial lane) into a separate accumulator and adds the
+// representative lane to all N lanes at the end; results are bit-identical lane by lane
+// (including NaN/Inf propagation, since the representative lane is really computed),
+// only the summation order changes, which the reduction tolerance already covers.
+// Every term of f is still evaluated in every chunk.  SHARE=false evaluates all N
+// lanes for every term (bench.py reports both).
+template <class F, int N, bool NS, int THREADS, bool SHARE>
+__global__ void __launch_bounds__(THREADS) gradient_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo,
+                                                                 int64_t nchunks_total, int lastchunksize,
+                                                                 double* __restrict__ grad, double* __restrict__ value_out) {
+    typedef Dual<double, N, NS> D;
+    typedef Dual<double, 1, NS> D1;
+    const int64_t c = chunk_lo + blockIdx.x;                       // 0-based chunk number
+    const bool last = (c == nchunks_total - 1);
+    const int chunksize = last ? lastchunksize : N;               // src/gradient.jl:123
+    const int64_t start = last ? (n - lastchunksize) : c * N;     // lastchunkindex-1, src/gradient.jl:124
+    SeedLoader<N, NS> xs{x, start, chunksize};
+    ZeroLoader<1, NS> xz{x};
+    D acc[F::K];
+    D1 acc1[F::K];
+    D like; like.v = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) like.p[k] = 0.0;
+    D1 like1; like1.v = 0.0; like1.p[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < F::K; k++) { acc[k] = F::init(k, like); acc1[k] = F::init(k, like1); }
+    const int64_t nt = F::nterms(n);
+    if (SHARE) {
+        // iterations [0,itA) and [itB,nit) touch no seeded position anywhere in the block
+        const int64_t nit = (nt + THREADS - 1) / THREADS;
+        int64_t itA = (start - F::HALO) / THREADS; if (itA < 0) itA = 0; if (itA > nit) itA = nit;
+        int64_t itB = (start + chunksize + THREADS - 1) / THREADS; if (itB > nit) itB = nit; if (itB < itA) itB = itA;
+#pragma unroll 4
+        for (int64_t it = 0; it < itA; it++) F::term(xz, it * THREADS + threadIdx.x, n, acc1);
+        for (int64_t it = itA; it < itB; it++) {
+            const int64_t i = it * THREADS + threadIdx.x;
+            if (i < nt) F::term(xs, i, n, acc);
+        }
+        const int64_t full = nt / THREADS;      // iterations whose every lane is a valid term
+#pragma unroll 4
+        for (int64_t it = itB; it < full; it++) F::term(xz, it * THREADS + threadIdx.x, n, acc1);
+        for (int64_t it = (itB > full ? itB : full); it < nit; it++) {
+            const int64_t i = it * THREADS + threadIdx.x;
+            if (i < nt) F::term(xz, i, n, acc1);
+        }
+        // fold the shared accumulator into all N lanes
+#pragma unroll
+        for (int k = 0; k < F::K; k++) {
+            D e; e.v = acc1[k].v;
+#pragma unroll
+            for (int j = 0; j < N; j++) e.p[j] = acc1[k].p[0];
+            // for K > 1 or non-additive combines the neutral value lane must not be counted twice:
+            // acc[k] started from init, acc1[k] too; combine(init, z) == z for sum and prod.
+            acc[k] = F::combine(k, acc[k], e);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < nt; i += THREADS) F::term(xs, i, n, acc);
+    }
+    block_combine<F, D, THREADS>(acc);
+    if (threadIdx.x == 0) {
+        D y = F::finalize(acc, n);
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (k < chunksize) grad[start + k] = y.p[k];           // extract_gradient_chunk!, src/gradient.jl:74-81
+        if (last && value_out) value_out[0] = y.v;                 // extract_value!, src/gradient.jl:155
+    }
+}
+
+template <class F>
+static int gradient_launch(fdb_ctx* ctx, const fdb_array* x, int N, int64_t lo, int64_t hi, int64_t nchunks, int lastchunksize,
+                           fdb_array* grad, fdb_array* value_dev, const char* what) {
+    constexpr int THREADS = 256;
+    unsigned grid = (unsigned)(hi - lo);
+    double* vout = value_dev ? value_dev->data : nullptr;
+    if (ctx->lane_sharing) {
+        FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
+            (gradient_sweep_kernel<F, NN, NS, THREADS, true><<<grid, THREADS, 0, ctx->stream>>>(x->data, x->n, lo, nchunks, lastchunksize,
+                                                                                                 grad->data, vout))));
+    } else {
+        FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
+            (gradient_sweep_kernel<F, NN, NS, THREADS, false><<<grid, THREADS, 0, ctx->stream>>>(x->data, x->n, lo, nchunks, lastchunksize,
+                                                                                                  grad->data, vout))));
+    }
+    return finish(ctx, 1, what);
+}
+
+}  // namespace fdb
+
+using namespace fdb;
+
+extern "C" int fdb_gradient_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi,
+                                    fdb_array* grad, fdb_array* value_dev) {
+    if (!ctx || !x || !grad) return fail(ctx, FDB_ERR_BADARG, "fdb_gradient_chunked: null argument");
+    if (x->level != 0 || grad->level != 0 || (value_dev && value_dev->level != 0))
+        return fail(ctx, FDB_ERR_BADARG, "fdb_gradient_chunked: x, grad and value must be plain (level-0) arrays");
+    if (grad->n != x->n) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: gradient result has %lld entries, x has %lld",
+                                     (long long)grad->n, (long long)x->n);
+    if (value_dev && value_dev->n < 1) return fail(ctx, FDB_ERR_SHAPE, "fdb_gradient_chunked: value array is empty");
+    const int64_t n = x->n;
+    if (N < 1 || N > FDB_MAX_CHUNK) return fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", N);
+    if (n < N)   // src/gradient.jl:116-118
+        return fail(ctx, FDB_ERR_CHUNK, "chunk size cannot be greater than ForwardDiff.structural_length(x) (%d > %lld)", N, (long long)n);
+    // N == n is vector mode (src/gradient.jl:19-23): one sweep seeding all N positions,
+    // which is exactly the single "last" chunk of the formulas below.
+    Plan p = make_plan(n, N);
+    int64_t nchunks = (n == N) ? 1 : p.nchunks;
+    if (chunk_hi < 0) chunk_hi = nchunks;
+    if (chunk_lo < 0 || chunk_lo > chunk_hi || chunk_hi > nchunks)
+        return fail(ctx, FDB_ERR_BADARG, "chunk range [%lld,%lld) outside [0,%lld)", (long long)chunk_lo, (long long)chunk_hi, (long long)nchunks);
+    if (chunk_lo == chunk_hi) return FDB_OK;
+    switch (fn) {
+        case FDB_FN_ROSENBROCK: return gradient_launch<Rosenbrock>(ctx, x, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, grad, value_dev, "fdb_gradient_chunked(rosenbrock)");
+        case FDB_FN_ACKLEY: return gradient_launch<Ackley>(ctx, x, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, grad, value_dev, "fdb_gradient_chunked(ackley)");
+        case FDB_FN_SUMSQ: return gradient_launch<SumSq>(ctx, x, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, grad, value_dev, "fdb_gradient_chunked(sumsq)");
+        case FDB_FN_PROD: return gradient_launch<ProdAll>(ctx, x, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, grad, value_dev, "fdb_gradient_chunked(prod)");
+    }
+    return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_gradient_chunked: unknown target %d", fn);
+}
+
+// ForwardDiff.gradient!(out, f, x, cfg) on host Vectors: H2D of x through pinned staging,
+// the sweeps, D2H of the gradient slice of the requested chunks (and the value).
+extern "C" int fdb_gradient_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, int N, int64_t chunk_lo,
+                                 int64_t chunk_hi, double* grad_host, double* value_host) {
+    if (!ctx || !x_host || !grad_host) return fail(ctx, FDB_ERR_BADARG, "fdb_gradient_host: null argument");
+    if (xlen == 0) { if (value_host) *value_host = 0.0; return FDB_OK; }   // Chunk{0}: fill!(result, 0) on an empty result
+    if (N < 1 || N > FDB_MAX_CHUNK) return fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", N);
+    if (xlen < N) return fail(ctx, FDB_ERR_CHUNK, "chunk size cannot be greater than ForwardDiff.structural_length(x) (%d > %lld)", N, (long long)xlen);
+    Plan p = make_plan(xlen, N);
+    int64_t nchunks = (xlen == N) ? 1 : p.nchunks;
+    if (chunk_hi < 0) chunk_hi = nchunks;
+    if (chunk_lo < 0 || chunk_lo > chunk_hi || chunk_hi > nchunks) return fail(ctx, FDB_ERR_BADARG, "bad chunk range");
+    int64_t ld = round_up(xlen, 32);
+    int rc = ensure_scratch(ctx, (size_t)(2 * ld + 32) * sizeof(double)); if (rc) return rc;
+    fdb_array xa, ga, va;
+    xa.ctx = ga.ctx = va.ctx = ctx; xa.owned = ga.owned = va.owned = false;
+    xa.data = ctx->scratch; xa.n = xlen; xa.ld = ld;
+    ga.data = ctx->scratch + ld; ga.n = xlen; ga.ld = ld;
+    va.data = ctx->scratch + 2 * ld; va.n = 1; va.ld = 32;
+    FDB_CUDA(ctx, cudaMemcpyAsync(xa.data, x_host, (size_t)xlen * 8, cudaMemcpyHostToDevice, ctx->stream));
+    bool was_async = ctx->async; ctx->async = true;
+    rc = fdb_gradient_chunked(ctx, fn, &xa, N, chunk_lo, chunk_hi, &ga, &va);
+    ctx->async = was_async;
+    if (rc) return rc;
+    int64_t e0 = chunk_lo * N, e1 = chunk_hi * N < xlen ? chunk_hi * N : xlen;
+    if (chunk_hi == nchunks) e1 = xlen;
+    if (e1 > e0) FDB_CUDA(ctx, cudaMemcpyAsync(grad_host + e0, ga.data + e0, (size_t)(e1 - e0) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (value_host && chunk_hi == nchunks)
+        FDB_CUDA(ctx, cudaMemcpyAsync(value_host, va.data, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FDB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 issue-rate probe for the roofline denominator of the sweep kernels
+// (MEASURED_PEAKS.json carries no FP64 figure).
+// ---------------------------------------------------------------------------
+namespace fdb {
+template <bool FUSED>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double r[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) r[j] = a + (double)(threadIdx.x + j);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (FUSED) r[j] = fma(r[j], b, a);
+            else { r[j] = r[j] * b; r[j] = r[j] + a; }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) s += r[j];
+    if (s == 12345.678) out[0] = s;     // never true; keeps the chain alive
+}
+}  // namespace fdb
+
+extern "C" int fdb_measure_fp64_peak(fdb_ctx* ctx, double* dp_ops_per_s, double* dfma_per_s) {
+    if (!ctx) return FDB_ERR_BADARG;
+    int rc = ensure_scratch(ctx, 4096); if (rc) return rc;
+    cudaEvent_t e0, e1;
+    FDB_CUDA(ctx, cudaEventCreate(&e0)); FDB_CUDA(ctx, cudaEventCreate(&e1));
+    const int iters = 4096; const int blocks = ctx->sm_count * 8;
+    double results[2] = {0, 0};
+    for (int fused = 0; fused < 2; fused++) {
+        double best = 1e30;
+        for (int rep = 0; rep < 4; rep++) {
+            FDB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+            if (fused) fp64_peak_kernel<true><<<blocks, 256, 0, ctx->stream>>>(ctx->scratch, iters, 1.0000001, 0.9999999);
+            else fp64_peak_kernel<false><<<blocks, 256, 0, ctx->stream>>>(ctx->scratch, iters, 1.0000001, 0.9999999);
+            FDB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+            FDB_CUDA(ctx, cudaEventSynchronize(e1));
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best) best = ms;
+            ctx->launches++;
+        }
+        double instr = (double)blocks * 256.0 * iters * 16.0 * (fused ? 1.0 : 2.0);
+        results[fused] = instr / (best * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (dp_ops_per_s) *dp_ops_per_s = results[0];
+    if (dfma_per_s) *dfma_per_s = results[1];
+    return FDB_OK;
+}

@@ -1,0 +1,153 @@
+// fdb_targets.cuh -- the device catalogue of target functions `f`.
+//
+// A scalar target is written ONCE as a map-reduce over "terms":
+//     acc[k] = combine(acc[k], term_k(i))   for i in [0, nterms(n))   then   y = finalize(acc, n)
+// and is evaluated through a *loader* that yields the Dual at position i.  Two
+// loaders exist: SoALoader reads a materialised dual array (the reference's
+// cfg.duals after seed!), SeedLoader reads only x[i] and builds the seeded Dual
+// in registers (the batched chunk sweep).  The op sequence per term is exactly
+// what Julia executes on Dual numbers for the reference definitions cited at each
+// target, so elementwise results are bit-identical to the oracle; only the
+// reduction order differs (tolerance 1e-12 relative, BASELINE.json north_star).
+#pragma once
+#include "fdb_dual.cuh"
+
+namespace fdb {
+
+template <int N, bool NS> struct SoALoader {
+    const double* base; int64_t ld;
+    FDB_DEV Dual<double, N, NS> operator()(int64_t i) const {
+        Dual<double, N, NS> d; d.v = base[i];
+#pragma unroll
+        for (int k = 0; k < N; k++) d.p[k] = base[(int64_t)(k + 1) * ld + i];
+        return d;
+    }
+};
+template <int N, bool NS> struct SeedLoader {
+    const double* x; int64_t start; int chunksize;
+    FDB_DEV Dual<double, N, NS> operator()(int64_t i) const { return seeded<N, NS>(x[i], i, start, chunksize); }
+};
+// Positions outside the seeded window hold Dual(x[i], zero(Partials)) -- what
+// seed_zero_partials! left there (src/apiutils.jl:89-105).  Same arithmetic as
+// SeedLoader for such positions, minus the N compare/select pairs per load.
+template <int N, bool NS> struct ZeroLoader {
+    const double* x;
+    FDB_DEV Dual<double, N, NS> operator()(int64_t i) const {
+        Dual<double, N, NS> d; d.v = x[i];
+#pragma unroll
+        for (int k = 0; k < N; k++) d.p[k] = 0.0;
+        return d;
+    }
+};
+
+// ---- Rosenbrock: docs/src/user/advanced.md:36-44 (= DiffTests.rosenbrock_1) -----
+//   a = one(eltype(x)); b = 100 * a; result += (a - x[i])^2 + b*(x[i+1] - x[i]^2)^2
+// a and b are Duals with zero partials, so `a - x[i]` is Dual-Dual and `b*(..)` is
+// Dual*Dual.
+struct Rosenbrock {
+    static constexpr int K = 1;
+    static constexpr int HALO = 1;   // term i reads positions i .. i+HALO
+    static __host__ __device__ int64_t nterms(int64_t n) { return n > 0 ? n - 1 : 0; }
+    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }
+    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }
+    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t, D (&acc)[K]) {
+        D xi = x(i), xn = x(i + 1);
+        D a = one_of(xi);
+        D b = 100.0 * a;
+        D t = pow2(a - xi) + b * pow2(xn - pow2(xi));
+        acc[0] = acc[0] + t;
+    }
+    template <class D> static FDB_DEV D finalize(const D (&acc)[K], int64_t) { return acc[0]; }
+};
+
+// ---- Ackley: DiffTests.ackley (C++ twin benchmarks/cpp/benchmarks.cpp:10-21) -----
+//   sum_cos += cos(c*x_i); sum_sqrs += x_i^2;
+//   -a*exp(b*sqrt(len_recip*sum_sqrs)) - exp(len_recip*sum_cos) + a + e
+struct Ackley {
+    static constexpr int K = 2;
+    static constexpr int HALO = 0;   // acc[0] = sum_cos, acc[1] = sum_sqrs
+    static __host__ __device__ int64_t nterms(int64_t n) { return n; }
+    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }
+    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }
+    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t, D (&acc)[K]) {
+        const double c = 2.0 * 3.141592653589793;   // 2.0*pi rounds to 6.283185307179586
+        D xi = x(i);
+        acc[0] = acc[0] + cos_v(c * xi);
+        acc[1] = acc[1] + pow2(xi);
+    }
+    template <class D> static FDB_DEV D finalize(const D (&acc)[K], int64_t n) {
+        const double a = 20.0, b = -0.2, e = 2.718281828459045;
+        double len_recip = 1.0 / (double)n;
+        return (-a) * exp_v(b * sqrt_v(len_recip * acc[1])) - exp_v(len_recip * acc[0]) + a + e;
+    }
+};
+
+// ---- sum(x.^2) ---------------------------------------------------------------------
+struct SumSq {
+    static constexpr int K = 1;
+    static constexpr int HALO = 0;
+    static __host__ __device__ int64_t nterms(int64_t n) { return n; }
+    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }
+    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }
+    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t, D (&acc)[K]) {
+        acc[0] = acc[0] + pow2(x(i));
+    }
+    template <class D> static FDB_DEV D finalize(const D (&acc)[K], int64_t) { return acc[0]; }
+};
+
+// ---- prod(x) -------------------------------------------------------------------------
+struct ProdAll {
+    static constexpr int K = 1;
+    static constexpr int HALO = 0;
+    static __host__ __device__ int64_t nterms(int64_t n) { return n; }
+    template <class D> static FDB_DEV D init(int, const D& like) { return one_of(like); }
+    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a * b; }
+    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t, D (&acc)[K]) {
+        acc[0] = acc[0] * x(i);
+    }
+    template <class D> static FDB_DEV D finalize(const D (&acc)[K], int64_t) { return acc[0]; }
+};
+
+// ---- plain sum / prod of an array (fdb_reduce) -----------------------------------------
+struct SumAll {
+    static constexpr int K = 1;
+    static constexpr int HALO = 0;
+    static __host__ __device__ int64_t nterms(int64_t n) { return n; }
+    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }
+    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }
+    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t, D (&acc)[K]) {
+        acc[0] = acc[0] + x(i);
+    }
+    template <class D> static FDB_DEV D finalize(const D (&acc)[K], int64_t) { return acc[0]; }
+};
+
+// ---- block-level combine of K Dual accumulators ---------------------------------------
+// Warp shuffles, then a shared-memory tree over the warps; thread 0 ends with the
+// block's result.  THREADS must be a multiple of 32 and <= 1024.
+template <class F, class D, int THREADS>
+FDB_DEV void block_combine(D (&acc)[F::K]) {
+    constexpr int WARPS = THREADS / 32;
+    __shared__ D sm[F::K][WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < F::K; k++) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc[k] = F::combine(k, acc[k], shfl_down(acc[k], off));
+        if (lane == 0) sm[k][warp] = acc[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < F::K; k++) {
+            D v = (lane < WARPS) ? sm[k][lane] : F::init(k, acc[k]);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                D o = shfl_down(v, off);
+                if (off < WARPS) v = F::combine(k, v, o);
+            }
+            acc[k] = v;
+        }
+    }
+}
+
+}  // namespace fdb

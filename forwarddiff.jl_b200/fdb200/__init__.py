@@ -1,0 +1,18 @@
+"""fdb200 -- Python host for the B200-native engine behind ForwardDiff.jl's
+chunked dual-number sweep (ctypes over include/fdb200.h; no CPU fallback).
+
+The directory `forwarddiff.jl_b200/` is not an importable name; add it to
+sys.path (tests/conftest.py, bench.py and __graft_entry__.py do) and
+`import fdb200`.
+"""
+from . import _lib
+from ._lib import (ChunkSizeError, CudaError, DimensionMismatch, FdbError, InvalidTagException, UnsupportedOp, LIB_PATH)
+from .array import (B200Array, B200DualArray, Context, abs2, abs_, cos, exp, fma, inv, log, maximum, minimum, sin, sqrt,
+                    tanh)
+from .api import (Chunk, DiffResult, GradientConfig, GradientResult, HessianConfig, HessianResult, JacobianConfig,
+                  JacobianResult, Tag, checktag, chunk_plan, default_context, gradient, gradient_b, hessian, hessian_b,
+                  jacobian, jacobian_b, pickchunksize)
+from . import functions
+from . import dist
+
+__all__ = [n for n in dir() if not n.startswith("_")]

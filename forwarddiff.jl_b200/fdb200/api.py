@@ -1,0 +1,482 @@
+"""Host-side mirror of ForwardDiff's API for the chunk-mode path.
+
+Julia is not available in this image, so this module plays the role of the Julia
+shim (julia/ForwardDiffB200.jl): same names, argument meaning and error behaviour
+as the reference, every device action a call into the C ABI.
+
+    reference                                   here
+    ---------------------------------------     ------------------------------------------
+    Chunk{N}(), Chunk(x)                        Chunk(N), Chunk.pick(x)     src/prelude.jl:8-38
+    Tag(f, V), checktag                         Tag(f), checktag            src/config.jl:5-43
+    GradientConfig(f, x, Chunk{N}(), tag)       GradientConfig(f, x, chunk, tag)   config.jl:117-124
+    JacobianConfig(f[, y], x, chunk, tag)       JacobianConfig(f, x, chunk, tag, y=None)   :154-189
+    HessianConfig(f[, result], x, chunk, tag)   HessianConfig(f, x, chunk, tag, result=None)  :221-254
+    gradient / gradient!                        gradient / gradient_b       src/gradient.jl:16-44
+    jacobian / jacobian!  (f and f! forms)      jacobian / jacobian_b       src/jacobian.jl:18-87
+    hessian / hessian!                          hessian / hessian_b         src/hessian.jl:14-71
+    DiffResults.GradientResult etc.             GradientResult, JacobianResult, HessianResult
+
+`x` may be a host numpy vector (the call uploads, sweeps, downloads -- the
+`*_host` entry points) or a device B200Array (results stay on the device).
+
+Two execution paths, as in the Julia shim:
+  * catalogue targets (fdb200.functions.*) -> one fused, batched launch for all chunks
+    (fdb_gradient_chunked / fdb_jacobian_chunked / fdb_hessian_chunked);
+  * any other callable written against B200DualArray arithmetic -> the reference's
+    chunk loop statement by statement (src/gradient.jl:114-159, src/jacobian.jl:169-216)
+    on materialised device duals, every step a C-ABI kernel (seed!, f, extract, unseed).
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+
+from . import _lib
+from ._lib import ChunkPlan, ChunkSizeError, DimensionMismatch, FdbError, InvalidTagException
+from .array import B200Array, B200DualArray, Context, _DeviceArray
+
+_dp = C.POINTER(C.c_double)
+DEFAULT_CHUNK_THRESHOLD = 12        # src/prelude.jl:2
+
+
+# ---------------------------------------------------------------------------
+# Chunk, Tag
+# ---------------------------------------------------------------------------
+def pickchunksize(input_length, threshold=DEFAULT_CHUNK_THRESHOLD):
+    """src/prelude.jl:29-36 (evaluated by the library's host code)."""
+    return int(_lib.load().fdb_pickchunksize(int(input_length), int(threshold)))
+
+
+class Chunk:
+    """Chunk{N} (src/prelude.jl:8-13)."""
+
+    def __init__(self, N):
+        self.N = int(N)
+
+    @classmethod
+    def pick(cls, x_or_len, threshold=DEFAULT_CHUNK_THRESHOLD):
+        n = x_or_len if isinstance(x_or_len, int) else _length(x_or_len)
+        return cls(pickchunksize(n, threshold))
+
+    def __repr__(self):
+        return f"Chunk{{{self.N}}}()"
+
+
+_TAGCOUNT = itertools.count()
+
+
+class Tag:
+    """Tag{F,V} with the global ordering counter (src/config.jl:5-26)."""
+
+    def __init__(self, f, V=np.float64):
+        self.f, self.V = f, V
+        self.count = next(_TAGCOUNT)
+
+    def __repr__(self):
+        return f"Tag({getattr(self.f, '__name__', self.f)!r}, {np.dtype(self.V).name})"
+
+
+_DEFAULT = object()
+
+
+def checktag(tag, f, x):
+    """src/config.jl:34-43: a Tag built for another function is an error; custom tags pass."""
+    if isinstance(tag, Tag):
+        if isinstance(tag.f, tuple):           # Tag{<:Tuple}: Hessian tags are not checked
+            return True
+        if tag.f is not f:
+            raise InvalidTagException(f"Invalid Tag object:\n  Expected Tag({f!r}),\n  Observed {tag!r}.")
+    return True
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _length(x):
+    return x.n if isinstance(x, _DeviceArray) else int(np.asarray(x).size)
+
+
+def _ctx_of(x, ctx=None):
+    if ctx is not None:
+        return ctx
+    return x.ctx if isinstance(x, _DeviceArray) else default_context()
+
+
+def _catalogue_id(f, table):
+    name = getattr(f, "fdb_catalogue", None)
+    return table.get(name) if name else None
+
+
+def chunk_plan(xlen, N, rank=0, world=1):
+    """Reference bookkeeping (src/gradient.jl:121-125) + this rank's chunk range (fdb_plan_chunks)."""
+    p = ChunkPlan()
+    rc = _lib.load().fdb_plan_chunks(int(xlen), int(N), int(rank), int(world), C.byref(p))
+    if rc == 6:
+        raise ChunkSizeError(f"chunk size cannot be greater than ForwardDiff.structural_length(x) ({N} > {xlen})")
+    if rc != 0:
+        raise FdbError(f"fdb_plan_chunks failed ({rc})")
+    return p.asdict()
+
+
+# ---------------------------------------------------------------------------
+# DiffResults
+# ---------------------------------------------------------------------------
+class DiffResult:
+    """MutableDiffResult: value plus derivative arrays (DiffResults.jl)."""
+
+    def __init__(self, value, *derivs):
+        self.value = value
+        self.derivs = list(derivs)
+
+
+def GradientResult(x):
+    return DiffResult(0.0, np.zeros(_length(x)))
+
+
+def JacobianResult(y, x):
+    return DiffResult(np.zeros(_length(y)), np.zeros((_length(y), _length(x)), order="F"))
+
+
+def HessianResult(x):
+    n = _length(x)
+    return DiffResult(0.0, np.zeros(n), np.zeros((n, n), order="F"))
+
+
+# ---------------------------------------------------------------------------
+# Configs  (src/config.jl)
+# ---------------------------------------------------------------------------
+class _Config:
+    def __init__(self, f, x, chunk, tag):
+        self.chunk = chunk if chunk is not None else Chunk.pick(x)
+        self.N = self.chunk.N
+        self.tag = Tag(f) if tag is _DEFAULT else tag
+        self.xlen = _length(x)
+        self._duals = None           # allocated lazily: only the materialised path needs them
+
+    @property
+    def chunksize(self):
+        return self.N
+
+
+class GradientConfig(_Config):
+    """GradientConfig(f, x, Chunk{N}(), tag): owns `duals = similar(x, Dual{T,V,N})` (config.jl:117-124)."""
+
+    def __init__(self, f, x, chunk=None, tag=_DEFAULT, level=1):
+        super().__init__(f, x, chunk, tag)
+        self.level = level
+
+    def duals(self, ctx):
+        if self._duals is None or self._duals.ctx is not ctx:
+            self._duals = B200DualArray.alloc(ctx, self.xlen, self.N, self.level)
+        return self._duals
+
+
+class JacobianConfig(_Config):
+    """JacobianConfig(f, x, chunk, tag) / JacobianConfig(f!, y, x, chunk, tag) (config.jl:154-189)."""
+
+    def __init__(self, f, x, chunk=None, tag=_DEFAULT, y=None):
+        super().__init__(f, x, chunk, tag)
+        self.ylen = None if y is None else _length(y)
+        self._yduals = None
+
+    def duals(self, ctx):
+        if self._duals is None or self._duals.ctx is not ctx:
+            self._duals = B200DualArray.alloc(ctx, self.xlen, self.N, 1)
+        if self.ylen is not None and (self._yduals is None or self._yduals.ctx is not ctx):
+            self._yduals = B200DualArray.alloc(ctx, self.ylen, self.N, 1)
+        return (self._yduals, self._duals) if self.ylen is not None else self._duals
+
+
+class HessianConfig(_Config):
+    """HessianConfig(f, x, chunk, tag): a JacobianConfig plus a GradientConfig over its duals
+    (Dual{T,Dual{T,V,N},N}, same tag on both levels; config.jl:221-254)."""
+
+    def __init__(self, f, x, chunk=None, tag=_DEFAULT, result=None):
+        super().__init__(f, x, chunk, tag)
+        self.jacobian_config = JacobianConfig(f, x, self.chunk, self.tag)
+        self.gradient_config = GradientConfig(f, x, self.chunk, self.tag, level=2)
+
+
+# ---------------------------------------------------------------------------
+# gradient
+# ---------------------------------------------------------------------------
+def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None):
+    """ForwardDiff.gradient(f, x, cfg, Val{check}()) (src/gradient.jl:16-24)."""
+    result = np.zeros(_length(x)) if not isinstance(x, _DeviceArray) else x.similar()
+    return gradient_b(result, f, x, cfg, check, ctx, chunks)
+
+
+def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None):
+    """ForwardDiff.gradient!(result, f, x, cfg, Val{check}()) (src/gradient.jl:35-44).
+    `chunks=(lo, hi)` restricts the call to a 0-based chunk range (the sharding hook)."""
+    cfg = cfg if cfg is not None else GradientConfig(f, x)
+    if check:
+        checktag(cfg.tag, f, x)
+    n = _length(x)
+    out = result.derivs[0] if isinstance(result, DiffResult) else result
+    if _length(out) != n:
+        raise DimensionMismatch(f"gradient result has {_length(out)} entries, x has {n}")
+    fid = _catalogue_id(f, _lib.FN)
+    if n == 0:      # Chunk{0}: vector mode, f returns a plain Real, fill!(result, 0) (gradient.jl:65)
+        if isinstance(result, DiffResult):
+            result.value = float(f(np.zeros(0))) if callable(f) and fid is None else 0.0
+        return result
+    N = cfg.N
+    if N > n:
+        raise ChunkSizeError(f"chunk size cannot be greater than ForwardDiff.structural_length(x) ({N} > {n})")
+    ctx = _ctx_of(x, ctx)
+    lo, hi = (0, -1) if chunks is None else chunks
+    if fid is not None:
+        value = _fused_gradient(ctx, fid, x, N, lo, hi, out)
+    else:
+        value = _loop_gradient(ctx, f, x, cfg, lo, hi, out)
+    if isinstance(result, DiffResult) and value is not None:
+        result.value = value
+    return result
+
+
+def _fused_gradient(ctx, fid, x, N, lo, hi, out):
+    lib = ctx.lib
+    if isinstance(x, _DeviceArray):
+        val = B200Array.alloc(ctx, 1)
+        ctx.check(lib.fdb_gradient_chunked(ctx.h, fid, x.h, N, lo, hi, out.h, val.h))
+        plan = chunk_plan(x.n, N) if x.n != N else dict(nchunks=1)
+        return float(val.numpy()[0]) if hi < 0 or hi == plan["nchunks"] else None
+    xh = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
+        raise FdbError("gradient!: result must be a contiguous float64 array")
+    val = C.c_double(float("nan"))
+    ctx.check(lib.fdb_gradient_host(ctx.h, fid, xh.ctypes.data_as(_dp), xh.size, N, lo, hi,
+                                    out.ctypes.data_as(_dp), C.byref(val)))
+    return None if np.isnan(val.value) and not (hi < 0) else val.value
+
+
+def _loop_gradient(ctx, f, x, cfg, lo, hi, out):
+    """The reference chunk loop on materialised device duals (src/gradient.jl:114-159 / :97-108)."""
+    lib = ctx.lib
+    xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
+    n, N = xd.n, cfg.N
+    res = out if isinstance(out, _DeviceArray) else B200Array.alloc(ctx, n)
+    xdual = cfg.duals(ctx)
+
+    def call_f():
+        ydual = f(xdual)
+        if not isinstance(ydual, B200DualArray) or ydual.n != 1:   # GRAD_ERROR, gradient.jl:88-91
+            raise DimensionMismatch("gradient(f, x) expects that f(x) is a real number. Perhaps you meant jacobian(f, x)?")
+        return ydual
+
+    if n == N:                                                     # vector mode
+        ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, 0, 0))
+        ydual = call_f()
+        ctx.check(lib.fdb_extract_gradient(ctx.h, res.h, ydual.h))
+    else:
+        p = chunk_plan(n, N)
+        nchunks = p["nchunks"]
+        hi = nchunks if hi < 0 else hi
+        full = (lo == 0 and hi == nchunks)
+        if not full:
+            ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, 0, 0))
+        ydual = None
+        for c in range(lo, hi):
+            c1 = c + 1
+            if c1 == nchunks:                                       # final chunk, gradient.jl:150-152
+                i, cs = p["lastchunkindex"], p["lastchunksize"]
+                ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, i, cs))
+                ydual = call_f()
+                ctx.check(lib.fdb_extract_gradient_chunk(ctx.h, res.h, ydual.h, i, cs))
+            elif c1 == 1 and full:                                  # first chunk, gradient.jl:133-138
+                ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, 1, N))
+                ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, N + 1, n - N))
+                ydual = call_f()
+                ctx.check(lib.fdb_extract_gradient_chunk(ctx.h, res.h, ydual.h, 1, N))
+                ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, 1, N))
+            else:                                                   # middle chunks, gradient.jl:141-147
+                i = (c1 - 1) * N + 1
+                ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, i, N))
+                ydual = call_f()
+                ctx.check(lib.fdb_extract_gradient_chunk(ctx.h, res.h, ydual.h, i, N))
+                ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, i, N))
+        if ydual is None:
+            return None
+    if res is not out:
+        out[...] = res.numpy().reshape(np.shape(out))
+    return float(ydual.numpy()[0, 0])                               # extract_value!, gradient.jl:155
+
+
+# ---------------------------------------------------------------------------
+# jacobian
+# ---------------------------------------------------------------------------
+def jacobian(f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=None, m=None):
+    """ForwardDiff.jacobian(f, x, cfg) and, with `y`, jacobian(f!, y, x, cfg) (src/jacobian.jl:18-44).
+    Returns the dense column-major length(y) x length(x) matrix (jacobian.jl:221)."""
+    ylen = _length(y) if y is not None else (m if m is not None else getattr(f, "output_length", lambda n: None)(_length(x)))
+    if ylen is None:
+        raise FdbError("jacobian: output length unknown; pass m= or y=")
+    n = _length(x)
+    if isinstance(x, _DeviceArray):
+        result = B200Array.alloc(x.ctx, ylen * n)
+    else:
+        result = np.zeros((ylen, n), order="F")
+    return jacobian_b(result, f, x, cfg, check, ctx, y, params, chunks)
+
+
+def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=None):
+    """ForwardDiff.jacobian!(result, f, x, cfg) / jacobian!(result, f!, y, x, cfg) (src/jacobian.jl:57-87)."""
+    cfg = cfg if cfg is not None else JacobianConfig(f, x, y=y)
+    if check:
+        checktag(cfg.tag, f, x)
+    n, N = _length(x), cfg.N
+    if N > n:
+        raise ChunkSizeError(f"chunk size cannot be greater than ForwardDiff.structural_length(x) ({N} > {n})")
+    ctx = _ctx_of(x, ctx)
+    lib = ctx.lib
+    out = result.derivs[0] if isinstance(result, DiffResult) else result
+    fid = _catalogue_id(f, _lib.JFN)
+    lo, hi = (0, -1) if chunks is None else chunks
+    if fid is None:
+        return _loop_jacobian(ctx, result, out, f, x, cfg, y, lo, hi)
+    params = params or getattr(f, "params", {}) or {}
+    host = not isinstance(x, _DeviceArray)
+    xd = ctx.array(x) if host else x
+    if isinstance(out, _DeviceArray):
+        m = out.n // n
+        Jd = out
+    else:
+        m = out.shape[0]
+        Jd = B200Array.alloc(ctx, m * n)
+    yd = B200Array.alloc(ctx, m)
+    A, b, alpha = params.get("A"), params.get("b"), float(params.get("alpha", 0.0))
+    Ad = None if A is None else (A if isinstance(A, _DeviceArray) else ctx.array(np.asfortranarray(A).ravel(order="F")))
+    bd = None if b is None else (b if isinstance(b, _DeviceArray) else ctx.array(b))
+    lda = m
+    ctx.check(lib.fdb_jacobian_chunked(ctx.h, fid, xd.h, m, N, Ad.h if Ad else None, lda, bd.h if bd else None, alpha,
+                                       lo, hi, Jd.h, m, yd.h))
+    if Jd is not out:
+        out[...] = Jd.numpy().reshape((m, n), order="F")
+    last = hi < 0 or hi == (1 if n == N else chunk_plan(n, N)["nchunks"])
+    if last:
+        yv = yd.numpy()
+        if y is not None and not isinstance(y, _DeviceArray):
+            y[...] = yv                                              # map!(d -> value(T,d), y, ydual), jacobian.jl:229
+        if isinstance(result, DiffResult):
+            result.value = yv
+    return result
+
+
+def _loop_jacobian(ctx, result, out, f, x, cfg, y, lo, hi):
+    """Reference chunk loop on materialised duals (src/jacobian.jl:169-216); f(xdual) -> ydual or f!(ydual, xdual)."""
+    lib = ctx.lib
+    xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
+    n, N = xd.n, cfg.N
+    inplace = y is not None
+    duals = cfg.duals(ctx)
+    ydual_buf, xdual = duals if inplace else (None, duals)
+    yd0 = (y if isinstance(y, _DeviceArray) else ctx.array(y)) if inplace else None
+
+    def compute():
+        if inplace:
+            ctx.check(lib.fdb_seed_zero(ctx.h, ydual_buf.h, yd0.h, 0, 0))    # jacobian.jl:227
+            f(ydual_buf, xdual)
+            return ydual_buf
+        yd = f(xdual)
+        if not isinstance(yd, B200DualArray):                                   # JACOBIAN_ERROR
+            raise DimensionMismatch("jacobian(f, x) expects that f(x) is an array. Perhaps you meant gradient(f, x)?")
+        return yd
+
+    state = {}
+
+    def extract(ydual, index, cs):
+        if "J" not in state:
+            m = ydual.n
+            state["m"] = m
+            state["J"] = out if isinstance(out, _DeviceArray) else B200Array.alloc(ctx, m * n)
+            if state["J"].n != m * n:
+                raise DimensionMismatch(f"Jacobian result has {state['J'].n} entries, expected {m}x{n}")
+        ctx.check(lib.fdb_extract_jacobian_chunk(ctx.h, state["J"].h, state["m"], ydual.h, index, cs))
+
+    if n == N:
+        ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, 0, 0))
+        ydual = compute()
+        extract(ydual, 1, N)
+    else:
+        p = chunk_plan(n, N)
+        nchunks = p["nchunks"]
+        hi = nchunks if hi < 0 else hi
+        full = (lo == 0 and hi == nchunks)
+        if not full:
+            ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, 0, 0))
+        ydual = None
+        for c in range(lo, hi):
+            c1 = c + 1
+            if c1 == nchunks:
+                i, cs = p["lastchunkindex"], p["lastchunksize"]
+                ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, i, cs))
+                ydual = compute(); extract(ydual, i, cs)
+            elif c1 == 1 and full:
+                ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, 1, N))
+                ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, N + 1, n - N))
+                ydual = compute(); extract(ydual, 1, N)
+                ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, 1, N))
+            else:
+                i = (c1 - 1) * N + 1
+                ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, i, N))
+                ydual = compute(); extract(ydual, i, N)
+                ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, i, N))
+    J, m = state["J"], state["m"]
+    if J is not out:
+        if out.shape != (m, n):
+            raise DimensionMismatch(f"Jacobian result has shape {out.shape}, expected {(m, n)}")
+        out[...] = J.numpy().reshape((m, n), order="F")
+    yv = ydual.values().numpy()
+    if inplace and not isinstance(y, _DeviceArray):
+        y[...] = yv
+    if isinstance(result, DiffResult):
+        result.value = yv
+    return result
+
+
+# ---------------------------------------------------------------------------
+# hessian
+# ---------------------------------------------------------------------------
+def hessian(f, x, cfg=None, check=True, ctx=None, chunks=None):
+    """ForwardDiff.hessian(f, x, cfg) (src/hessian.jl:14-19)."""
+    n = _length(x)
+    result = np.zeros((n, n), order="F")
+    return hessian_b(result, f, x, cfg, check, ctx, chunks)
+
+
+def hessian_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None):
+    """ForwardDiff.hessian!(result, f, x, cfg) for an array or a HessianResult (src/hessian.jl:31-37,66-71)."""
+    cfg = cfg if cfg is not None else HessianConfig(f, x)
+    if check:
+        checktag(cfg.tag, f, x)
+    n, N = _length(x), cfg.N
+    if N > n:
+        raise ChunkSizeError(f"chunk size cannot be greater than ForwardDiff.structural_length(x) ({N} > {n})")
+    fid = _catalogue_id(f, _lib.FN)
+    if fid is None:
+        raise _lib.UnsupportedOp("hessian: only catalogue targets have a nested-dual device kernel")
+    ctx = _ctx_of(x, ctx)
+    lo, hi = (0, -1) if chunks is None else chunks
+    H = result.derivs[1] if isinstance(result, DiffResult) else result
+    if H.shape != (n, n) or not H.flags.f_contiguous:
+        raise DimensionMismatch("hessian!: result must be a column-major n x n float64 matrix")
+    xh = np.ascontiguousarray(x.numpy() if isinstance(x, _DeviceArray) else x, dtype=np.float64).ravel()
+    g = np.zeros(n)
+    val = C.c_double(0.0)
+    ctx.check(ctx.lib.fdb_hessian_host(ctx.h, fid, xh.ctypes.data_as(_dp), n, N, lo, hi, H.ctypes.data_as(_dp), n,
+                                       g.ctypes.data_as(_dp), C.byref(val)))
+    if isinstance(result, DiffResult):
+        result.value = val.value
+        result.derivs[0][...] = g
+    return result

@@ -1,0 +1,212 @@
+/* fdb200.h -- C ABI of the B200-native engine for ForwardDiff.jl's chunked
+ * dual-number sweep.
+ *
+ * This is the drop-in boundary: every entry point replaces one piece of the
+ * reference's chunk-mode path (file:line under /root/reference given with each
+ * declaration).  A Julia host reaches it through `ccall` (see INTEGRATION.md and
+ * forwarddiff.jl_b200/julia/ForwardDiffB200.jl); the Python harness in
+ * forwarddiff.jl_b200/fdb200/ binds the same symbols through ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ or torch types cross the boundary;
+ *  - every function returns an fdb_status (0 = ok); the message of the last
+ *    failure on a context is available from fdb_last_error();
+ *  - indices follow the reference: `index` arguments are 1-based structural
+ *    positions exactly as in src/apiutils.jl and src/gradient.jl; chunk ranges
+ *    [chunk_lo, chunk_hi) are 0-based chunk numbers (chunk c seeds structural
+ *    positions c*N+1 .. min((c+1)*N, n), src/gradient.jl:141-152);
+ *  - device arrays are SoA: an array of n Dual{T,Float64,N} is stored as N+1
+ *    planes of `ld` doubles (plane 0 = values, plane k = partial k); a nested
+ *    Dual{T,Dual{T,Float64,N},N} array has (N+1)^2 planes ordered
+ *    plane(a,b) = a*(N+1)+b with a the outer and b the inner index (0 = value),
+ *    which is the reference's AoS field order (src/dual.jl:14-16,357-360);
+ *  - host-side `*_aos` buffers use that AoS order: element e occupies
+ *    doubles [e*P, (e+1)*P), P = number of planes;
+ *  - one context per process and per GPU (one process per GPU); calls on a
+ *    context are issued on its CUDA stream and are synchronous unless the
+ *    context was put in async mode with fdb_set_async(ctx, 1);
+ *  - there is no CPU fallback: without a CUDA device fdb_init fails.
+ */
+#ifndef FDB200_H
+#define FDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdb_ctx fdb_ctx;     /* opaque: device, stream, scratch, last error */
+typedef struct fdb_array fdb_array; /* opaque: SoA device array (plain, Dual or nested Dual) */
+
+typedef enum {
+    FDB_OK = 0,
+    FDB_ERR_BADARG = 1,      /* null pointer, bad enum, bad N (1..12; nested 1..8,12 unsupported above 8) */
+    FDB_ERR_SHAPE = 2,       /* DimensionMismatch (src/gradient.jl:46,88-91; src/jacobian.jl:89,164) */
+    FDB_ERR_CUDA = 3,
+    FDB_ERR_OOM = 4,
+    FDB_ERR_UNSUPPORTED = 5, /* op / function id not in the device catalogue */
+    FDB_ERR_CHUNK = 6        /* ArgumentError "chunk size cannot be greater than structural_length(x)"
+                                (src/gradient.jl:116-118, src/jacobian.jl:172-174) */
+} fdb_status;
+
+#define FDB_MAX_CHUNK 12 /* DEFAULT_CHUNK_THRESHOLD, src/prelude.jl:2 */
+
+/* unary ops: src/dual.jl:476-490 (DiffRules loop), :519 (-), :587-597 (literal_pow), :709-717 (sin/cos) */
+typedef enum {
+    FDB_NEG = 1, FDB_EXP, FDB_LOG, FDB_SIN, FDB_COS, FDB_TANH, FDB_SQRT, FDB_ABS, FDB_ABS2, FDB_INV,
+    FDB_POW0, FDB_POW1, FDB_POW2, FDB_POW3
+} fdb_op1;
+/* binary ops: src/dual.jl:499-519 (+ -), DiffRules * max min, :532-544 (/), :549-585 (^) */
+typedef enum { FDB_ADD = 1, FDB_SUB, FDB_MUL, FDB_DIV, FDB_POW, FDB_MAX, FDB_MIN } fdb_op2;
+typedef enum { FDB_SUM = 1, FDB_PROD = 2 } fdb_redop;
+
+/* scalar-valued catalogue targets for fdb_gradient_chunked / fdb_hessian_chunked */
+typedef enum {
+    FDB_FN_ROSENBROCK = 1, /* docs/src/user/advanced.md:36-44 (= DiffTests.rosenbrock_1) */
+    FDB_FN_ACKLEY = 2,     /* DiffTests.ackley; C++ twin benchmarks/cpp/benchmarks.cpp:10-21 */
+    FDB_FN_SUMSQ = 3,      /* sum of x[i]^2 */
+    FDB_FN_PROD = 4        /* prod(x) */
+} fdb_scalar_fn;
+/* array-valued catalogue targets for fdb_jacobian_chunked */
+typedef enum {
+    FDB_JFN_TANH_AFFINE = 1, /* f(x) = tanh.(A*x .+ b) */
+    FDB_JFN_BRUSSELATOR = 2, /* f!(dx, x): 1-D Brusselator RHS, x = [u; v] */
+    FDB_JFN_JACTEST = 3      /* test/JacobianTest.jl:23-31 (n = 3, m = 4) */
+} fdb_array_fn;
+
+/* structural index sets of src/apiutils.jl:44-71 */
+typedef enum { FDB_DENSE = 0, FDB_UPPER = 1, FDB_LOWER = 2, FDB_DIAGONAL = 3 } fdb_structure;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int fdb_device_count(int* count);
+int fdb_init(int device, fdb_ctx** ctx);          /* binds the context to one GPU, creates its stream */
+int fdb_shutdown(fdb_ctx* ctx);
+const char* fdb_last_error(fdb_ctx* ctx);          /* ctx may be NULL: last error of a failed fdb_init */
+int fdb_sync(fdb_ctx* ctx);
+int fdb_set_async(fdb_ctx* ctx, int async);       /* 1: calls return after enqueueing (benchmarks) */
+int fdb_set_stream(fdb_ctx* ctx, void* cuda_stream); /* adopt a caller-owned cudaStream_t (NULL = own stream) */
+int fdb_get_stream(fdb_ctx* ctx, void** cuda_stream);
+int fdb_set_nansafe(fdb_ctx* ctx, int enabled);   /* `nansafe_mode` preference, src/prelude.jl:1 */
+/* 1 (default): terms that touch no seeded position are evaluated on one representative
+ * partial lane (bit-identical results; see fdb_sweep.cu).  0: all N lanes for every term. */
+int fdb_set_lane_sharing(fdb_ctx* ctx, int enabled);
+int fdb_kernel_launches(fdb_ctx* ctx, int64_t* count); /* kernels launched on this context so far */
+const char* fdb_version(void);
+
+/* ---- memory ------------------------------------------------------------------
+ * fdb_array_alloc replaces `similar(x, Dual{T,V,N})` in the config constructors
+ * (src/config.jl:122,159,185-186,225-226).  level 0 = Vector{Float64} (N ignored),
+ * 1 = Vector{Dual{T,Float64,N}}, 2 = Vector{Dual{T,Dual{T,Float64,N},N}}. */
+int fdb_array_alloc(fdb_ctx* ctx, int64_t n, int N, int level, fdb_array** out);
+int fdb_array_wrap(fdb_ctx* ctx, double* device_ptr, int64_t n, int64_t ld, int N, int level, fdb_array** out);
+int fdb_array_free(fdb_array* a);
+int fdb_array_info(const fdb_array* a, int64_t* n, int* N, int* level, int64_t* ld, double** device_ptr);
+int fdb_upload_values(fdb_array* a, const double* host);      /* plane 0 <- host[0..n) */
+int fdb_download_values(const fdb_array* a, double* host);    /* host[0..n) <- plane 0 */
+int fdb_upload_duals_aos(fdb_array* a, const double* host_aos);   /* AoS (src/dual.jl:357-360) -> SoA planes */
+int fdb_download_duals_aos(const fdb_array* a, double* host_aos);
+int fdb_copy(fdb_array* dst, const fdb_array* src);            /* same shape, device to device */
+
+/* ---- host-side planning (pure host code, no GPU needed) ------------------ */
+/* pickchunksize, src/prelude.jl:29-36 */
+int64_t fdb_pickchunksize(int64_t input_length, int64_t threshold);
+/* structural_length, src/prelude.jl:15-20 (rows = length for FDB_DENSE) */
+int64_t fdb_structural_length(int structure, int64_t rows);
+/* 0-based column-major storage index of structural position pos (0-based), src/apiutils.jl:44-71 */
+int64_t fdb_structural_index(int structure, int64_t rows, int64_t pos);
+/* chunk bookkeeping of src/gradient.jl:121-125 (= src/jacobian.jl:177-181) and the
+ * contiguous chunk range owned by `rank` of `world`. */
+typedef struct {
+    int64_t xlen, remainder, lastchunksize, lastchunkindex; /* lastchunkindex is 1-based */
+    int64_t middle_lo, middle_hi;                            /* middlechunks = middle_lo:middle_hi (1-based) */
+    int64_t nchunks;
+    int64_t chunk_lo, chunk_hi;                              /* this rank's chunks, 0-based half-open */
+    int64_t elem_lo, elem_hi;                                /* structural positions they seed, 0-based half-open */
+} fdb_chunk_plan;
+int fdb_plan_chunks(int64_t xlen, int N, int rank, int world, fdb_chunk_plan* out);
+
+/* ---- sweep utilities (bit-exact) --------------------------------------------
+ * duals: level-1 (or level-2) array; x: array one level below holding the values. */
+/* seed!(duals, x, index, seeds, chunksize), src/apiutils.jl:125-143; index<=0 selects
+ * seed!(duals, x, seeds), src/apiutils.jl:107-123 (first N structural positions) */
+int fdb_seed(fdb_ctx* ctx, fdb_array* duals, const fdb_array* x, int64_t index, int64_t chunksize);
+/* seed_zero_partials!(duals, x, index, count), src/apiutils.jl:83-87; index<=0 selects
+ * seed_zero_partials!(duals, x), src/apiutils.jl:76-77 (every structural position) */
+int fdb_seed_zero(fdb_ctx* ctx, fdb_array* duals, const fdb_array* x, int64_t index, int64_t count);
+/* the same on UpperTriangular / LowerTriangular / Diagonal storage (rows x rows, column-major) */
+int fdb_seed_structured(fdb_ctx* ctx, fdb_array* duals, const fdb_array* x, int structure, int64_t rows,
+                        int64_t index, int64_t chunksize);
+int fdb_seed_zero_structured(fdb_ctx* ctx, fdb_array* duals, const fdb_array* x, int structure, int64_t rows,
+                             int64_t index, int64_t count);
+/* extract_gradient_chunk!(T, result, dual, index, chunksize), src/gradient.jl:74-81;
+ * ydual is a dual array of length 1 */
+int fdb_extract_gradient_chunk(fdb_ctx* ctx, fdb_array* result, const fdb_array* ydual, int64_t index,
+                               int64_t chunksize);
+/* extract_gradient!(T, result, dual), src/gradient.jl:66-72 (vector mode) */
+int fdb_extract_gradient(fdb_ctx* ctx, fdb_array* result, const fdb_array* ydual);
+/* extract_jacobian_chunk!(T, result, ydual, index, chunksize), src/jacobian.jl:109-118;
+ * result is a plain array viewed as column-major with leading dimension ld_result */
+int fdb_extract_jacobian_chunk(fdb_ctx* ctx, fdb_array* result, int64_t ld_result, const fdb_array* ydual,
+                               int64_t index, int64_t chunksize);
+/* extract_jacobian!(T, result, ydual, n), src/jacobian.jl:95-102 */
+int fdb_extract_jacobian(fdb_ctx* ctx, fdb_array* result, int64_t ld_result, const fdb_array* ydual, int64_t n);
+/* extract_value!: map!(d -> value(T,d), y, ydual), src/apiutils.jl:9-12 */
+int fdb_extract_value(fdb_ctx* ctx, fdb_array* y, const fdb_array* ydual);
+
+/* ---- array arithmetic on Dual arrays (what a user `f` is made of) ----------
+ * Operands of fdb_map2 may each be a level-1 Dual array or a level-0 plain
+ * array (a Vector{Float64} broadcast against duals = the Real (x)or Dual bodies
+ * of src/dual.jl:150-210); at least one must be level 1.  A length-1 operand
+ * broadcasts. */
+int fdb_map1(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a);
+int fdb_map2(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a, const fdb_array* b);
+/* scalar_first = 0: a (op) s ; 1: s (op) a */
+int fdb_map2_scalar(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a, double s, int scalar_first);
+/* fma, src/dual.jl:625-665.  kind 0: fma(a,b,c) all dual; 1: fma(a,b,s); 2: fma(a,s,c) */
+int fdb_fma(fdb_ctx* ctx, int kind, fdb_array* out, const fdb_array* a, const fdb_array* b, const fdb_array* c,
+            double s);
+/* sum / prod of a Dual array -> Dual array of length 1 (two-pass, deterministic) */
+int fdb_reduce(fdb_ctx* ctx, int redop, fdb_array* out1, const fdb_array* a);
+/* evaluate a catalogue target on a materialised dual array: out1 = f(xdual) */
+int fdb_eval_scalar_fn(fdb_ctx* ctx, int fn, fdb_array* out1, const fdb_array* xdual);
+
+/* ---- whole-path drivers ---------------------------------------------------------
+ * Each replaces one chunk-mode loop of the reference and runs ALL requested chunk
+ * sweeps batched on the device (seeds generated in registers, partials never leave
+ * the SM, extraction fused).  x, grad, J, H, y are level-0 arrays.  Chunks
+ * [chunk_lo, chunk_hi) are evaluated (chunk_hi < 0 = all) -- this is the sharding
+ * hook: ranks own disjoint chunk ranges and therefore disjoint slices of grad / J / H.
+ * N == xlen selects vector mode (src/gradient.jl:19-23). */
+/* chunk_mode_gradient!, src/gradient.jl:114-159.  value_dev (level-0 array of length >= 1,
+ * may be NULL) receives f(x) when the range includes the last chunk (gradient.jl:155). */
+int fdb_gradient_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi,
+                         fdb_array* grad, fdb_array* value_dev);
+/* chunk_mode_jacobian(!), src/jacobian.jl:169-244.  J: column-major m x n with leading
+ * dimension ldJ, columns of the requested chunks written; y (may be NULL) <- value.(ydual).
+ * A (m x n column-major, lda), b (m) and alpha are the target's Float64 parameters. */
+int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int64_t m, int N, const fdb_array* A,
+                         int64_t lda, const fdb_array* b, double alpha, int64_t chunk_lo, int64_t chunk_hi,
+                         fdb_array* J, int64_t ldJ, fdb_array* y);
+/* hessian / hessian!(::DiffResult), src/hessian.jl:14-71: outer chunks [lo,hi) of the
+ * Jacobian of the chunked gradient; H column-major n x n (ldH); grad, value_dev may be NULL. */
+int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi,
+                        fdb_array* H, int64_t ldH, fdb_array* grad, fdb_array* value_dev);
+
+/* ---- host-buffer entry points (what ForwardDiff.gradient!(out, f, x, cfg) with
+ * host Vectors binds to): upload x, run the sweeps, download the result slice.  grad_host has
+ * xlen entries; only the entries of the requested chunks are written. ------------ */
+int fdb_gradient_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, int N, int64_t chunk_lo,
+                      int64_t chunk_hi, double* grad_host, double* value_host);
+int fdb_hessian_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, int N, int64_t chunk_lo,
+                     int64_t chunk_hi, double* H_host, int64_t ldH, double* grad_host, double* value_host);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------- */
+/* FP64 instruction-issue peak: a register-only chain of independent DMUL/DADD pairs;
+ * returns achieved non-fused FP64 operations per second on this device. */
+int fdb_measure_fp64_peak(fdb_ctx* ctx, double* dp_ops_per_s, double* dfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDB200_H */

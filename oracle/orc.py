@@ -173,16 +173,24 @@ class Oracle:
         assert rc == 0
         return g, val.value
 
-    def jacobian(self, fn, x, m, N, A=None, b=None, alpha=0.0, inplace=False, y0=None, chunks=None, want_J=True):
+    def jacobian(self, fn, x, m, N, A=None, b=None, alpha=0.0, inplace=False, y0=None, chunks=None, want_J=True,
+                 cols=None):
+        """cols=(c0, c1): return only Jacobian columns [c0, c1) (must cover the requested chunks) so that a
+        chunk range of a Jacobian too large for host memory can be checked."""
         x = _f64(x); n = x.size
-        J = np.zeros((m, n), order="F") if want_J else None
         y = np.zeros(m) if y0 is None else _f64(y0).copy()
         Af = None if A is None else np.asfortranarray(A, dtype=np.float64)
         lda = 0 if A is None else A.shape[0]
         clo, chi = (0, -1) if chunks is None else chunks
+        if cols is not None:
+            J = np.zeros((m, cols[1] - cols[0]), order="F")
+            Jp = C.cast(C.c_void_p(J.ctypes.data - cols[0] * m * 8), _dp)   # column c lands at J[:, c - c0]
+        else:
+            J = np.zeros((m, n), order="F") if want_J else None
+            Jp = _p(J)
         rc = self.lib.orc_jacobian(JFN[fn], int(inplace), _p(x), n, m, N, _p(Af), lda,
                                    _p(None if b is None else _f64(b)), float(alpha),
-                                   _p(J), m, _p(y), clo, chi)
+                                   Jp, m, _p(y), clo, chi)
         if rc == -3:
             raise ValueError("chunk size cannot be greater than structural_length(x)")
         assert rc == 0

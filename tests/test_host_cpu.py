@@ -1,0 +1,154 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/fdb200.h
+declares, the host-side planning code reproduces the reference's bookkeeping, the API mirror
+raises the reference's errors before touching the device, the product never imports the oracle,
+and the multi-rank sharding + all-gather logic works under gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import fdb200
+from fdb200 import functions as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fdb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fdb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    lib = C.CDLL(fdb200.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    # the ctypes table binds exactly the declared set
+    assert set(fdb200._lib.SIGNATURES) == declared
+    assert fdb200._lib.load().fdb_version().decode().startswith("fdb200")
+
+
+def test_no_cpu_fallback_without_gpu():
+    n = C.c_int(-1)
+    rc = fdb200._lib.load().fdb_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fdb200.CudaError):
+        fdb200.Context(0)
+    with pytest.raises(fdb200.CudaError):      # the public API fails loudly, it does not compute on the host
+        fdb200.gradient(F.rosenbrock, np.ones(5), fdb200.GradientConfig(F.rosenbrock, np.ones(5), fdb200.Chunk(2)))
+
+
+def test_product_never_references_the_oracle():
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "forwarddiff.jl_b200")):
+        if os.sep + "build" in base or os.sep + "lib" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".jl", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                if re.search(r"\b(import orc|from orc|liboracle|oracle/|orc_[a-z])", txt):
+                    bad.append(os.path.join(base, f))
+    assert not bad, bad
+
+
+def test_pickchunksize_and_plan_match_reference(oracle):
+    for n in list(range(0, 60)) + [100, 1000, 8192, 10_000, 65_536, 1_000_000]:
+        assert fdb200.pickchunksize(n) == oracle.pickchunksize(n)
+        for thr in (1, 5, 8):
+            assert fdb200.pickchunksize(n, thr) == oracle.pickchunksize(n, thr)
+    for n, N in ((13, 4), (13, 6), (13, 12), (10_000, 10), (1_000_000, 12), (8192, 12), (65_536, 8), (2048, 8), (25, 5)):
+        p = fdb200.chunk_plan(n, N)
+        q = oracle.chunk_plan(n, N)
+        for k in ("remainder", "lastchunksize", "lastchunkindex", "middle_hi", "nchunks"):
+            assert p[k] == q[k], (n, N, k)
+        assert p["middle_lo"] == 2
+    assert fdb200.chunk_plan(12, 12)["nchunks"] == 1           # N == n: vector mode, one sweep
+    with pytest.raises(fdb200.ChunkSizeError):
+        fdb200.chunk_plan(3, 4)
+
+
+@pytest.mark.parametrize("n,N", [(1_000_000, 12), (65_536, 8), (13, 4), (100, 7), (24, 12)])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_rank_chunk_ranges_partition_the_chunks(n, N, world):
+    plans = [fdb200.chunk_plan(n, N, r, world) for r in range(world)]
+    nchunks = plans[0]["nchunks"]
+    covered = []
+    for p in plans:
+        covered += list(range(p["chunk_lo"], p["chunk_hi"])) if nchunks < 10_000 else []
+        assert 0 <= p["chunk_lo"] <= p["chunk_hi"] <= nchunks
+        assert p["elem_lo"] == min(p["chunk_lo"] * N, n) and p["elem_hi"] == min(p["chunk_hi"] * N, n)
+    assert plans[0]["chunk_lo"] == 0 and plans[-1]["chunk_hi"] == nchunks or any(p["chunk_hi"] == nchunks for p in plans)
+    for a, b in zip(plans, plans[1:]):
+        assert a["chunk_hi"] == b["chunk_lo"] or b["chunk_lo"] == b["chunk_hi"] == nchunks
+    if nchunks < 10_000:
+        assert covered == list(range(nchunks))
+    lay = fdb200.dist.slice_layout(n, N, world)
+    assert lay["per"] * world >= n and lay["per"] % N == 0
+    assert 0 <= fdb200.dist.owner_of_last_chunk(n, N, world) < world
+
+
+def test_structural_index_sets(oracle):
+    lib = fdb200._lib.load()
+    for name, kind in fdb200._lib.STRUCTURE.items():
+        for rows in (1, 2, 5, 6, 17):
+            sidx = oracle.structural_indices(kind, rows)
+            assert lib.fdb_structural_length(kind, rows) == len(sidx)
+            assert [lib.fdb_structural_index(kind, rows, p) for p in range(len(sidx))] == sidx.tolist(), (name, rows)
+
+
+def test_api_errors_raised_on_the_host_before_any_device_work():
+    x = np.ones(5)
+    with pytest.raises(fdb200.ChunkSizeError):
+        fdb200.gradient(F.rosenbrock, x, fdb200.GradientConfig(F.rosenbrock, x, fdb200.Chunk(6)))
+    with pytest.raises(fdb200.InvalidTagException):
+        fdb200.gradient(F.rosenbrock, x, fdb200.GradientConfig(F.ackley, x, fdb200.Chunk(2)))
+    with pytest.raises(fdb200.DimensionMismatch):
+        fdb200.gradient_b(np.zeros(4), F.rosenbrock, x, fdb200.GradientConfig(F.rosenbrock, x, fdb200.Chunk(2)))
+    with pytest.raises(fdb200.ChunkSizeError):
+        fdb200.hessian(F.rosenbrock, x, fdb200.HessianConfig(F.rosenbrock, x, fdb200.Chunk(12)))
+    assert fdb200.GradientConfig(F.rosenbrock, np.zeros(13)).N == 7       # Chunk(x) heuristic
+    assert fdb200.gradient(F.rosenbrock, np.zeros(0), fdb200.GradientConfig(F.rosenbrock, np.zeros(0), fdb200.Chunk(0))).size == 0
+    t1, t2 = fdb200.Tag(F.rosenbrock), fdb200.Tag(F.ackley)
+    assert t1.count < t2.count                                            # tag ordering counter, config.jl:8-19
+    assert fdb200.checktag(None, F.rosenbrock, x) and fdb200.checktag(fdb200.Tag((F.rosenbrock, 1)), F.ackley, x)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, os.path.join(sys.argv[1], "forwarddiff.jl_b200")); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
+import numpy as np, torch, torch.distributed as dist
+import fdb200, orc
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+o = orc.Oracle()                       # the oracle stands in for the device sweep: this test is about the plumbing
+for n, N, fn in ((1003, 12, "rosenbrock"), (50, 4, "ackley"), (24, 12, "sumsq")):
+    x = np.random.default_rng(7).uniform(0.5, 1.5, n)
+    p = fdb200.chunk_plan(n, N, rank, world)
+    lay = fdb200.dist.slice_layout(n, N, world)
+    g_local, v_local = o.gradient(fn, x, N, chunks=(p["chunk_lo"], p["chunk_hi"])) if p["chunk_hi"] > p["chunk_lo"] else (np.zeros(n), 0.0)
+    mine = torch.zeros(lay["per"], dtype=torch.float64)
+    mine[: p["elem_hi"] - p["elem_lo"]] = torch.from_numpy(g_local[p["elem_lo"]:p["elem_hi"]])
+    full = fdb200.dist.allgather_slices(mine, world)[:n].numpy()
+    v = torch.tensor([v_local], dtype=torch.float64)
+    dist.broadcast(v, src=fdb200.dist.owner_of_last_chunk(n, N, world))
+    g_ref, v_ref = o.gradient(fn, x, N)
+    assert np.array_equal(full, g_ref), (rank, n, N)
+    assert v.item() == v_ref
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_sharding_and_allgather_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

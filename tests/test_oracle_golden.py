@@ -1,0 +1,278 @@
+"""Pins the CPU oracle (oracle/oracle.cpp) against every known-answer vector the reference's
+own tests hold for the chunk-mode path (tests/golden/reference_vectors.json, each entry cites
+its source), against the reference's benchmarks/cpp program compiled into oracle/_ref, and --
+for the DiffRules-derived formulas that have no golden in the reference tree -- against
+central finite differences with the reference's own tolerance (test/utils.jl: 3e-5)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))
+
+
+def _f(v):
+    return [float(t) for t in v]
+
+
+# ---- chunk heuristic and bookkeeping (src/prelude.jl:29-36, src/gradient.jl:121-125) ----------
+def test_pickchunksize(oracle):
+    for n, expect in G["chunk_heuristic"]["pickchunksize"]:
+        assert oracle.pickchunksize(n) == expect
+
+
+def test_chunk_plan_configs(oracle):
+    p = oracle.chunk_plan(1_000_000, 12)      # C2 of BASELINE.json: 83 333 full chunks + last of 4 at 999 997
+    assert (p["nchunks"], p["lastchunksize"], p["lastchunkindex"], p["remainder"]) == (83334, 4, 999997, 4)
+    p = oracle.chunk_plan(8192, 12)           # C3: 682 full + last of 8 at 8185
+    assert (p["nchunks"], p["lastchunksize"], p["lastchunkindex"]) == (683, 8, 8185)
+    p = oracle.chunk_plan(65536, 8)           # C4
+    assert (p["nchunks"], p["lastchunksize"], p["lastchunkindex"]) == (8192, 8, 65529)
+    p = oracle.chunk_plan(13, 4)              # test/utils.jl XLEN=13: 3*4+1
+    assert (p["nchunks"], p["lastchunksize"], p["lastchunkindex"], p["middle_hi"]) == (4, 1, 13, 3)
+    with pytest.raises(ValueError):
+        oracle.chunk_plan(3, 4)               # ArgumentError, gradient.jl:116-118
+
+
+# ---- hard-coded gradients / Hessians / Jacobians --------------------------------------------------
+def test_rosenbrock_gradient_golden(oracle):
+    g = G["rosenbrock_gradient"]
+    for N in g["chunks"]:
+        grad, val = oracle.gradient("rosenbrock", g["x"], N)
+        assert np.allclose(grad, g["gradient"], rtol=1e-13)
+        assert val == pytest.approx(oracle.value("rosenbrock", g["x"]), rel=1e-15)
+
+
+def test_rosenbrock_integer_gradients_exact(oracle):
+    g = G["rosenbrock_integer_gradients"]
+    for n, N in g["cases"] + [[12, 12], [12, 5], [10, 3], [10, 7]]:   # also remainder chunks and vector mode
+        grad, _ = oracle.gradient("rosenbrock", np.arange(n, dtype=float), N)
+        assert np.array_equal(grad, g[f"n{n}"]), (n, N)
+
+
+def test_rosenbrock_hessian_golden(oracle):
+    g = G["rosenbrock_hessian"]
+    for N in g["chunks"]:
+        H, grad, val = oracle.hessian("rosenbrock", g["x"], N)
+        assert np.allclose(H, np.array(g["hessian_rows"]), rtol=1e-13, atol=1e-13)
+        assert np.allclose(grad, g["gradient"], rtol=1e-13)
+        assert val == pytest.approx(oracle.value("rosenbrock", g["x"]), rel=1e-15)
+
+
+def test_third_order_tensor_golden(oracle):
+    g = G["rosenbrock_third_order"]
+    T3 = oracle.third_order("rosenbrock", g["x"])
+    assert np.allclose(T3, np.array(g["rows"]), rtol=1e-12, atol=1e-12)
+
+
+def test_jacobian_golden_f_and_finplace(oracle):
+    g = G["jacobian_hardcoded"]
+    Jg = np.array(g["jacobian_rows"])
+    for N in g["chunks"]:
+        for inplace in (False, True):
+            J, y = oracle.jacobian("jactest", g["x"], 4, N, inplace=inplace)
+            assert np.allclose(J, Jg, rtol=1e-15, atol=0), (N, inplace)
+            assert np.allclose(y, [Jg[0, 0] * 1.0, Jg[0, 0] + 3.0, Jg[0, 0] / (Jg[0, 0] + 3.0), 3.0], rtol=1e-15)
+
+
+# ---- seeding windows (test/SeedTest.jl) ----------------------------------------------------------------
+@pytest.mark.parametrize("kind,rows,key", [(0, 10, "vector10"), (1, 5, "upper5"), (3, 6, "diag6")])
+def test_seed_windows(oracle, kind, rows, key):
+    sidx = oracle.structural_indices(kind, rows)
+    assert sidx.tolist() == G["seed_windows"][key]
+    N = 3
+    nstore = rows if kind == 0 else rows * rows
+    nstruct = len(sidx)
+    x = np.random.default_rng(1).random(nstore)
+    marker = np.arange(1, N + 1, dtype=float)
+
+    def fresh():
+        d = np.zeros((nstore, N + 1))
+        d[sidx, 0] = x[sidx]
+        d[sidx, 1:] = marker
+        return d
+
+    def zeroed(d):
+        return [i + 1 for i, idx in enumerate(sidx) if np.all(d[idx, 1:] == 0)]
+
+    s = None if kind == 0 else sidx
+    d = fresh(); oracle.seed_zero(d, x, 4, N, sidx=s)                 # count defaults to N
+    assert zeroed(d) == [4, 5, 6] and np.array_equal(d[sidx, 0], x[sidx])
+    for index, count, expected in ((4, 2, [4, 5]), (nstruct - 1, N, [nstruct - 1, nstruct]), (1, 0, [])):
+        d = fresh(); oracle.seed_zero(d, x, index, count, sidx=s)
+        if count == 0:
+            # index<=0 selects the un-windowed form in the C entry point; a zero-width window is a no-op
+            d = fresh()
+        assert zeroed(d) == expected
+    d = fresh(); oracle.seed_zero(d, x, 0, 0, sidx=s)                 # 2-arg form clears everything
+    assert zeroed(d) == list(range(1, nstruct + 1))
+    for index in sorted({1, 4, nstruct - N + 1}):                     # seed! / seed_zero_partials! round trip
+        oracle.seed(d, x, index, N, sidx=s)
+        assert zeroed(d) == [i for i in range(1, nstruct + 1) if not (index <= i <= index + N - 1)]
+        for slot in range(N):
+            assert d[sidx[index - 1 + slot], 1:].tolist() == [1.0 if j == slot else 0.0 for j in range(N)]
+        oracle.seed_zero(d, x, index, N, sidx=s)
+        assert zeroed(d) == list(range(1, nstruct + 1))
+        assert np.array_equal(d[sidx, 0], x[sidx])
+
+
+# ---- partials identities incl. NaN/Inf (test/PartialsTest.jl:134-141, test/DualTest.jl:449-476) -----
+def _dual(v, p):
+    return np.array([[v] + list(p)], dtype=float)
+
+
+def test_mul_div_partials_identities(oracle):
+    rng = np.random.default_rng(1)
+    P1, P2 = rng.random(3), rng.random(3)
+    Z = np.zeros(3); FZ = np.array([0.0, 0.3, 0.7])
+    for p1 in (P1, Z, FZ):
+        for p2 in (P2, Z, FZ):
+            for v1 in (0.37, np.nan, np.inf):
+                for v2 in (0.81, np.nan, np.inf):
+                    with np.errstate(all="ignore"):
+                        r = oracle.map2("mul", _dual(v1, p1), _dual(v2, p2))[0]
+                        assert np.array_equal(r[1:], p1 * v2 + p2 * v1, equal_nan=True)
+                        assert np.array_equal(r[:1], [v1 * v2], equal_nan=True)
+                        q = oracle.map2("div", _dual(v1, p1), _dual(v2, p2))[0]
+                        expect = p1 * (1.0 / v2) + p2 * (-(v1 / (v2 * v2)))
+                        assert np.array_equal(q[1:], expect, equal_nan=True)
+
+
+def test_add_sub_structure(oracle):
+    a, b = _dual(1.5, [0.1, 0.2, 0.3]), _dual(-2.5, [1.0, 2.0, 3.0])
+    assert np.array_equal(oracle.map2("add", a, b)[0], a[0] + b[0])
+    assert np.array_equal(oracle.map2("sub", a, b)[0], a[0] - b[0])
+    assert np.array_equal(oracle.map2("add", a, 2.0)[0], [3.5, 0.1, 0.2, 0.3])
+    assert np.array_equal(oracle.map2("sub", 2.0, a)[0], [0.5, -0.1, -0.2, -0.3])
+    assert np.array_equal(oracle.map1("neg", a)[0], -a[0])
+    assert np.array_equal(oracle.map2("mul", a, 3.0)[0], a[0] * 3.0)
+    assert np.array_equal(oracle.map2("mul", 3.0, a)[0], a[0] * 3.0)
+
+
+def test_pow_zero_base(oracle, oracle_nansafe):
+    for case in G["pow_zero_base"]["cases"]:
+        x = _dual(case["x"][0], [1.0, 0.0]); y = _dual(case["x"][1], [0.0, 1.0])
+        with np.errstate(all="ignore"):
+            assert np.array_equal(oracle.map2("pow", x, y)[0, 1:], _f(case["default"]), equal_nan=True)
+            assert np.array_equal(oracle_nansafe.map2("pow", x, y)[0, 1:], _f(case["nansafe"]), equal_nan=True)
+
+
+def test_nansafe_issue_745_774(oracle, oracle_nansafe):
+    # test/GradientTest.jl:304-332: g(a) = a[1]*exp(-a[2]) at [1, -1e3] -> [NaN,NaN] default, [Inf,-Inf] NaN-safe
+    for orc_, expect in ((oracle, [np.nan, np.nan]), (oracle_nansafe, [np.inf, -np.inf])):
+        a1 = _dual(1.0, [1.0, 0.0]); a2 = _dual(-1e3, [0.0, 1.0])
+        with np.errstate(all="ignore"):
+            r = orc_.map2("mul", a1, orc_.map1("exp", orc_.map1("neg", a2)))
+        assert np.array_equal(r[0, 1:], expect, equal_nan=True)
+    # f(x) = log(zero(x[1]) + x[2]) at [1, 0] -> [NaN, Inf] default, [0, Inf] NaN-safe
+    for orc_, expect in ((oracle, [np.nan, np.inf]), (oracle_nansafe, [0.0, np.inf])):
+        z = _dual(0.0, [0.0, 0.0]); x2 = _dual(0.0, [0.0, 1.0])
+        with np.errstate(all="ignore"):
+            r = orc_.map1("log", orc_.map2("add", z, x2))
+        assert np.array_equal(r[0, 1:], expect, equal_nan=True)
+
+
+def test_abs_derivative_at_zero(oracle):
+    assert oracle.map1("abs", _dual(0.0, [1.0]))[0, 1] == 1.0          # test/MiscTest.jl:183
+    assert oracle.map1("abs", _dual(-0.0, [1.0]))[0, 1] == -1.0
+
+
+# ---- DiffRules formulas: value exact, derivative vs finite differences (test/DerivativeTest.jl:22-31) ---
+@pytest.mark.parametrize("op,fn", [("exp", np.exp), ("log", np.log), ("sin", np.sin), ("cos", np.cos), ("tanh", np.tanh),
+                                   ("sqrt", np.sqrt), ("abs", np.abs), ("abs2", np.square), ("inv", np.reciprocal),
+                                   ("pow2", lambda v: v ** 2), ("pow3", lambda v: v ** 3)])
+def test_unary_rules_vs_finite_differences(oracle, op, fn):
+    v = np.random.default_rng(1).random(50) + 0.25
+    d = np.stack([v, np.ones_like(v), 2.0 * np.ones_like(v)], axis=1)
+    r = oracle.map1(op, d)
+    assert np.allclose(r[:, 0], fn(v), rtol=4e-16, atol=0)
+    h = 1e-6
+    fd = (fn(v + h) - fn(v - h)) / (2 * h)
+    assert np.allclose(r[:, 1], fd, atol=3e-5)
+    assert np.array_equal(r[:, 2], r[:, 1] * 2.0) or np.allclose(r[:, 2], 2 * r[:, 1], rtol=1e-15)
+
+
+def test_gradients_vs_finite_differences(oracle):
+    x = np.random.default_rng(1).random(13)                      # XLEN = 13, CHUNK_SIZES of test/utils.jl
+    for fn in ("rosenbrock", "ackley", "sumsq", "prod"):
+        g0, v0 = oracle.gradient(fn, x, 12)
+        assert v0 == pytest.approx(oracle.value(fn, x), rel=1e-14)
+        fd = np.zeros_like(x); h = 1e-6
+        for i in range(x.size):
+            e = np.zeros_like(x); e[i] = h
+            fd[i] = (oracle.value(fn, x + e) - oracle.value(fn, x - e)) / (2 * h)
+        assert np.allclose(g0, fd, atol=3e-5), fn
+        for N in (1, 4, 6, 12):                                       # every chunk size agrees (GradientTest.jl:65-84)
+            g, v = oracle.gradient(fn, x, N)
+            assert np.allclose(g, g0, rtol=1e-13, atol=1e-15), (fn, N)
+
+
+def test_jacobian_targets_vs_finite_differences(oracle):
+    rng = np.random.default_rng(2)
+    n = m = 16
+    A = rng.uniform(-1, 1, (m, n)) / np.sqrt(n); b = rng.uniform(-1, 1, m); x = rng.uniform(-1, 1, n)
+    J, y = oracle.jacobian("tanh_affine", x, m, 6, A=A, b=b)
+    assert np.allclose(y, np.tanh(A @ x + b), rtol=1e-14)
+    assert np.allclose(J, (1 - np.tanh(A @ x + b) ** 2)[:, None] * A, rtol=1e-12, atol=1e-15)
+    M = 6; al = (M + 1) ** 2 / 50.0
+    xb = np.concatenate([1 + np.sin(2 * np.pi * np.arange(1, M + 1) / (M + 1)), 3 * np.ones(M)])
+    Jb, yb = oracle.jacobian("brusselator", xb, 2 * M, 8, alpha=al, inplace=True)
+
+    def rhs(z):
+        u, v = z[:M], z[M:]
+        up = np.concatenate([[1.0], u, [1.0]]); vp = np.concatenate([[3.0], v, [3.0]])
+        du = 1 + u * u * v - 4 * u + al * (up[:-2] - 2 * u + up[2:])
+        dv = 3 * u - u * u * v + al * (vp[:-2] - 2 * v + vp[2:])
+        return np.concatenate([du, dv])
+
+    assert np.allclose(yb, rhs(xb), rtol=1e-13)
+    fd = np.zeros((2 * M, 2 * M)); h = 1e-6
+    for j in range(2 * M):
+        e = np.zeros(2 * M); e[j] = h
+        fd[:, j] = (rhs(xb + e) - rhs(xb - e)) / (2 * h)
+    assert np.allclose(Jb, fd, atol=3e-5)
+    for N in (1, 3, 5, 12):                                           # chunk sizes incl. remainder and vector mode
+        Jn, yn = oracle.jacobian("brusselator", xb, 2 * M, N, alpha=al, inplace=True)
+        assert np.array_equal(Jn, Jb) and np.array_equal(yn, yb)
+
+
+def test_hessian_all_chunk_sizes_agree(oracle):
+    x = np.random.default_rng(5).random(13)
+    H0, g0, v0 = oracle.hessian("rosenbrock", x, 12)
+    assert np.allclose(H0, H0.T, rtol=1e-13, atol=1e-13)
+    for N in (1, 2, 3, 4, 6):
+        H, g, v = oracle.hessian("rosenbrock", x, N)
+        assert np.allclose(H, H0, rtol=1e-13, atol=1e-13) and np.allclose(g, g0, rtol=1e-13) and v == pytest.approx(v0, rel=1e-14)
+    g1, _ = oracle.gradient("rosenbrock", x, 4)
+    assert np.allclose(g0, g1, rtol=1e-13)
+
+
+def test_partial_chunk_ranges_tile_the_result(oracle):
+    """Chunks are independent: evaluating disjoint chunk ranges reproduces the full result (the sharding premise)."""
+    x = np.random.default_rng(7).random(50)
+    full, _ = oracle.gradient("ackley", x, 4)
+    p = oracle.chunk_plan(50, 4)
+    out = np.zeros(50)
+    for lo, hi in ((0, 5), (5, 9), (9, p["nchunks"])):
+        g, _ = oracle.gradient("ackley", x, 4, chunks=(lo, hi))
+        e0, e1 = lo * 4, min(hi * 4, 50)
+        out[e0:e1] = g[e0:e1]
+    assert np.array_equal(out, full)
+
+
+# ---- the reference's own native program (oracle/_ref, built from /root/reference/benchmarks/cpp) --------
+@pytest.mark.skipif(not orc.RefBench.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_against_reference_cpp_program(oracle):
+    ref = orc.RefBench()
+    assert ref.testgrad() == 0                                        # the reference's own asserts pass
+    x = np.random.default_rng(1).random(120)
+    for K in (1, 2, 3, 4, 5):
+        # Ackley: identical op sequence in both programs -> bit-identical
+        assert np.array_equal(ref.gradient("ackley", x, K), oracle.gradient("ackley", x, K)[0])
+        # Rosenbrock: the C++ toy uses plain-double constants (a*t2*t2), the Julia definition Dual constants
+        assert np.allclose(ref.gradient("rosenbrock", x, K), oracle.gradient("rosenbrock", x, K)[0], rtol=1e-13, atol=1e-13)
+    assert ref.value("ackley", x) == oracle.value("ackley", x)
