@@ -109,7 +109,8 @@ def test_seed_dense_entry_points_and_nested(ctx, oracle):
         expect[4 + slot, slot + 1, 0] = 1.0
     assert np.array_equal(got, expect)
     with pytest.raises(fdb200.DimensionMismatch):
-        ctx.check(ctx.lib.fdb_seed(ctx.h, dev.h, ctx.array(np.zeros(n + 1)).h, 1, 1))
+        longer = ctx.array(np.zeros(n + 1))            # keep a reference: handles must outlive the call
+        ctx.check(ctx.lib.fdb_seed(ctx.h, dev.h, longer.h, 1, 1))
 
 
 @pytest.mark.parametrize("N", [1, 5, 12])
@@ -133,7 +134,8 @@ def test_extract_bit_exact(ctx, oracle, N):
         assert np.array_equal(Jd.numpy().reshape((m, ncols), order="F"), Jh)
     assert np.array_equal(ydm.values().numpy(), ym[:, 0])
     with pytest.raises(fdb200.DimensionMismatch):       # GRAD_ERROR: f(x) must be a real number
-        ctx.check(ctx.lib.fdb_extract_gradient_chunk(ctx.h, ctx.zeros(n).h, ydm.h, 1, 1))
+        res = ctx.zeros(n)
+        ctx.check(ctx.lib.fdb_extract_gradient_chunk(ctx.h, res.h, ydm.h, 1, 1))
 
 
 # ---------------------------------------------------------------------------
@@ -158,8 +160,10 @@ def test_map1_all_ops(ctx, oracle, N, n):
         if op in EXACT1:
             assert np.array_equal(got, ref), op
         else:
-            # value: device libm vs glibc <= 2 ulp; partials: same formula applied to the device primal.
-            assert ulp_diff(got[:, 0], ref[:, 0]) <= 2, op
+            # value: CUDA libdevice and glibc are each within 2 ulp of the true value (neither is Julia's
+            # pure-Julia implementation), so they may differ by up to 4 ulp from each other.
+            # partials: the SAME formula applied to the device primal must match bit for bit.
+            assert ulp_diff(got[:, 0], ref[:, 0]) <= ULP_TOL, op
             # recompute the reference partials from the DEVICE primal so only the formula is compared
             val = got[:, 0]
             if op == "exp": deriv = val
@@ -272,7 +276,8 @@ def test_eval_scalar_fn_on_materialised_duals(ctx, oracle, fn, N):
     n = 3000 if fn != "prod" else 200
     xdual = rand_duals(rng, n, N, 0.8, 1.2)
     out = fdb200.B200DualArray.alloc(ctx, 1, N, 1)
-    ctx.check(ctx.lib.fdb_eval_scalar_fn(ctx.h, fdb200._lib.FN[fn], out.h, ctx.duals(xdual).h))
+    xd = ctx.duals(xdual)                               # (a temporary would be freed before the kernel runs)
+    ctx.check(ctx.lib.fdb_eval_scalar_fn(ctx.h, fdb200._lib.FN[fn], out.h, xd.h))
     got = out.numpy()[0]; ref = oracle.eval_scalar_fn(fn, xdual)
     scale = np.abs(ref).max()
     assert np.allclose(got, ref, rtol=1e-11, atol=1e-12 * scale), fn
@@ -350,7 +355,8 @@ def test_gradient_device_resident_and_chunk_ranges(ctx, oracle):
     cfg = fdb200.GradientConfig(F.ackley, xd, fdb200.Chunk(N))
     full = fdb200.gradient(F.ackley, xd, cfg).numpy()
     g_ref, _ = oracle.gradient("ackley", x, N)
-    assert np.allclose(full, g_ref, rtol=RED_RTOL, atol=0)
+    # two terms of opposite sign cancel in Ackley's gradient entries: tolerance relative to the largest entry
+    assert np.allclose(full, g_ref, rtol=RED_RTOL, atol=RED_RTOL * np.abs(g_ref).max())
     out = ctx.zeros(n)
     world = 3
     for r in range(world):                         # three "ranks" tile the result
