@@ -1,0 +1,149 @@
+# ForwardDiffB200.jl -- the Julia side of the drop-in: a device array type whose methods are one
+# `ccall` each into libfdb200.so (include/fdb200.h).
+#
+# NOT RUNNABLE IN THIS IMAGE (no `julia` binary): this file is the declarative statement of the
+# bindings a ForwardDiff maintainer would add; the same C ABI is exercised by the Python/ctypes host
+# in forwarddiff.jl_b200/fdb200/, which is what the tests and the benchmark run.  All logic that needs
+# verification lives below the C ABI.
+#
+# Seam: ForwardDiff's config constructors call `similar(x, Dual{T,V,N})` (src/config.jl:122,159,
+# 185-186,225-226).  For `x::B200Array` that returns a `B200DualArray{T,Float64,N}`; from then on
+# Julia's dispatch routes seed!/extract_*/chunk_mode_* to the methods below.
+module ForwardDiffB200
+
+using ForwardDiff
+using ForwardDiff: Dual, Partials, Chunk, GradientConfig, JacobianConfig, HessianConfig, DiffResults
+import ForwardDiff: seed!, seed_zero_partials!, extract_gradient_chunk!, extract_jacobian_chunk!,
+                    extract_jacobian!, extract_value!, chunk_mode_gradient, chunk_mode_gradient!,
+                    chunk_mode_jacobian, chunk_mode_jacobian!, hessian!, structural_length
+
+const libfdb200 = joinpath(@__DIR__, "..", "lib", "libfdb200.so")
+
+# ---- status -> Julia exceptions (fdb_status, include/fdb200.h) ---------------------------------
+struct FdbError <: Exception; code::Cint; msg::String; end
+function check(ctx::Ptr{Cvoid}, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:fdb_last_error, libfdb200), Cstring, (Ptr{Cvoid},), ctx))
+    rc == 2 && throw(DimensionMismatch(msg))          # src/gradient.jl:46,88-91; src/jacobian.jl:89,164
+    rc == 6 && throw(ArgumentError(msg))              # chunk size > structural_length, src/gradient.jl:116-118
+    rc == 4 && throw(OutOfMemoryError())
+    throw(FdbError(rc, msg))
+end
+
+# ---- context: one per process and GPU -------------------------------------------------------------
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:fdb_init, libfdb200), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r)
+        rc == 0 || error(unsafe_string(ccall((:fdb_last_error, libfdb200), Cstring, (Ptr{Cvoid},), C_NULL)))
+        c = new(r[]); finalizer(c -> ccall((:fdb_shutdown, libfdb200), Cint, (Ptr{Cvoid},), c.h), c); c
+    end
+end
+const CTX = Ref{Context}()
+context() = isassigned(CTX) ? CTX[] : (CTX[] = Context(parse(Int, get(ENV, "LOCAL_RANK", "0"))))
+
+# ---- device arrays -----------------------------------------------------------------------------------
+# level 0: Vector{Float64}; level 1: Vector{Dual{T,Float64,N}}; level 2: Vector{Dual{T,Dual{T,Float64,N},N}}
+mutable struct B200Array{E} <: AbstractVector{E}
+    h::Ptr{Cvoid}; n::Int; ctx::Context
+end
+dual_level(::Type{Float64}) = 0
+dual_level(::Type{Dual{T,V,N}}) where {T,V,N} = 1 + dual_level(V)
+chunk_of(::Type{Float64}) = 0
+chunk_of(::Type{Dual{T,V,N}}) where {T,V,N} = N
+
+function B200Array{E}(::UndefInitializer, n::Integer; ctx = context()) where {E}
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx.h, ccall((:fdb_array_alloc, libfdb200), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Ref{Ptr{Cvoid}}),
+                       ctx.h, n, chunk_of(E), dual_level(E), r))
+    a = B200Array{E}(r[], n, ctx)
+    finalizer(a -> ccall((:fdb_array_free, libfdb200), Cint, (Ptr{Cvoid},), a.h), a)
+end
+function B200Array(x::Vector{Float64}; ctx = context())
+    a = B200Array{Float64}(undef, length(x); ctx)
+    GC.@preserve x check(ctx.h, ccall((:fdb_upload_values, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), a.h, x)); a
+end
+Base.size(a::B200Array) = (a.n,)
+Base.Array(a::B200Array{Float64}) = (out = Vector{Float64}(undef, a.n);
+    check(a.ctx.h, ccall((:fdb_download_values, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Float64}), a.h, out)); out)
+Base.getindex(::B200Array, i...) = error("scalar indexing of a B200Array is not supported")
+# THE seam: src/config.jl:122,159,185-186,225-226
+Base.similar(a::B200Array, ::Type{D}) where {D<:Dual} = B200Array{D}(undef, a.n; ctx = a.ctx)
+Base.similar(a::B200Array, ::Type{D}, dims::Dims) where {D} = B200Array{D}(undef, prod(dims); ctx = a.ctx)
+
+# ---- sweep utilities (src/apiutils.jl:76-143; src/gradient.jl:74-81; src/jacobian.jl:95-118) ---------
+function seed!(d::B200Array{Dual{T,V,N}}, x::B200Array{V}, index, seeds::NTuple{N,Partials{N,V}}, chunksize = N) where {T,V,N}
+    check(d.ctx.h, ccall((:fdb_seed, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64), d.ctx.h, d.h, x.h, index, chunksize)); d
+end
+seed!(d::B200Array{Dual{T,V,N}}, x::B200Array{V}, seeds::NTuple{N,Partials{N,V}}) where {T,V,N} = seed!(d, x, 0, seeds, 0)
+function seed_zero_partials!(d::B200Array{Dual{T,V,N}}, x::B200Array{V}, index = 0, count = (index == 0 ? 0 : N)) where {T,V,N}
+    check(d.ctx.h, ccall((:fdb_seed_zero, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64), d.ctx.h, d.h, x.h, index, count)); d
+end
+function extract_gradient_chunk!(::Type{T}, result::B200Array, ydual::B200Array{<:Dual}, index, chunksize) where {T}
+    check(result.ctx.h, ccall((:fdb_extract_gradient_chunk, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64),
+                              result.ctx.h, result.h, ydual.h, index, chunksize)); result
+end
+function extract_jacobian_chunk!(::Type{T}, result::B200Array, ydual::B200Array{<:Dual}, index, chunksize) where {T}
+    check(result.ctx.h, ccall((:fdb_extract_jacobian_chunk, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64),
+                              result.ctx.h, result.h, length(ydual), ydual.h, index, chunksize)); result
+end
+function extract_jacobian!(::Type{T}, result::B200Array, ydual::B200Array{<:Dual}, n) where {T}
+    check(result.ctx.h, ccall((:fdb_extract_jacobian, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64),
+                              result.ctx.h, result.h, length(ydual), ydual.h, n)); result
+end
+
+# ---- array arithmetic: Base.broadcast / sum / prod on B200Array{<:Dual} ------------------------------
+# op codes = fdb_op1 / fdb_op2 of include/fdb200.h (src/dual.jl:476-597,709-717)
+const OP1 = Dict(:- => 1, :exp => 2, :log => 3, :sin => 4, :cos => 5, :tanh => 6, :sqrt => 7, :abs => 8, :abs2 => 9, :inv => 10)
+const OP2 = Dict(:+ => 1, :- => 2, :* => 3, :/ => 4, :^ => 5, :max => 6, :min => 7)
+function map1(op::Symbol, a::B200Array{D}) where {D<:Dual}
+    out = similar(a, D)
+    check(a.ctx.h, ccall((:fdb_map1, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), a.ctx.h, OP1[op], out.h, a.h)); out
+end
+function map2(op::Symbol, a::B200Array, b::B200Array)
+    D = a isa B200Array{<:Dual} ? eltype(a) : eltype(b); out = similar(a, D)
+    check(a.ctx.h, ccall((:fdb_map2, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), a.ctx.h, OP2[op], out.h, a.h, b.h)); out
+end
+function map2(op::Symbol, a::B200Array{D}, s::Real, scalar_first::Bool = false) where {D<:Dual}
+    out = similar(a, D)
+    check(a.ctx.h, ccall((:fdb_map2_scalar, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),
+                         a.ctx.h, OP2[op], out.h, a.h, Float64(s), scalar_first)); out
+end
+# A BroadcastStyle for B200Array would flatten a `Broadcasted` tree into these calls (or, next round,
+# into one fused op-program launch); literal_pow maps `x .^ 2` to FDB_POW2 (src/dual.jl:587-597).
+struct B200Style <: Base.Broadcast.AbstractArrayStyle{1} end
+Base.BroadcastStyle(::Type{<:B200Array}) = B200Style()
+function Base.sum(a::B200Array{D}) where {D<:Dual}
+    out = B200Array{D}(undef, 1; ctx = a.ctx)
+    check(a.ctx.h, ccall((:fdb_reduce, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), a.ctx.h, 1, out.h, a.h)); out
+end
+function Base.prod(a::B200Array{D}) where {D<:Dual}
+    out = B200Array{D}(undef, 1; ctx = a.ctx)
+    check(a.ctx.h, ccall((:fdb_reduce, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), a.ctx.h, 2, out.h, a.h)); out
+end
+
+# ---- whole-path drivers: catalogue targets run every chunk in one fused launch -------------------------
+# (src/gradient.jl:114-167, src/jacobian.jl:169-244, src/hessian.jl:14-71)
+catalogue_id(f) = nothing                 # users opt in:  ForwardDiffB200.catalogue_id(::typeof(rosenbrock)) = 1
+function chunk_mode_gradient!(result::B200Array{Float64}, f::F, x::B200Array{Float64}, cfg::GradientConfig{T,V,N}) where {F,T,V,N}
+    id = catalogue_id(f)
+    id === nothing && return invoke(chunk_mode_gradient!, Tuple{Any,F,Any,GradientConfig{T,V,N}}, result, f, x, cfg)  # reference loop on device arrays
+    rank, world = parse(Int, get(ENV, "RANK", "0")), parse(Int, get(ENV, "WORLD_SIZE", "1"))
+    plan = Ref{NTuple{11,Int64}}()
+    ccall((:fdb_plan_chunks, libfdb200), Cint, (Int64, Cint, Cint, Cint, Ptr{Cvoid}), length(x), N, rank, world, plan)
+    value = B200Array{Float64}(undef, 1; ctx = x.ctx)
+    check(x.ctx.h, ccall((:fdb_gradient_chunked, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                         x.ctx.h, id, x.h, N, plan[][8], plan[][9], result.h, value.h))
+    return result                          # multi-rank: followed by the NCCL all-gather of the slices (INTEGRATION.md)
+end
+# Host Vectors: ForwardDiff.gradient!(out::Vector, f, x::Vector, cfg) for a catalogue f -> fdb_gradient_host
+function gradient_host!(out::Vector{Float64}, f, x::Vector{Float64}, ::Chunk{N}; ctx = context()) where {N}
+    value = Ref{Float64}(NaN)
+    GC.@preserve out x check(ctx.h, ccall((:fdb_gradient_host, libfdb200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Cint, Int64, Int64, Ptr{Float64}, Ref{Float64}),
+        ctx.h, catalogue_id(f), x, length(x), N, 0, -1, out, value))
+    return out, value[]
+end
+
+end # module
