@@ -24,6 +24,12 @@ int ensure_scratch(fdb_ctx* ctx, size_t bytes) {
     ctx->scratch_bytes = want;
     return FDB_OK;
 }
+int ensure_counter(fdb_ctx* ctx) {
+    if (ctx->counter) return FDB_OK;
+    FDB_CUDA(ctx, cudaMalloc(&ctx->counter, 256));
+    FDB_CUDA(ctx, cudaMemsetAsync(ctx->counter, 0, 256, ctx->stream));
+    return FDB_OK;
+}
 int ensure_pinned(fdb_ctx* ctx, size_t bytes) {
     if (ctx->pinned_bytes >= bytes) return FDB_OK;
     if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
@@ -106,6 +112,24 @@ __global__ void seed_zero_kernel(double* __restrict__ d, int64_t ldd, const doub
     int a = q / PB, b = q - a * PB;
     d[(int64_t)q * ldd + idx] = (a == 0) ? x[(int64_t)b * ldx + idx] : 0.0;
 }
+// dense windows of many elements (the O(n) calls: a fresh buffer, chunk mode's first-chunk tail):
+// one thread owns two consecutive elements and writes all planes with 16-byte stores.
+__global__ void __launch_bounds__(256) seed_zero_dense_kernel(double* __restrict__ d, int64_t ldd, const double* __restrict__ x, int64_t ldx,
+                                                              int P, int PB, int64_t first, int64_t count, bool vec) {
+    int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (e >= count) return;
+    const bool pair = e + 1 < count;
+    const int64_t idx = first + e;
+    if (pair && vec) {
+        for (int b = 0; b < PB; b++)
+            *reinterpret_cast<double2*>(d + (int64_t)b * ldd + idx) = __ldg(reinterpret_cast<const double2*>(x + (int64_t)b * ldx + idx));
+        const double2 z = make_double2(0.0, 0.0);
+        for (int q = PB; q < P; q++) *reinterpret_cast<double2*>(d + (int64_t)q * ldd + idx) = z;
+    } else {
+        for (int b = 0; b < PB; b++) { d[(int64_t)b * ldd + idx] = x[(int64_t)b * ldx + idx]; if (pair) d[(int64_t)b * ldd + idx + 1] = x[(int64_t)b * ldx + idx + 1]; }
+        for (int q = PB; q < P; q++) { d[(int64_t)q * ldd + idx] = 0.0; if (pair) d[(int64_t)q * ldd + idx + 1] = 0.0; }
+    }
+}
 // extract_gradient_chunk!: result[idx(index-1+k)] = partials(ydual, k+1), k = 0..chunksize-1.
 // result has PB planes (PB > 1 when the partials are themselves Duals).
 __global__ void extract_gradient_chunk_kernel(double* __restrict__ res, int64_t ldr, const double* __restrict__ y, int64_t ldy,
@@ -178,6 +202,7 @@ extern "C" int fdb_shutdown(fdb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->counter) cudaFree(ctx->counter);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FDB_OK;
@@ -193,6 +218,7 @@ extern "C" int fdb_sync(fdb_ctx* ctx) {
 extern "C" int fdb_set_async(fdb_ctx* ctx, int async) { if (!ctx) return FDB_ERR_BADARG; ctx->async = async != 0; return FDB_OK; }
 extern "C" int fdb_set_nansafe(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->nansafe = en != 0; return FDB_OK; }
 extern "C" int fdb_set_lane_sharing(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->lane_sharing = en != 0; return FDB_OK; }
+extern "C" int fdb_set_dmma(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->use_dmma = en != 0; return FDB_OK; }
 extern "C" int fdb_set_stream(fdb_ctx* ctx, void* s) {
     if (!ctx) return FDB_ERR_BADARG;
     cudaStreamSynchronize(ctx->stream);
@@ -363,6 +389,13 @@ static int seed_zero_impl(fdb_ctx* ctx, fdb_array* d, const fdb_array* x, int st
     if (count <= 0 || index > nstruct) return FDB_OK;     // zero-width window is a no-op (test/SeedTest.jl:74-79)
     if (index - 1 + count > nstruct) count = nstruct - (index - 1);
     int PB = x->planes(); int P = (d->N + 1) * PB;
+    if (structure == FDB_DENSE && count >= 1024) {
+        const int64_t first = index - 1;
+        const bool vec = ((((uintptr_t)(d->data + first)) & 15) == 0) && ((((uintptr_t)(x->data + first)) & 15) == 0) &&
+                         ((d->ld & 1) == 0) && ((x->ld & 1) == 0);
+        seed_zero_dense_kernel<<<(unsigned)cdiv(cdiv(count, 2), 256), 256, 0, ctx->stream>>>(d->data, d->ld, x->data, x->ld, P, PB, first, count, vec);
+        return finish(ctx, 1, "fdb_seed_zero");
+    }
     dim3 grid((unsigned)cdiv(count, 256), (unsigned)P);
     seed_zero_kernel<<<grid, 256, 0, ctx->stream>>>(d->data, d->ld, x->data, x->ld, d->N, PB, structure, rows, nstruct, index, count);
     return finish(ctx, 1, "fdb_seed_zero");

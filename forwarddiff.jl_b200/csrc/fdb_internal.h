@@ -15,12 +15,14 @@ struct fdb_ctx {
     bool async = false;
     bool nansafe = false;
     bool lane_sharing = true;   // see fdb_sweep.cu (SHARE)
+    bool use_dmma = true;       // tanh_affine: DMMA contraction (fdb_dmma.cu) vs CUDA-core kernel
     int sm_count = 148;
     int64_t launches = 0;
     // reusable device scratch (block partials of reductions, staging of host entry points)
     double* scratch = nullptr;
     size_t scratch_bytes = 0;
     // pinned host staging for the *_host entry points
+    unsigned* counter = nullptr;   // zero-initialised ticket for single-launch reductions
     double* pinned = nullptr;
     size_t pinned_bytes = 0;
     std::string err;
@@ -74,6 +76,12 @@ inline int finish(fdb_ctx* ctx, int nlaunch, const char* what) {
 
 int ensure_scratch(fdb_ctx* ctx, size_t bytes);
 int ensure_pinned(fdb_ctx* ctx, size_t bytes);
+int ensure_counter(fdb_ctx* ctx);
+
+// fdb_dmma.cu: batched tanh.(A*x .+ b) chunk sweeps on the FP64 tensor-core contraction
+int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_array* b, const fdb_array* x, int64_t m, int N, int64_t lo,
+                     int64_t hi, int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ, double* yout, bool* used_dmma);
+bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k);
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -204,6 +204,10 @@ extern "C" int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, in
             if (!A || !b) return fail(ctx, FDB_ERR_BADARG, "tanh_affine needs A and b");
             if (A->level != 0 || b->level != 0 || lda < m || A->n < lda * (n - 1) + m || b->n != m)
                 return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: A must be %lld x %lld, b of length %lld", (long long)m, (long long)n, (long long)m);
+            if (ctx->use_dmma && dmma_eligible(A->data, lda, m, n)) {
+                // contraction on FP64 tensor cores (fdb_dmma.cu); all requested chunks in one GEMM
+                return tanh_affine_dmma(ctx, A, lda, b, x, m, N, chunk_lo, chunk_hi, nchunks, lcs, J, ldJ, yp, nullptr);
+            }
             constexpr int CH = 4; constexpr int TT = 128;
             dim3 grid((unsigned)cdiv(chunk_hi - chunk_lo, CH), (unsigned)cdiv(m, TT));
             if (ctx->lane_sharing) {

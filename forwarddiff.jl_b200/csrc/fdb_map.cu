@@ -180,11 +180,21 @@ __global__ void __launch_bounds__(256) fma_kernel(int kind, double* __restrict__
 // pass 1: each block reduces a grid-strided set of terms and writes its K accumulators
 // (AoS, K*(N+1) doubles) to scratch; pass 2: one block combines them in block order
 // (deterministic) and applies F::finalize.
+// A thread's register window over W = 2 + HALO consecutive elements: the pair (i, i+1) comes
+// from one 16-byte load per plane when the planes are 16-byte aligned, the halo from 8-byte loads
+// (the neighbouring thread's pair: an L1 hit).  Terms i and i+1 then index it with compile-time
+// offsets after inlining.
+template <int N, bool NS, int W> struct WindowLoader {
+    Dual<double, N, NS> e[W];
+    int64_t base;
+    FDB_DEV const Dual<double, N, NS>& operator()(int64_t j) const { return e[j - base]; }
+};
 template <class F, int N, bool NS, int THREADS>
-__global__ void __launch_bounds__(THREADS) mapreduce_pass1(const double* __restrict__ base, int64_t ld, int64_t n,
-                                                           double* __restrict__ partial) {
+__global__ void __launch_bounds__(THREADS, 2) mapreduce_pass1(const double* __restrict__ base, int64_t ld, int64_t n,
+                                                              double* __restrict__ partial, unsigned* __restrict__ counter, bool vec,
+                                                              double* __restrict__ out, int64_t ldo) {
     typedef Dual<double, N, NS> D;
-    SoALoader<N, NS> x{base, ld};
+    constexpr int W = 2 + F::HALO;
     D acc[F::K];
     D like; like.v = 0.0;
 #pragma unroll
@@ -192,9 +202,23 @@ __global__ void __launch_bounds__(THREADS) mapreduce_pass1(const double* __restr
 #pragma unroll
     for (int k = 0; k < F::K; k++) acc[k] = F::init(k, like);
     const int64_t nt = F::nterms(n);
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < nt; i += (int64_t)gridDim.x * THREADS)
+    for (int64_t i = ((int64_t)blockIdx.x * THREADS + threadIdx.x) * 2; i < nt; i += (int64_t)gridDim.x * THREADS * 2) {
+        WindowLoader<N, NS, W> x; x.base = i;
+        const bool pair = i + 1 < n;
+        Dual2<N, NS> p2 = load2<N, NS>(base, ld, i, pair, false, vec);
+        x.e[0] = p2.a; x.e[1] = p2.b;
+#pragma unroll
+        for (int w = 2; w < W; w++) {
+            const int64_t j = i + w < n ? i + w : n - 1;     // clamp: only read by terms that do not exist
+            x.e[w].v = base[j];
+#pragma unroll
+            for (int k = 0; k < N; k++) x.e[w].p[k] = base[(int64_t)(k + 1) * ld + j];
+        }
         F::term(x, i, n, acc);
+        if (i + 1 < nt) F::term(x, i + 1, n, acc);
+    }
     block_combine<F, D, THREADS>(acc);
+    __shared__ bool is_last;
     if (threadIdx.x == 0) {
         double* o = partial + (int64_t)blockIdx.x * F::K * (N + 1);
 #pragma unroll
@@ -203,6 +227,34 @@ __global__ void __launch_bounds__(THREADS) mapreduce_pass1(const double* __restr
 #pragma unroll
             for (int j = 0; j < N; j++) o[k * (N + 1) + 1 + j] = acc[k].p[j];
         }
+        __threadfence();
+        const unsigned ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+        if (is_last) *counter = 0u;            // self-cleaning for the next launch on this stream
+    }
+    __syncthreads();
+    if (!is_last) return;
+    // ---- the last block to finish combines all block partials in block order (deterministic) ----
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < F::K; k++) acc[k] = F::init(k, like);
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += THREADS) {
+        const double* o = partial + (int64_t)b * F::K * (N + 1);
+#pragma unroll
+        for (int k = 0; k < F::K; k++) {
+            D t; t.v = __ldcg(o + k * (N + 1));
+#pragma unroll
+            for (int j = 0; j < N; j++) t.p[j] = __ldcg(o + k * (N + 1) + 1 + j);
+            acc[k] = F::combine(k, acc[k], t);
+        }
+    }
+    __syncthreads();
+    block_combine<F, D, THREADS>(acc);
+    if (threadIdx.x == 0) {
+        D y = F::finalize(acc, n);
+        out[0] = y.v;
+#pragma unroll
+        for (int j = 0; j < N; j++) out[(int64_t)(j + 1) * ldo] = y.p[j];
     }
 }
 template <class F, int N, bool NS, int THREADS>
@@ -238,14 +290,16 @@ template <class F>
 static int mapreduce_launch(fdb_ctx* ctx, fdb_array* out1, const fdb_array* a, const char* what) {
     constexpr int THREADS = 256;
     int64_t nt = F::nterms(a->n);
-    int64_t want = cdiv(nt > 0 ? nt : 1, THREADS * 4);
-    int nblocks = (int)(want < (int64_t)ctx->sm_count * 8 ? want : (int64_t)ctx->sm_count * 8);
+    int64_t want = cdiv(nt > 0 ? nt : 1, THREADS * 2 * 2);       // >= 2 pairs per thread
+    int nblocks = (int)(want < (int64_t)ctx->sm_count * 6 ? want : (int64_t)ctx->sm_count * 6);
     if (nblocks < 1) nblocks = 1;
+    const bool vec = ((((uintptr_t)a->data) & 15) == 0) && ((a->ld & 1) == 0);
     int rc = ensure_scratch(ctx, (size_t)nblocks * F::K * (a->N + 1) * sizeof(double)); if (rc) return rc;
+    rc = ensure_counter(ctx); if (rc) return rc;
     FDB_DISPATCH_N(a->N, FDB_DISPATCH_NS(ctx->nansafe,
-        (mapreduce_pass1<F, NN, NS, THREADS><<<nblocks, THREADS, 0, ctx->stream>>>(a->data, a->ld, a->n, ctx->scratch),
-         mapreduce_pass2<F, NN, NS, THREADS><<<1, THREADS, 0, ctx->stream>>>(ctx->scratch, nblocks, a->n, out1->data, out1->ld))));
-    return finish(ctx, 2, what);
+        (mapreduce_pass1<F, NN, NS, THREADS><<<nblocks, THREADS, 0, ctx->stream>>>(a->data, a->ld, a->n, ctx->scratch, ctx->counter, vec,
+                                                                                    out1->data, out1->ld))));
+    return finish(ctx, 1, what);
 }
 
 }  // namespace fdb

@@ -61,6 +61,7 @@ SIGNATURES = {
     "fdb_get_stream": (C.c_int, [c_ctx, C.POINTER(C.c_void_p)]),
     "fdb_set_nansafe": (C.c_int, [c_ctx, C.c_int]),
     "fdb_set_lane_sharing": (C.c_int, [c_ctx, C.c_int]),
+    "fdb_set_dmma": (C.c_int, [c_ctx, C.c_int]),
     "fdb_kernel_launches": (C.c_int, [c_ctx, C.POINTER(i64)]),
     "fdb_version": (C.c_char_p, []),
     "fdb_array_alloc": (C.c_int, [c_ctx, i64, C.c_int, C.c_int, C.POINTER(c_arr)]),
@@ -90,6 +91,8 @@ SIGNATURES = {
     "fdb_map2": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr, c_arr]),
     "fdb_map2_scalar": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr, C.c_double, C.c_int]),
     "fdb_fma": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr, c_arr, c_arr, C.c_double]),
+    "fdb_dual_matvec": (C.c_int, [c_ctx, c_arr, i64, i64, i64, c_arr, c_arr]),
+    "fdb_matmul": (C.c_int, [c_ctx, c_arr, i64, i64, i64, c_arr, i64, i64, c_arr, i64]),
     "fdb_reduce": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr]),
     "fdb_eval_scalar_fn": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr]),
     "fdb_gradient_chunked": (C.c_int, [c_ctx, C.c_int, c_arr, C.c_int, i64, i64, c_arr, c_arr]),

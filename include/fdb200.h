@@ -91,6 +91,8 @@ int fdb_set_nansafe(fdb_ctx* ctx, int enabled);   /* `nansafe_mode` preference, 
 /* 1 (default): terms that touch no seeded position are evaluated on one representative
  * partial lane (bit-identical results; see fdb_sweep.cu).  0: all N lanes for every term. */
 int fdb_set_lane_sharing(fdb_ctx* ctx, int enabled);
+/* 1 (default): A*xdual contractions run on FP64 tensor cores (DMMA) when shapes allow; 0: CUDA-core kernels */
+int fdb_set_dmma(fdb_ctx* ctx, int enabled);
 int fdb_kernel_launches(fdb_ctx* ctx, int64_t* count); /* kernels launched on this context so far */
 const char* fdb_version(void);
 
@@ -166,6 +168,13 @@ int fdb_map2_scalar(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a, do
 /* fma, src/dual.jl:625-665.  kind 0: fma(a,b,c) all dual; 1: fma(a,b,s); 2: fma(a,s,c) */
 int fdb_fma(fdb_ctx* ctx, int kind, fdb_array* out, const fdb_array* a, const fdb_array* b, const fdb_array* c,
             double s);
+/* Dual matvec / matmul (Julia: A * xdual through LinearAlgebra.generic_matvecmul! on Vector{Dual}): a dense
+ * contraction of A (m x n, plain, column-major, lda) against the planes [value | partials] of xdual, on FP64
+ * tensor-core (DMMA) tiles staged by TMA bulk copies.  fdb_matmul is the same contraction on plain arrays:
+ * C[m x ncols] = A[m x k] * B[k x ncols], all column-major. */
+int fdb_dual_matvec(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t n, const fdb_array* xdual, fdb_array* ydual);
+int fdb_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t k, const fdb_array* B, int64_t ldb, int64_t ncols,
+               fdb_array* C, int64_t ldc);
 /* sum / prod of a Dual array -> Dual array of length 1 (two-pass, deterministic) */
 int fdb_reduce(fdb_ctx* ctx, int redop, fdb_array* out1, const fdb_array* a);
 /* evaluate a catalogue target on a materialised dual array: out1 = f(xdual) */

@@ -1,0 +1,82 @@
+"""GPU parity of the FP64 tensor-core (DMMA) contraction: fdb_matmul, fdb_dual_matvec and the
+batched tanh.(A*x .+ b) Jacobian that runs on it, against numpy / the CPU oracle.
+A*x is a reordered (and, on DMMA, fused) summation: tolerance 1e-12 relative (north_star)."""
+import numpy as np
+import pytest
+
+import fdb200
+from fdb200 import functions as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _fortran(ctx, M):
+    return ctx.array(np.asfortranarray(M).ravel(order="F"))
+
+
+@pytest.mark.parametrize("m,k,ncols", [(128, 32, 64), (256, 96, 13), (130, 64, 70), (512, 256, 200), (64, 32, 5), (129, 33, 7)])
+def test_matmul_vs_numpy(ctx, m, k, ncols):
+    rng = np.random.default_rng(m + k + ncols)
+    A = rng.uniform(-1, 1, (m, k)); B = rng.uniform(-1, 1, (k, ncols))
+    Ad, Bd = _fortran(ctx, A), _fortran(ctx, B)
+    Cd = ctx.zeros(m * ncols)
+    ctx.check(ctx.lib.fdb_matmul(ctx.h, Ad.h, m, m, k, Bd.h, k, ncols, Cd.h, m))
+    C = Cd.numpy().reshape((m, ncols), order="F")
+    ref = A @ B
+    assert np.allclose(C, ref, rtol=1e-12, atol=1e-12 * np.abs(A).sum(axis=1).max())
+
+
+@pytest.mark.parametrize("N", [1, 7, 12])
+def test_dual_matvec_vs_oracle(ctx, oracle, N):
+    rng = np.random.default_rng(N)
+    for m, n in ((128, 64), (256, 160), (50, 33)):
+        A = rng.uniform(-1, 1, (m, n)) / np.sqrt(n)
+        xdual = rng.uniform(-1, 1, (n, N + 1))
+        Ad = _fortran(ctx, A); xd = ctx.duals(xdual)
+        yd = fdb200.B200DualArray.alloc(ctx, m, N)
+        ctx.check(ctx.lib.fdb_dual_matvec(ctx.h, Ad.h, m, m, n, xd.h, yd.h))
+        got = yd.numpy()
+        ref = A @ xdual                                  # planes are columns: Y = A * [value | partials]
+        assert np.allclose(got, ref, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("N", [1, 8, 12])
+@pytest.mark.parametrize("share", [True, False])
+def test_tanh_affine_jacobian_on_dmma(ctx, oracle, N, share):
+    rng = np.random.default_rng(3)
+    for m, n in ((128, 96), (256, 128), (384, 160)):       # DMMA-eligible: m >= 128 even, n % 32 == 0
+        A = rng.uniform(-1, 1, (m, n)) / np.sqrt(n); b = rng.uniform(-1, 1, m); x = rng.uniform(-1, 1, n)
+        f = F.tanh_affine.with_params(A=A, b=b)
+        res = fdb200.JacobianResult(np.zeros(m), x)
+        ctx.set_lane_sharing(share)
+        try:
+            fdb200.jacobian_b(res, f, x, fdb200.JacobianConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+        finally:
+            ctx.set_lane_sharing(True)
+        J_ref, y_ref = oracle.jacobian("tanh_affine", x, m, N, A=A, b=b)
+        assert np.allclose(res.value, y_ref, rtol=1e-13, atol=1e-15)
+        assert np.allclose(res.derivs[0], J_ref, rtol=1e-12, atol=1e-15), (m, n, N, share)
+        # same result from the CUDA-core kernel
+        ctx.check(ctx.lib.fdb_set_dmma(ctx.h, 0))
+        try:
+            res2 = fdb200.JacobianResult(np.zeros(m), x)
+            fdb200.jacobian_b(res2, f, x, fdb200.JacobianConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+        finally:
+            ctx.check(ctx.lib.fdb_set_dmma(ctx.h, 1))
+        assert np.allclose(res.derivs[0], res2.derivs[0], rtol=1e-12, atol=1e-15)
+
+
+def test_tanh_affine_chunk_ranges_tile_on_dmma(ctx):
+    rng = np.random.default_rng(9)
+    m, n, N = 256, 128, 12
+    A = rng.uniform(-1, 1, (m, n)) / np.sqrt(n); b = rng.uniform(-1, 1, m); x = rng.uniform(-1, 1, n)
+    f = F.tanh_affine.with_params(A=A, b=b)
+    cfg = fdb200.JacobianConfig(f, x, fdb200.Chunk(N))
+    full = fdb200.jacobian(f, x, cfg, ctx=ctx, m=m)
+    out = np.zeros((m, n), order="F")
+    for r in range(3):
+        p = fdb200.chunk_plan(n, N, r, 3)
+        part = np.zeros((m, n), order="F")
+        fdb200.jacobian_b(part, f, x, cfg, ctx=ctx, chunks=(p["chunk_lo"], p["chunk_hi"]))
+        out[:, p["elem_lo"]:p["elem_hi"]] = part[:, p["elem_lo"]:p["elem_hi"]]
+    assert np.array_equal(out, full)
