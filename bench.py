@@ -346,8 +346,28 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
     m3 = 8192
     A = ctx.array(rng.uniform(-1, 1, m3 * m3) / np.sqrt(m3)); b = ctx.array(rng.uniform(-1, 1, m3)); x3 = ctx.array(rng.uniform(-1, 1, m3))
     J3 = ctx.zeros(m3 * m3); y3 = ctx.zeros(m3)
-    ms = t(lambda: ctx.check(lib.fdb_jacobian_chunked(ctx.h, fdb200._lib.JFN["tanh_affine"], x3.h, m3, 12, A.h, m3, b.h, 0.0, 0, -1, J3.h, m3, y3.h)), reps=1)
-    out["tanh_affine_jacobian_c3"] = {"evals_per_s": 1e3 / ms, "ms": ms}
+    run_c3 = lambda: ctx.check(lib.fdb_jacobian_chunked(ctx.h, fdb200._lib.JFN["tanh_affine"], x3.h, m3, 12, A.h, m3, b.h, 0.0, 0, -1, J3.h, m3, y3.h))
+    # FP64 tensor-core denominator: cuBLAS DGEMM 8192^3 on this GPU (MEASURED_PEAKS.json has no FP64 figure)
+    ta = torch.randn(m3, m3, dtype=torch.float64, device=dev); tb = torch.randn(m3, m3, dtype=torch.float64, device=dev)
+    dgemm_ms = t(lambda: torch.matmul(ta, tb), reps=3)
+    dgemm_tf = 2.0 * m3 ** 3 / (dgemm_ms * 1e-3) / 1e12
+    del ta, tb
+    ms = t(run_c3, reps=3)
+    cols = 2 * 683                                   # lane sharing: value column + representative zero column per chunk
+    out["tanh_affine_jacobian_c3"] = {"evals_per_s": 1e3 / ms, "ms": ms, "kernels": "pack_b + dmma_gemm_kernel + tanh_affine_epilogue",
+                                      "roofline": {"bound": "tensor", "achieved": 2.0 * m3 * m3 * cols / (ms * 1e-3) / 1e12, "peak": dgemm_tf,
+                                                   "unit": "TFLOP/s", "frac": 2.0 * m3 * m3 * cols / (ms * 1e-3) / 1e12 / dgemm_tf,
+                                                   "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run",
+                                                   "algorithmic": "2*m*n flops per operand column, 2 columns per chunk x 683 chunks (whole call incl. pack and epilogue)"}}
+    ctx.set_lane_sharing(False)
+    ms = t(run_c3, reps=2)
+    ctx.set_lane_sharing(True)
+    cols = 13 * 682 + 9
+    out["tanh_affine_jacobian_c3_all_lanes"] = {"evals_per_s": 1e3 / ms, "ms": ms,
+                                                "roofline": {"bound": "tensor", "achieved": 2.0 * m3 * m3 * 13 * 683 / (ms * 1e-3) / 1e12, "peak": dgemm_tf,
+                                                             "unit": "TFLOP/s", "frac": 2.0 * m3 * m3 * 13 * 683 / (ms * 1e-3) / 1e12 / dgemm_tf,
+                                                             "algorithmic": "2*m*n*13*683 = 1.19 TFLOP: A against [value | 12 one-hot partials] of every chunk"}}
+    out["cublas_dgemm_8192_tflops"] = dgemm_tf
     del A, J3
     # generic HBM-bound kernels on materialised Dual{12} arrays, n = 2^22 (436 MB per array > L2)
     nn = 1 << 22

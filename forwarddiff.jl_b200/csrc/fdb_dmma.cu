@@ -13,17 +13,19 @@
 // Arithmetic note: DMMA accumulates with fused multiply-adds in k order, the reference with separate
 // multiply and add; both are summation-order variants of the same dot product (tolerance 1e-12
 // relative, BASELINE.json north_star).
+#include <cuda.h>
+
 #include "fdb_internal.h"
 #include "fdb_targets.cuh"
 
 namespace fdb {
 
 constexpr int DM_BM = 128, DM_BN = 64, DM_KT = 32, DM_STAGES = 4;
-constexpr int DM_AS = DM_BM + 4;          // padded k-row of the A tile (doubles): stride = 8 mod 32 words
-constexpr int DM_BS = DM_KT + 4;          // padded column of the B tile (doubles): stride = 8 mod 32 words
-constexpr int DM_A_BYTES = DM_KT * DM_AS * 8, DM_B_BYTES = DM_BN * DM_BS * 8;
+constexpr int DM_BS = DM_KT + 4;          // padded column of the packed B tile (doubles): stride = 8 mod 32 words
+constexpr int DM_A_BYTES = DM_KT * DM_BM * 8;            // dense [KT][BM] box written by one tensor copy
+constexpr int DM_B_ELEMS = DM_BN * DM_BS, DM_B_BYTES = DM_B_ELEMS * 8;
 constexpr int DM_STAGE_BYTES = DM_A_BYTES + DM_B_BYTES;
-constexpr int DM_SMEM = DM_STAGES * DM_STAGE_BYTES + 2 * DM_STAGES * 8 + 16;
+constexpr int DM_SMEM = DM_STAGES * DM_STAGE_BYTES + 2 * DM_STAGES * 8 + 128;
 
 FDB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 FDB_DEV void mbar_init(uint64_t* bar, uint32_t count) {
@@ -46,59 +48,68 @@ FDB_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+// TMA bulk copy global -> shared (1-D), completion counted in bytes on an mbarrier
 FDB_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// TMA tensor copy (2-D box of the column-major A described by a CUtensorMap) global -> shared
+FDB_DEV void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
 FDB_DEV void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// C[m x ncols] = A[m x k] * B[k x ncols]; all column-major.  Column c of B is read from column
-// (bmod > 0 ? c % bmod : c) -- bmod lets a batch of chunks share identical operand columns.
-// Requirements (checked by the host): k % 32 == 0, m % 2 == 0, lda/ldb even, 16-byte aligned bases.
-__global__ void __launch_bounds__(288, 1) dmma_gemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
-                                                          double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols, int bmod) {
-    extern __shared__ __align__(128) unsigned char smem[];
+// Pack B (k x ncols, column-major) into the tile order the kernel consumes: tile (j, s) holds columns
+// [64j, 64j+64) x k-rows [32s, 32s+32) as 64 padded columns of 36 doubles, contiguous, so that one
+// bulk copy stages it.  Out-of-range entries are zero.  Column c of B is read from column c % bmod when
+// bmod > 0 (a batch of chunks sharing identical operand columns).
+__global__ void pack_b_kernel(const double* __restrict__ B, int64_t ldb, int64_t k, int64_t ncols, int bmod, int nslab,
+                              double* __restrict__ Bp) {
+    const int s = blockIdx.x, j = blockIdx.y;
+    double* tile = Bp + ((int64_t)j * nslab + s) * DM_B_ELEMS;
+    for (int e = threadIdx.x; e < DM_B_ELEMS; e += blockDim.x) {
+        const int c = e / DM_BS, kk = e - c * DM_BS;
+        const int64_t col = (int64_t)j * DM_BN + c, row = (int64_t)s * DM_KT + kk;
+        double v = 0.0;
+        if (kk < DM_KT && col < ncols && row < k) v = B[row + (bmod > 0 ? col % bmod : col) * ldb];
+        tile[e] = v;
+    }
+}
+
+// C[m x ncols] = A[m x k] * B[k x ncols]; A through a tensor map (box 128 x 32, zero fill out of bounds),
+// B pre-packed (pack_b_kernel); btiles = number of distinct packed column tiles (1 when every tile is identical).
+__global__ void __launch_bounds__(288, 1) dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles,
+                                                          double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + DM_STAGES * DM_STAGE_BYTES);
     uint64_t* empty = full + DM_STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n0 = (int64_t)blockIdx.x * DM_BN, m0 = (int64_t)blockIdx.y * DM_BM;
-    const int rows = (int)(m - m0 < DM_BM ? m - m0 : DM_BM);          // valid rows of this tile (even)
-    const int cols = (int)(ncols - n0 < DM_BN ? ncols - n0 : DM_BN);
-    const int nslab = (int)(k / DM_KT);
+    const int nslab = (int)((k + DM_KT - 1) / DM_KT);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < DM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // rows / columns beyond the matrix edge are never copied: clear them once so DMMA reads zeros
-    if (rows < DM_BM || cols < DM_BN) {
-        double* z = reinterpret_cast<double*>(smem);
-        for (int i = threadIdx.x; i < DM_STAGES * DM_STAGE_BYTES / 8; i += blockDim.x) z[i] = 0.0;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
     __syncthreads();
 
     if (warp == 8) {
-        // ---- producer: one thread drives the TMA engine ----------------------------------------
+        // ---- producer: one thread, two TMA copies per k-slab -----------------------------------
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)(DM_KT * rows * 8 + cols * DM_KT * 8);
+            const double* Bt = Bp + (int64_t)(blockIdx.x % btiles) * nslab * DM_B_ELEMS;
             for (int s = 0; s < nslab; s++) {
                 const int st = s % DM_STAGES;
                 if (s >= DM_STAGES) mbar_wait(&empty[st], ((s / DM_STAGES) - 1) & 1);
-                double* As = reinterpret_cast<double*>(smem + st * DM_STAGE_BYTES);
-                double* Bs = As + DM_KT * DM_AS;
-                mbar_expect_tx(&full[st], tx);
-                const int64_t k0 = (int64_t)s * DM_KT;
-                for (int kk = 0; kk < DM_KT; kk++)               // one k-row of the A tile: `rows` contiguous doubles of column k0+kk
-                    bulk_g2s(As + kk * DM_AS, A + m0 + (k0 + kk) * lda, (uint32_t)rows * 8, &full[st]);
-                for (int c = 0; c < cols; c++) {                 // one column of the B tile: KT contiguous doubles
-                    const int64_t bc = bmod > 0 ? (n0 + c) % bmod : (n0 + c);
-                    bulk_g2s(Bs + c * DM_BS, B + k0 + bc * ldb, DM_KT * 8, &full[st]);
-                }
+                unsigned char* stage = smem + st * DM_STAGE_BYTES;
+                mbar_expect_tx(&full[st], DM_STAGE_BYTES);
+                tma_load_2d(stage, &tmA, (int)m0, s * DM_KT, &full[st]);                         // A tile: [32 k][128 m]
+                bulk_g2s(stage + DM_A_BYTES, Bt + (int64_t)s * DM_B_ELEMS, DM_B_BYTES, &full[st]);   // packed B tile
             }
         }
     } else {
@@ -114,12 +125,12 @@ __global__ void __launch_bounds__(288, 1) dmma_gemm_kernel(const double* __restr
             const int st = s % DM_STAGES;
             mbar_wait(&full[st], (s / DM_STAGES) & 1);
             const double* As = reinterpret_cast<const double*>(smem + st * DM_STAGE_BYTES);
-            const double* Bs = As + DM_KT * DM_AS;
+            const double* Bs = As + DM_KT * DM_BM;
 #pragma unroll
             for (int k4 = 0; k4 < DM_KT / 4; k4++) {
                 double a[4], b[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) a[i] = As[(k4 * 4 + t) * DM_AS + wm * 32 + i * 8 + g];
+                for (int i = 0; i < 4; i++) a[i] = As[(k4 * 4 + t) * DM_BM + wm * 32 + i * 8 + g];
 #pragma unroll
                 for (int j = 0; j < 4; j++) b[j] = Bs[(wn * 32 + j * 8 + g) * DM_BS + k4 * 4 + t];
 #pragma unroll
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(288, 1) dmma_gemm_kernel(const double* __restr
     }
 }
 
-// shape-generic fallback (any m, k, alignment): one thread per output row, columns in registers
+// shape-generic fallback (any alignment): one thread per output row, columns in registers
 template <int PC>
 __global__ void __launch_bounds__(128) gemm_fallback_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
                                                             double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols, int bmod) {
@@ -169,29 +180,64 @@ __global__ void __launch_bounds__(128) gemm_fallback_kernel(const double* __rest
     for (int j = 0; j < PC; j++) if (c0 + j < ncols) C[r + (c0 + j) * ldc] = acc[j];
 }
 
-bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k) {
-    return (k % DM_KT == 0) && (m % 2 == 0) && (lda % 2 == 0) && ((((uintptr_t)A) & 15) == 0) && m >= DM_BM && k >= DM_KT;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
 }
 
+bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k) {
+    return (lda % 2 == 0) && ((((uintptr_t)A) & 15) == 0) && m >= DM_BM && k >= DM_KT && encode_tiled_fn() != nullptr;
+}
+size_t gemm_workspace_doubles(int64_t k, int64_t ncols, int bmod) {
+    const int64_t nslab = cdiv(k, DM_KT);
+    const int64_t btiles = (bmod > 0 && DM_BN % bmod == 0) ? 1 : cdiv(ncols, DM_BN);
+    return (size_t)(btiles * nslab * DM_B_ELEMS);
+}
+
+// ws: gemm_workspace_doubles() doubles of device scratch for the packed B operand
 int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m, int64_t k,
-                int64_t ncols, int bmod, bool* used_dmma) {
-    const bool ok = (k % DM_KT == 0) && (m % 2 == 0) && (lda % 2 == 0) && (ldb % 2 == 0) && ((((uintptr_t)A) & 15) == 0) &&
-                    ((((uintptr_t)B) & 15) == 0) && m > 0 && ncols > 0 && k > 0;
+                int64_t ncols, int bmod, double* ws, bool* used_dmma, int* nlaunch) {
+    if (m <= 0 || ncols <= 0) { if (nlaunch) *nlaunch = 0; return FDB_OK; }
+    EncodeTiledFn enc = encode_tiled_fn();
+    const bool ok = enc != nullptr && (lda % 2 == 0) && ((((uintptr_t)A) & 15) == 0) && k > 0 && ws != nullptr;
     if (used_dmma) *used_dmma = ok;
-    if (ok) {
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
-            if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(dmma_gemm_kernel): %s", cudaGetErrorString(e));
-            configured = true;
-        }
-        dim3 grid((unsigned)cdiv(ncols, DM_BN), (unsigned)cdiv(m, DM_BM));
-        dmma_gemm_kernel<<<grid, 288, DM_SMEM, ctx->stream>>>(A, lda, B, ldb, C, ldc, m, k, ncols, bmod);
-    } else if (m > 0 && ncols > 0) {
+    if (!ok) {
         constexpr int PC = 13;
         dim3 grid((unsigned)cdiv(m, 128), (unsigned)cdiv(ncols, PC));
         gemm_fallback_kernel<PC><<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, m, k, ncols, bmod);
+        if (nlaunch) *nlaunch = 1;
+        return FDB_OK;
     }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
+        if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(dmma_gemm_kernel): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t)m, (cuuint64_t)k};
+    const cuuint64_t gstride[1] = {(cuuint64_t)lda * 8};
+    const cuuint32_t box[2] = {DM_BM, DM_KT};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(ctx, FDB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    const int nslab = (int)cdiv(k, DM_KT);
+    const int btiles = (bmod > 0 && DM_BN % bmod == 0) ? 1 : (int)cdiv(ncols, DM_BN);
+    dim3 pg((unsigned)nslab, (unsigned)btiles);
+    pack_b_kernel<<<pg, 256, 0, ctx->stream>>>(B, ldb, k, ncols, bmod, nslab, ws);
+    dim3 grid((unsigned)cdiv(ncols, DM_BN), (unsigned)cdiv(m, DM_BM));
+    dmma_gemm_kernel<<<grid, 288, DM_SMEM, ctx->stream>>>(tm, ws, btiles, C, ldc, m, k, ncols);
+    if (nlaunch) *nlaunch = 2;
     return FDB_OK;
 }
 
@@ -250,15 +296,18 @@ int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_ar
     const int64_t ldb = round_up(n, 32), ldy = round_up(m, 32);
     // scratch: operand columns + product columns
     const int64_t bcols = share ? 2 : nc * P;
-    size_t need = (size_t)(ldb * bcols + ldy * nc * P) * sizeof(double);
+    const size_t wsd = gemm_workspace_doubles(n, nc * P, share ? 2 : 0);
+    size_t need = ((size_t)(ldb * bcols + ldy * nc * P) + wsd + 64) * sizeof(double);
     int rc = ensure_scratch(ctx, need); if (rc) return rc;
     double* Bop = ctx->scratch; double* Y = ctx->scratch + ldb * bcols;
+    double* ws = Y + ldy * nc * P; ws = (double*)((((uintptr_t)ws) + 127) & ~(uintptr_t)127);
     if (share) build_operand_shared_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(x->data, n, Bop, ldb);
     else {
         dim3 g((unsigned)cdiv(n, 256), (unsigned)nc);
         build_operand_dense_kernel<<<g, 256, 0, ctx->stream>>>(x->data, n, N, lo, nchunks, lcs, Bop, ldb);
     }
-    rc = launch_gemm(ctx, A->data, lda, Bop, ldb, Y, ldy, m, n, nc * P, share ? 2 : 0, used_dmma); if (rc) return rc;
+    int ngemm = 0;
+    rc = launch_gemm(ctx, A->data, lda, Bop, ldb, Y, ldy, m, n, nc * P, share ? 2 : 0, ws, used_dmma, &ngemm); if (rc) return rc;
     dim3 ge((unsigned)cdiv(m, 256), (unsigned)nc);
     if (ctx->nansafe) {
         if (share) tanh_affine_epilogue_kernel<true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
@@ -267,7 +316,7 @@ int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_ar
         if (share) tanh_affine_epilogue_kernel<false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
         else tanh_affine_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
     }
-    return finish(ctx, 3, "fdb_jacobian_chunked(tanh_affine, dmma)");
+    return finish(ctx, 2 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma)");
 }
 
 }  // namespace fdb
@@ -281,8 +330,11 @@ extern "C" int fdb_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t
     if (A->level != 0 || B->level != 0 || C->level != 0) return fail(ctx, FDB_ERR_BADARG, "fdb_matmul: operands must be plain arrays");
     if (lda < m || ldb < k || ldc < m || A->n < lda * (k - 1) + m || B->n < ldb * (ncols - 1) + k || C->n < ldc * (ncols - 1) + m)
         return fail(ctx, FDB_ERR_SHAPE, "fdb_matmul: DimensionMismatch");
-    int rc = launch_gemm(ctx, A->data, lda, B->data, ldb, C->data, ldc, m, k, ncols, 0, nullptr); if (rc) return rc;
-    return finish(ctx, 1, "fdb_matmul");
+    int rc = ensure_scratch(ctx, (gemm_workspace_doubles(k, ncols, 0) + 64) * sizeof(double)); if (rc) return rc;
+    double* ws = (double*)((((uintptr_t)ctx->scratch) + 127) & ~(uintptr_t)127);
+    int nl = 0;
+    rc = launch_gemm(ctx, A->data, lda, B->data, ldb, C->data, ldc, m, k, ncols, 0, ws, nullptr, &nl); if (rc) return rc;
+    return finish(ctx, nl, "fdb_matmul");
 }
 
 // ydual = A * xdual  (A: m x n plain column-major; xdual: n Duals; ydual: m Duals): the planes are the columns
@@ -292,6 +344,9 @@ extern "C" int fdb_dual_matvec(fdb_ctx* ctx, const fdb_array* A, int64_t lda, in
         return fail(ctx, FDB_ERR_BADARG, "fdb_dual_matvec: A plain, xdual/ydual Dual arrays of the same type");
     if (xdual->n != n || ydual->n != m || lda < m || A->n < lda * (n - 1) + m)
         return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: A is %lld x %lld, x has %lld, y has %lld", (long long)m, (long long)n, (long long)xdual->n, (long long)ydual->n);
-    int rc = launch_gemm(ctx, A->data, lda, xdual->data, xdual->ld, ydual->data, ydual->ld, m, n, xdual->planes(), 0, nullptr); if (rc) return rc;
-    return finish(ctx, 1, "fdb_dual_matvec");
+    int rc = ensure_scratch(ctx, (gemm_workspace_doubles(n, xdual->planes(), 0) + 64) * sizeof(double)); if (rc) return rc;
+    double* ws = (double*)((((uintptr_t)ctx->scratch) + 127) & ~(uintptr_t)127);
+    int nl = 0;
+    rc = launch_gemm(ctx, A->data, lda, xdual->data, xdual->ld, ydual->data, ydual->ld, m, n, xdual->planes(), 0, ws, nullptr, &nl); if (rc) return rc;
+    return finish(ctx, nl, "fdb_dual_matvec");
 }
