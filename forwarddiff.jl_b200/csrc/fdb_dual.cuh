@@ -192,6 +192,34 @@ template <int N, bool NS> FDB_DEV Dual<double, N, NS> abs2_v(const Dual<double, 
 template <int N, bool NS> FDB_DEV Dual<double, N, NS> abs_v(const Dual<double, N, NS>& x) {
     return chain(fabs(x.v), signbit(x.v) ? -1.0 : 1.0, x);     // abs'(0) = +1, test/MiscTest.jl:183
 }
+// further DiffRules unary rules: val = f(v), deriv shares sub-expressions with val
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> tan_v(const Dual<double, N, NS>& x) { double val = tan(x.v); return chain(val, 1.0 + val * val, x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> exp2_v(const Dual<double, N, NS>& x) { double val = exp2(x.v); return chain(val, val * 0.6931471805599453, x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> log2_v(const Dual<double, N, NS>& x) { return chain(log2(x.v), (1.0 / x.v) / 0.6931471805599453, x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> log10_v(const Dual<double, N, NS>& x) { return chain(log10(x.v), (1.0 / x.v) / 2.302585092994046, x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> log1p_v(const Dual<double, N, NS>& x) { return chain(log1p(x.v), 1.0 / (x.v + 1.0), x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> expm1_v(const Dual<double, N, NS>& x) { return chain(expm1(x.v), exp(x.v), x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> sinh_v(const Dual<double, N, NS>& x) { return chain(sinh(x.v), cosh(x.v), x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> cosh_v(const Dual<double, N, NS>& x) { return chain(cosh(x.v), sinh(x.v), x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> asin_v(const Dual<double, N, NS>& x) { return chain(asin(x.v), 1.0 / sqrt(1.0 - x.v * x.v), x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> acos_v(const Dual<double, N, NS>& x) { return chain(acos(x.v), -(1.0 / sqrt(1.0 - x.v * x.v)), x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> atan_v(const Dual<double, N, NS>& x) { return chain(atan(x.v), 1.0 / (1.0 + x.v * x.v), x); }
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> cbrt_v(const Dual<double, N, NS>& x) { double val = cbrt(x.v); return chain(val, 1.0 / (3.0 * (val * val)), x); }
+// binary atan(y, x) and hypot(x, y)
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> atan2_v(const Dual<double, N, NS>& y, const Dual<double, N, NS>& x) {
+    Dual<double, N, NS> r; r.v = atan2(y.v, x.v);
+    double den = y.v * y.v + x.v * x.v; double dy = x.v / den, dx = -y.v / den;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.p[i] = mulp<NS>(y.p[i], dy) + mulp<NS>(x.p[i], dx);
+    return r;
+}
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> hypot_v(const Dual<double, N, NS>& x, const Dual<double, N, NS>& y) {
+    Dual<double, N, NS> r; double h = hypot(x.v, y.v); r.v = h;
+    double dx = x.v / h, dy = y.v / h;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.p[i] = mulp<NS>(x.p[i], dx) + mulp<NS>(y.p[i], dy);
+    return r;
+}
 // sin / cos: one sincos, cos partial is (-s)*p  (src/dual.jl:709-717)
 template <int N, bool NS> FDB_DEV Dual<double, N, NS> sin_v(const Dual<double, N, NS>& x) {
     double s, c; sincos(x.v, &s, &c); return chain(s, c, x);

@@ -84,7 +84,19 @@ template <int N, bool NS> FDB_DEV Dual<double, N, NS> apply1(int op, const Dual<
         case FDB_POW0: return pow0(x);
         case FDB_POW1: return pow1(x);
         case FDB_POW2: return pow2(x);
-        default: return pow3(x);
+        case FDB_POW3: return pow3(x);
+        case FDB_TAN: return tan_v(x);
+        case FDB_EXP2: return exp2_v(x);
+        case FDB_LOG2: return log2_v(x);
+        case FDB_LOG10: return log10_v(x);
+        case FDB_LOG1P: return log1p_v(x);
+        case FDB_EXPM1: return expm1_v(x);
+        case FDB_SINH: return sinh_v(x);
+        case FDB_COSH: return cosh_v(x);
+        case FDB_ASIN: return asin_v(x);
+        case FDB_ACOS: return acos_v(x);
+        case FDB_ATAN: return atan_v(x);
+        default: return cbrt_v(x);
     }
 }
 template <int N, bool NS> FDB_DEV Dual<double, N, NS> apply2_dd(int op, const Dual<double, N, NS>& x, const Dual<double, N, NS>& y) {
@@ -95,7 +107,9 @@ template <int N, bool NS> FDB_DEV Dual<double, N, NS> apply2_dd(int op, const Du
         case FDB_DIV: return x / y;
         case FDB_POW: return pow_v(x, y);
         case FDB_MAX: return max_v(x, y);
-        default: return min_v(x, y);
+        case FDB_MIN: return min_v(x, y);
+        case FDB_ATAN2: return atan2_v(x, y);
+        default: return hypot_v(x, y);
     }
 }
 template <int N, bool NS> FDB_DEV Dual<double, N, NS> apply2_dr(int op, const Dual<double, N, NS>& x, double s) {
@@ -318,7 +332,7 @@ static int check_same(fdb_ctx* ctx, const fdb_array* out, const fdb_array* a, co
 
 extern "C" int fdb_map1(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a) {
     int rc = check_same(ctx, out, a, "fdb_map1"); if (rc) return rc;
-    if (op < FDB_NEG || op > FDB_POW3) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map1: unknown op %d", op);
+    if (op < FDB_NEG || op > FDB_CBRT) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map1: unknown op %d", op);
     if (out->n != a->n) return fail(ctx, FDB_ERR_SHAPE, "fdb_map1: DimensionMismatch");
     if (a->n == 0) return FDB_OK;
     unsigned grid = (unsigned)cdiv(cdiv(a->n, 2), 256);
@@ -330,7 +344,7 @@ extern "C" int fdb_map1(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a
 
 extern "C" int fdb_map2(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a, const fdb_array* b) {
     if (!ctx || !out || !a || !b) return fail(ctx, FDB_ERR_BADARG, "fdb_map2: null argument");
-    if (op < FDB_ADD || op > FDB_MIN) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map2: unknown op %d", op);
+    if (op < FDB_ADD || op > FDB_HYPOT) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map2: unknown op %d", op);
     if (out->level != 1 || a->level > 1 || b->level > 1 || (a->level == 0 && b->level == 0))
         return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map2: need a level-1 output and at least one level-1 operand");
     int N = out->N;

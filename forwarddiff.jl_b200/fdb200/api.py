@@ -210,15 +210,31 @@ class HessianConfig(_Config):
 # ---------------------------------------------------------------------------
 # gradient
 # ---------------------------------------------------------------------------
-def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None):
+def _try_trace(kind, f, n):
+    """Flatten a non-catalogue callable into an op-program; None when its shape is not supported."""
+    from . import trace
+    try:
+        return (trace.trace_scalar if kind == "scalar" else trace.trace_array)(f, n)
+    except (trace.TraceError, TypeError, AttributeError, ValueError):
+        return None
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a.size else None
+
+
+def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True):
     """ForwardDiff.gradient(f, x, cfg, Val{check}()) (src/gradient.jl:16-24)."""
     result = np.zeros(_length(x)) if not isinstance(x, _DeviceArray) else x.similar()
-    return gradient_b(result, f, x, cfg, check, ctx, chunks)
+    return gradient_b(result, f, x, cfg, check, ctx, chunks, fuse)
 
 
-def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None):
+def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True):
     """ForwardDiff.gradient!(result, f, x, cfg, Val{check}()) (src/gradient.jl:35-44).
-    `chunks=(lo, hi)` restricts the call to a 0-based chunk range (the sharding hook)."""
+    `chunks=(lo, hi)` restricts the call to a 0-based chunk range (the sharding hook).
+    A non-catalogue callable is flattened into an op-program and run as one batched launch when its
+    shape allows (`fuse=True`); otherwise -- or with `fuse=False` -- the reference chunk loop runs on
+    materialised device duals."""
     cfg = cfg if cfg is not None else GradientConfig(f, x)
     if check:
         checktag(cfg.tag, f, x)
@@ -239,10 +255,30 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None):
     if fid is not None:
         value = _fused_gradient(ctx, fid, x, N, lo, hi, out)
     else:
-        value = _loop_gradient(ctx, f, x, cfg, lo, hi, out)
+        prog = _try_trace("scalar", f, n) if fuse else None
+        if prog is not None:
+            value = _program_gradient(ctx, prog, x, N, lo, hi, out)
+        else:
+            value = _loop_gradient(ctx, f, x, cfg, lo, hi, out)
     if isinstance(result, DiffResult) and value is not None:
         result.value = value
     return result
+
+
+def _program_gradient(ctx, prog, x, N, lo, hi, out):
+    """A flattened user f through the batched sweep (fdb_program_gradient_chunked)."""
+    lib = ctx.lib
+    xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
+    res = out if isinstance(out, _DeviceArray) else B200Array.alloc(ctx, xd.n)
+    val = B200Array.alloc(ctx, 1)
+    ctx.check(lib.fdb_program_gradient_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
+                                               prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
+                                               prog.n_acc, prog.halo, prog.result_reg, xd.h, N, lo, hi, res.h, val.h))
+    nchunks = 1 if xd.n == N else chunk_plan(xd.n, N)["nchunks"]
+    lo_e, hi_e = lo * N, (xd.n if (hi < 0 or hi == nchunks) else hi * N)
+    if res is not out:
+        out[lo_e:hi_e] = res.numpy()[lo_e:hi_e]
+    return float(val.numpy()[0]) if (hi < 0 or hi == nchunks) else None
 
 
 def _fused_gradient(ctx, fid, x, N, lo, hi, out):
@@ -316,21 +352,24 @@ def _loop_gradient(ctx, f, x, cfg, lo, hi, out):
 # ---------------------------------------------------------------------------
 # jacobian
 # ---------------------------------------------------------------------------
-def jacobian(f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=None, m=None):
+def jacobian(f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=None, m=None, fuse=True):
     """ForwardDiff.jacobian(f, x, cfg) and, with `y`, jacobian(f!, y, x, cfg) (src/jacobian.jl:18-44).
     Returns the dense column-major length(y) x length(x) matrix (jacobian.jl:221)."""
-    ylen = _length(y) if y is not None else (m if m is not None else getattr(f, "output_length", lambda n: None)(_length(x)))
+    n = _length(x)
+    ylen = _length(y) if y is not None else (m if m is not None else getattr(f, "output_length", lambda n: None)(n))
+    if ylen is None and fuse and _catalogue_id(f, _lib.JFN) is None:
+        prog = _try_trace("array", f, n)            # the flattened f knows its output length
+        ylen = prog.out_len if prog is not None else None
     if ylen is None:
         raise FdbError("jacobian: output length unknown; pass m= or y=")
-    n = _length(x)
     if isinstance(x, _DeviceArray):
         result = B200Array.alloc(x.ctx, ylen * n)
     else:
         result = np.zeros((ylen, n), order="F")
-    return jacobian_b(result, f, x, cfg, check, ctx, y, params, chunks)
+    return jacobian_b(result, f, x, cfg, check, ctx, y, params, chunks, fuse)
 
 
-def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=None):
+def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=None, fuse=True):
     """ForwardDiff.jacobian!(result, f, x, cfg) / jacobian!(result, f!, y, x, cfg) (src/jacobian.jl:57-87)."""
     cfg = cfg if cfg is not None else JacobianConfig(f, x, y=y)
     if check:
@@ -344,6 +383,9 @@ def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None
     fid = _catalogue_id(f, _lib.JFN)
     lo, hi = (0, -1) if chunks is None else chunks
     if fid is None:
+        prog = _try_trace("array", f, n) if (fuse and y is None) else None
+        if prog is not None:
+            return _program_jacobian(ctx, prog, result, out, x, N, lo, hi)
         return _loop_jacobian(ctx, result, out, f, x, cfg, y, lo, hi)
     params = params or getattr(f, "params", {}) or {}
     host = not isinstance(x, _DeviceArray)
@@ -370,6 +412,33 @@ def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None
             y[...] = yv                                              # map!(d -> value(T,d), y, ydual), jacobian.jl:229
         if isinstance(result, DiffResult):
             result.value = yv
+    return result
+
+
+def _program_jacobian(ctx, prog, result, out, x, N, lo, hi):
+    """A flattened elementwise / stencil f through the batched sweep (fdb_program_jacobian_chunked)."""
+    lib = ctx.lib
+    xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
+    n, m = xd.n, prog.out_len
+    if isinstance(out, _DeviceArray):
+        if out.n != m * n:
+            raise DimensionMismatch(f"Jacobian result has {out.n} entries, expected {m}x{n}")
+        Jd = out
+    else:
+        if out.shape != (m, n):
+            raise DimensionMismatch(f"Jacobian result has shape {out.shape}, expected {(m, n)}")
+        Jd = B200Array.alloc(ctx, m * n)
+    yd = B200Array.alloc(ctx, m)
+    ctx.check(lib.fdb_program_jacobian_chunked(ctx.h, _i32p(prog.term), len(prog.term),
+                                               prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
+                                               prog.halo, prog.result_reg, xd.h, N, lo, hi, Jd.h, m, yd.h))
+    nchunks = 1 if n == N else chunk_plan(n, N)["nchunks"]
+    last = hi < 0 or hi == nchunks
+    if Jd is not out:
+        c0, c1 = lo * N, (n if last else hi * N)
+        out[:, c0:c1] = Jd.numpy().reshape((m, n), order="F")[:, c0:c1]
+    if last and isinstance(result, DiffResult):
+        result.value = yd.numpy()
     return result
 
 

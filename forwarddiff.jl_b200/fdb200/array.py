@@ -263,6 +263,8 @@ def _unary(op):
     def f(x):
         if isinstance(x, B200DualArray):
             return x._map1(op)
+        if hasattr(x, "_trace_unary"):          # symbolic array while a user f is flattened into an op-program
+            return x._trace_unary(op)
         return getattr(np, {"abs2": "square", "inv": "reciprocal"}.get(op, op))(x)
     f.__name__ = op
     return f
@@ -270,6 +272,8 @@ def _unary(op):
 
 exp, log, sin, cos, tanh, sqrt, abs_, abs2, inv = (_unary(o) for o in
                                                   ("exp", "log", "sin", "cos", "tanh", "sqrt", "abs", "abs2", "inv"))
+tan, exp2, log2, log10, log1p, expm1, sinh, cosh, asin, acos, atan, cbrt = (
+    _unary(o) for o in ("tan", "exp2", "log2", "log10", "log1p", "expm1", "sinh", "cosh", "asin", "acos", "atan", "cbrt"))
 
 
 def maximum(a, b):
@@ -278,6 +282,15 @@ def maximum(a, b):
 
 def minimum(a, b):
     return a._map2("min", b)
+
+
+def atan2(y, x):
+    """atan(y, x) on two Dual arrays (DiffRules binary rule)."""
+    return y._map2("atan2", x)
+
+
+def hypot(x, y):
+    return x._map2("hypot", y)
 
 
 def fma(x, y, z):

@@ -1,0 +1,237 @@
+"""Flatten a user function into an op-program (include/fdb200.h, fdb_program_*).
+
+The Julia shim would do this by walking the `Broadcasted` tree of `f`'s broadcast expressions
+(a custom BroadcastStyle); here the same flattening is done by calling `f` once on a symbolic array
+whose operators record instead of compute.  Supported shape: elementwise src/dual.jl arithmetic on
+unit-stride views `x[a:b]` of the input (all of one common length), `sum()` reductions of such arrays,
+and scalar Dual arithmetic on the reduced values.  Anything else raises TraceError and the caller
+falls back to the reference chunk loop on materialised device duals.
+"""
+import numpy as np
+
+from ._lib import OP1, OP2
+
+K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC, K_MOV = range(7)
+MAX_INSTR, MAX_CONST, MAX_REG, MAX_ACC = 48, 24, 12, 4
+
+
+class TraceError(Exception):
+    pass
+
+
+_NUM = (int, float, np.floating, np.integer)
+
+
+class _Node:
+    __slots__ = ("kind", "op", "args", "const", "stage", "id")
+
+    def __init__(self, tr, kind, op=0, args=(), const=None, stage="term"):
+        self.kind, self.op, self.args, self.const, self.stage = kind, op, args, const, stage
+        self.id = len(tr.nodes)
+        tr.nodes.append(self)
+
+
+class _Sym:
+    """Common operator plumbing of the symbolic array (stage 'term') and symbolic scalar (stage 'scalar')."""
+
+    def __init__(self, tr, node, length):
+        self.tr, self.node, self.n = tr, node, length
+
+    def _like(self, node):
+        return type(self)(self.tr, node, self.n)
+
+    def _check(self, other):
+        if not isinstance(other, _Sym) or other.tr is not self.tr:
+            raise TraceError("operand is not part of this trace")
+        if type(other) is not type(self):
+            raise TraceError("mixing reduced scalars and arrays inside one broadcast needs two passes")
+        if other.n != self.n:
+            from ._lib import DimensionMismatch
+            raise DimensionMismatch(f"arrays could not be broadcast to a common size ({self.n} vs {other.n})")
+
+    def _map1(self, op):
+        return self._like(_Node(self.tr, K_UNARY, OP1[op], (self.node,), stage=self.node.stage))
+
+    _trace_unary = _map1
+
+    def _map2(self, op, other, reverse=False):
+        code = OP2[op]
+        if isinstance(other, _NUM):
+            if code > OP2["pow"]:
+                raise TraceError(f"{op} needs two Dual operands")
+            kind = K_CD if reverse else K_DC
+            return self._like(_Node(self.tr, kind, code, (self.node,), const=float(other), stage=self.node.stage))
+        self._check(other)
+        a, b = (other.node, self.node) if reverse else (self.node, other.node)
+        return self._like(_Node(self.tr, K_DD, code, (a, b), stage=self.node.stage))
+
+    def __add__(self, o): return self._map2("add", o)
+    def __radd__(self, o): return self._map2("add", o, True)
+    def __sub__(self, o): return self._map2("sub", o)
+    def __rsub__(self, o): return self._map2("sub", o, True)
+    def __mul__(self, o): return self._map2("mul", o)
+    def __rmul__(self, o): return self._map2("mul", o, True)
+    def __truediv__(self, o): return self._map2("div", o)
+    def __rtruediv__(self, o): return self._map2("div", o, True)
+    def __neg__(self): return self._map1("neg")
+
+    def __pow__(self, o):
+        if isinstance(o, int) and not isinstance(o, bool) and 0 <= o <= 3:      # Base.literal_pow, src/dual.jl:587-597
+            return self._map1(f"pow{o}")
+        return self._map2("pow", o)
+
+    def __rpow__(self, o): return self._map2("pow", o, True)
+
+
+class TScalar(_Sym):
+    """A reduced Dual (result of sum) or scalar Dual math on such values: the epilogue stage."""
+
+
+class TArray(_Sym):
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, sl):
+        if self.node.kind != K_LOADX or self.node.args:
+            raise TraceError("views are only supported directly on the input array")
+        if not isinstance(sl, slice):
+            raise TraceError("scalar indexing")
+        start, stop, step = sl.indices(self.n)
+        if step != 1:
+            raise TraceError("non-unit stride")
+        node = _Node(self.tr, K_LOADX, 0, (), const=self.node.const + start)
+        return TArray(self.tr, node, max(stop - start, 0))
+
+    def sum(self):
+        tr = self.tr
+        if len(tr.accs) >= MAX_ACC:
+            raise TraceError("too many reductions")
+        tr.accs.append(self.node)
+        tr.term_lengths.add(self.n)
+        node = _Node(tr, K_ACC, len(tr.accs) - 1, (), stage="scalar")
+        return TScalar(tr, node, 1)
+
+    def prod(self):
+        raise TraceError("prod is not an additive reduction")
+
+
+class _Trace:
+    def __init__(self, n):
+        self.n = n
+        self.nodes, self.accs, self.term_lengths = [], [], set()
+
+
+def _emit(tr, roots, stage, preloaded):
+    """Linearise the DAG reachable from `roots` (restricted to `stage`) into instructions with register reuse."""
+    order, seen = [], set()
+
+    def visit(nd):
+        if nd.id in seen or nd.stage != stage:
+            return
+        seen.add(nd.id)
+        for a in nd.args:
+            visit(a)
+        order.append(nd)
+
+    for r in roots:
+        visit(r)
+    last_use = {}
+    for pos, nd in enumerate(order):
+        for a in nd.args:
+            last_use[a.id] = pos
+    for r in roots:
+        last_use[r.id] = len(order) + 1
+    consts, instrs, reg = tr.consts, [], dict(preloaded)
+    free = [r for r in range(MAX_REG - 1, -1, -1) if r not in reg.values()]
+
+    def cidx(v):
+        for i, c in enumerate(consts):
+            if c == v and np.signbit(c) == np.signbit(v):
+                return i
+        if len(consts) >= MAX_CONST:
+            raise TraceError("too many constants")
+        consts.append(v)
+        return len(consts) - 1
+
+    for pos, nd in enumerate(order):
+        if nd.id in reg:                         # preloaded accumulator register
+            continue
+        srcs = [reg[a.id] for a in nd.args]
+        for a in nd.args:                        # release operands whose last use is this instruction
+            if last_use.get(a.id) == pos and a.id in reg and reg[a.id] not in free and a.id not in preloaded:
+                free.append(reg[a.id])
+        if not free:
+            raise TraceError("expression needs more than %d live Dual registers" % MAX_REG)
+        dst = free.pop()
+        reg[nd.id] = dst
+        if nd.kind == K_LOADX:
+            instrs.append((K_LOADX << 6, dst, 0, int(nd.const)))
+        elif nd.kind == K_UNARY:
+            instrs.append(((K_UNARY << 6) | nd.op, dst, srcs[0], 0))
+        elif nd.kind == K_DD:
+            instrs.append(((K_DD << 6) | nd.op, dst, srcs[0], srcs[1]))
+        elif nd.kind == K_DC:
+            instrs.append(((K_DC << 6) | nd.op, dst, srcs[0], cidx(nd.const)))
+        elif nd.kind == K_CD:
+            instrs.append(((K_CD << 6) | nd.op, dst, cidx(nd.const), srcs[0]))
+        else:
+            raise TraceError("unexpected node in stage " + stage)
+        if len(instrs) > MAX_INSTR:
+            raise TraceError("program too long")
+    return instrs, reg
+
+
+class Program:
+    """term/epilogue instruction arrays + constants, ready for fdb_program_*_chunked."""
+
+    def __init__(self, term, epi, consts, n_acc, halo, result_reg, out_len):
+        self.term = np.asarray(term, dtype=np.int32).reshape(-1, 4)
+        self.epi = np.asarray(epi, dtype=np.int32).reshape(-1, 4)
+        self.consts = np.asarray(consts, dtype=np.float64)
+        self.n_acc, self.halo, self.result_reg, self.out_len = n_acc, halo, result_reg, out_len
+
+
+def _common_halo(tr, lengths):
+    if len(lengths) != 1:
+        raise TraceError("reductions over arrays of different lengths")
+    L = lengths.pop()
+    halo = tr.n - L
+    offs = [nd.const for nd in tr.nodes if nd.kind == K_LOADX and nd.stage == "term"]
+    if halo < 0 or any(o > halo for o in offs):
+        raise TraceError("view outside the input")
+    return L, halo
+
+
+def trace_scalar(f, n):
+    """f(x) -> scalar: returns a Program for fdb_program_gradient_chunked, or raises TraceError."""
+    tr = _Trace(n)
+    tr.consts = []
+    x = TArray(tr, _Node(tr, K_LOADX, 0, (), const=0), n)
+    y = f(x)
+    if not isinstance(y, TScalar):
+        raise TraceError("f did not return a reduced scalar")
+    L, halo = _common_halo(tr, set(tr.term_lengths))
+    # term part: evaluate every accumulated expression, then ACC
+    term, reg = _emit(tr, tr.accs, "term", {})
+    for k, nd in enumerate(tr.accs):
+        term.append((K_ACC << 6, k, reg[nd.id], 0))
+    if len(term) > MAX_INSTR:
+        raise TraceError("program too long")
+    pre = {nd.id: nd.op for nd in tr.nodes if nd.kind == K_ACC}
+    epi, ereg = _emit(tr, [y.node], "scalar", pre)
+    return Program(term, epi, tr.consts, len(tr.accs), halo, ereg[y.node.id], 1)
+
+
+def trace_array(f, n):
+    """f(x) -> array (elementwise / stencil): Program for fdb_program_jacobian_chunked."""
+    tr = _Trace(n)
+    tr.consts = []
+    x = TArray(tr, _Node(tr, K_LOADX, 0, (), const=0), n)
+    y = f(x)
+    if not isinstance(y, TArray):
+        raise TraceError("f did not return an array")
+    if tr.accs:
+        raise TraceError("reductions inside an array-valued f need two passes")
+    L, halo = _common_halo(tr, {y.n})
+    term, reg = _emit(tr, [y.node], "term", {})
+    return Program(term, [], tr.consts, 0, halo, reg[y.node.id], L)

@@ -55,10 +55,11 @@ typedef enum {
 /* unary ops: src/dual.jl:476-490 (DiffRules loop), :519 (-), :587-597 (literal_pow), :709-717 (sin/cos) */
 typedef enum {
     FDB_NEG = 1, FDB_EXP, FDB_LOG, FDB_SIN, FDB_COS, FDB_TANH, FDB_SQRT, FDB_ABS, FDB_ABS2, FDB_INV,
-    FDB_POW0, FDB_POW1, FDB_POW2, FDB_POW3
+    FDB_POW0, FDB_POW1, FDB_POW2, FDB_POW3,
+    FDB_TAN, FDB_EXP2, FDB_LOG2, FDB_LOG10, FDB_LOG1P, FDB_EXPM1, FDB_SINH, FDB_COSH, FDB_ASIN, FDB_ACOS, FDB_ATAN, FDB_CBRT
 } fdb_op1;
 /* binary ops: src/dual.jl:499-519 (+ -), DiffRules * max min, :532-544 (/), :549-585 (^) */
-typedef enum { FDB_ADD = 1, FDB_SUB, FDB_MUL, FDB_DIV, FDB_POW, FDB_MAX, FDB_MIN } fdb_op2;
+typedef enum { FDB_ADD = 1, FDB_SUB, FDB_MUL, FDB_DIV, FDB_POW, FDB_MAX, FDB_MIN, FDB_ATAN2, FDB_HYPOT } fdb_op2;
 typedef enum { FDB_SUM = 1, FDB_PROD = 2 } fdb_redop;
 
 /* scalar-valued catalogue targets for fdb_gradient_chunked / fdb_hessian_chunked */
@@ -201,6 +202,28 @@ int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int64_t m, in
  * Jacobian of the chunked gradient; H column-major n x n (ldH); grad, value_dev may be NULL. */
 int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi,
                         fdb_array* H, int64_t ldH, fdb_array* grad, fdb_array* value_dev);
+
+/* ---- op-programs: fused broadcast trees for an arbitrary user f -----------------------------
+ * What Julia's `Broadcasted` tree + `sum` gives for a user function is flattened by the host into a small
+ * program (no JIT): instructions are 4 int32 words {op, dst, a, b} with op = kind*64 + code,
+ *   kind 0 LOADX  dst <- seeded Dual of x[i + b]            (term part only; 0 <= b <= halo)
+ *   kind 1 UNARY  dst <- code(a)                            code = fdb_op1
+ *   kind 2 DD     dst <- a (code) b                         code = fdb_op2, both Dual registers
+ *   kind 3 DC     dst <- a (code) consts[b]                 Dual (op) Real
+ *   kind 4 CD     dst <- consts[a] (code) b                 Real (op) Dual
+ *   kind 5 ACC    accumulator dst += a                      (`sum`; term part only)
+ *   kind 6 MOV    dst <- a
+ * The term part runs for every i in [0, n - halo); the epilogue part runs once per chunk with registers
+ * 0..n_acc-1 preloaded with the reduced accumulators; `result_reg` holds f(xdual).  Limits: 48 instructions
+ * per part, 24 constants, 12 registers, 4 accumulators (FDB_ERR_UNSUPPORTED beyond).  Same chunk-range
+ * semantics as fdb_gradient_chunked / fdb_jacobian_chunked.  The Jacobian form evaluates
+ * y[i] = program(x[i .. i+halo]), i in [0, n - halo) (elementwise / stencil array functions). */
+int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi,
+                                 const double* consts, int n_consts, int n_acc, int halo, int result_reg, const fdb_array* x, int N,
+                                 int64_t chunk_lo, int64_t chunk_hi, fdb_array* grad, fdb_array* value_dev);
+int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, int n_instr, const double* consts, int n_consts, int halo,
+                                 int result_reg, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* J,
+                                 int64_t ldJ, fdb_array* y);
 
 /* ---- host-buffer entry points (what ForwardDiff.gradient!(out, f, x, cfg) with
  * host Vectors binds to): upload x, run the sweeps, download the result slice.  grad_host has

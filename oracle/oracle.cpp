@@ -200,6 +200,32 @@ template <class V, int N> inline Dual<V, N> abs_v(const Dual<V, N>& x) {
     V o = one_of(x.v);
     return signbit_v(x.v) ? chain(abs_v(x.v), -o, x) : chain(abs_v(x.v), o, x);
 }
+// further DiffRules unary rules (V = double only)
+template <int N> inline Dual<double, N> tan_v(const Dual<double, N>& x) { double val = std::tan(x.v); return chain(val, 1.0 + val * val, x); }
+template <int N> inline Dual<double, N> exp2_v(const Dual<double, N>& x) { double val = std::exp2(x.v); return chain(val, val * 0.6931471805599453, x); }
+template <int N> inline Dual<double, N> log2_v(const Dual<double, N>& x) { return chain(std::log2(x.v), (1.0 / x.v) / 0.6931471805599453, x); }
+template <int N> inline Dual<double, N> log10_v(const Dual<double, N>& x) { return chain(std::log10(x.v), (1.0 / x.v) / 2.302585092994046, x); }
+template <int N> inline Dual<double, N> log1p_v(const Dual<double, N>& x) { return chain(std::log1p(x.v), 1.0 / (x.v + 1.0), x); }
+template <int N> inline Dual<double, N> expm1_v(const Dual<double, N>& x) { return chain(std::expm1(x.v), std::exp(x.v), x); }
+template <int N> inline Dual<double, N> sinh_v(const Dual<double, N>& x) { return chain(std::sinh(x.v), std::cosh(x.v), x); }
+template <int N> inline Dual<double, N> cosh_v(const Dual<double, N>& x) { return chain(std::cosh(x.v), std::sinh(x.v), x); }
+template <int N> inline Dual<double, N> asin_v(const Dual<double, N>& x) { return chain(std::asin(x.v), 1.0 / std::sqrt(1.0 - x.v * x.v), x); }
+template <int N> inline Dual<double, N> acos_v(const Dual<double, N>& x) { return chain(std::acos(x.v), -(1.0 / std::sqrt(1.0 - x.v * x.v)), x); }
+template <int N> inline Dual<double, N> atan_v(const Dual<double, N>& x) { return chain(std::atan(x.v), 1.0 / (1.0 + x.v * x.v), x); }
+template <int N> inline Dual<double, N> cbrt_v(const Dual<double, N>& x) { double val = std::cbrt(x.v); return chain(val, 1.0 / (3.0 * (val * val)), x); }
+// binary atan(y, x) and hypot(x, y) (DiffRules)
+template <int N> inline Dual<double, N> atan2_v(const Dual<double, N>& y, const Dual<double, N>& x) {
+    Dual<double, N> r; r.v = std::atan2(y.v, x.v);
+    double den = y.v * y.v + x.v * x.v; double dy = x.v / den, dx = -y.v / den;
+    for (int i = 0; i < N; i++) r.p[i] = mul_partial(y.p[i], dy) + mul_partial(x.p[i], dx);
+    return r;
+}
+template <int N> inline Dual<double, N> hypot_v(const Dual<double, N>& x, const Dual<double, N>& y) {
+    Dual<double, N> r; double h = std::hypot(x.v, y.v); r.v = h;
+    double dx = x.v / h, dy = y.v / h;
+    for (int i = 0; i < N; i++) r.p[i] = mul_partial(x.p[i], dx) + mul_partial(y.p[i], dy);
+    return r;
+}
 // sin / cos share one sincos (src/dual.jl:709-717): cos partial is (-s)*p
 template <class V, int N> inline Dual<V, N> sin_v(const Dual<V, N>& x) { V s = sin_v(x.v), c = cos_v(x.v); return chain(s, c, x); }
 template <class V, int N> inline Dual<V, N> cos_v(const Dual<V, N>& x) { V s = sin_v(x.v), c = cos_v(x.v); return chain(c, -s, x); }
@@ -602,8 +628,9 @@ void third_order_vector_mode(int fn, const double* x, double* T3) {
 
 // elementwise maps over AoS arrays (the array-level ops of a user `f`)
 enum Op1 { OP_NEG = 1, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_TANH, OP_SQRT, OP_ABS, OP_ABS2, OP_INV,
-           OP_POW0, OP_POW1, OP_POW2, OP_POW3 };
-enum Op2 { OP_ADD = 1, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_MAX, OP_MIN };
+           OP_POW0, OP_POW1, OP_POW2, OP_POW3, OP_TAN, OP_EXP2, OP_LOG2, OP_LOG10, OP_LOG1P, OP_EXPM1, OP_SINH, OP_COSH,
+           OP_ASIN, OP_ACOS, OP_ATAN, OP_CBRT };
+enum Op2 { OP_ADD = 1, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_MAX, OP_MIN, OP_ATAN2, OP_HYPOT };
 
 template <int N> int map1(int op, Dual<double, N>* out, const Dual<double, N>* a, long n) {
     for (long i = 0; i < n; i++) {
@@ -616,6 +643,12 @@ template <int N> int map1(int op, Dual<double, N>* out, const Dual<double, N>* a
             case OP_ABS2: out[i] = abs2_v(x); break;  case OP_INV: out[i] = inv_v(x); break;
             case OP_POW0: out[i] = pow0(x); break;    case OP_POW1: out[i] = pow1(x); break;
             case OP_POW2: out[i] = pow2(x); break;    case OP_POW3: out[i] = pow3(x); break;
+            case OP_TAN: out[i] = tan_v(x); break;    case OP_EXP2: out[i] = exp2_v(x); break;
+            case OP_LOG2: out[i] = log2_v(x); break;  case OP_LOG10: out[i] = log10_v(x); break;
+            case OP_LOG1P: out[i] = log1p_v(x); break; case OP_EXPM1: out[i] = expm1_v(x); break;
+            case OP_SINH: out[i] = sinh_v(x); break;  case OP_COSH: out[i] = cosh_v(x); break;
+            case OP_ASIN: out[i] = asin_v(x); break;  case OP_ACOS: out[i] = acos_v(x); break;
+            case OP_ATAN: out[i] = atan_v(x); break;  case OP_CBRT: out[i] = cbrt_v(x); break;
             default: return -2;
         }
     }
@@ -631,7 +664,8 @@ template <int N> int map2(int op, int kind, Dual<double, N>* out, const Dual<dou
             const D &x = a[i], &y = b[i];
             switch (op) { case OP_ADD: r = x + y; break; case OP_SUB: r = x - y; break; case OP_MUL: r = x * y; break;
                           case OP_DIV: r = x / y; break; case OP_POW: r = pow_v(x, y); break;
-                          case OP_MAX: r = max_v(x, y); break; case OP_MIN: r = min_v(x, y); break; default: return -2; }
+                          case OP_MAX: r = max_v(x, y); break; case OP_MIN: r = min_v(x, y); break;
+                          case OP_ATAN2: r = atan2_v(x, y); break; case OP_HYPOT: r = hypot_v(x, y); break; default: return -2; }
         } else if (kind == 1) {
             const D& x = a[i];
             switch (op) { case OP_ADD: r = x + s; break; case OP_SUB: r = x - s; break; case OP_MUL: r = x * s; break;

@@ -20,8 +20,9 @@ _lp = C.POINTER(C.c_long)
 
 # op codes shared with oracle.cpp (enum Op1 / Op2)
 OP1 = dict(neg=1, exp=2, log=3, sin=4, cos=5, tanh=6, sqrt=7, abs=8, abs2=9, inv=10,
-           pow0=11, pow1=12, pow2=13, pow3=14)
-OP2 = dict(add=1, sub=2, mul=3, div=4, pow=5, max=6, min=7)
+           pow0=11, pow1=12, pow2=13, pow3=14, tan=15, exp2=16, log2=17, log10=18, log1p=19, expm1=20, sinh=21, cosh=22,
+           asin=23, acos=24, atan=25, cbrt=26)
+OP2 = dict(add=1, sub=2, mul=3, div=4, pow=5, max=6, min=7, atan2=8, hypot=9)
 FN = dict(rosenbrock=1, ackley=2, sumsq=3, prod=4)
 JFN = dict(tanh_affine=1, brusselator=2, jactest=3)
 

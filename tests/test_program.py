@@ -1,0 +1,116 @@
+"""Op-programs: an arbitrary user f flattened into the interpreter's instruction set and run through
+the batched chunk sweep (fdb_program_gradient_chunked / fdb_program_jacobian_chunked).
+CPU part: the tracer.  GPU part: parity with the oracle and with the reference loop on materialised duals."""
+import numpy as np
+import pytest
+
+import fdb200
+from fdb200 import functions as F
+from fdb200 import trace
+
+
+# ---- tracer (no GPU) -------------------------------------------------------------------------------
+def test_tracer_flattens_rosenbrock_and_ackley():
+    p = trace.trace_scalar(F.rosenbrock_generic, 100)
+    assert p.halo == 1 and p.n_acc == 1 and len(p.epi) == 0 and p.consts.tolist() == [1.0, 100.0]
+    kinds = [int(op) >> 6 for op in p.term[:, 0]]
+    assert kinds.count(trace.K_LOADX) == 2 and kinds[-1] == trace.K_ACC
+    assert sorted(p.term[[k == trace.K_LOADX for k in kinds], 3].tolist()) == [0, 1]
+    q = trace.trace_scalar(F.ackley_generic, 50)
+    assert q.halo == 0 and q.n_acc == 2 and len(q.epi) > 0 and q.consts[1] == 1.0 / 50
+
+
+def test_tracer_rejects_what_the_interpreter_cannot_run():
+    with pytest.raises(trace.TraceError):
+        trace.trace_scalar(F.prod_generic, 10)                       # not an additive reduction
+    with pytest.raises(trace.TraceError):
+        trace.trace_scalar(lambda x: (x * x.sum()).sum(), 10)        # reduced value inside a broadcast: two passes
+    with pytest.raises(trace.TraceError):
+        trace.trace_scalar(lambda x: x * 2.0, 10)                    # not a scalar
+    with pytest.raises(fdb200.DimensionMismatch):
+        trace.trace_scalar(lambda x: (x + x[1:]).sum(), 10)
+    with pytest.raises(trace.TraceError):
+        trace.trace_scalar(lambda x: (x[::2]).sum(), 10)
+    a = trace.trace_array(lambda x: x[2:] - 2.0 * x[1:-1] + x[:-2], 20)
+    assert a.halo == 2 and a.out_len == 18
+
+
+# ---- GPU parity ---------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 4, 7, 12])
+def test_program_gradient_vs_oracle_and_loop(ctx, oracle, N):
+    for n in (13, 257, 1003):
+        x = np.random.default_rng(n).uniform(0.5, 1.5, n)
+        for gen, fn in ((F.rosenbrock_generic, "rosenbrock"), (F.ackley_generic, "ackley"), (F.sumsq_generic, "sumsq")):
+            res = fdb200.GradientResult(x)
+            fdb200.gradient_b(res, gen, x, fdb200.GradientConfig(gen, x, fdb200.Chunk(N)), ctx=ctx)      # fused op-program
+            g_ref, v_ref = oracle.gradient(fn, x, N)
+            scale = np.abs(g_ref).max()
+            assert np.allclose(res.derivs[0], g_ref, rtol=1e-11, atol=1e-12 * scale), (fn, n, N)
+            assert res.value == pytest.approx(v_ref, rel=1e-12)
+            if n <= 257:
+                res2 = fdb200.GradientResult(x)
+                fdb200.gradient_b(res2, gen, x, fdb200.GradientConfig(gen, x, fdb200.Chunk(N)), ctx=ctx, fuse=False)   # reference loop
+                assert np.allclose(res.derivs[0], res2.derivs[0], rtol=1e-11, atol=1e-12 * scale)
+
+
+@pytest.mark.gpu
+def test_program_gradient_lane_sharing_chunk_ranges_and_fallback(ctx, oracle):
+    n, N = 1000, 12
+    x = np.random.default_rng(4).uniform(0.5, 1.5, n)
+    cfg = fdb200.GradientConfig(F.rosenbrock_generic, x, fdb200.Chunk(N))
+    a = fdb200.gradient(F.rosenbrock_generic, x, cfg, ctx=ctx)
+    ctx.set_lane_sharing(False)
+    try:
+        b = fdb200.gradient(F.rosenbrock_generic, x, cfg, ctx=ctx)
+    finally:
+        ctx.set_lane_sharing(True)
+    assert np.array_equal(a, b)
+    out = np.zeros(n)
+    for r in range(3):
+        p = fdb200.chunk_plan(n, N, r, 3)
+        fdb200.gradient_b(out, F.rosenbrock_generic, x, cfg, ctx=ctx, chunks=(p["chunk_lo"], p["chunk_hi"]))
+    assert np.array_equal(out, a)
+    # prod cannot be flattened: the call silently takes the reference loop on materialised duals
+    xs = x[:40]
+    g = fdb200.gradient(F.prod_generic, xs, fdb200.GradientConfig(F.prod_generic, xs, fdb200.Chunk(4)), ctx=ctx)
+    assert np.allclose(g, oracle.gradient("prod", xs, 4)[0], rtol=1e-11)
+    # a user function with every op family: unary rules, Real (x) Dual both ways, literal and real powers, max
+    def f(xd):
+        u = fdb200.tanh(xd[:-1]) * fdb200.log1p(xd[1:]) + 2.0 / xd[:-1] - (xd[1:] ** 2.5) / 3.0
+        return (fdb200.maximum(u, xd[1:]) ** 3).sum() + fdb200.sqrt((xd ** 2).sum())
+    gf = fdb200.gradient(f, xs, fdb200.GradientConfig(f, xs, fdb200.Chunk(5)), ctx=ctx)
+    gl = fdb200.gradient(f, xs, fdb200.GradientConfig(f, xs, fdb200.Chunk(5)), ctx=ctx, fuse=False)
+    assert np.allclose(gf, gl, rtol=1e-11, atol=1e-12 * np.abs(gl).max())
+    h = 1e-6
+    def fv(z):
+        u = np.tanh(z[:-1]) * np.log1p(z[1:]) + 2.0 / z[:-1] - z[1:] ** 2.5 / 3.0
+        return (np.maximum(u, z[1:]) ** 3).sum() + np.sqrt((z ** 2).sum())
+    fd = np.array([(fv(xs + h * np.eye(40)[i]) - fv(xs - h * np.eye(40)[i])) / (2 * h) for i in range(40)])
+    assert np.allclose(gf, fd, atol=3e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 6, 12])
+def test_program_jacobian_elementwise_and_stencil(ctx, N):
+    n = 61
+    x = np.random.default_rng(6).uniform(0.5, 1.5, n)
+
+    def f(xd):
+        return fdb200.sin(xd) * xd + xd ** 3 / 2.0
+
+    J = fdb200.jacobian(f, x, fdb200.JacobianConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+    assert np.allclose(J, np.diag(np.cos(x) * x + np.sin(x) + 1.5 * x * x), rtol=1e-14, atol=1e-15)
+    Jl = fdb200.jacobian(f, x, fdb200.JacobianConfig(f, x, fdb200.Chunk(N)), ctx=ctx, m=n, fuse=False)
+    assert np.array_equal(J, Jl)                                   # same device functions per op: bit identical
+
+    def lap(xd):
+        return xd[2:] - 2.0 * xd[1:-1] + xd[:-2] ** 2
+
+    res = fdb200.JacobianResult(np.zeros(n - 2), x)
+    fdb200.jacobian_b(res, lap, x, fdb200.JacobianConfig(lap, x, fdb200.Chunk(N)), ctx=ctx)
+    expect = np.zeros((n - 2, n))
+    for i in range(n - 2):
+        expect[i, i + 2] = 1.0; expect[i, i + 1] = -2.0; expect[i, i] = 2.0 * x[i]
+    assert np.array_equal(res.derivs[0], expect)
+    assert np.allclose(res.value, x[2:] - 2.0 * x[1:-1] + x[:-2] ** 2, rtol=1e-15)
