@@ -25,8 +25,10 @@ for p in (os.path.join(ROOT, "forwarddiff.jl_b200"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+import ctypes
 import numpy as np
 
+C_DP = ctypes.POINTER(ctypes.c_double)
 N_ELEMS = 1_000_000
 CHUNK = 12
 WORKLOAD = "C2: ForwardDiff.gradient of Rosenbrock, n=1_000_000 Float64, Chunk{12} (83334 chunk sweeps)"
@@ -323,6 +325,17 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
                                             "fp64_frac": DP_OPS_PER_TERM_FULL * (N_ELEMS - 1) * 8192 / (ms * 1e-3) / dp_peak}
     ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["ackley"], x.h, CHUNK, 0, -1, g.h, v.h)), reps=2)
     out["ackley_gradient_c2"] = {"evals_per_s": 1e3 / ms, "ms": ms}
+    # the same Rosenbrock written as an ordinary callable on the device Dual array (broadcast + sum), flattened into
+    # an op-program and interpreted per thread: what an arbitrary user f costs on the batched sweep
+    from fdb200 import trace
+    from fdb200.api import _i32p
+    prog = trace.trace_scalar(F.rosenbrock_generic, N_ELEMS)
+    cp = prog.consts.ctypes.data_as(C_DP)
+    ms = t(lambda: ctx.check(lib.fdb_program_gradient_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi), cp,
+                                                              prog.consts.size, prog.n_acc, prog.halo, prog.result_reg, x.h, CHUNK, 0, 8192,
+                                                              g.h, v.h)), reps=2)
+    out["rosenbrock_gradient_generic_callable_op_program"] = {"evals_per_s": 1.0 / (ms * 1e-3 * 83334 / 8192), "timed": "8192 of 83334 chunks, scaled",
+                                                              "instructions": int(len(prog.term))}
     # C1: n = 10 000, Chunk{10} (the reference's published 0.2825 s case, docs/src/user/advanced.md:70-72)
     x1 = ctx.array(rng.random(10_000)); g1 = ctx.zeros(10_000)
     ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["rosenbrock"], x1.h, 10, 0, -1, g1.h, v.h)), reps=5)
