@@ -155,6 +155,15 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to stdout) are
+    # pointed at stderr for the duration of the run; the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     import torch
     import torch.distributed as dist
     import fdb200
@@ -291,7 +300,7 @@ def main():
             line["extra"] = extras(ctx, torch, dev, flush, hbm_peak, dp_peak)
         except Exception as e:                                    # extras never invalidate the headline line
             line["extra"] = {"error": repr(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
