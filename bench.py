@@ -217,8 +217,14 @@ def main():
             sg.sweep()
         sg.gather()
 
+    x_np, out_np = x_host.numpy(), out_host.numpy()           # views of the pinned host buffers
+
     def step_e2e():
-        sg(x_host, out_host)
+        if world == 1:
+            # the public API call with host buffers: ForwardDiff.gradient!(out, f, x, cfg) -> fdb_gradient_host
+            fdb200.gradient_b(out_np, F.rosenbrock, x_np, cfg, ctx=ctx)
+        else:
+            sg(x_host, out_host)
 
     # ---- device-resident steps -------------------------------------------------------------
     for _ in range(W):
@@ -285,7 +291,10 @@ def main():
                        "lane_sharing": True, "verified_against_closed_form": ok},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": 8 * N_ELEMS, "d2h_bytes_per_step": 8 * N_ELEMS,
-                    "ms_per_step": tot_ems / K, "api": "fdb200.dist.ShardedGradient.__call__ (pinned host x -> H2D -> sweeps -> gather -> D2H)"},
+                    "ms_per_step": tot_ems / K,
+                    "api": ("fdb200.gradient_b(out, rosenbrock, x, GradientConfig(rosenbrock, x, Chunk(12))) on pinned host arrays -> C ABI fdb_gradient_host "
+                            "(H2D x, all chunk sweeps, D2H gradient + value)") if world == 1 else
+                           "fdb200.dist.ShardedGradient.__call__ (pinned host x -> H2D -> this rank's sweeps -> NCCL all-gather -> D2H)"},
             "gpu_launches": int(launches), "clocks": clocks}
 
     if world == 1 and not args.no_cpu_baseline:

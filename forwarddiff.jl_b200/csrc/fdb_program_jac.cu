@@ -1,0 +1,69 @@
+// fdb_program_jac.cu -- Jacobian chunk sweeps of a flattened elementwise / stencil user function
+// (see fdb_program.cu; split into its own translation unit to keep build times down).
+#include "fdb_program.cuh"
+
+namespace fdb {
+
+// elementwise / stencil array targets: y[i] = program(x[i .. i+halo]) for i in [0, n - halo);
+// J[i, start+k] = partials(y[i], k) -- the f(x)-form Jacobian chunk sweep (src/jacobian.jl:169-216)
+template <int N, bool NS, int THREADS>
+__global__ void __launch_bounds__(THREADS) program_jacobian_kernel(const __grid_constant__ Program P, const bool SHARE, const double* __restrict__ x, int64_t n,
+                                                                   int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
+                                                                   double* __restrict__ J, int64_t ldJ, double* __restrict__ yout) {
+    typedef Dual<double, N, NS> D;
+    typedef Dual<double, 1, NS> D1;
+    const int64_t c = chunk_lo + blockIdx.x;
+    const bool last = (c == nchunks_total - 1);
+    const int chunksize = last ? lastchunksize : N;
+    const int64_t start = last ? (n - lastchunksize) : c * N;
+    const int64_t i = (int64_t)blockIdx.y * THREADS + threadIdx.x;
+    const int64_t m = n - P.halo;
+    const int64_t w0 = i - (threadIdx.x & 31);
+    const bool far = SHARE && ((w0 + 31 + P.halo < start) || (w0 >= start + chunksize));
+    if (i >= m) return;
+    if (far) {
+        D1 R1[PG_MAXR]; D1 acc1[1];
+        pg_run<D1, 1, NS>(P.term, P.n_term, P.consts, ZeroLoader<1, NS>{x}, i, R1, acc1);
+        const D1 y = R1[P.result_reg];
+        for (int k = 0; k < chunksize; k++) __stcs(J + i + (start + k) * ldJ, y.p[0]);
+        if (yout && last) yout[i] = y.v;
+    } else {
+        D R[PG_MAXR]; D acc[1];
+        pg_run<D, N, NS>(P.term, P.n_term, P.consts, SeedLoader<N, NS>{x, start, chunksize}, i, R, acc);
+        const D y = R[P.result_reg];
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (k < chunksize) __stcs(J + i + (start + k) * ldJ, y.p[k]);
+        if (yout && last) yout[i] = y.v;
+    }
+}
+
+}  // namespace fdb
+
+using namespace fdb;
+
+extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, int n_instr, const double* consts, int n_consts, int halo,
+                                            int result_reg, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* J,
+                                            int64_t ldJ, fdb_array* y) {
+    if (!ctx || !x || !J) return fail(ctx, FDB_ERR_BADARG, "fdb_program_jacobian_chunked: null argument");
+    if (x->level != 0 || J->level != 0 || (y && y->level != 0)) return fail(ctx, FDB_ERR_BADARG, "x, J, y must be plain arrays");
+    const int64_t n = x->n, m = n - halo;
+    if (N < 1 || N > FDB_MAX_CHUNK) return fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", N);
+    if (n < N) return fail(ctx, FDB_ERR_CHUNK, "chunk size cannot be greater than ForwardDiff.structural_length(x) (%d > %lld)", N, (long long)n);
+    if (m <= 0) return fail(ctx, FDB_ERR_SHAPE, "op-program Jacobian: empty output");
+    if (ldJ < m || J->n < ldJ * (n - 1) + m) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: Jacobian result must hold %lld x %lld", (long long)m, (long long)n);
+    if (y && y->n != m) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: y has %lld entries, f(x) has %lld", (long long)y->n, (long long)m);
+    Program P;
+    int rc = build_program(ctx, P, prog, n_instr, nullptr, 0, consts, n_consts, 0, halo, result_reg, true); if (rc) return rc;
+    Plan p = make_plan(n, N);
+    const int64_t nchunks = (n == N) ? 1 : p.nchunks;
+    if (chunk_hi < 0) chunk_hi = nchunks;
+    if (chunk_lo < 0 || chunk_lo > chunk_hi || chunk_hi > nchunks) return fail(ctx, FDB_ERR_BADARG, "bad chunk range");
+    if (chunk_lo == chunk_hi) return FDB_OK;
+    constexpr int T = 128;
+    dim3 grid((unsigned)(chunk_hi - chunk_lo), (unsigned)cdiv(m, T));
+    double* yp = y ? y->data : nullptr;
+    FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
+        (program_jacobian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, J->data, ldJ, yp))));
+    return finish(ctx, 1, "fdb_program_jacobian_chunked");
+}
