@@ -399,7 +399,15 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
                                                              "unit": "TFLOP/s", "frac": 2.0 * m3 * m3 * 13 * 683 / (ms * 1e-3) / 1e12 / dgemm_tf,
                                                              "algorithmic": "2*m*n*13*683 = 1.19 TFLOP: A against [value | 12 one-hot partials] of every chunk"}}
     out["cublas_dgemm_8192_tflops"] = dgemm_tf
-    del A, J3
+    # two layers tanh.(A2*tanh.(A1*x .+ b1) .+ b2), n = h = m = 8192: the second contraction has DENSE partials
+    A2 = ctx.array(rng.uniform(-1, 1, m3 * m3) / np.sqrt(m3)); b2 = ctx.array(rng.uniform(-1, 1, m3))
+    ms = t(lambda: ctx.check(lib.fdb_jacobian_mlp2_chunked(ctx.h, x3.h, m3, m3, 12, A.h, m3, b.h, A2.h, m3, b2.h, 0, -1, J3.h, m3, y3.h)), reps=2)
+    fl = 2.0 * m3 * m3 * (2 * 683 + 13 * 683)
+    out["mlp2_jacobian_8192_dense_partials"] = {"evals_per_s": 1e3 / ms, "ms": ms,
+                                                "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": dgemm_tf, "unit": "TFLOP/s",
+                                                             "frac": fl / (ms * 1e-3) / 1e12 / dgemm_tf,
+                                                             "algorithmic": "layer 1: 2 shared columns per chunk; layer 2: 13 dense columns per chunk; 683 chunks"}}
+    del A, J3, A2
     # generic HBM-bound kernels on materialised Dual{12} arrays, n = 2^22 (436 MB per array > L2)
     nn = 1 << 22
     a = fdb200.B200DualArray.alloc(ctx, nn, 12); bb = fdb200.B200DualArray.alloc(ctx, nn, 12); o = fdb200.B200DualArray.alloc(ctx, nn, 12)

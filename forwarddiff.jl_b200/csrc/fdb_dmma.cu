@@ -319,9 +319,97 @@ int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_ar
     return finish(ctx, 2 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma)");
 }
 
+// ---- two layers: f(x) = tanh.(A2 * tanh.(A1*x .+ b1) .+ b2) -------------------------------------------------
+// After the first layer the partials are dense, so the second `A * hdual` is a genuine dense contraction of A2
+// against [value | N partials] of every chunk: one DMMA GEMM m x h x (N+1)*nchunks.
+// Layer-1 epilogue that keeps the hidden Duals (value + N partial columns per chunk) instead of extracting:
+template <bool NS, bool SHARE>
+__global__ void __launch_bounds__(256) tanh_affine_hidden_kernel(const double* __restrict__ Y, int64_t ldy, int P, const double* __restrict__ A,
+                                                                int64_t lda, const double* __restrict__ b, int64_t h, int64_t n, int N,
+                                                                int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
+                                                                double* __restrict__ H, int64_t ldh) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t cl = blockIdx.y, c = chunk_lo + cl;
+    if (r >= h) return;
+    const bool last = (c == nchunks_total - 1);
+    const int cs = last ? lastchunksize : N;
+    const int64_t start = last ? n - lastchunksize : c * (int64_t)N;
+    const double* Yc = Y + cl * P * ldy + r;
+    double* Hc = H + cl * (N + 1) * ldh + r;
+    const double val = tanh(Yc[0] + b[r]);
+    const double deriv = 1.0 - val * val;
+    Hc[0] = val;
+    for (int kk = 0; kk < N; kk++) {
+        double p;
+        if (kk >= cs) p = SHARE ? Yc[ldy] : Yc[(int64_t)(kk + 1) * ldy];      // unseeded slots of the short last chunk: the zero lane
+        else if (SHARE) p = Yc[ldy] + A[r + (start + kk) * lda] * 1.0;
+        else p = Yc[(int64_t)(kk + 1) * ldy];
+        Hc[(int64_t)(kk + 1) * ldh] = mulp<NS>(p, deriv);
+    }
+}
+
+int mlp2_dmma(fdb_ctx* ctx, const fdb_array* A1, int64_t lda1, const fdb_array* b1, const fdb_array* A2, int64_t lda2, const fdb_array* b2,
+              const fdb_array* x, int64_t h, int64_t m, int N, int64_t lo, int64_t hi, int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ,
+              double* yout) {
+    const int64_t n = x->n, nc = hi - lo;
+    const bool share = ctx->lane_sharing;
+    const int P1 = share ? 2 : N + 1, P = N + 1;
+    const int64_t ldb = round_up(n, 32), ldy = round_up(h, 32), ldh = round_up(h, 32), ldz = round_up(m, 32);
+    const int64_t bcols = share ? 2 : nc * P1;
+    const size_t ws1 = gemm_workspace_doubles(n, nc * P1, share ? 2 : 0), ws2 = gemm_workspace_doubles(h, nc * P, 0);
+    const size_t wsd = ws1 > ws2 ? ws1 : ws2;
+    size_t need = ((size_t)(ldb * bcols + ldy * nc * P1 + ldh * nc * P + ldz * nc * P) + wsd + 64) * sizeof(double);
+    int rc = ensure_scratch(ctx, need); if (rc) return rc;
+    double* Bop = ctx->scratch; double* Y1 = Bop + ldb * bcols; double* H1 = Y1 + ldy * nc * P1; double* Z2 = H1 + ldh * nc * P;
+    double* ws = Z2 + ldz * nc * P; ws = (double*)((((uintptr_t)ws) + 127) & ~(uintptr_t)127);
+    if (share) build_operand_shared_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(x->data, n, Bop, ldb);
+    else {
+        dim3 g((unsigned)cdiv(n, 256), (unsigned)nc);
+        build_operand_dense_kernel<<<g, 256, 0, ctx->stream>>>(x->data, n, N, lo, nchunks, lcs, Bop, ldb);
+    }
+    int n1 = 0, n2 = 0;
+    rc = launch_gemm(ctx, A1->data, lda1, Bop, ldb, Y1, ldy, h, n, nc * P1, share ? 2 : 0, ws, nullptr, &n1); if (rc) return rc;
+    dim3 gh((unsigned)cdiv(h, 256), (unsigned)nc);
+    if (ctx->nansafe) {
+        if (share) tanh_affine_hidden_kernel<true, true><<<gh, 256, 0, ctx->stream>>>(Y1, ldy, P1, A1->data, lda1, b1->data, h, n, N, lo, nchunks, lcs, H1, ldh);
+        else tanh_affine_hidden_kernel<true, false><<<gh, 256, 0, ctx->stream>>>(Y1, ldy, P1, A1->data, lda1, b1->data, h, n, N, lo, nchunks, lcs, H1, ldh);
+    } else {
+        if (share) tanh_affine_hidden_kernel<false, true><<<gh, 256, 0, ctx->stream>>>(Y1, ldy, P1, A1->data, lda1, b1->data, h, n, N, lo, nchunks, lcs, H1, ldh);
+        else tanh_affine_hidden_kernel<false, false><<<gh, 256, 0, ctx->stream>>>(Y1, ldy, P1, A1->data, lda1, b1->data, h, n, N, lo, nchunks, lcs, H1, ldh);
+    }
+    // second layer: dense partials -> DMMA contraction of A2 against all hidden planes of all chunks
+    rc = launch_gemm(ctx, A2->data, lda2, H1, ldh, Z2, ldz, m, h, nc * P, 0, ws, nullptr, &n2); if (rc) return rc;
+    dim3 ge((unsigned)cdiv(m, 256), (unsigned)nc);
+    if (ctx->nansafe) tanh_affine_epilogue_kernel<true, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
+    else tanh_affine_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
+    return finish(ctx, 3 + n1 + n2, "fdb_jacobian_mlp2_chunked");
+}
+
 }  // namespace fdb
 
 using namespace fdb;
+
+// jacobian(x -> tanh.(A2*tanh.(A1*x .+ b1) .+ b2), x, JacobianConfig(f, x, Chunk{N}())): chunk sweeps [lo, hi)
+extern "C" int fdb_jacobian_mlp2_chunked(fdb_ctx* ctx, const fdb_array* x, int64_t h, int64_t m, int N, const fdb_array* A1, int64_t lda1,
+                                         const fdb_array* b1, const fdb_array* A2, int64_t lda2, const fdb_array* b2, int64_t chunk_lo,
+                                         int64_t chunk_hi, fdb_array* J, int64_t ldJ, fdb_array* y) {
+    if (!ctx || !x || !A1 || !b1 || !A2 || !b2 || !J) return fail(ctx, FDB_ERR_BADARG, "fdb_jacobian_mlp2_chunked: null argument");
+    const fdb_array* all[] = {x, A1, b1, A2, b2, J};
+    for (const fdb_array* a : all) if (a->level != 0) return fail(ctx, FDB_ERR_BADARG, "fdb_jacobian_mlp2_chunked: operands must be plain arrays");
+    const int64_t n = x->n;
+    if (N < 1 || N > FDB_MAX_CHUNK) return fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", N);
+    if (n < N) return fail(ctx, FDB_ERR_CHUNK, "chunk size cannot be greater than ForwardDiff.structural_length(x) (%d > %lld)", N, (long long)n);
+    if (h <= 0 || m <= 0 || lda1 < h || lda2 < m || A1->n < lda1 * (n - 1) + h || A2->n < lda2 * (h - 1) + m || b1->n != h || b2->n != m ||
+        ldJ < m || J->n < ldJ * (n - 1) + m || (y && (y->level != 0 || y->n != m)))
+        return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: A1 must be %lld x %lld, A2 %lld x %lld, J %lld x %lld", (long long)h, (long long)n,
+                    (long long)m, (long long)h, (long long)m, (long long)n);
+    Plan p = make_plan(n, N);
+    const int64_t nchunks = (n == N) ? 1 : p.nchunks;
+    if (chunk_hi < 0) chunk_hi = nchunks;
+    if (chunk_lo < 0 || chunk_lo > chunk_hi || chunk_hi > nchunks) return fail(ctx, FDB_ERR_BADARG, "bad chunk range");
+    if (chunk_lo == chunk_hi) return FDB_OK;
+    return mlp2_dmma(ctx, A1, lda1, b1, A2, lda2, b2, x, h, m, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, J, ldJ, y ? y->data : nullptr);
+}
 
 // C[m x ncols] = A[m x k] * B[k x ncols] on plain column-major arrays
 extern "C" int fdb_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t k, const fdb_array* B, int64_t ldb, int64_t ncols,

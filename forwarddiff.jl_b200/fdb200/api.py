@@ -357,7 +357,12 @@ def jacobian(f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=N
     Returns the dense column-major length(y) x length(x) matrix (jacobian.jl:221)."""
     n = _length(x)
     ylen = _length(y) if y is not None else (m if m is not None else getattr(f, "output_length", lambda n: None)(n))
-    if ylen is None and fuse and _catalogue_id(f, _lib.JFN) is None:
+    fp = getattr(f, "params", None) or {}
+    if ylen is None and fp.get("A2") is not None:
+        ylen = np.shape(fp["A2"])[0]
+    elif ylen is None and fp.get("A") is not None:
+        ylen = np.shape(fp["A"])[0]
+    if ylen is None and fuse and _catalogue_id(f, _lib.JFN) is None and not fp:
         prog = _try_trace("array", f, n)            # the flattened f knows its output length
         ylen = prog.out_len if prog is not None else None
     if ylen is None:
@@ -382,6 +387,8 @@ def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None
     out = result.derivs[0] if isinstance(result, DiffResult) else result
     fid = _catalogue_id(f, _lib.JFN)
     lo, hi = (0, -1) if chunks is None else chunks
+    if getattr(f, "fdb_catalogue", None) == "mlp2":
+        return _mlp2_jacobian(ctx, result, out, f, x, N, lo, hi)
     if fid is None:
         prog = _try_trace("array", f, n) if (fuse and y is None) else None
         if prog is not None:
@@ -412,6 +419,27 @@ def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None
             y[...] = yv                                              # map!(d -> value(T,d), y, ydual), jacobian.jl:229
         if isinstance(result, DiffResult):
             result.value = yv
+    return result
+
+
+def _mlp2_jacobian(ctx, result, out, f, x, N, lo, hi):
+    """jacobian(x -> tanh.(A2*tanh.(A1*x .+ b1) .+ b2), x, cfg): fdb_jacobian_mlp2_chunked (dense partials on DMMA)."""
+    lib, p = ctx.lib, f.params
+    xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
+    n = xd.n
+    h, m = np.shape(p["A1"])[0], np.shape(p["A2"])[0]
+    dev = lambda M: M if isinstance(M, _DeviceArray) else ctx.array(np.asfortranarray(M).ravel(order="F"))
+    A1, A2, b1, b2 = dev(p["A1"]), dev(p["A2"]), dev(p["b1"]), dev(p["b2"])
+    Jd = out if isinstance(out, _DeviceArray) else B200Array.alloc(ctx, m * n)
+    yd = B200Array.alloc(ctx, m)
+    ctx.check(lib.fdb_jacobian_mlp2_chunked(ctx.h, xd.h, h, m, N, A1.h, h, b1.h, A2.h, m, b2.h, lo, hi, Jd.h, m, yd.h))
+    nchunks = 1 if n == N else chunk_plan(n, N)["nchunks"]
+    last = hi < 0 or hi == nchunks
+    if Jd is not out:
+        c0, c1 = lo * N, (n if last else hi * N)
+        out[:, c0:c1] = Jd.numpy().reshape((m, n), order="F")[:, c0:c1]
+    if last and isinstance(result, DiffResult):
+        result.value = yd.numpy()
     return result
 
 

@@ -41,6 +41,7 @@ sumsq = CatalogueFn("sumsq", "sum(x.^2)")
 prod = CatalogueFn("prod", "prod(x)")
 tanh_affine = CatalogueFn("tanh_affine", "f(x) = tanh.(A*x .+ b); params A (m x n), b (m)")
 brusselator = CatalogueFn("brusselator", "f!(dx, x): 1-D Brusselator RHS, x = [u; v]; param alpha", lambda n: n)
+mlp2 = CatalogueFn("mlp2", "f(x) = tanh.(A2 * tanh.(A1*x .+ b1) .+ b2); params A1 (h x n), b1 (h), A2 (m x h), b2 (m)")
 jactest = CatalogueFn("jactest", "test/JacobianTest.jl:23-31 target (n=3, m=4)", lambda n: 4)
 
 

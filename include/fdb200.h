@@ -198,6 +198,12 @@ int fdb_gradient_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_
 int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int64_t m, int N, const fdb_array* A,
                          int64_t lda, const fdb_array* b, double alpha, int64_t chunk_lo, int64_t chunk_hi,
                          fdb_array* J, int64_t ldJ, fdb_array* y);
+/* the two-layer target f(x) = tanh.(A2 * tanh.(A1*x .+ b1) .+ b2) (A1: h x n, A2: m x h): after the first layer
+ * the partials are dense, so the second A*hdual is a dense FP64 tensor-core contraction against
+ * [value | N partials] of every chunk.  Same chunk-range semantics as above. */
+int fdb_jacobian_mlp2_chunked(fdb_ctx* ctx, const fdb_array* x, int64_t h, int64_t m, int N, const fdb_array* A1, int64_t lda1,
+                              const fdb_array* b1, const fdb_array* A2, int64_t lda2, const fdb_array* b2, int64_t chunk_lo,
+                              int64_t chunk_hi, fdb_array* J, int64_t ldJ, fdb_array* y);
 /* hessian / hessian!(::DiffResult), src/hessian.jl:14-71: outer chunks [lo,hi) of the
  * Jacobian of the chunked gradient; H column-major n x n (ldH); grad, value_dev may be NULL. */
 int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi,

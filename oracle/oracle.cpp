@@ -387,7 +387,8 @@ template <class D> D eval_scalar_fn(int fn, const D* x, long n) {
 }
 
 // Array-valued targets.  `par` carries the plain-Float64 parameters.
-struct JacParams { const double* A; long lda; const double* b; double alpha; };
+struct JacParams { const double* A; long lda; const double* b; double alpha;
+                   const double* A2 = nullptr; long lda2 = 0; const double* b2 = nullptr; long h = 0; };
 
 // f(x) = tanh.(A*x .+ b);  A*x is Julia's generic column sweep
 // (LinearAlgebra.generic_matvecmul!: C[i] = zero; for k: C[i] += A[i,k]*x[k]).
@@ -414,6 +415,15 @@ template <class D> void brusselator(D* dx, const D* x, long n, const JacParams& 
         dx[M + i] = (3.0 * u[i] - pow2(u[i]) * v[i]) + al * lapv;
     }
 }
+// two-layer target f(x) = tanh.(A2 * tanh.(A1*x .+ b1) .+ b2): the second A*xdual sees dense partials
+// (SURVEY.md section 8f-4).  A1 is h x n (par.A, par.b), A2 is m x h (par.A2, par.b2).
+template <class D> void mlp2(D* y, long m, const D* x, long n, const JacParams& par) {
+    std::vector<D> hid(par.h);
+    JacParams p1 = {par.A, par.lda, par.b, 0.0};
+    tanh_affine(hid.data(), par.h, x, n, p1);
+    JacParams p2 = {par.A2, par.lda2, par.b2, 0.0};
+    tanh_affine(y, m, hid.data(), par.h, p2);
+}
 // test/JacobianTest.jl:23-31 hard-coded target (n=3, m=4)
 template <class D> void jactest(D* y, const D* x) {
     y[0] = x[0] * x[1];
@@ -427,6 +437,7 @@ template <class D> void eval_array_fn(int fn, D* y, long m, const D* x, long n, 
         case 1: tanh_affine(y, m, x, n, par); break;
         case 2: brusselator(y, x, n, par); break;
         case 3: jactest(y, x); break;
+        case 4: mlp2(y, m, x, n, par); break;
     }
 }
 
@@ -826,6 +837,18 @@ int orc_gradient(int fn, const double* x, long n, int N, double* grad, double* v
         auto f = [&](const D* z, long nn) { return eval_scalar_fn<D>(fn, z, nn); };
         if (n != NN && chi < 0) chi = make_plan(n, NN).nchunks;
         gradient_any<double, NN>(f, x, n, grad, value, clo, chi, xdual.data());
+    }));
+    return 0;
+}
+// jacobian of the two-layer target (fn 4): A1 h x n, A2 m x h
+int orc_jacobian_mlp2(const double* x, long n, long h, long m, int N, const double* A1, long lda1, const double* b1, const double* A2,
+                      long lda2, const double* b2, double* J, long ldJ, double* y, long clo, long chi) {
+    if (N > n) return -3;
+    JacParams par = {A1, lda1, b1, 0.0, A2, lda2, b2, h};
+    ORC_DISPATCH_N(N, ({
+        if (n == NN) vector_mode_jacobian<NN>(4, false, x, n, m, par, J, ldJ, y);
+        else { if (chi < 0) chi = make_plan(n, NN).nchunks;
+               chunk_mode_jacobian<NN>(4, false, x, n, m, par, J, ldJ, y, clo, chi); }
     }));
     return 0;
 }

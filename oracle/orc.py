@@ -72,6 +72,8 @@ class Oracle:
         L.orc_gradient.argtypes = [C.c_int, _dp, C.c_long, C.c_int, _dp, _dp, C.c_long, C.c_long]
         L.orc_jacobian.argtypes = [C.c_int, C.c_int, _dp, C.c_long, C.c_long, C.c_int, _dp, C.c_long, _dp,
                                    C.c_double, _dp, C.c_long, _dp, C.c_long, C.c_long]
+        L.orc_jacobian_mlp2.argtypes = [_dp, C.c_long, C.c_long, C.c_long, C.c_int, _dp, C.c_long, _dp, _dp, C.c_long, _dp,
+                                        _dp, C.c_long, _dp, C.c_long, C.c_long]
         L.orc_hessian.argtypes = [C.c_int, _dp, C.c_long, C.c_int, _dp, C.c_long, _dp, _dp, C.c_long, C.c_long]
         L.orc_third_order.argtypes = [C.c_int, _dp, C.c_int, _dp]
 
@@ -195,6 +197,15 @@ class Oracle:
         if rc == -3:
             raise ValueError("chunk size cannot be greater than structural_length(x)")
         assert rc == 0
+        return J, y
+
+    def jacobian_mlp2(self, x, N, A1, b1, A2, b2, chunks=None):
+        x = _f64(x); n = x.size; h, m = A1.shape[0], A2.shape[0]
+        A1f = np.asfortranarray(A1, dtype=np.float64); A2f = np.asfortranarray(A2, dtype=np.float64)
+        J = np.zeros((m, n), order="F"); y = np.zeros(m)
+        clo, chi = (0, -1) if chunks is None else chunks
+        rc = self.lib.orc_jacobian_mlp2(_p(x), n, h, m, N, _p(A1f), h, _p(_f64(b1)), _p(A2f), m, _p(_f64(b2)), _p(J), m, _p(y), clo, chi)
+        assert rc == 0, rc
         return J, y
 
     def hessian(self, fn, x, N, chunks=None, want_H=True):

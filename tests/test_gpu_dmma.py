@@ -80,3 +80,25 @@ def test_tanh_affine_chunk_ranges_tile_on_dmma(ctx):
         fdb200.jacobian_b(part, f, x, cfg, ctx=ctx, chunks=(p["chunk_lo"], p["chunk_hi"]))
         out[:, p["elem_lo"]:p["elem_hi"]] = part[:, p["elem_lo"]:p["elem_hi"]]
     assert np.array_equal(out, full)
+
+
+@pytest.mark.parametrize("N", [1, 7, 12])
+@pytest.mark.parametrize("share", [True, False])
+def test_two_layer_dense_partials_on_dmma(ctx, oracle, N, share):
+    """tanh.(A2*tanh.(A1*x .+ b1) .+ b2): the second contraction sees dense partials."""
+    rng = np.random.default_rng(21)
+    for n, h, m in ((96, 128, 160), (130, 256, 128), (37, 50, 20)):       # last shape: not TMA-eligible -> fallback contraction
+        A1 = rng.uniform(-1, 1, (h, n)) / np.sqrt(n); b1 = rng.uniform(-1, 1, h)
+        A2 = rng.uniform(-1, 1, (m, h)) / np.sqrt(h); b2 = rng.uniform(-1, 1, m); x = rng.uniform(-1, 1, n)
+        f = F.mlp2.with_params(A1=A1, b1=b1, A2=A2, b2=b2)
+        res = fdb200.JacobianResult(np.zeros(m), x)
+        ctx.set_lane_sharing(share)
+        try:
+            fdb200.jacobian_b(res, f, x, fdb200.JacobianConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+        finally:
+            ctx.set_lane_sharing(True)
+        J_ref, y_ref = oracle.jacobian_mlp2(x, N, A1, b1, A2, b2)
+        assert np.allclose(res.value, y_ref, rtol=1e-13, atol=1e-15)
+        assert np.allclose(res.derivs[0], J_ref, rtol=1e-11, atol=1e-14), (n, h, m, N, share)
+        h1 = np.tanh(A1 @ x + b1); yy = np.tanh(A2 @ h1 + b2)
+        assert np.allclose(res.derivs[0], (1 - yy ** 2)[:, None] * A2 @ ((1 - h1 ** 2)[:, None] * A1), rtol=1e-10, atol=1e-13)
