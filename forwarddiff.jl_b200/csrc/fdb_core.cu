@@ -133,13 +133,13 @@ __global__ void __launch_bounds__(256) seed_zero_dense_kernel(double* __restrict
 // extract_gradient_chunk!: result[idx(index-1+k)] = partials(ydual, k+1), k = 0..chunksize-1.
 // result has PB planes (PB > 1 when the partials are themselves Duals).
 __global__ void extract_gradient_chunk_kernel(double* __restrict__ res, int64_t ldr, const double* __restrict__ y, int64_t ldy,
-                                              int PB, int64_t nstruct, int64_t index, int64_t chunksize) {
+                                              int PB, int structure, int64_t rows, int64_t nstruct, int64_t index, int64_t chunksize) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= chunksize * PB) return;
     int64_t k = t / PB; int b = (int)(t - k * PB);
     int64_t pos = index - 1 + k;
     if (pos >= nstruct) return;
-    res[(int64_t)b * ldr + pos] = y[((k + 1) * PB + b) * ldy];
+    res[(int64_t)b * ldr + structural_index(structure, rows, pos)] = y[((k + 1) * PB + b) * ldy];   // structural_eachindex(result), gradient.jl:76
 }
 // extract_jacobian_chunk!: result[r, index-1+k] = partials(ydual[r], k+1)
 __global__ void extract_jacobian_chunk_kernel(double* __restrict__ res, int64_t ldplane, int64_t ldres,
@@ -424,18 +424,34 @@ extern "C" int fdb_seed_zero_structured(fdb_ctx* ctx, fdb_array* d, const fdb_ar
     return seed_zero_impl(ctx, d, x, structure, rows, fdb_structural_length(structure, rows), index, count);
 }
 
-extern "C" int fdb_extract_gradient_chunk(fdb_ctx* ctx, fdb_array* res, const fdb_array* y, int64_t index, int64_t chunksize) {
+extern "C" int fdb_extract_gradient_chunk_structured(fdb_ctx* ctx, fdb_array* res, const fdb_array* y, int structure, int64_t rows,
+                                                     int64_t index, int64_t chunksize) {
     if (!ctx || !res || !y) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient_chunk: null argument");
     if (y->level < 1 || res->level != y->level - 1) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient_chunk: result must be one level below ydual");
     if (y->n != 1)   // GRAD_ERROR, src/gradient.jl:88-91
         return fail(ctx, FDB_ERR_SHAPE, "gradient(f, x) expects that f(x) is a real number. Perhaps you meant jacobian(f, x)?");
+    if (structure < 0 || structure > 3) return fail(ctx, FDB_ERR_BADARG, "unknown structure %d", structure);
+    if (structure != FDB_DENSE && res->n != rows * rows) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: structured result needs rows*rows storage");
     if (chunksize > y->N) return fail(ctx, FDB_ERR_BADARG, "chunksize > N");
     if (chunksize <= 0) return FDB_OK;
     int PB = res->planes();
     int64_t total = chunksize * PB;
-    extract_gradient_chunk_kernel<<<(unsigned)cdiv(total, 128), 128, 0, ctx->stream>>>(res->data, res->ld, y->data, y->ld, PB,
-                                                                                      res->n, index, chunksize);
+    const int64_t nstruct = structure == FDB_DENSE ? res->n : fdb_structural_length(structure, rows);
+    extract_gradient_chunk_kernel<<<(unsigned)cdiv(total, 128), 128, 0, ctx->stream>>>(res->data, res->ld, y->data, y->ld, PB, structure, rows,
+                                                                                      nstruct, index, chunksize);
     return finish(ctx, 1, "fdb_extract_gradient_chunk");
+}
+extern "C" int fdb_extract_gradient_chunk(fdb_ctx* ctx, fdb_array* res, const fdb_array* y, int64_t index, int64_t chunksize) {
+    return fdb_extract_gradient_chunk_structured(ctx, res, y, FDB_DENSE, res ? res->n : 0, index, chunksize);
+}
+extern "C" int fdb_fill(fdb_ctx* ctx, fdb_array* a, double value) {
+    // fill!(a, value) on every plane (used to zero the off-structure entries of structured work buffers)
+    if (!ctx || !a) return fail(ctx, FDB_ERR_BADARG, "fdb_fill: null argument");
+    if (value != 0.0) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_fill: only zero fill is implemented");
+    if (a->n == 0) return FDB_OK;
+    FDB_CUDA(ctx, cudaMemset2DAsync(a->data, (size_t)a->ld * sizeof(double), 0, (size_t)a->n * sizeof(double), (size_t)a->planes(), ctx->stream));
+    if (!ctx->async) FDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FDB_OK;
 }
 extern "C" int fdb_extract_gradient(fdb_ctx* ctx, fdb_array* res, const fdb_array* y) {
     if (!y) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient: null argument");

@@ -84,6 +84,8 @@ SIGNATURES = {
     "fdb_seed_zero_structured": (C.c_int, [c_ctx, c_arr, c_arr, C.c_int, i64, i64, i64]),
     "fdb_extract_gradient_chunk": (C.c_int, [c_ctx, c_arr, c_arr, i64, i64]),
     "fdb_extract_gradient": (C.c_int, [c_ctx, c_arr, c_arr]),
+    "fdb_extract_gradient_chunk_structured": (C.c_int, [c_ctx, c_arr, c_arr, C.c_int, i64, i64, i64]),
+    "fdb_fill": (C.c_int, [c_ctx, c_arr, C.c_double]),
     "fdb_extract_jacobian_chunk": (C.c_int, [c_ctx, c_arr, i64, c_arr, i64, i64]),
     "fdb_extract_jacobian": (C.c_int, [c_ctx, c_arr, i64, c_arr, i64]),
     "fdb_extract_value": (C.c_int, [c_ctx, c_arr, c_arr]),

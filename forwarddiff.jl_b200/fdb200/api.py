@@ -103,6 +103,8 @@ def default_context():
 
 
 def _length(x):
+    if isinstance(x, _Structured):
+        return x.structural_length()
     return x.n if isinstance(x, _DeviceArray) else int(np.asarray(x).size)
 
 
@@ -126,6 +128,49 @@ def chunk_plan(xlen, N, rank=0, world=1):
     if rc != 0:
         raise FdbError(f"fdb_plan_chunks failed ({rc})")
     return p.asdict()
+
+
+# ---------------------------------------------------------------------------
+# structured inputs (LinearAlgebra wrappers): only structurally non-zero entries are seeded
+# (src/prelude.jl:15-20, src/apiutils.jl:44-71)
+# ---------------------------------------------------------------------------
+class _Structured:
+    kind = "dense"
+
+    def __init__(self, M):
+        self.M = np.asfortranarray(np.array(M, dtype=np.float64))
+        if self.M.ndim != 2 or self.M.shape[0] != self.M.shape[1]:
+            raise DimensionMismatch("structured wrappers need a square matrix")
+        self.rows = self.M.shape[0]
+        self.M = self.M * self.mask(self.rows)            # off-structure entries read as zero, whatever the parent holds
+
+    @property
+    def structure(self):
+        return _lib.STRUCTURE[self.kind]
+
+    def structural_length(self):
+        return int(_lib.load().fdb_structural_length(self.structure, self.rows))
+
+    def storage(self):
+        return self.M.ravel(order="F")
+
+    def __eq__(self, other):
+        return type(other) is type(self) and np.array_equal(self.M, other.M)
+
+
+class UpperTriangular(_Structured):
+    kind = "upper"
+    mask = staticmethod(lambda n: np.triu(np.ones((n, n))))
+
+
+class LowerTriangular(_Structured):
+    kind = "lower"
+    mask = staticmethod(lambda n: np.tril(np.ones((n, n))))
+
+
+class Diagonal(_Structured):
+    kind = "diagonal"
+    mask = staticmethod(lambda n: np.eye(n))
 
 
 # ---------------------------------------------------------------------------
@@ -225,6 +270,8 @@ def _i32p(a):
 
 def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True):
     """ForwardDiff.gradient(f, x, cfg, Val{check}()) (src/gradient.jl:16-24)."""
+    if isinstance(x, _Structured):
+        return gradient_b(None, f, x, cfg, check, ctx)
     result = np.zeros(_length(x)) if not isinstance(x, _DeviceArray) else x.similar()
     return gradient_b(result, f, x, cfg, check, ctx, chunks, fuse)
 
@@ -238,6 +285,8 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
     cfg = cfg if cfg is not None else GradientConfig(f, x)
     if check:
         checktag(cfg.tag, f, x)
+    if isinstance(x, _Structured):
+        return _structured_gradient(_ctx_of(x, ctx), result, f, x, cfg)
     n = _length(x)
     out = result.derivs[0] if isinstance(result, DiffResult) else result
     if _length(out) != n:
@@ -263,6 +312,47 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
     if isinstance(result, DiffResult) and value is not None:
         result.value = value
     return result
+
+
+def _structured_gradient(ctx, result, f, X, cfg):
+    """gradient(f, x::Union{UpperTriangular,LowerTriangular,Diagonal}): the reference loop with structural seeding.
+    `f` receives the rows*rows Dual storage (column-major) whose off-structure entries are zero(Dual), exactly what
+    the Julia wrapper types return for them.  Sets cfg.fevals = number of evaluations of f (GradientTest.jl:257-274)."""
+    lib = ctx.lib
+    S, rows, n, N = X.structure, X.rows, X.structural_length(), cfg.N
+    if N > n:
+        raise ChunkSizeError(f"chunk size cannot be greater than ForwardDiff.structural_length(x) ({N} > {n})")
+    xd = ctx.array(X.storage())
+    xdual = B200DualArray.alloc(ctx, rows * rows, N, 1)
+    ctx.check(lib.fdb_fill(ctx.h, xdual.h, 0.0))
+    res = ctx.zeros(rows * rows)
+    cfg.fevals = 0
+
+    def call_f():
+        cfg.fevals += 1
+        ydual = f(xdual)
+        if not isinstance(ydual, B200DualArray) or ydual.n != 1:
+            raise DimensionMismatch("gradient(f, x) expects that f(x) is a real number. Perhaps you meant jacobian(f, x)?")
+        return ydual
+
+    seed = lambda i, c: ctx.check(lib.fdb_seed_structured(ctx.h, xdual.h, xd.h, S, rows, i, c))
+    unseed = lambda i, c: ctx.check(lib.fdb_seed_zero_structured(ctx.h, xdual.h, xd.h, S, rows, i, c))
+    extract = lambda yd, i, c: ctx.check(lib.fdb_extract_gradient_chunk_structured(ctx.h, res.h, yd.h, S, rows, i, c))
+    if n == N:                                                      # vector mode
+        seed(1, N); ydual = call_f(); extract(ydual, 1, N)
+    else:
+        p = chunk_plan(n, N)
+        seed(1, N); unseed(N + 1, n - N); ydual = call_f(); extract(ydual, 1, N); unseed(1, N)
+        for c in range(2, p["middle_hi"] + 1):
+            i = (c - 1) * N + 1
+            seed(i, N); ydual = call_f(); extract(ydual, i, N); unseed(i, N)
+        i, cs = p["lastchunkindex"], p["lastchunksize"]
+        seed(i, cs); ydual = call_f(); extract(ydual, i, cs)
+    G = type(X)(res.numpy().reshape((rows, rows), order="F"))
+    if isinstance(result, DiffResult):
+        result.value = float(ydual.numpy()[0, 0]); result.derivs[0] = G
+        return result
+    return G
 
 
 def _program_gradient(ctx, prog, x, N, lo, hi, out):

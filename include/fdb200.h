@@ -146,6 +146,12 @@ int fdb_seed_zero_structured(fdb_ctx* ctx, fdb_array* duals, const fdb_array* x,
  * ydual is a dual array of length 1 */
 int fdb_extract_gradient_chunk(fdb_ctx* ctx, fdb_array* result, const fdb_array* ydual, int64_t index,
                                int64_t chunksize);
+/* the same with `structural_eachindex(result)` of an UpperTriangular / LowerTriangular / Diagonal result
+ * (rows x rows column-major storage; test/GradientTest.jl:250-276) */
+int fdb_extract_gradient_chunk_structured(fdb_ctx* ctx, fdb_array* result, const fdb_array* ydual, int structure, int64_t rows,
+                                          int64_t index, int64_t chunksize);
+/* fill!(a, 0.0) on every plane: off-structure entries of a structured Dual work buffer read as zero(Dual) */
+int fdb_fill(fdb_ctx* ctx, fdb_array* a, double value);
 /* extract_gradient!(T, result, dual), src/gradient.jl:66-72 (vector mode) */
 int fdb_extract_gradient(fdb_ctx* ctx, fdb_array* result, const fdb_array* ydual);
 /* extract_jacobian_chunk!(T, result, ydual, index, chunksize), src/jacobian.jl:109-118;

@@ -585,3 +585,27 @@ def test_full_size_c4_brusselator_jacobian_sample(ctx, oracle):
         cols = nz[:, 1] + c0; rows = nz[:, 0]
         same = np.abs((rows % M) - (cols % M)) <= 1
         assert same.all()
+
+
+# ---------------------------------------------------------------------------
+# structured inputs: only structurally non-zero entries are seeded (test/GradientTest.jl:250-276, issue #738)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [3, 10, 20])
+@pytest.mark.parametrize("T", ["LowerTriangular", "UpperTriangular", "Diagonal"])
+def test_structured_gradients_and_eval_accounting(ctx, n, T):
+    W = getattr(fdb200, T)
+    rng = np.random.default_rng(n)
+    M = rng.random((n, n))
+    X = W(rng.standard_normal((n, n)))
+    Md = ctx.array(np.asfortranarray(M).ravel(order="F"))
+    assert fdb200.gradient(lambda xd: xd.sum(), X, ctx=ctx) == W(np.ones((n, n)))           # gradient(sum, T(...)) == T(ones)
+    assert fdb200.gradient(lambda xd: (xd * Md).sum(), X, ctx=ctx) == W(M)                   # gradient(x -> dot(M, x), T(...)) == T(M)
+    cfg = fdb200.GradientConfig(None, X, tag=None)
+    y = fdb200.gradient(lambda xd: xd.sum(), X, cfg, ctx=ctx)
+    nstruct = X.structural_length()
+    assert cfg.N == fdb200.pickchunksize(nstruct)
+    npartials = cfg.fevals * cfg.N
+    if nstruct <= 12:
+        assert cfg.fevals == 1 and npartials == y.M.sum()                                   # vector mode: a single evaluation
+    else:
+        assert cfg.fevals > 1 and y.M.sum() <= npartials < y.M.sum() + cfg.fevals           # chunk mode accounting
