@@ -203,6 +203,7 @@ extern "C" int fdb_shutdown(fdb_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->counter) cudaFree(ctx->counter);
+    if (ctx->cursor) cudaFree(ctx->cursor);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FDB_OK;
@@ -266,6 +267,8 @@ extern "C" int fdb_array_wrap(fdb_ctx* ctx, double* ptr, int64_t n, int64_t ld, 
 }
 extern "C" int fdb_array_free(fdb_array* a) {
     if (!a) return FDB_ERR_BADARG;
+    if (a->ctx->capturing && a->owned)     // freeing synchronises the stream, which is illegal during graph capture
+        return fail(a->ctx, FDB_ERR_BADARG, "fdb_array_free: arrays allocated while a graph is captured must outlive the graph");
     if (a->owned && a->data) { cudaStreamSynchronize(a->ctx->stream); cudaFree(a->data); }
     delete a;
     return FDB_OK;

@@ -23,6 +23,9 @@ struct fdb_ctx {
     size_t scratch_bytes = 0;
     // pinned host staging for the *_host entry points
     unsigned* counter = nullptr;   // zero-initialised ticket for single-launch reductions
+    int64_t* cursor = nullptr;     // device-resident chunk window {index, chunksize} (fdb_graph.cu)
+    bool capturing = false;        // between fdb_graph_begin and fdb_graph_end
+    bool saved_async = false;
     double* pinned = nullptr;
     size_t pinned_bytes = 0;
     std::string err;

@@ -89,6 +89,17 @@ SIGNATURES = {
     "fdb_extract_jacobian_chunk": (C.c_int, [c_ctx, c_arr, i64, c_arr, i64, i64]),
     "fdb_extract_jacobian": (C.c_int, [c_ctx, c_arr, i64, c_arr, i64]),
     "fdb_extract_value": (C.c_int, [c_ctx, c_arr, c_arr]),
+    "fdb_cursor_set": (C.c_int, [c_ctx, i64, i64]),
+    "fdb_cursor_advance": (C.c_int, [c_ctx, i64, i64]),
+    "fdb_cursor_get": (C.c_int, [c_ctx, C.POINTER(i64), C.POINTER(i64)]),
+    "fdb_seed_at_cursor": (C.c_int, [c_ctx, c_arr, c_arr]),
+    "fdb_seed_zero_at_cursor": (C.c_int, [c_ctx, c_arr, c_arr]),
+    "fdb_extract_gradient_chunk_at_cursor": (C.c_int, [c_ctx, c_arr, c_arr]),
+    "fdb_extract_jacobian_chunk_at_cursor": (C.c_int, [c_ctx, c_arr, i64, c_arr]),
+    "fdb_graph_begin": (C.c_int, [c_ctx]),
+    "fdb_graph_end": (C.c_int, [c_ctx, C.POINTER(C.c_void_p)]),
+    "fdb_graph_launch": (C.c_int, [c_ctx, C.c_void_p, i64]),
+    "fdb_graph_destroy": (C.c_int, [C.c_void_p]),
     "fdb_map1": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr]),
     "fdb_map2": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr, c_arr]),
     "fdb_map2_scalar": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr, C.c_double, C.c_int]),

@@ -268,15 +268,15 @@ def _i32p(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32)) if a.size else None
 
 
-def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True):
+def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True, graph=True):
     """ForwardDiff.gradient(f, x, cfg, Val{check}()) (src/gradient.jl:16-24)."""
     if isinstance(x, _Structured):
         return gradient_b(None, f, x, cfg, check, ctx)
     result = np.zeros(_length(x)) if not isinstance(x, _DeviceArray) else x.similar()
-    return gradient_b(result, f, x, cfg, check, ctx, chunks, fuse)
+    return gradient_b(result, f, x, cfg, check, ctx, chunks, fuse, graph)
 
 
-def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True):
+def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True, graph=True):
     """ForwardDiff.gradient!(result, f, x, cfg, Val{check}()) (src/gradient.jl:35-44).
     `chunks=(lo, hi)` restricts the call to a 0-based chunk range (the sharding hook).
     A non-catalogue callable is flattened into an op-program and run as one batched launch when its
@@ -308,7 +308,7 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
         if prog is not None:
             value = _program_gradient(ctx, prog, x, N, lo, hi, out)
         else:
-            value = _loop_gradient(ctx, f, x, cfg, lo, hi, out)
+            value = _loop_gradient(ctx, f, x, cfg, lo, hi, out, graph)
     if isinstance(result, DiffResult) and value is not None:
         result.value = value
     return result
@@ -387,7 +387,7 @@ def _fused_gradient(ctx, fid, x, N, lo, hi, out):
     return None if np.isnan(val.value) and not (hi < 0) else val.value
 
 
-def _loop_gradient(ctx, f, x, cfg, lo, hi, out):
+def _loop_gradient(ctx, f, x, cfg, lo, hi, out, graph=True):
     """The reference chunk loop on materialised device duals (src/gradient.jl:114-159 / :97-108)."""
     lib = ctx.lib
     xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
@@ -413,6 +413,29 @@ def _loop_gradient(ctx, f, x, cfg, lo, hi, out):
         if not full:
             ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, 0, 0))
         ydual = None
+        if graph and full and nchunks >= 4:
+            # first chunk eagerly (gradient.jl:133-138; it also sizes the library's scratch buffers), then ONE
+            # iteration  seed! -> f -> extract -> unseed -> advance  captured at the device-resident chunk cursor
+            # and replayed for chunks 2..nchunks (the cursor's chunksize shrinks for the short last chunk)
+            ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, 1, N))
+            ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, N + 1, n - N))
+            ydual = call_f()
+            ctx.check(lib.fdb_extract_gradient_chunk(ctx.h, res.h, ydual.h, 1, N))
+            ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, 1, N))
+            ctx.check(lib.fdb_cursor_set(ctx.h, N + 1, min(N, n - N)))
+            with ctx.capture() as cap:
+                ctx.check(lib.fdb_seed_at_cursor(ctx.h, xdual.h, xd.h))
+                ydual = call_f()
+                ctx.check(lib.fdb_extract_gradient_chunk_at_cursor(ctx.h, res.h, ydual.h))
+                ctx.check(lib.fdb_seed_zero_at_cursor(ctx.h, xdual.h, xd.h))
+                ctx.check(lib.fdb_cursor_advance(ctx.h, N, n))
+            cap.graph.launch(nchunks - 1)
+            ctx.sync()
+            value = float(ydual.numpy()[0, 0])
+            if res is not out:
+                out[...] = res.numpy().reshape(np.shape(out))
+            cap.graph.destroy()
+            return value
         for c in range(lo, hi):
             c1 = c + 1
             if c1 == nchunks:                                       # final chunk, gradient.jl:150-152

@@ -29,6 +29,13 @@ class Context:
             raise _lib.CudaError((msg.decode() if msg else "fdb_init failed") + f" (status {rc})")
         self.h = h
         self.device = device
+        self._capturing = False
+        self._graph_handles = []
+
+    def capture(self):
+        """Context manager: capture the enclosed C-ABI calls into a CUDA graph (fdb_graph_begin / fdb_graph_end).
+        Device arrays created or dropped inside stay alive until the returned Graph is destroyed."""
+        return _Capture(self)
 
     def close(self):
         if getattr(self, "h", None):
@@ -106,6 +113,56 @@ class Context:
         return a
 
 
+class Graph:
+    """An instantiated CUDA graph of one chunk-loop iteration plus the device arrays it references."""
+
+    def __init__(self, ctx, exec_handle, handles):
+        self.ctx, self.exec, self.handles = ctx, exec_handle, handles
+
+    def launch(self, times=1):
+        self.ctx.check(self.ctx.lib.fdb_graph_launch(self.ctx.h, self.exec, int(times)))
+
+    def destroy(self):
+        if self.exec:
+            self.ctx.sync()
+            self.ctx.lib.fdb_graph_destroy(self.exec)
+            self.exec = None
+            for h in self.handles:
+                self.ctx.lib.fdb_array_free(h)
+            self.handles = []
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class _Capture:
+    def __init__(self, ctx):
+        self.ctx, self.graph = ctx, None
+
+    def __enter__(self):
+        c = self.ctx
+        c.check(c.lib.fdb_graph_begin(c.h))
+        c._capturing, c._graph_handles = True, []
+        return self
+
+    def __exit__(self, et, ev, tb):
+        c = self.ctx
+        ex = C.c_void_p()
+        rc = c.lib.fdb_graph_end(c.h, C.byref(ex))
+        c._capturing = False
+        handles, c._graph_handles = c._graph_handles, []
+        if et is None:
+            c.check(rc)
+            self.graph = Graph(c, ex, handles)
+        else:
+            for h in handles:
+                c.lib.fdb_array_free(h)
+        return False
+
+
 class _DeviceArray:
     def _init(self, ctx, h, n, N, level, ld, ptr, keepalive=None):
         self.ctx, self.h, self.n, self.N, self.level, self.ld, self.ptr = ctx, h, n, N, level, ld, ptr
@@ -124,7 +181,10 @@ class _DeviceArray:
     def __del__(self):
         try:
             if self.h and self.ctx.h:
-                self.ctx.lib.fdb_array_free(self.h)
+                if self.ctx._capturing:          # freeing synchronises the stream: defer to Graph.destroy()
+                    self.ctx._graph_handles.append(self.h)
+                else:
+                    self.ctx.lib.fdb_array_free(self.h)
                 self.h = None
         except Exception:
             pass

@@ -163,6 +163,25 @@ int fdb_extract_jacobian(fdb_ctx* ctx, fdb_array* result, int64_t ld_result, con
 /* extract_value!: map!(d -> value(T,d), y, ydual), src/apiutils.jl:9-12 */
 int fdb_extract_value(fdb_ctx* ctx, fdb_array* y, const fdb_array* ydual);
 
+/* ---- the reference chunk loop as a replayed CUDA graph (fdb_graph.cu) ----------------------------------
+ * The window {index, chunksize} of the current chunk lives in device memory (the context's chunk cursor);
+ * the `_at_cursor` sweep utilities read it, fdb_cursor_advance moves it by one chunk (index += step,
+ * chunksize = min(step, xlen - index + 1): the short last chunk of src/gradient.jl:121-125 falls out).
+ * One loop iteration  seed -> f -> extract -> unseed -> advance  then has constant launch parameters: capture
+ * it once between fdb_graph_begin / fdb_graph_end and replay it with fdb_graph_launch for the remaining chunks.
+ * Arrays allocated during capture must stay alive until fdb_graph_destroy. */
+int fdb_cursor_set(fdb_ctx* ctx, int64_t index, int64_t chunksize);
+int fdb_cursor_advance(fdb_ctx* ctx, int64_t step, int64_t xlen);
+int fdb_cursor_get(fdb_ctx* ctx, int64_t* index, int64_t* chunksize);
+int fdb_seed_at_cursor(fdb_ctx* ctx, fdb_array* duals, const fdb_array* x);
+int fdb_seed_zero_at_cursor(fdb_ctx* ctx, fdb_array* duals, const fdb_array* x);
+int fdb_extract_gradient_chunk_at_cursor(fdb_ctx* ctx, fdb_array* result, const fdb_array* ydual);
+int fdb_extract_jacobian_chunk_at_cursor(fdb_ctx* ctx, fdb_array* result, int64_t ld_result, const fdb_array* ydual);
+int fdb_graph_begin(fdb_ctx* ctx);
+int fdb_graph_end(fdb_ctx* ctx, void** graph_exec);
+int fdb_graph_launch(fdb_ctx* ctx, void* graph_exec, int64_t times);
+int fdb_graph_destroy(void* graph_exec);
+
 /* ---- array arithmetic on Dual arrays (what a user `f` is made of) ----------
  * Operands of fdb_map2 may each be a level-1 Dual array or a level-0 plain
  * array (a Vector{Float64} broadcast against duals = the Real (x)or Dual bodies

@@ -114,3 +114,39 @@ def test_program_jacobian_elementwise_and_stencil(ctx, N):
         expect[i, i + 2] = 1.0; expect[i, i + 1] = -2.0; expect[i, i] = 2.0 * x[i]
     assert np.array_equal(res.derivs[0], expect)
     assert np.allclose(res.value, x[2:] - 2.0 * x[1:-1] + x[:-2] ** 2, rtol=1e-15)
+
+
+# ---- the reference loop as a replayed CUDA graph (fdb_graph.cu) ------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 5, 12])
+def test_graph_replayed_chunk_loop_matches_eager_loop(ctx, oracle, N):
+    for n in (53, 257):
+        x = np.random.default_rng(n + N).uniform(0.5, 1.5, n)
+        for gen, fn in ((F.prod_generic, "prod"), (F.rosenbrock_generic, "rosenbrock"), (F.ackley_generic, "ackley")):
+            if fn == "prod" and n > 100:
+                continue
+            cfg = fdb200.GradientConfig(gen, x, fdb200.Chunk(N))
+            r_graph = fdb200.GradientResult(x); r_eager = fdb200.GradientResult(x)
+            fdb200.gradient_b(r_graph, gen, x, cfg, ctx=ctx, fuse=False, graph=True)
+            fdb200.gradient_b(r_eager, gen, x, cfg, ctx=ctx, fuse=False, graph=False)
+            assert np.array_equal(r_graph.derivs[0], r_eager.derivs[0]), (fn, n, N)        # same kernels, same order: bit identical
+            assert r_graph.value == r_eager.value
+            g_ref, v_ref = oracle.gradient(fn, x, N)
+            assert np.allclose(r_graph.derivs[0], g_ref, rtol=1e-11, atol=1e-12 * np.abs(g_ref).max())
+
+
+@pytest.mark.gpu
+def test_chunk_cursor_follows_the_reference_bookkeeping(ctx):
+    import ctypes as C
+    lib = ctx.lib
+    for n, N in ((13, 4), (24, 12), (100, 7)):
+        p = fdb200.chunk_plan(n, N)
+        ctx.check(lib.fdb_cursor_set(ctx.h, 1, N))
+        seen = []
+        for _ in range(p["nchunks"]):
+            i, cs = C.c_int64(), C.c_int64()
+            ctx.check(lib.fdb_cursor_get(ctx.h, C.byref(i), C.byref(cs)))
+            seen.append((i.value, cs.value))
+            ctx.check(lib.fdb_cursor_advance(ctx.h, N, n))
+        expect = [((c - 1) * N + 1, N) for c in range(1, p["nchunks"])] + [(p["lastchunkindex"], p["lastchunksize"])]
+        assert seen == expect
