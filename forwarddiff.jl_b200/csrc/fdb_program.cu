@@ -35,12 +35,13 @@ __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < N; j++) acc[k].p[j] = 0.0;
     }
-    D R[PG_MAXR]; D1 R1[PG_MAXR];
+    D R[PG_MAXR];
+    __shared__ double rf1[PG_MAXR][2][THREADS];          // Dual{1} register file of the lane-shared path
     const int64_t nt = n - P.halo;
     for (int64_t i = threadIdx.x; i < nt; i += THREADS) {
         const int64_t w0 = i - (threadIdx.x & 31);
         const bool far = SHARE && ((w0 + 31 + P.halo < start) || (w0 >= start + chunksize));   // warp-uniform
-        if (far) pg_run<D1, 1, NS>(P.term, P.n_term, P.consts, xz, i, R1, acc1);
+        if (far) pg_run_shared1<NS, THREADS>(P.term, P.n_term, P.consts, xz, i, rf1, acc1);
         else pg_run<D, N, NS>(P.term, P.n_term, P.consts, xs, i, R, acc);
     }
     if (SHARE) {

@@ -101,9 +101,35 @@ FDB_DEV void pg_run(const short (*code)[4], int ninstr, const double* consts, co
         }
     }
 }
-struct NoLoader {
-    template <class T> FDB_DEV T operator()(int64_t) const { return T(); }
-};
+// The same pass for the lane-shared path (Dual{1}: value + one representative partial), with the virtual
+// register file in SHARED memory -- rf[reg][component][thread], conflict free -- instead of a dynamically
+// indexed local array (whose traffic spilled to L2/DRAM: ncu showed 1.4 GB of DRAM traffic per launch for
+// the local-memory version), and the K accumulators in real registers (predicated update).
+template <bool NS, int THREADS, class L>
+FDB_DEV void pg_run_shared1(const short (*code)[4], int ninstr, const double* consts, const L& x, int64_t i,
+                            double (*rf)[2][THREADS], Dual<double, 1, NS> (&acc)[PG_MAXK]) {
+    typedef Dual<double, 1, NS> D1;
+    const int t = threadIdx.x;
+    auto get = [&](int r) { D1 d; d.v = rf[r][0][t]; d.p[0] = rf[r][1][t]; return d; };
+    auto put = [&](int r, const D1& d) { rf[r][0][t] = d.v; rf[r][1][t] = d.p[0]; };
+    for (int pc = 0; pc < ninstr; pc++) {
+        const int op = code[pc][0], dst = code[pc][1], a = code[pc][2], b = code[pc][3];
+        const int kind = op >> 6, c = op & 63;
+        switch (kind) {
+            case PK_LOADX: put(dst, x(i + b)); break;
+            case PK_UNARY: put(dst, pg_unary<1, NS>(c, get(a))); break;
+            case PK_DD: put(dst, pg_dd<1, NS>(c, get(a), get(b))); break;
+            case PK_DC: put(dst, pg_dc<1, NS>(c, get(a), consts[b])); break;
+            case PK_CD: put(dst, pg_cd<1, NS>(c, consts[a], get(b))); break;
+            case PK_ACC: {
+                const D1 v = get(a);
+#pragma unroll
+                for (int k = 0; k < PG_MAXK; k++) if (dst == k) acc[k] = acc[k] + v;
+            } break;
+            default: put(dst, get(a)); break;
+        }
+    }
+}
 
 struct SumK {   // block_combine policy: K sum accumulators
     static constexpr int K = PG_MAXK;

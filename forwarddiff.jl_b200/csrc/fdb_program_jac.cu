@@ -20,11 +20,12 @@ __global__ void __launch_bounds__(THREADS) program_jacobian_kernel(const __grid_
     const int64_t m = n - P.halo;
     const int64_t w0 = i - (threadIdx.x & 31);
     const bool far = SHARE && ((w0 + 31 + P.halo < start) || (w0 >= start + chunksize));
+    __shared__ double rf1[PG_MAXR][2][THREADS];          // Dual{1} register file of the lane-shared path
     if (i >= m) return;
     if (far) {
-        D1 R1[PG_MAXR]; D1 acc1[1];
-        pg_run<D1, 1, NS>(P.term, P.n_term, P.consts, ZeroLoader<1, NS>{x}, i, R1, acc1);
-        const D1 y = R1[P.result_reg];
+        D1 acc1[PG_MAXK];
+        pg_run_shared1<NS, THREADS>(P.term, P.n_term, P.consts, ZeroLoader<1, NS>{x}, i, rf1, acc1);
+        D1 y; y.v = rf1[P.result_reg][0][threadIdx.x]; y.p[0] = rf1[P.result_reg][1][threadIdx.x];
         for (int k = 0; k < chunksize; k++) __stcs(J + i + (start + k) * ldJ, y.p[0]);
         if (yout && last) yout[i] = y.v;
     } else {
