@@ -228,6 +228,50 @@ template <int N, bool NS> FDB_DEV Dual<double, N, NS> cos_v(const Dual<double, N
     double s, c; sincos(x.v, &s, &c); return chain(c, -s, x);
 }
 
+// ----- the same rules one level up: value type V = Dual{T,Float64,M} (Hessians) ------------------------------
+// Same definitions as above with every scalar operation replaced by the inner Dual operation, exactly what
+// Julia's dispatch does for Dual{T,Dual{T,V,M},N} (same tag on both levels, src/config.jl:198-201).
+#define FDB_NESTED template <int M, int N, bool NS> FDB_DEV Dual<Dual<double, M, NS>, N, NS>
+#define FDB_NARG const Dual<Dual<double, M, NS>, N, NS>&
+FDB_NESTED exp_v(FDB_NARG x) { Dual<double, M, NS> val = exp_v(x.v); return chain(val, val, x); }
+FDB_NESTED log_v(FDB_NARG x) { return chain(log_v(x.v), inv_v(x.v), x); }
+FDB_NESTED sqrt_v(FDB_NARG x) { Dual<double, M, NS> val = sqrt_v(x.v); return chain(val, inv_v(2.0 * val), x); }
+FDB_NESTED tanh_v(FDB_NARG x) { Dual<double, M, NS> val = tanh_v(x.v); return chain(val, 1.0 - pow2(val), x); }
+FDB_NESTED inv_v(FDB_NARG x) { Dual<double, M, NS> val = inv_v(x.v); return chain(val, -abs2_v(val), x); }
+FDB_NESTED abs2_v(FDB_NARG x) { return chain(abs2_v(x.v), x.v + x.v, x); }
+FDB_NESTED abs_v(FDB_NARG x) {
+    Dual<double, M, NS> o = one_of(x.v);
+    return signbit(x.v.v) ? chain(abs_v(x.v), -o, x) : chain(abs_v(x.v), o, x);
+}
+FDB_NESTED sin_v(FDB_NARG x) { return chain(sin_v(x.v), cos_v(x.v), x); }         // Base.sincos(::Dual), src/dual.jl:719-722
+FDB_NESTED cos_v(FDB_NARG x) { return chain(cos_v(x.v), -sin_v(x.v), x); }
+FDB_NESTED operator/(FDB_NARG x, FDB_NARG y) {
+    Dual<Dual<double, M, NS>, N, NS> r; r.v = x.v / y.v;
+    Dual<double, M, NS> fa = inv_v(y.v);
+    Dual<double, M, NS> fb = -(x.v / (y.v * y.v));
+#pragma unroll
+    for (int i = 0; i < N; i++) r.p[i] = mulp<NS>(x.p[i], fa) + mulp<NS>(y.p[i], fb);
+    return r;
+}
+FDB_NESTED operator/(FDB_NARG x, double s) {
+    Dual<Dual<double, M, NS>, N, NS> r; r.v = x.v / s;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        r.p[i] = x.p[i] / s;
+        if (NS) { if (iszero_v(x.p[i])) r.p[i] = zero_of(x.p[i]); }
+    }
+    return r;
+}
+FDB_NESTED operator/(double s, FDB_NARG y) {
+    Dual<Dual<double, M, NS>, N, NS> r; Dual<double, M, NS> divv = s / y.v; r.v = divv;
+    Dual<double, M, NS> c = -(divv / y.v);
+#pragma unroll
+    for (int i = 0; i < N; i++) r.p[i] = mulp<NS>(y.p[i], c);
+    return r;
+}
+#undef FDB_NESTED
+#undef FDB_NARG
+
 // ----- ^ with a run-time exponent  (src/dual.jl:549-585) --------------------
 template <int N, bool NS> FDB_DEV bool partials_iszero(const Dual<double, N, NS>& x) {
     bool z = true;

@@ -35,14 +35,26 @@ __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < N; j++) acc[k].p[j] = 0.0;
     }
-    D R[PG_MAXR];
-    __shared__ double rf1[PG_MAXR][2][THREADS];          // Dual{1} register file of the lane-shared path
+    D R[PG_MAXR]; D1 R1[PG_MAXR];
+    extern __shared__ double rfv[];                      // Dual{1} register file of the vectorised lane-shared path
+    constexpr int V = PG_VEC;
     const int64_t nt = n - P.halo;
-    for (int64_t i = threadIdx.x; i < nt; i += THREADS) {
-        const int64_t w0 = i - (threadIdx.x & 31);
-        const bool far = SHARE && ((w0 + 31 + P.halo < start) || (w0 >= start + chunksize));   // warp-uniform
-        if (far) pg_run_shared1<NS, THREADS>(P.term, P.n_term, P.consts, xz, i, rf1, acc1);
-        else pg_run<D, N, NS>(P.term, P.n_term, P.consts, xs, i, R, acc);
+    const int64_t blk = (int64_t)V * THREADS;
+    for (int64_t i0 = 0; i0 < nt; i0 += blk) {
+        // block-uniform: a full block of V*THREADS terms none of which reads a seeded position
+        const bool far_blk = SHARE && (i0 + blk <= nt) && ((i0 + blk - 1 + P.halo < start) || (i0 >= start + chunksize));
+        if (far_blk) {
+            pg_run_shared_vec<NS, THREADS, V>(P.term, P.n_term, P.consts, xz, i0 + threadIdx.x, rfv, acc1);
+        } else {
+            for (int v = 0; v < V; v++) {
+                const int64_t i = i0 + (int64_t)v * THREADS + threadIdx.x;
+                if (i >= nt) break;
+                const int64_t w0 = i - (threadIdx.x & 31);
+                const bool far = SHARE && ((w0 + 31 + P.halo < start) || (w0 >= start + chunksize));   // warp-uniform
+                if (far) pg_run<D1, 1, NS>(P.term, P.n_term, P.consts, xz, i, R1, acc1);
+                else pg_run<D, N, NS>(P.term, P.n_term, P.consts, xs, i, R, acc);
+            }
+        }
     }
     if (SHARE) {
 #pragma unroll
@@ -64,6 +76,20 @@ __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_
             if (k < chunksize) grad[start + k] = y.p[k];
         if (last && value_out) value_out[0] = y.v;
     }
+}
+
+template <int N, bool NS, int T>
+static int launch_program_gradient(fdb_ctx* ctx, unsigned grid, size_t smem, const Program& P, const double* x, int64_t n, int64_t chunk_lo,
+                                   int64_t nchunks, int lcs, double* grad, double* vout) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(program_gradient_kernel<N, NS, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(PG_MAXR * 2 * PG_VEC * T * sizeof(double)));
+        if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(program_gradient_kernel): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    program_gradient_kernel<N, NS, T><<<grid, T, smem, ctx->stream>>>(P, ctx->lane_sharing, x, n, chunk_lo, nchunks, lcs, grad, vout);
+    return FDB_OK;
 }
 
 int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, const int32_t* epi, int n_epi, const double* consts,
@@ -119,8 +145,12 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
     constexpr int T = 128;
     const unsigned grid = (unsigned)(chunk_hi - chunk_lo);
     double* vout = value_dev ? value_dev->data : nullptr;
+    int nregs = 1;
+    for (int i = 0; i < n_term; i++) { const int d = term_prog[4 * i + 1]; if ((term_prog[4 * i] >> 6) != PK_ACC && d + 1 > nregs) nregs = d + 1; }
+    const size_t smem = (size_t)nregs * 2 * PG_VEC * T * sizeof(double);
     FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-        (program_gradient_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, grad->data, vout))));
+        (rc = launch_program_gradient<NN, NS, T>(ctx, grid, smem, P, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, grad->data, vout))));
+    if (rc) return rc;
     return finish(ctx, 1, "fdb_program_gradient_chunked");
 }
 

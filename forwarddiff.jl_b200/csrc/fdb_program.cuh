@@ -12,6 +12,7 @@ constexpr int PG_MAXI = 48;      // instructions per program part
 constexpr int PG_MAXC = 24;      // Float64 constants
 constexpr int PG_MAXR = 12;      // virtual Dual registers
 constexpr int PG_MAXK = 4;       // sum accumulators
+constexpr int PG_VEC = 4;        // terms per thread per decoded instruction on the lane-shared path
 
 struct Program {
     int n_term, n_epi, n_acc, halo, result_reg, pad;
@@ -128,6 +129,93 @@ FDB_DEV void pg_run_shared1(const short (*code)[4], int ninstr, const double* co
             } break;
             default: put(dst, get(a)); break;
         }
+    }
+}
+
+// Vector form of the lane-shared pass: each thread carries V terms (i, i+T, ..., i+(V-1)T) through one decode
+// of every instruction, so the interpreter's per-instruction overhead (fetch, two-level dispatch, loop) is
+// paid once per V terms.  rf[reg][component][v][thread] in dynamic shared memory (nregs registers only).
+template <bool NS, int THREADS, int V, class L>
+FDB_DEV void pg_run_shared_vec(const short (*code)[4], int ninstr, const double* consts, const L& x, int64_t i0, double* rf,
+                               Dual<double, 1, NS> (&acc)[PG_MAXK]) {
+    typedef Dual<double, 1, NS> D1;
+    const int t = threadIdx.x;
+    auto at = [&](int r, int comp, int v) -> double& { return rf[((r * 2 + comp) * V + v) * THREADS + t]; };
+    for (int pc = 0; pc < ninstr; pc++) {
+        const int op = code[pc][0], dst = code[pc][1], a = code[pc][2], b = code[pc][3];
+        const int kind = op >> 6, c = op & 63;
+        D1 xa[V], xb[V], r[V];
+        if (kind != PK_LOADX) {
+#pragma unroll
+            for (int v = 0; v < V; v++) { const int ra = (kind == PK_CD) ? b : a; xa[v].v = at(ra, 0, v); xa[v].p[0] = at(ra, 1, v); }
+        }
+        if (kind == PK_DD) {
+#pragma unroll
+            for (int v = 0; v < V; v++) { xb[v].v = at(b, 0, v); xb[v].p[0] = at(b, 1, v); }
+        }
+        // one flat dispatch per instruction; every case runs its V terms back to back
+#define PGV(EXPR) { _Pragma("unroll") for (int v = 0; v < V; v++) r[v] = (EXPR); } break;
+        const double s = (kind == PK_DC) ? consts[b] : ((kind == PK_CD) ? consts[a] : 0.0);
+        switch (op) {
+            case (PK_LOADX << 6): PGV(x(i0 + (int64_t)v * THREADS + b))
+            case (PK_UNARY << 6) | FDB_NEG: PGV(-xa[v])
+            case (PK_UNARY << 6) | FDB_EXP: PGV(exp_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_LOG: PGV(log_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_SIN: PGV(sin_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_COS: PGV(cos_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_TANH: PGV(tanh_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_SQRT: PGV(sqrt_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_ABS: PGV(abs_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_ABS2: PGV(abs2_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_INV: PGV(inv_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_POW0: PGV(pow0(xa[v]))
+            case (PK_UNARY << 6) | FDB_POW1: PGV(pow1(xa[v]))
+            case (PK_UNARY << 6) | FDB_POW2: PGV(pow2(xa[v]))
+            case (PK_UNARY << 6) | FDB_POW3: PGV(pow3(xa[v]))
+            case (PK_UNARY << 6) | FDB_TAN: PGV(tan_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_EXP2: PGV(exp2_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_LOG2: PGV(log2_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_LOG10: PGV(log10_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_LOG1P: PGV(log1p_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_EXPM1: PGV(expm1_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_SINH: PGV(sinh_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_COSH: PGV(cosh_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_ASIN: PGV(asin_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_ACOS: PGV(acos_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_ATAN: PGV(atan_v(xa[v]))
+            case (PK_UNARY << 6) | FDB_CBRT: PGV(cbrt_v(xa[v]))
+            case (PK_DD << 6) | FDB_ADD: PGV(xa[v] + xb[v])
+            case (PK_DD << 6) | FDB_SUB: PGV(xa[v] - xb[v])
+            case (PK_DD << 6) | FDB_MUL: PGV(xa[v] * xb[v])
+            case (PK_DD << 6) | FDB_DIV: PGV(xa[v] / xb[v])
+            case (PK_DD << 6) | FDB_POW: PGV(pow_v(xa[v], xb[v]))
+            case (PK_DD << 6) | FDB_MAX: PGV(max_v(xa[v], xb[v]))
+            case (PK_DD << 6) | FDB_MIN: PGV(min_v(xa[v], xb[v]))
+            case (PK_DD << 6) | FDB_ATAN2: PGV(atan2_v(xa[v], xb[v]))
+            case (PK_DD << 6) | FDB_HYPOT: PGV(hypot_v(xa[v], xb[v]))
+            case (PK_DC << 6) | FDB_ADD: PGV(xa[v] + s)
+            case (PK_DC << 6) | FDB_SUB: PGV(xa[v] - s)
+            case (PK_DC << 6) | FDB_MUL: PGV(xa[v] * s)
+            case (PK_DC << 6) | FDB_DIV: PGV(xa[v] / s)
+            case (PK_DC << 6) | FDB_POW: PGV(pow_v(xa[v], s))
+            case (PK_CD << 6) | FDB_ADD: PGV(s + xa[v])
+            case (PK_CD << 6) | FDB_SUB: PGV(s - xa[v])
+            case (PK_CD << 6) | FDB_MUL: PGV(s * xa[v])
+            case (PK_CD << 6) | FDB_DIV: PGV(s / xa[v])
+            case (PK_CD << 6) | FDB_POW: PGV(pow_v(s, xa[v]))
+            case (PK_ACC << 6):
+#pragma unroll
+                for (int k = 0; k < PG_MAXK; k++)
+                    if (dst == k) {
+#pragma unroll
+                        for (int v = 0; v < V; v++) acc[k] = acc[k] + xa[v];
+                    }
+                continue;
+            default: PGV(xa[v])
+        }
+#undef PGV
+#pragma unroll
+        for (int v = 0; v < V; v++) { at(dst, 0, v) = r[v].v; at(dst, 1, v) = r[v].p[0]; }
     }
 }
 

@@ -118,6 +118,8 @@ SIGNATURES = {
                                                C.c_int, C.c_int, C.c_int, c_arr, C.c_int, i64, i64, c_arr, c_arr]),
     "fdb_program_jacobian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, C.c_int, c_arr,
                                                C.c_int, i64, i64, c_arr, i64, c_arr]),
+    "fdb_program_hessian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, c_arr, C.c_int, i64, i64,
+                                              c_arr, i64, c_arr, c_arr]),
     "fdb_gradient_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, C.c_int, i64, i64, _dp, _dp]),
     "fdb_hessian_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, C.c_int, i64, i64, _dp, i64, _dp, _dp]),
     "fdb_measure_fp64_peak": (C.c_int, [c_ctx, _dp, _dp]),

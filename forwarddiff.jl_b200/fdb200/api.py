@@ -355,6 +355,28 @@ def _structured_gradient(ctx, result, f, X, cfg):
     return G
 
 
+def _program_hessian(ctx, result, H, f, x, N, lo, hi):
+    """hessian(f, x, cfg) of a user f flattened into an op-program (fdb_program_hessian_chunked)."""
+    n = _length(x)
+    prog = _try_trace("scalar", f, n)
+    if prog is None or prog.n_acc != 1 or len(prog.epi) != 0:
+        raise _lib.UnsupportedOp("hessian: f must be a catalogue target or flatten to a single sum of terms "
+                                 "(no prod, no arithmetic after the reduction)")
+    xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
+    Hd = B200Array.alloc(ctx, n * n); gd = B200Array.alloc(ctx, n); vd = B200Array.alloc(ctx, 1)
+    ctx.check(ctx.lib.fdb_program_hessian_chunked(ctx.h, _i32p(prog.term), len(prog.term),
+                                                  prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
+                                                  prog.halo, xd.h, N, lo, hi, Hd.h, n, gd.h, vd.h))
+    nchunks = 1 if n == N else chunk_plan(n, N)["nchunks"]
+    last = hi < 0 or hi == nchunks
+    c0, c1 = lo * N, (n if last else hi * N)
+    H[:, c0:c1] = Hd.numpy().reshape((n, n), order="F")[:, c0:c1]
+    if last and isinstance(result, DiffResult):
+        result.value = float(vd.numpy()[0])
+        result.derivs[0][...] = gd.numpy()
+    return result
+
+
 def _program_gradient(ctx, prog, x, N, lo, hi, out):
     """A flattened user f through the batched sweep (fdb_program_gradient_chunked)."""
     lib = ctx.lib
@@ -674,13 +696,13 @@ def hessian_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None):
     if N > n:
         raise ChunkSizeError(f"chunk size cannot be greater than ForwardDiff.structural_length(x) ({N} > {n})")
     fid = _catalogue_id(f, _lib.FN)
-    if fid is None:
-        raise _lib.UnsupportedOp("hessian: only catalogue targets have a nested-dual device kernel")
     ctx = _ctx_of(x, ctx)
     lo, hi = (0, -1) if chunks is None else chunks
     H = result.derivs[1] if isinstance(result, DiffResult) else result
     if H.shape != (n, n) or not H.flags.f_contiguous:
         raise DimensionMismatch("hessian!: result must be a column-major n x n float64 matrix")
+    if fid is None:
+        return _program_hessian(ctx, result, H, f, x, N, lo, hi)
     xh = np.ascontiguousarray(x.numpy() if isinstance(x, _DeviceArray) else x, dtype=np.float64).ravel()
     g = np.zeros(n)
     val = C.c_double(0.0)

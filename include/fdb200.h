@@ -256,6 +256,12 @@ int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, int n_instr,
                                  int result_reg, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* J,
                                  int64_t ldJ, fdb_array* y);
 
+/* hessian(f, x, cfg) of a flattened f = sum_i term(x[i .. i+halo]) (one accumulator, no epilogue; ops with a
+ * nested-dual rule: + - * / neg, literal powers, exp log sin cos tanh sqrt abs abs2 inv).  Outer chunks [lo, hi). */
+int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const double* consts, int n_consts, int halo,
+                                const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* H, int64_t ldH,
+                                fdb_array* grad, fdb_array* value_dev);
+
 /* ---- host-buffer entry points (what ForwardDiff.gradient!(out, f, x, cfg) with
  * host Vectors binds to): upload x, run the sweeps, download the result slice.  grad_host has
  * xlen entries; only the entries of the requested chunks are written. ------------ */

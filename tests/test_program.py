@@ -150,3 +150,45 @@ def test_chunk_cursor_follows_the_reference_bookkeeping(ctx):
             ctx.check(lib.fdb_cursor_advance(ctx.h, N, n))
         expect = [((c - 1) * N + 1, N) for c in range(1, p["nchunks"])] + [(p["lastchunkindex"], p["lastchunksize"])]
         assert seen == expect
+
+
+# ---- Hessians of flattened user functions (fdb_program_hess.cu) ------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 3, 8, 12])
+def test_program_hessian_vs_oracle_and_finite_differences(ctx, oracle, N):
+    for n in (13, 60):
+        x = np.random.default_rng(n).uniform(0.5, 1.5, n)
+        for gen, fn in ((F.rosenbrock_generic, "rosenbrock"), (F.sumsq_generic, "sumsq")):
+            res = fdb200.HessianResult(x)
+            fdb200.hessian_b(res, gen, x, fdb200.HessianConfig(gen, x, fdb200.Chunk(N)), ctx=ctx)
+            H_ref, g_ref, v_ref = oracle.hessian(fn, x, N if N in (1, 2, 3, 4, 5, 6, 7, 8, 12) else 8)
+            assert np.allclose(res.derivs[1], H_ref, rtol=1e-11, atol=1e-11), (fn, n, N)
+            assert np.allclose(res.derivs[0], g_ref, rtol=1e-11, atol=1e-11)
+            assert res.value == pytest.approx(v_ref, rel=1e-12)
+
+    def f(xd):      # every op family that has a nested rule
+        a, b = xd[:-1], xd[1:]
+        return (fdb200.exp(a * b) + fdb200.sin(a) * fdb200.cos(b) + fdb200.tanh(a - b) ** 2 + fdb200.sqrt(a + b) / (1.0 + a ** 2)
+                + fdb200.log(b) * 2.0 - 1.0 / a + fdb200.abs_(a - 1.0) ** 3).sum()
+
+    def fv(z):
+        a, b = z[:-1], z[1:]
+        return (np.exp(a * b) + np.sin(a) * np.cos(b) + np.tanh(a - b) ** 2 + np.sqrt(a + b) / (1.0 + a ** 2)
+                + np.log(b) * 2.0 - 1.0 / a + np.abs(a - 1.0) ** 3).sum()
+
+    n = 17
+    x = np.random.default_rng(3).uniform(0.6, 1.4, n)
+    res = fdb200.HessianResult(x)
+    fdb200.hessian_b(res, f, x, fdb200.HessianConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+    H = res.derivs[1]
+    assert np.allclose(H, H.T, rtol=1e-12, atol=1e-12)
+    assert res.value == pytest.approx(fv(x), rel=1e-13)
+    g = fdb200.gradient(f, x, fdb200.GradientConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+    assert np.allclose(res.derivs[0], g, rtol=1e-12, atol=1e-13)
+    h = 1e-5
+    E = np.eye(n)
+    fd = np.array([[(fv(x + h * E[i] + h * E[j]) - fv(x + h * E[i] - h * E[j]) - fv(x - h * E[i] + h * E[j]) + fv(x - h * E[i] - h * E[j])) / (4 * h * h)
+                    for j in range(n)] for i in range(n)])
+    assert np.allclose(H, fd, atol=2e-2 * max(1.0, np.abs(H).max()) * 1e-2 + 1e-4)      # Calculus.hessian-style tolerance (HessianTest.jl:65-88)
+    with pytest.raises(fdb200.UnsupportedOp):
+        fdb200.hessian(F.ackley_generic, x, fdb200.HessianConfig(F.ackley_generic, x, fdb200.Chunk(N)), ctx=ctx)
