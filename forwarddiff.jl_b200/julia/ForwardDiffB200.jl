@@ -146,4 +146,55 @@ function gradient_host!(out::Vector{Float64}, f, x::Vector{Float64}, ::Chunk{N};
     return out, value[]
 end
 
+# ---- op-programs: a non-catalogue f is flattened from its Broadcasted tree into {op,dst,a,b} words and run as ONE
+# batched launch (include/fdb200.h "op-programs"); Program mirrors fdb200/trace.py:Program --------------------
+struct Program
+    term::Matrix{Int32}; epi::Matrix{Int32}; consts::Vector{Float64}; n_acc::Int; halo::Int; result_reg::Int
+end
+function program_gradient!(result::B200Array{Float64}, p::Program, x::B200Array{Float64}, ::Chunk{N}; lo = 0, hi = -1) where {N}
+    value = B200Array{Float64}(undef, 1; ctx = x.ctx)
+    GC.@preserve p check(x.ctx.h, ccall((:fdb_program_gradient_chunked, libfdb200), Cint,
+        (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Ptr{Float64}, Cint, Cint, Cint, Cint, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+        x.ctx.h, p.term, size(p.term, 2), p.epi, size(p.epi, 2), p.consts, length(p.consts), p.n_acc, p.halo, p.result_reg,
+        x.h, N, lo, hi, result.h, value.h))
+    return result, value
+end
+function program_hessian!(H::B200Array{Float64}, grad::B200Array{Float64}, p::Program, x::B200Array{Float64}, ::Chunk{N}; lo = 0, hi = -1) where {N}
+    value = B200Array{Float64}(undef, 1; ctx = x.ctx)
+    GC.@preserve p check(x.ctx.h, ccall((:fdb_program_hessian_chunked, libfdb200), Cint,
+        (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+        x.ctx.h, p.term, size(p.term, 2), p.consts, length(p.consts), p.halo, x.h, N, lo, hi, H.h, length(x), grad.h, value.h))
+    return H, grad, value
+end
+
+# ---- the generic chunk loop as a replayed CUDA graph (fdb_graph.cu): chunk_mode_gradient! for a B200Array when f is an
+# arbitrary Julia function of B200Array{<:Dual} (every array op inside f is a ccall recorded by stream capture) ----------
+function chunk_mode_gradient_graph!(result::B200Array{Float64}, f::F, x::B200Array{Float64}, cfg::GradientConfig{T,V,N}) where {F,T,V,N}
+    ctx, xdual, n = x.ctx, cfg.duals, length(x)
+    seed!(xdual, x, 1, cfg.seeds); seed_zero_partials!(xdual, x, N + 1, n - N)        # first chunk eagerly, src/gradient.jl:133-138
+    ydual = f(xdual); extract_gradient_chunk!(T, result, ydual, 1, N); seed_zero_partials!(xdual, x, 1)
+    check(ctx.h, ccall((:fdb_cursor_set, libfdb200), Cint, (Ptr{Cvoid}, Int64, Int64), ctx.h, N + 1, min(N, n - N)))
+    check(ctx.h, ccall((:fdb_graph_begin, libfdb200), Cint, (Ptr{Cvoid},), ctx.h))
+    check(ctx.h, ccall((:fdb_seed_at_cursor, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, xdual.h, x.h))
+    ydual = f(xdual)                                                                   # temporaries must outlive the graph
+    check(ctx.h, ccall((:fdb_extract_gradient_chunk_at_cursor, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, result.h, ydual.h))
+    check(ctx.h, ccall((:fdb_seed_zero_at_cursor, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, xdual.h, x.h))
+    check(ctx.h, ccall((:fdb_cursor_advance, libfdb200), Cint, (Ptr{Cvoid}, Int64, Int64), ctx.h, N, n))
+    exec = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx.h, ccall((:fdb_graph_end, libfdb200), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), ctx.h, exec))
+    nchunks = cld(n, N)
+    check(ctx.h, ccall((:fdb_graph_launch, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), ctx.h, exec[], nchunks - 1))
+    ccall((:fdb_graph_destroy, libfdb200), Cint, (Ptr{Cvoid},), exec[])
+    return result
+end
+
+# ---- structured inputs (src/apiutils.jl:44-71): seed only structurally non-zero entries --------------------------------
+const STRUCTURE = Dict(:dense => 0, :upper => 1, :lower => 2, :diagonal => 3)
+seed_structured!(d::B200Array, x::B200Array, s::Symbol, rows, index, chunksize) =
+    check(d.ctx.h, ccall((:fdb_seed_structured, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Int64, Int64),
+                         d.ctx.h, d.h, x.h, STRUCTURE[s], rows, index, chunksize))
+extract_gradient_chunk_structured!(res::B200Array, y::B200Array, s::Symbol, rows, index, chunksize) =
+    check(res.ctx.h, ccall((:fdb_extract_gradient_chunk_structured, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Int64, Int64),
+                           res.ctx.h, res.h, y.h, STRUCTURE[s], rows, index, chunksize))
+
 end # module

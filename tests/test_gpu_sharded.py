@@ -15,3 +15,13 @@ def test_sharded_drivers_single_rank():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_sharded.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "match the single-rank results" in out.stdout
+
+
+def test_c_abi_demo_runs_from_plain_c(tmp_path):
+    """examples/c_abi_demo.c: the reference's golden vectors through the C ABI from a C program."""
+    libdir = os.path.join(ROOT, "forwarddiff.jl_b200", "lib")
+    exe = str(tmp_path / "c_abi_demo")
+    subprocess.run(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L" + libdir,
+                    "-lfdb200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "c_abi_demo ok" in r.stdout, r.stdout + r.stderr

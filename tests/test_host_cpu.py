@@ -152,3 +152,23 @@ def test_two_rank_sharding_and_allgather_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def _build_c_demo(tmp_path):
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.join(ROOT, "forwarddiff.jl_b200", "lib")
+    subprocess.run(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L" + libdir,
+                    "-lfdb200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    return exe
+
+
+def test_c_abi_links_from_plain_c_and_fails_loudly_without_gpu(tmp_path):
+    """The boundary is a self-contained C library: a C program links against it with gcc alone (no torch, no Python)."""
+    exe = _build_c_demo(tmp_path)
+    n = C.c_int(-1)
+    has_gpu = fdb200._lib.load().fdb_device_count(C.byref(n)) == 0 and n.value > 0
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    if has_gpu:
+        assert r.returncode == 0 and "c_abi_demo ok" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
