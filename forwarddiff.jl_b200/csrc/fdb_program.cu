@@ -16,6 +16,20 @@
 
 namespace fdb {
 
+// scalar Dual{1} pass for far terms in partial blocks; not inlined for the same reason as pg_run_shared_vec
+template <bool NS>
+__device__ __noinline__ void pg_run_far_scalar(const short (*code)[4], int ninstr, const double* consts, const ZeroLoader<1, NS>& x, int64_t i,
+                                               Dual<double, 1, NS>* R, Dual<double, 1, NS>* acc) {
+    pg_run<Dual<double, 1, NS>, 1, NS>(code, ninstr, consts, x, i, R, acc);
+}
+
+// the N-lane pass is used twice per kernel (near terms, epilogue): one out-of-line copy per (N, NS)
+template <int N, bool NS>
+__device__ __noinline__ void pg_run_near(const short (*code)[4], int ninstr, const double* consts, const SeedLoader<N, NS>& x, int64_t i,
+                                         Dual<double, N, NS>* R, Dual<double, N, NS>* acc) {
+    pg_run<Dual<double, N, NS>, N, NS>(code, ninstr, consts, x, i, R, acc);
+}
+
 template <int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_constant__ Program P, const bool SHARE, const double* __restrict__ x, int64_t n,
                                                                    int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
@@ -51,8 +65,8 @@ __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_
                 if (i >= nt) break;
                 const int64_t w0 = i - (threadIdx.x & 31);
                 const bool far = SHARE && ((w0 + 31 + P.halo < start) || (w0 >= start + chunksize));   // warp-uniform
-                if (far) pg_run<D1, 1, NS>(P.term, P.n_term, P.consts, xz, i, R1, acc1);
-                else pg_run<D, N, NS>(P.term, P.n_term, P.consts, xs, i, R, acc);
+                if (far) pg_run_far_scalar<NS>(P.term, P.n_term, P.consts, xz, i, R1, acc1);
+                else pg_run_near<N, NS>(P.term, P.n_term, P.consts, xs, i, R, acc);
             }
         }
     }
@@ -69,7 +83,7 @@ __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < PG_MAXK; k++) R[k] = acc[k];
-        pg_run<D, N, NS>(P.epi, P.n_epi, P.consts, xs, 0, R, acc);
+        pg_run_near<N, NS>(P.epi, P.n_epi, P.consts, xs, 0, R, acc);
         const D y = R[P.result_reg];
 #pragma unroll
         for (int k = 0; k < N; k++)

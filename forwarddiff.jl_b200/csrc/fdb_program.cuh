@@ -132,11 +132,12 @@ FDB_DEV void pg_run_shared1(const short (*code)[4], int ninstr, const double* co
     }
 }
 
+// (not inlined: the Dual{1} paths do not depend on the chunk size N, one copy per NS serves all 12 kernels)
 // Vector form of the lane-shared pass: each thread carries V terms (i, i+T, ..., i+(V-1)T) through one decode
 // of every instruction, so the interpreter's per-instruction overhead (fetch, two-level dispatch, loop) is
 // paid once per V terms.  rf[reg][component][v][thread] in dynamic shared memory (nregs registers only).
 template <bool NS, int THREADS, int V, class L>
-FDB_DEV void pg_run_shared_vec(const short (*code)[4], int ninstr, const double* consts, const L& x, int64_t i0, double* rf,
+__device__ __noinline__ void pg_run_shared_vec(const short (*code)[4], int ninstr, const double* consts, const L& x, int64_t i0, double* rf,
                                Dual<double, 1, NS> (&acc)[PG_MAXK]) {
     typedef Dual<double, 1, NS> D1;
     const int t = threadIdx.x;
