@@ -235,6 +235,20 @@ def main():
     ms, kms = timed(step_dev, K, kernel_only=sg.sweep)
     launches = ctx.launches() - l0
     barrier()
+    # ---- the same steps with the result exchange done by an NCCL all-gather after the sweeps (comparison only) ----
+    nccl_ms = None
+    if world > 1 and sg.exchange == "p2p":
+        sg_n = fdb200.dist.ShardedGradient(ctx, F.rosenbrock, N_ELEMS, cfg, exchange="nccl")
+        sg_n.x_t.copy_(x_host)
+
+        def step_nccl():
+            sg_n.sweep(); sg_n.gather()
+        for _ in range(W):
+            step_nccl()
+        barrier()
+        nms, _ = timed(step_nccl, K)
+        barrier()
+        nccl_ms = sum(nms)
     # ---- end-to-end steps (host buffers, copies inside the timed region) --------------------
     for _ in range(2):
         step_e2e()
@@ -243,10 +257,10 @@ def main():
     barrier()
     clocks = sampler.stop() if sampler else None
 
-    tot = torch.tensor([sum(ms), sum(ems), sum(kms)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([sum(ms), sum(ems), sum(kms), nccl_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    tot_ms, tot_ems, tot_kms = (float(t) for t in tot.tolist())
+    tot_ms, tot_ems, tot_kms, tot_nccl = (float(t) for t in tot.tolist())
     ms_per_step = tot_ms / K
     value = 1e3 / ms_per_step
     e2e_value = 1e3 / (tot_ems / K)
@@ -258,7 +272,10 @@ def main():
     a[1:] += 200.0 * (xh[1:] - xh[:-1] ** 2)
     ok = bool(np.allclose(g, a, rtol=1e-12, atol=1e-11))
 
+    exchange = sg.exchange
+    xch_timeouts = sg.xch.timeouts() if sg.xch is not None else 0
     if rank != 0:
+        sg.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -286,7 +303,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "fdb200",
-            "config": {"workload": WORKLOAD, "n": N_ELEMS, "chunk": CHUNK, "sharding": f"{world} ranks x contiguous chunk ranges + all-gather",
+            "config": {"workload": WORKLOAD, "n": N_ELEMS, "chunk": CHUNK, "sharding": f"{world} ranks x contiguous chunk ranges" + ("" if world == 1 else
+                                    " + sweep kernel stores its gradient slice into every peer's arena over NVLink (fdb_exchange_*), device-side flag barrier"
+                                    if exchange == "p2p" else " + NCCL all-gather"),
+                       "exchange": None if world == 1 else exchange,
                        "l2": "256 MB buffer written between timed steps (x is 8 MB and meant to be L2-resident within a step)",
                        "lane_sharing": True, "verified_against_closed_form": ok},
             "roofline": roofline,
@@ -294,7 +314,7 @@ def main():
                     "ms_per_step": tot_ems / K,
                     "api": ("fdb200.gradient_b(out, rosenbrock, x, GradientConfig(rosenbrock, x, Chunk(12))) on pinned host arrays -> C ABI fdb_gradient_host "
                             "(H2D x, all chunk sweeps, D2H gradient + value)") if world == 1 else
-                           "fdb200.dist.ShardedGradient.__call__ (pinned host x -> H2D -> this rank's sweeps -> NCCL all-gather -> D2H)"},
+                           f"fdb200.dist.ShardedGradient.__call__ (pinned host x -> H2D -> this rank's sweeps, result exchange: {exchange} -> D2H)"},
             "gpu_launches": int(launches), "clocks": clocks}
 
     if world == 1 and not args.no_cpu_baseline:
@@ -309,7 +329,11 @@ def main():
             line["extra"] = extras(ctx, torch, dev, flush, hbm_peak, dp_peak)
         except Exception as e:                                    # extras never invalidate the headline line
             line["extra"] = {"error": repr(e)}
+    if world > 1 and exchange == "p2p":
+        line["exchange_compare"] = {"p2p_fused_ms_per_step": ms_per_step, "nccl_allgather_ms_per_step": tot_nccl / K,
+                                    "barrier_timeouts": int(xch_timeouts)}
     emit(line)
+    sg.close()
     if world > 1:
         dist.destroy_process_group()
 

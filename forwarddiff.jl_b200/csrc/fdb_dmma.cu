@@ -16,6 +16,7 @@
 #include <cuda.h>
 
 #include "fdb_internal.h"
+#include "fdb_mirror.cuh"
 #include "fdb_targets.cuh"
 
 namespace fdb {
@@ -268,7 +269,8 @@ template <bool NS, bool SHARE>
 __global__ void __launch_bounds__(256) tanh_affine_epilogue_kernel(const double* __restrict__ Y, int64_t ldy, int P, const double* __restrict__ A,
                                                                   int64_t lda, const double* __restrict__ b, int64_t m, int64_t n, int N,
                                                                   int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
-                                                                  double* __restrict__ J, int64_t ldJ, double* __restrict__ yout) {
+                                                                  double* __restrict__ J, int64_t ldJ, double* __restrict__ yout,
+                                                                  const fdb_mirrors Mr) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t cl = blockIdx.y, c = chunk_lo + cl;
     if (r >= m) return;
@@ -283,13 +285,13 @@ __global__ void __launch_bounds__(256) tanh_affine_epilogue_kernel(const double*
         double p;
         if (SHARE) p = Yc[ldy] + A[r + (start + kk) * lda] * 1.0;   // shared zero lane + the one seeded column of the window
         else p = Yc[(int64_t)(kk + 1) * ldy];
-        __stcs(J + r + (start + kk) * ldJ, mulp<NS>(p, deriv));
+        mstore_cs(Mr, J + r + (start + kk) * ldJ, mulp<NS>(p, deriv));
     }
-    if (yout && last) yout[r] = val;
+    if (yout && last) mstore(Mr, &yout[r], val);
 }
 
 int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_array* b, const fdb_array* x, int64_t m, int N, int64_t lo, int64_t hi,
-                     int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ, double* yout, bool* used_dmma) {
+                     int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ, double* yout, bool* used_dmma, const fdb_mirrors& Mr) {
     const int64_t n = x->n, nc = hi - lo;
     const bool share = ctx->lane_sharing;
     const int P = share ? 2 : N + 1;
@@ -310,11 +312,11 @@ int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_ar
     rc = launch_gemm(ctx, A->data, lda, Bop, ldb, Y, ldy, m, n, nc * P, share ? 2 : 0, ws, used_dmma, &ngemm); if (rc) return rc;
     dim3 ge((unsigned)cdiv(m, 256), (unsigned)nc);
     if (ctx->nansafe) {
-        if (share) tanh_affine_epilogue_kernel<true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
-        else tanh_affine_epilogue_kernel<true, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
+        if (share) tanh_affine_epilogue_kernel<true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
+        else tanh_affine_epilogue_kernel<true, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
     } else {
-        if (share) tanh_affine_epilogue_kernel<false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
-        else tanh_affine_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
+        if (share) tanh_affine_epilogue_kernel<false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
+        else tanh_affine_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
     }
     return finish(ctx, 2 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma)");
 }
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(256) tanh_affine_hidden_kernel(const double* _
 
 int mlp2_dmma(fdb_ctx* ctx, const fdb_array* A1, int64_t lda1, const fdb_array* b1, const fdb_array* A2, int64_t lda2, const fdb_array* b2,
               const fdb_array* x, int64_t h, int64_t m, int N, int64_t lo, int64_t hi, int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ,
-              double* yout) {
+              double* yout, const fdb_mirrors& Mr) {
     const int64_t n = x->n, nc = hi - lo;
     const bool share = ctx->lane_sharing;
     const int P1 = share ? 2 : N + 1, P = N + 1;
@@ -380,8 +382,8 @@ int mlp2_dmma(fdb_ctx* ctx, const fdb_array* A1, int64_t lda1, const fdb_array* 
     // second layer: dense partials -> DMMA contraction of A2 against all hidden planes of all chunks
     rc = launch_gemm(ctx, A2->data, lda2, H1, ldh, Z2, ldz, m, h, nc * P, 0, ws, nullptr, &n2); if (rc) return rc;
     dim3 ge((unsigned)cdiv(m, 256), (unsigned)nc);
-    if (ctx->nansafe) tanh_affine_epilogue_kernel<true, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
-    else tanh_affine_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout);
+    if (ctx->nansafe) tanh_affine_epilogue_kernel<true, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
+    else tanh_affine_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
     return finish(ctx, 3 + n1 + n2, "fdb_jacobian_mlp2_chunked");
 }
 
@@ -408,7 +410,10 @@ extern "C" int fdb_jacobian_mlp2_chunked(fdb_ctx* ctx, const fdb_array* x, int64
     if (chunk_hi < 0) chunk_hi = nchunks;
     if (chunk_lo < 0 || chunk_lo > chunk_hi || chunk_hi > nchunks) return fail(ctx, FDB_ERR_BADARG, "bad chunk range");
     if (chunk_lo == chunk_hi) return FDB_OK;
-    return mlp2_dmma(ctx, A1, lda1, b1, A2, lda2, b2, x, h, m, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, J, ldJ, y ? y->data : nullptr);
+    fdb_mirrors Mr;
+    const fdb_array* outs[2] = {J, y};
+    int rc = mirrors_for(ctx, &Mr, outs, 2, "fdb_jacobian_mlp2_chunked"); if (rc) return rc;
+    return mlp2_dmma(ctx, A1, lda1, b1, A2, lda2, b2, x, h, m, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, J, ldJ, y ? y->data : nullptr, Mr);
 }
 
 // C[m x ncols] = A[m x k] * B[k x ncols] on plain column-major arrays

@@ -1,0 +1,173 @@
+// fdb_exchange.cu -- multi-GPU result exchange over NVLink peer memory (one process per GPU).
+//
+// The chunk sweeps of src/gradient.jl:141-152 / src/jacobian.jl:199-210 are independent, so each rank
+// sweeps a contiguous chunk range and owns a contiguous slice of the result.  The
+// reference's caller expects the whole `result`; rather than all-gathering after the sweeps, every rank
+// keeps its result in a symmetric arena that the peers map through CUDA IPC, and the driver kernels
+// repeat each extraction store into every peer's arena (fdb_mirror.cuh).  What is left of the collective
+// is a barrier: flag words at the end of each arena, written with release/system scope by the peers and
+// polled with acquire/system scope locally, enqueued on the context's stream like any other kernel.
+#include <string.h>
+
+#include "fdb_internal.h"
+
+struct fdb_exchange {
+    fdb_ctx* ctx = nullptr;
+    char* base = nullptr;          // local arena: data | flag page
+    size_t data_bytes = 0;
+    int rank = 0, world = 1;
+    char* peer[FDB_MAX_RANKS] = {nullptr};   // peer[r] = rank r's arena mapped here (peer[rank] = base)
+    bool connected = false;
+    unsigned long long epoch = 0;
+};
+
+namespace fdb {
+
+static constexpr size_t FLAG_PAGE = 256;            // FDB_MAX_RANKS u64 arrival flags, then the timeout counter
+static constexpr size_t TIMEOUT_OFF = 128;
+
+struct PeerFlags { unsigned long long* flags[FDB_MAX_RANKS]; };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+
+// thread r: tell rank r that this rank has arrived at `epoch`, then wait until rank r has.
+__global__ void exchange_barrier_kernel(PeerFlags P, int rank, int world, unsigned long long epoch, unsigned long long timeout_ns) {
+    const int r = threadIdx.x;
+    if (r >= world || r == rank) return;
+    __threadfence_system();       // everything this stream stored into peer arenas is ordered before the flag
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.flags[r] + rank), "l"(epoch) : "memory");
+    const unsigned long long* mine = P.flags[rank] + r;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= epoch) break;
+        if (globaltimer_ns() - t0 > timeout_ns) {      // a peer died: give up instead of hanging the GPU
+            atomicAdd(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(P.flags[rank]) + TIMEOUT_OFF), 1u);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
+int mirrors_for(fdb_ctx* ctx, fdb_mirrors* m, const fdb_array* const* outs, int nouts, const char* what) {
+    *m = fdb_mirrors();
+    fdb_exchange* x = ctx->xch;
+    if (!x) return FDB_OK;
+    for (int i = 0; i < nouts; i++) {
+        if (!outs[i]) continue;
+        const char* p = reinterpret_cast<const char*>(outs[i]->data);
+        if (p < x->base || p + (size_t)outs[i]->n * sizeof(double) > x->base + x->data_bytes)
+            return fail(ctx, FDB_ERR_BADARG, "%s: with a peer exchange enabled every result array must be a view of the exchange arena "
+                                             "(fdb_exchange_view); output %d is not", what, i);
+    }
+    for (int r = 0; r < x->world; r++)
+        if (r != x->rank) m->delta[m->count++] = (long long)(x->peer[r] - x->base);
+    return FDB_OK;
+}
+
+}  // namespace fdb
+
+using namespace fdb;
+
+extern "C" int fdb_exchange_create(fdb_ctx* ctx, int64_t n_doubles, int rank, int world, fdb_exchange** out) {
+    if (!ctx || !out || n_doubles < 0) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_create: bad argument");
+    if (world < 1 || world > FDB_MAX_RANKS || rank < 0 || rank >= world)
+        return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_create: rank %d of %d (at most %d ranks, one NVSwitch domain)", rank, world, FDB_MAX_RANKS);
+    fdb_exchange* x = new fdb_exchange();
+    x->ctx = ctx; x->rank = rank; x->world = world;
+    x->data_bytes = (size_t)round_up(n_doubles > 0 ? n_doubles : 1, 32) * sizeof(double);
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(&x->base, x->data_bytes + FLAG_PAGE);     // cudaMalloc, not a pool: IPC needs a plain allocation
+    if (e != cudaSuccess) { delete x; return fail(ctx, e == cudaErrorMemoryAllocation ? FDB_ERR_OOM : FDB_ERR_CUDA,
+                                                  "cudaMalloc(%zu bytes): %s", x->data_bytes + FLAG_PAGE, cudaGetErrorString(e)); }
+    e = cudaMemset(x->base, 0, x->data_bytes + FLAG_PAGE);
+    if (e != cudaSuccess) { cudaFree(x->base); delete x; return fail(ctx, FDB_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
+    x->peer[rank] = x->base;
+    x->connected = (world == 1);
+    *out = x;
+    return FDB_OK;
+}
+
+extern "C" int fdb_exchange_handle(fdb_exchange* x, unsigned char handle[FDB_IPC_HANDLE_BYTES]) {
+    if (!x || !handle) return FDB_ERR_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == FDB_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    FDB_CUDA(x->ctx, cudaIpcGetMemHandle(&h, x->base));
+    memcpy(handle, &h, sizeof h);
+    return FDB_OK;
+}
+
+extern "C" int fdb_exchange_connect(fdb_exchange* x, const unsigned char* handles) {
+    if (!x || !handles) return FDB_ERR_BADARG;
+    fdb_ctx* ctx = x->ctx;
+    if (x->connected) return FDB_OK;
+    cudaSetDevice(ctx->device);
+    for (int r = 0; r < x->world; r++) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * FDB_IPC_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; q++) if (q != x->rank && x->peer[q]) { cudaIpcCloseMemHandle(x->peer[q]); x->peer[q] = nullptr; }
+            return fail(ctx, FDB_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d's arena): %s", r, cudaGetErrorString(e));
+        }
+        x->peer[r] = static_cast<char*>(p);
+    }
+    x->connected = true;
+    return FDB_OK;
+}
+
+extern "C" int fdb_exchange_view(fdb_exchange* x, int64_t offset, int64_t n, int64_t ld, fdb_array** out) {
+    if (!x || !out) return FDB_ERR_BADARG;
+    if (offset < 0 || n < 0 || ld < n || (size_t)(offset + ld) * sizeof(double) > x->data_bytes)
+        return fail(x->ctx, FDB_ERR_BADARG, "fdb_exchange_view: [%lld, %lld) outside the arena of %zu doubles", (long long)offset,
+                    (long long)(offset + ld), x->data_bytes / sizeof(double));
+    return fdb_array_wrap(x->ctx, reinterpret_cast<double*>(x->base) + offset, n, ld, 0, 0, out);
+}
+
+extern "C" int fdb_exchange_enable(fdb_ctx* ctx, fdb_exchange* x) {
+    if (!ctx) return FDB_ERR_BADARG;
+    if (x && x->ctx != ctx) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_enable: exchange belongs to another context");
+    if (x && !x->connected) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_enable: call fdb_exchange_connect first");
+    ctx->xch = x;
+    return FDB_OK;
+}
+
+extern "C" int fdb_exchange_barrier(fdb_exchange* x) {
+    if (!x) return FDB_ERR_BADARG;
+    fdb_ctx* ctx = x->ctx;
+    if (!x->connected) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_barrier: not connected");
+    if (ctx->capturing) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_exchange_barrier: the epoch is a launch argument; not capturable");
+    if (x->world == 1) return FDB_OK;
+    PeerFlags P;
+    for (int r = 0; r < FDB_MAX_RANKS; r++)
+        P.flags[r] = r < x->world ? reinterpret_cast<unsigned long long*>(x->peer[r] + x->data_bytes) : nullptr;
+    x->epoch++;
+    exchange_barrier_kernel<<<1, 32, 0, ctx->stream>>>(P, x->rank, x->world, x->epoch, 20ull * 1000000000ull);
+    return finish(ctx, 1, "fdb_exchange_barrier");
+}
+
+extern "C" int fdb_exchange_timeouts(fdb_exchange* x, int64_t* count) {
+    if (!x || !count) return FDB_ERR_BADARG;
+    unsigned v = 0;
+    FDB_CUDA(x->ctx, cudaMemcpyAsync(&v, x->base + x->data_bytes + TIMEOUT_OFF, sizeof v, cudaMemcpyDeviceToHost, x->ctx->stream));
+    FDB_CUDA(x->ctx, cudaStreamSynchronize(x->ctx->stream));
+    *count = v;
+    return FDB_OK;
+}
+
+extern "C" int fdb_exchange_destroy(fdb_exchange* x) {
+    if (!x) return FDB_ERR_BADARG;
+    fdb_ctx* ctx = x->ctx;
+    if (ctx->xch == x) ctx->xch = nullptr;
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < x->world; r++)
+        if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    cudaFree(x->base);
+    delete x;
+    return FDB_OK;
+}

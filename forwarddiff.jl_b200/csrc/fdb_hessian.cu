@@ -16,6 +16,7 @@
 // per inner lane k on Dual{Dual{N},1}; their contributions are summed in term order.
 // Restricted to additive targets (K = 1, combine = +, finalize = identity).
 #include "fdb_internal.h"
+#include "fdb_mirror.cuh"
 #include "fdb_targets.cuh"
 
 namespace fdb {
@@ -48,7 +49,8 @@ template <int N, bool NS> struct NearLoader {
 template <class F, int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) hessian_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t outer_lo,
                                                                 int64_t nchunks_total, int lastchunksize, double* __restrict__ H,
-                                                                int64_t ldH, double* __restrict__ grad, double* __restrict__ value_out) {
+                                                                int64_t ldH, double* __restrict__ grad, double* __restrict__ value_out,
+                                                                const fdb_mirrors M) {
     typedef Dual<double, N, NS> DI;
     typedef Dual<DI, 1, NS> DG;
     typedef Dual<Dual<double, 1, NS>, 1, NS> DF;
@@ -122,13 +124,13 @@ __global__ void __launch_bounds__(THREADS) hessian_sweep_kernel(const double* __
         double s = 0.0;
         for (int t = 0; t < nnear; t++) s = s + s_p[t][k][j];
         s = s + (j == 0 ? s_ff[2] : s_ff[3]);
-        if (j == 0) { if (olast && grad) grad[istart + k] = s; }
-        else if (j - 1 < ocs && H) H[(istart + k) + (ostart + j - 1) * ldH] = s;
+        if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
+        else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
     }
     if (threadIdx.x == 0 && olast && ilast && value_out) {
         double s = 0.0;
         for (int t = 0; t < nnear; t++) s = s + s_v[t][0];
-        value_out[0] = s + s_ff[0];
+        mstore(M, value_out, s + s_ff[0]);
     }
 }
 
@@ -138,8 +140,11 @@ static int hessian_launch(fdb_ctx* ctx, const fdb_array* x, int N, int64_t lo, i
     constexpr int T = 128;
     dim3 grid((unsigned)nchunks, (unsigned)(hi - lo));
     double* Hp = H ? H->data : nullptr; double* gp = grad ? grad->data : nullptr; double* vp = value_dev ? value_dev->data : nullptr;
+    fdb_mirrors M;
+    const fdb_array* outs[3] = {H, grad, value_dev};
+    { int mrc = mirrors_for(ctx, &M, outs, 3, what); if (mrc) return mrc; }
     FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-        (hessian_sweep_kernel<F, NN, NS, T><<<grid, T, 0, ctx->stream>>>(x->data, x->n, lo, nchunks, lcs, Hp, ldH, gp, vp))));
+        (hessian_sweep_kernel<F, NN, NS, T><<<grid, T, 0, ctx->stream>>>(x->data, x->n, lo, nchunks, lcs, Hp, ldH, gp, vp, M))));
     return finish(ctx, 1, what);
 }
 

@@ -28,7 +28,15 @@ struct fdb_ctx {
     bool saved_async = false;
     double* pinned = nullptr;
     size_t pinned_bytes = 0;
+    struct fdb_exchange* xch = nullptr;   // enabled peer-memory result exchange (fdb_exchange.cu), or null
     std::string err;
+};
+
+// byte offsets from the local exchange arena to every peer's arena; passed by value to the driver kernels,
+// which repeat each result store at p + delta[r] (fdb_mirror.cuh).  count == 0: single rank / exchange off.
+struct fdb_mirrors {
+    int count = 0;
+    long long delta[FDB_MAX_RANKS - 1] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 struct fdb_array {
@@ -80,10 +88,13 @@ inline int finish(fdb_ctx* ctx, int nlaunch, const char* what) {
 int ensure_scratch(fdb_ctx* ctx, size_t bytes);
 int ensure_pinned(fdb_ctx* ctx, size_t bytes);
 int ensure_counter(fdb_ctx* ctx);
+// fdb_exchange.cu: mirrors for a driver whose outputs are `outs` (null entries skipped); fails unless every
+// output lies inside the enabled exchange's arena
+int mirrors_for(fdb_ctx* ctx, fdb_mirrors* m, const fdb_array* const* outs, int nouts, const char* what);
 
 // fdb_dmma.cu: batched tanh.(A*x .+ b) chunk sweeps on the FP64 tensor-core contraction
 int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_array* b, const fdb_array* x, int64_t m, int N, int64_t lo,
-                     int64_t hi, int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ, double* yout, bool* used_dmma);
+                     int64_t hi, int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ, double* yout, bool* used_dmma, const fdb_mirrors& Mr);
 bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k);
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

@@ -10,6 +10,7 @@
 // coalesced along rows, streaming stores).  Bound: the 8*m*n bytes of J that must be
 // written (HBM), DESIGN.md.
 #include "fdb_internal.h"
+#include "fdb_mirror.cuh"
 #include "fdb_targets.cuh"
 
 namespace fdb {
@@ -39,7 +40,8 @@ FDB_DEV void brusselator_rows(const L& X, int64_t i, int64_t M, double al, D& du
 template <int N, bool NS, int THREADS, bool SHARE>
 __global__ void __launch_bounds__(THREADS) brusselator_jacobian_kernel(const double* __restrict__ x, int64_t n, double alpha,
                                                                        int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
-                                                                       double* __restrict__ J, int64_t ldJ, double* __restrict__ y) {
+                                                                       double* __restrict__ J, int64_t ldJ, double* __restrict__ y,
+                                                                       const fdb_mirrors Mr) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t M = n / 2;
@@ -61,22 +63,22 @@ __global__ void __launch_bounds__(THREADS) brusselator_jacobian_kernel(const dou
         brusselator_rows(ZeroLoader<1, NS>{x}, i, M, alpha, du, dv);
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < chunksize) { __stcs(Ju + k * ldJ, du.p[0]); __stcs(Jv + k * ldJ, dv.p[0]); }
-        if (write_y) { y[i] = du.v; y[M + i] = dv.v; }
+            if (k < chunksize) { mstore_cs(Mr, Ju + k * ldJ, du.p[0]); mstore_cs(Mr, Jv + k * ldJ, dv.p[0]); }
+        if (write_y) { mstore(Mr, &y[i], du.v); mstore(Mr, &y[M + i], dv.v); }
     } else {
         D du, dv;
         brusselator_rows(SeedLoader<N, NS>{x, start, chunksize}, i, M, alpha, du, dv);
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < chunksize) { __stcs(Ju + k * ldJ, du.p[k]); __stcs(Jv + k * ldJ, dv.p[k]); }   // extract_jacobian_chunk!, jacobian.jl:109-118
-        if (write_y) { y[i] = du.v; y[M + i] = dv.v; }
+            if (k < chunksize) { mstore_cs(Mr, Ju + k * ldJ, du.p[k]); mstore_cs(Mr, Jv + k * ldJ, dv.p[k]); }   // extract_jacobian_chunk!, jacobian.jl:109-118
+        if (write_y) { mstore(Mr, &y[i], du.v); mstore(Mr, &y[M + i], dv.v); }
     }
 }
 
 // ---- test/JacobianTest.jl:23-31 target (n = 3, m = 4): one thread per chunk -------------------
 template <int N, bool NS>
 __global__ void jactest_jacobian_kernel(const double* __restrict__ x, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
-                                        double* __restrict__ J, int64_t ldJ, double* __restrict__ yout) {
+                                        double* __restrict__ J, int64_t ldJ, double* __restrict__ yout, const fdb_mirrors Mr) {
     typedef Dual<double, N, NS> D;
     const int64_t c = chunk_lo + blockIdx.x;
     int64_t start; int chunksize;
@@ -90,8 +92,8 @@ __global__ void jactest_jacobian_kernel(const double* __restrict__ x, int64_t ch
     y[3] = X(2);
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int k = 0; k < N; k++) if (k < chunksize) J[r + (start + k) * ldJ] = y[r].p[k];
-        if (yout && c == nchunks_total - 1) yout[r] = y[r].v;
+        for (int k = 0; k < N; k++) if (k < chunksize) mstore(Mr, &J[r + (start + k) * ldJ], y[r].p[k]);
+        if (yout && c == nchunks_total - 1) mstore(Mr, &yout[r], y[r].v);
     }
 }
 
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(THREADS) tanh_affine_jacobian_kernel(const dou
                                                                        const double* __restrict__ x, int64_t n, int64_t m,
                                                                        int64_t chunk_lo, int64_t chunk_hi, int64_t nchunks_total,
                                                                        int lastchunksize, double* __restrict__ J, int64_t ldJ,
-                                                                       double* __restrict__ yout) {
+                                                                       double* __restrict__ yout, const fdb_mirrors Mr) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t r = (int64_t)blockIdx.y * THREADS + threadIdx.x;
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(THREADS) tanh_affine_jacobian_kernel(const dou
         D yv = tanh_v(z + bi);
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < csz[q]) __stcs(J + r + (start[q] + k) * ldJ, yv.p[k]);
-        if (yout && c == nchunks_total - 1) yout[r] = yv.v;
+            if (k < csz[q]) mstore_cs(Mr, J + r + (start[q] + k) * ldJ, yv.p[k]);
+        if (yout && c == nchunks_total - 1) mstore(Mr, &yout[r], yv.v);
     }
 }
 
@@ -179,6 +181,9 @@ extern "C" int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, in
     if (chunk_lo == chunk_hi) return FDB_OK;
     const int lcs = (int)p.lastchunksize;
     double* yp = y ? y->data : nullptr;
+    fdb_mirrors Mr;
+    const fdb_array* outs[2] = {J, y};
+    { int mrc = mirrors_for(ctx, &Mr, outs, 2, "fdb_jacobian_chunked"); if (mrc) return mrc; }
     constexpr int T = 256;
     switch (fn) {
         case FDB_JFN_BRUSSELATOR: {
@@ -186,10 +191,10 @@ extern "C" int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, in
             dim3 grid((unsigned)(chunk_hi - chunk_lo), (unsigned)cdiv(n / 2, T));
             if (ctx->lane_sharing) {
                 FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-                    (brusselator_jacobian_kernel<NN, NS, T, true><<<grid, T, 0, ctx->stream>>>(x->data, n, alpha, chunk_lo, nchunks, lcs, J->data, ldJ, yp))));
+                    (brusselator_jacobian_kernel<NN, NS, T, true><<<grid, T, 0, ctx->stream>>>(x->data, n, alpha, chunk_lo, nchunks, lcs, J->data, ldJ, yp, Mr))));
             } else {
                 FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-                    (brusselator_jacobian_kernel<NN, NS, T, false><<<grid, T, 0, ctx->stream>>>(x->data, n, alpha, chunk_lo, nchunks, lcs, J->data, ldJ, yp))));
+                    (brusselator_jacobian_kernel<NN, NS, T, false><<<grid, T, 0, ctx->stream>>>(x->data, n, alpha, chunk_lo, nchunks, lcs, J->data, ldJ, yp, Mr))));
             }
             return finish(ctx, 1, "fdb_jacobian_chunked(brusselator)");
         }
@@ -197,7 +202,7 @@ extern "C" int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, in
             if (n != 3 || m != 4) return fail(ctx, FDB_ERR_SHAPE, "jactest target needs n = 3, m = 4");
             if (N > 3) return fail(ctx, FDB_ERR_CHUNK, "chunk size cannot be greater than ForwardDiff.structural_length(x)");
             FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-                (jactest_jacobian_kernel<NN, NS><<<(unsigned)(chunk_hi - chunk_lo), 1, 0, ctx->stream>>>(x->data, chunk_lo, nchunks, lcs, J->data, ldJ, yp))));
+                (jactest_jacobian_kernel<NN, NS><<<(unsigned)(chunk_hi - chunk_lo), 1, 0, ctx->stream>>>(x->data, chunk_lo, nchunks, lcs, J->data, ldJ, yp, Mr))));
             return finish(ctx, 1, "fdb_jacobian_chunked(jactest)");
         }
         case FDB_JFN_TANH_AFFINE: {
@@ -206,18 +211,18 @@ extern "C" int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, in
                 return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: A must be %lld x %lld, b of length %lld", (long long)m, (long long)n, (long long)m);
             if (ctx->use_dmma && dmma_eligible(A->data, lda, m, n)) {
                 // contraction on FP64 tensor cores (fdb_dmma.cu); all requested chunks in one GEMM
-                return tanh_affine_dmma(ctx, A, lda, b, x, m, N, chunk_lo, chunk_hi, nchunks, lcs, J, ldJ, yp, nullptr);
+                return tanh_affine_dmma(ctx, A, lda, b, x, m, N, chunk_lo, chunk_hi, nchunks, lcs, J, ldJ, yp, nullptr, Mr);
             }
             constexpr int CH = 4; constexpr int TT = 128;
             dim3 grid((unsigned)cdiv(chunk_hi - chunk_lo, CH), (unsigned)cdiv(m, TT));
             if (ctx->lane_sharing) {
                 FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
                     (tanh_affine_jacobian_kernel<NN, NS, TT, CH, true><<<grid, TT, 0, ctx->stream>>>(A->data, lda, b->data, x->data, n, m, chunk_lo, chunk_hi,
-                                                                                                  nchunks, lcs, J->data, ldJ, yp))));
+                                                                                                  nchunks, lcs, J->data, ldJ, yp, Mr))));
             } else {
                 FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
                     (tanh_affine_jacobian_kernel<NN, NS, TT, CH, false><<<grid, TT, 0, ctx->stream>>>(A->data, lda, b->data, x->data, n, m, chunk_lo, chunk_hi,
-                                                                                                   nchunks, lcs, J->data, ldJ, yp))));
+                                                                                                   nchunks, lcs, J->data, ldJ, yp, Mr))));
             }
             return finish(ctx, 1, "fdb_jacobian_chunked(tanh_affine)");
         }

@@ -33,7 +33,8 @@ __device__ __noinline__ void pg_run_near(const short (*code)[4], int ninstr, con
 template <int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_constant__ Program P, const bool SHARE, const double* __restrict__ x, int64_t n,
                                                                    int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
-                                                                   double* __restrict__ grad, double* __restrict__ value_out) {
+                                                                   double* __restrict__ grad, double* __restrict__ value_out,
+                                                                   const fdb_mirrors M) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t c = chunk_lo + blockIdx.x;
@@ -87,14 +88,14 @@ __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_
         const D y = R[P.result_reg];
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < chunksize) grad[start + k] = y.p[k];
-        if (last && value_out) value_out[0] = y.v;
+            if (k < chunksize) mstore(M, &grad[start + k], y.p[k]);
+        if (last && value_out) mstore(M, value_out, y.v);
     }
 }
 
 template <int N, bool NS, int T>
 static int launch_program_gradient(fdb_ctx* ctx, unsigned grid, size_t smem, const Program& P, const double* x, int64_t n, int64_t chunk_lo,
-                                   int64_t nchunks, int lcs, double* grad, double* vout) {
+                                   int64_t nchunks, int lcs, double* grad, double* vout, const fdb_mirrors& M) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(program_gradient_kernel<N, NS, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -102,7 +103,7 @@ static int launch_program_gradient(fdb_ctx* ctx, unsigned grid, size_t smem, con
         if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(program_gradient_kernel): %s", cudaGetErrorString(e));
         configured = true;
     }
-    program_gradient_kernel<N, NS, T><<<grid, T, smem, ctx->stream>>>(P, ctx->lane_sharing, x, n, chunk_lo, nchunks, lcs, grad, vout);
+    program_gradient_kernel<N, NS, T><<<grid, T, smem, ctx->stream>>>(P, ctx->lane_sharing, x, n, chunk_lo, nchunks, lcs, grad, vout, M);
     return FDB_OK;
 }
 
@@ -159,11 +160,14 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
     constexpr int T = 128;
     const unsigned grid = (unsigned)(chunk_hi - chunk_lo);
     double* vout = value_dev ? value_dev->data : nullptr;
+    fdb_mirrors M;
+    const fdb_array* outs[2] = {grad, value_dev};
+    rc = mirrors_for(ctx, &M, outs, 2, "fdb_program_gradient_chunked"); if (rc) return rc;
     int nregs = 1;
     for (int i = 0; i < n_term; i++) { const int d = term_prog[4 * i + 1]; if ((term_prog[4 * i] >> 6) != PK_ACC && d + 1 > nregs) nregs = d + 1; }
     const size_t smem = (size_t)nregs * 2 * PG_VEC * T * sizeof(double);
     FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-        (rc = launch_program_gradient<NN, NS, T>(ctx, grid, smem, P, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, grad->data, vout))));
+        (rc = launch_program_gradient<NN, NS, T>(ctx, grid, smem, P, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, grad->data, vout, M))));
     if (rc) return rc;
     return finish(ctx, 1, "fdb_program_gradient_chunked");
 }

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "fdb_internal.h"
+#include "fdb_mirror.cuh"
 #include "fdb_targets.cuh"
 
 namespace fdb {

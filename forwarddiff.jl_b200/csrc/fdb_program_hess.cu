@@ -94,7 +94,7 @@ template <int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) program_hessian_kernel(const __grid_constant__ Program P, const double* __restrict__ x, int64_t n,
                                                                   int64_t outer_lo, int64_t nchunks_total, int lastchunksize,
                                                                   double* __restrict__ H, int64_t ldH, double* __restrict__ grad,
-                                                                  double* __restrict__ value_out) {
+                                                                  double* __restrict__ value_out, const fdb_mirrors M) {
     typedef Dual<double, N, NS> DI;
     typedef Dual<DI, 1, NS> DG;
     typedef Dual<Dual<double, 1, NS>, 1, NS> DF;
@@ -168,13 +168,13 @@ __global__ void __launch_bounds__(THREADS) program_hessian_kernel(const __grid_c
         double s = 0.0;
         for (int t = 0; t < nnear; t++) s = s + s_p[t][k][j];
         s = s + (j == 0 ? s_ff[2] : s_ff[3]);
-        if (j == 0) { if (olast && grad) grad[istart + k] = s; }
-        else if (j - 1 < ocs && H) H[(istart + k) + (ostart + j - 1) * ldH] = s;
+        if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
+        else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
     }
     if (threadIdx.x == 0 && olast && ilast && value_out) {
         double s = 0.0;
         for (int t = 0; t < nnear; t++) s = s + s_v[t][0];
-        value_out[0] = s + s_ff[0];
+        mstore(M, value_out, s + s_ff[0]);
     }
 }
 
@@ -211,7 +211,10 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
     constexpr int T = 128;
     dim3 grid((unsigned)nchunks, (unsigned)(chunk_hi - chunk_lo));
     double* Hp = H ? H->data : nullptr; double* gp = grad ? grad->data : nullptr; double* vp = value_dev ? value_dev->data : nullptr;
+    fdb_mirrors M;
+    const fdb_array* outs[3] = {H, grad, value_dev};
+    { int mrc = mirrors_for(ctx, &M, outs, 3, "fdb_program_hessian_chunked"); if (mrc) return mrc; }
     FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-        (program_hessian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, Hp, ldH, gp, vp))));
+        (program_hessian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, Hp, ldH, gp, vp, M))));
     return finish(ctx, 1, "fdb_program_hessian_chunked");
 }

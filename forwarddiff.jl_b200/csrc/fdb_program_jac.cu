@@ -9,7 +9,8 @@ namespace fdb {
 template <int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) program_jacobian_kernel(const __grid_constant__ Program P, const bool SHARE, const double* __restrict__ x, int64_t n,
                                                                    int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
-                                                                   double* __restrict__ J, int64_t ldJ, double* __restrict__ yout) {
+                                                                   double* __restrict__ J, int64_t ldJ, double* __restrict__ yout,
+                                                                   const fdb_mirrors M) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t c = chunk_lo + blockIdx.x;
@@ -26,16 +27,16 @@ __global__ void __launch_bounds__(THREADS) program_jacobian_kernel(const __grid_
         D1 acc1[PG_MAXK];
         pg_run_shared1<NS, THREADS>(P.term, P.n_term, P.consts, ZeroLoader<1, NS>{x}, i, rf1, acc1);
         D1 y; y.v = rf1[P.result_reg][0][threadIdx.x]; y.p[0] = rf1[P.result_reg][1][threadIdx.x];
-        for (int k = 0; k < chunksize; k++) __stcs(J + i + (start + k) * ldJ, y.p[0]);
-        if (yout && last) yout[i] = y.v;
+        for (int k = 0; k < chunksize; k++) mstore_cs(M, J + i + (start + k) * ldJ, y.p[0]);
+        if (yout && last) mstore(M, &yout[i], y.v);
     } else {
         D R[PG_MAXR]; D acc[1];
         pg_run<D, N, NS>(P.term, P.n_term, P.consts, SeedLoader<N, NS>{x, start, chunksize}, i, R, acc);
         const D y = R[P.result_reg];
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < chunksize) __stcs(J + i + (start + k) * ldJ, y.p[k]);
-        if (yout && last) yout[i] = y.v;
+            if (k < chunksize) mstore_cs(M, J + i + (start + k) * ldJ, y.p[k]);
+        if (yout && last) mstore(M, &yout[i], y.v);
     }
 }
 
@@ -64,7 +65,10 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
     constexpr int T = 128;
     dim3 grid((unsigned)(chunk_hi - chunk_lo), (unsigned)cdiv(m, T));
     double* yp = y ? y->data : nullptr;
+    fdb_mirrors M;
+    const fdb_array* outs[2] = {J, y};
+    rc = mirrors_for(ctx, &M, outs, 2, "fdb_program_jacobian_chunked"); if (rc) return rc;
     FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-        (program_jacobian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, J->data, ldJ, yp))));
+        (program_jacobian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, J->data, ldJ, yp, M))));
     return finish(ctx, 1, "fdb_program_jacobian_chunked");
 }

@@ -15,6 +15,7 @@
 // of f with N-wide partials; nothing is skipped for elements outside the seeded
 // window.  The kernel is therefore bound by FP64 issue, not HBM.
 #include "fdb_internal.h"
+#include "fdb_mirror.cuh"
 #include "fdb_targets.cuh"
 
 namespace fdb {
@@ -31,7 +32,8 @@ namespace fdb {
 template <class F, int N, bool NS, int THREADS, bool SHARE>
 __global__ void __launch_bounds__(THREADS) gradient_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo,
                                                                  int64_t nchunks_total, int lastchunksize,
-                                                                 double* __restrict__ grad, double* __restrict__ value_out) {
+                                                                 double* __restrict__ grad, double* __restrict__ value_out,
+                                                                 const fdb_mirrors M) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t c = chunk_lo + blockIdx.x;                       // 0-based chunk number
@@ -85,8 +87,8 @@ __global__ void __launch_bounds__(THREADS) gradient_sweep_kernel(const double* _
         D y = F::finalize(acc, n);
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < chunksize) grad[start + k] = y.p[k];           // extract_gradient_chunk!, src/gradient.jl:74-81
-        if (last && value_out) value_out[0] = y.v;                 // extract_value!, src/gradient.jl:155
+            if (k < chunksize) mstore(M, &grad[start + k], y.p[k]);   // extract_gradient_chunk!, src/gradient.jl:74-81 (+ peers)
+        if (last && value_out) mstore(M, value_out, y.v);          // extract_value!, src/gradient.jl:155
     }
 }
 
@@ -96,14 +98,17 @@ static int gradient_launch(fdb_ctx* ctx, const fdb_array* x, int N, int64_t lo, 
     constexpr int THREADS = 256;
     unsigned grid = (unsigned)(hi - lo);
     double* vout = value_dev ? value_dev->data : nullptr;
+    fdb_mirrors M;
+    const fdb_array* outs[2] = {grad, value_dev};
+    int rc = mirrors_for(ctx, &M, outs, 2, what); if (rc) return rc;
     if (ctx->lane_sharing) {
         FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
             (gradient_sweep_kernel<F, NN, NS, THREADS, true><<<grid, THREADS, 0, ctx->stream>>>(x->data, x->n, lo, nchunks, lastchunksize,
-                                                                                                 grad->data, vout))));
+                                                                                                 grad->data, vout, M))));
     } else {
         FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
             (gradient_sweep_kernel<F, NN, NS, THREADS, false><<<grid, THREADS, 0, ctx->stream>>>(x->data, x->n, lo, nchunks, lastchunksize,
-                                                                                                  grad->data, vout))));
+                                                                                                  grad->data, vout, M))));
     }
     return finish(ctx, 1, what);
 }

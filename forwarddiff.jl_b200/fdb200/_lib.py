@@ -122,8 +122,17 @@ SIGNATURES = {
                                               c_arr, i64, c_arr, c_arr]),
     "fdb_gradient_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, C.c_int, i64, i64, _dp, _dp]),
     "fdb_hessian_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, C.c_int, i64, i64, _dp, i64, _dp, _dp]),
+    "fdb_exchange_create": (C.c_int, [c_ctx, i64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fdb_exchange_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "fdb_exchange_connect": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "fdb_exchange_view": (C.c_int, [C.c_void_p, i64, i64, i64, C.POINTER(c_arr)]),
+    "fdb_exchange_enable": (C.c_int, [c_ctx, C.c_void_p]),
+    "fdb_exchange_barrier": (C.c_int, [C.c_void_p]),
+    "fdb_exchange_timeouts": (C.c_int, [C.c_void_p, C.POINTER(i64)]),
+    "fdb_exchange_destroy": (C.c_int, [C.c_void_p]),
     "fdb_measure_fp64_peak": (C.c_int, [c_ctx, _dp, _dp]),
 }
+IPC_HANDLE_BYTES = 64
 
 # enums of fdb200.h
 OP1 = dict(neg=1, exp=2, log=3, sin=4, cos=5, tanh=6, sqrt=7, abs=8, abs2=9, inv=10, pow0=11, pow1=12, pow2=13, pow3=14,

@@ -4,10 +4,19 @@ The reference runs its ceil(n/N) chunk sweeps sequentially on one thread
 (src/gradient.jl:141-147); they are independent (chunk c only produces gradient
 entries / Jacobian columns c*N+1 .. min((c+1)*N, n)), so rank r of W owns chunks
 [r*ceil(C/W), min((r+1)*ceil(C/W), C)) and therefore a contiguous slice of the
-result.  There is no collective inside the sweep; the only exchange is one
-all-gather of the (padded, equal-sized) slices, done with torch.distributed
-(NCCL over NVLink on GPUs, gloo in the CPU tests).  The value f(x) is taken from
-the rank that owns the last chunk, as the reference does (src/gradient.jl:155).
+result.  There is no collective inside the sweep.  The exchange that makes the result
+complete on every rank comes in two forms:
+
+  exchange="p2p"  (default on GPUs that can map each other's memory): the results
+      live in a symmetric arena (fdb_exchange_*), the ranks swap its CUDA IPC
+      handle once, and the sweep kernels store every extracted entry into all
+      peers' arenas over NVLink as they produce it -- the extraction IS the
+      gather; what remains is a device-side flag barrier.
+  exchange="nccl": one all-gather of the (padded, equal-sized) slices with
+      torch.distributed after the sweeps (also what the gloo CPU tests exercise).
+
+The value f(x) is taken from the rank that owns the last chunk, as the reference
+does (src/gradient.jl:155).
 
 torch is only the plumbing here (device memory for the gathered buffer, the
 process group); all compute is the C-ABI library.
@@ -40,6 +49,105 @@ def allgather_slices(local_padded, world, group=None):
     return out
 
 
+class _CudaView:
+    """__cuda_array_interface__ shim: lets torch address arena memory owned by the library (for D2H copies)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr="<f8", data=(int(ptr), False), version=3, strides=None)
+
+
+class PeerExchange:
+    """A symmetric result arena mapped by every peer (fdb_exchange_*).  The 64-byte IPC handles travel through
+    the process group once at construction; afterwards no host-side collective is involved."""
+
+    def __init__(self, ctx, n_doubles, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = _rank_world(group)
+        self.n = int(n_doubles)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.fdb_exchange_create(ctx.h, self.n, self.rank, self.world, C.byref(h)))
+        self.h = h
+        try:
+            buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+            ctx.check(ctx.lib.fdb_exchange_handle(h, buf))
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(buf.raw), group=group)
+                ok = ctx.lib.fdb_exchange_connect(h, b"".join(handles))
+                # every rank must agree that the mapping worked before anyone stores into a peer
+                flags = [None] * self.world
+                dist.all_gather_object(flags, int(ok), group=group)
+                if any(flags):
+                    ctx.check(ok)
+                    raise _lib.CudaError(f"peer arena mapping failed on rank(s) {[r for r, f in enumerate(flags) if f]}")
+        except Exception:
+            ctx.lib.fdb_exchange_destroy(h)
+            self.h = None
+            raise
+        v = self.view(0, 0)
+        self.base_ptr = v.ptr
+        self._views = []
+
+    def view(self, offset, n, ld=None):
+        import ctypes as C
+        from .array import B200Array
+        ld = int(n if ld is None else ld)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.fdb_exchange_view(self.h, int(offset), int(n), ld, C.byref(h)))
+        ptr = C.c_void_p()
+        self.ctx.check(self.ctx.lib.fdb_array_info(h, None, None, None, None, C.byref(ptr)))
+        a = B200Array.__new__(B200Array)
+        a._init(self.ctx, h, int(n), 0, 0, ld, ptr.value or 0, keepalive=self)
+        return a
+
+    def torch_view(self, offset, n):
+        import torch
+        return torch.as_tensor(_CudaView(self.base_ptr + 8 * int(offset), n), device=torch.device("cuda", self.ctx.device))
+
+    def enable(self):
+        self.ctx.check(self.ctx.lib.fdb_exchange_enable(self.ctx.h, self.h))
+
+    def disable(self):
+        self.ctx.check(self.ctx.lib.fdb_exchange_enable(self.ctx.h, None))
+
+    def barrier(self):
+        """Device-side barrier on the context's stream (no host synchronisation)."""
+        self.ctx.check(self.ctx.lib.fdb_exchange_barrier(self.h))
+
+    def timeouts(self):
+        import ctypes as C
+        c = C.c_int64()
+        self.ctx.check(self.ctx.lib.fdb_exchange_timeouts(self.h, C.byref(c)))
+        return c.value
+
+    def close(self):
+        """Collective: every rank must have stopped storing into the peers before an arena is unmapped."""
+        if self.h is None:
+            return
+        import torch.distributed as dist
+        self.ctx.sync()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.ctx.lib.fdb_exchange_destroy(self.h)
+        self.h = None
+
+
+def _make_exchange(ctx, n_doubles, group, mode):
+    """mode: "p2p" (raise if the peers cannot be mapped), "nccl" (no arena), "auto" (p2p, else nccl)."""
+    if mode == "nccl":
+        return None
+    try:
+        return PeerExchange(ctx, n_doubles, group)
+    except _lib.FdbError as e:
+        if mode == "p2p":
+            raise
+        import sys
+        print(f"fdb200.dist: peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+        return None
+
+
 def _rank_world(group=None):
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -54,7 +162,8 @@ class _ShardedColumns:
     the wrapped base pointer is shifted by -elem_lo columns.  `gather()` all-gathers the padded blocks
     into the full matrix on every rank (optional: C4's 34 GB Jacobian is normally left sharded)."""
 
-    def _setup(self, ctx, n, m, N, group):
+    def _setup(self, ctx, n, m, N, group, exchange="auto", extra=0):
+        """`extra` doubles are reserved behind the matrix in the arena for the driver's vector outputs (y, gradient, value)."""
         import torch
         self.torch = torch
         self.ctx, self.n, self.m, self.N, self.group = ctx, int(n), int(m), int(N), group
@@ -64,12 +173,38 @@ class _ShardedColumns:
         self.dev = torch.device("cuda", ctx.device)
         per = self.lay["per"]
         self.x_t = torch.empty(self.n, dtype=torch.float64, device=self.dev)
-        self.local = torch.zeros(self.m * per, dtype=torch.float64, device=self.dev)
-        self.full = None
         self.x_a = ctx.wrap(self.x_t.data_ptr(), self.n, keepalive=self.x_t)
-        shifted = self.local.data_ptr() - 8 * self.m * self.plan["elem_lo"]
-        self.J_a = ctx.wrap(shifted, self.m * self.n, keepalive=self.local)      # virtual m x n view, only own columns backed
         ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        self.full = None
+        self._mat = self.m * per * self.world                     # padded full matrix (whole chunks per rank)
+        self.xch = _make_exchange(ctx, self._mat + extra, group, exchange) if self.world > 1 or exchange == "p2p" else None
+        self.exchange = "p2p" if self.xch is not None else "nccl"
+        if self.xch is not None:
+            # every rank holds the full matrix in its arena; the kernels fill the peers' copies of this rank's columns
+            self.full = self.xch.torch_view(0, self._mat)
+            self.local = self.full[self.m * self.plan["elem_lo"]: self.m * self.plan["elem_lo"] + self.m * per]
+            self.J_a = self.xch.view(0, self.m * self.n)
+        else:
+            # only this rank's column block is backed; the kernels address columns absolutely, so shift the base
+            self.local = torch.zeros(self.m * per, dtype=torch.float64, device=self.dev)
+            shifted = self.local.data_ptr() - 8 * self.m * self.plan["elem_lo"]
+            self.J_a = ctx.wrap(shifted, self.m * self.n, keepalive=self.local)
+
+    def _vector(self, offset, n):
+        """A vector output: arena view (p2p) or a torch tensor (nccl).  Returns (torch tensor, device array)."""
+        if self.xch is not None:
+            return self.xch.torch_view(self._mat + offset, n), self.xch.view(self._mat + offset, n)
+        t = self.torch.zeros(n, dtype=self.torch.float64, device=self.dev)
+        return t, self.ctx.wrap(t.data_ptr(), n, keepalive=t)
+
+    def _sweep_begin(self):
+        if self.xch is not None:
+            self.xch.barrier()          # all peers have consumed the previous result before it is overwritten
+            self.xch.enable()
+
+    def _sweep_end(self):
+        if self.xch is not None:
+            self.xch.disable()
 
     def local_block(self):
         """This rank's column block as an (m, ncols) column-major numpy array."""
@@ -77,7 +212,12 @@ class _ShardedColumns:
         return self.local[: self.m * ncols].cpu().numpy().reshape((self.m, ncols), order="F")
 
     def gather(self):
+        """The full matrix on every rank: a device-side barrier (p2p: the sweeps already stored into every peer)
+        or one all-gather of the padded column blocks (nccl)."""
         import torch.distributed as dist
+        if self.xch is not None:
+            self.xch.barrier()
+            return self.full[: self.m * self.n]
         per = self.lay["per"]
         if self.full is None:
             self.full = self.torch.empty(self.m * per * self.world, dtype=self.torch.float64, device=self.dev)
@@ -90,17 +230,22 @@ class _ShardedColumns:
     def full_matrix(self):
         return self.gather().cpu().numpy().reshape((self.m, self.n), order="F")
 
+    def close(self):
+        if self.xch is not None:
+            self.xch.close()
+            self.xch = None
+
 
 class ShardedJacobian(_ShardedColumns):
     """ForwardDiff.jacobian!(J, f, x, cfg) / jacobian!(J, f!, y, x, cfg) with chunk sweeps sharded over the ranks."""
 
-    def __init__(self, ctx, f, xlen, m, cfg=None, group=None):
+    def __init__(self, ctx, f, xlen, m, cfg=None, group=None, exchange="auto"):
         self.f = f
         self.cfg = cfg if cfg is not None else JacobianConfig(f, np.empty(int(xlen)))
         self.fid = _catalogue_id(f, _lib.JFN)
         if self.fid is None:
             raise _lib.UnsupportedOp("sharded Jacobian needs a catalogue target")
-        self._setup(ctx, xlen, m, self.cfg.N, group)
+        self._setup(ctx, xlen, m, self.cfg.N, group, exchange, extra=-(-int(m) // 32) * 32)
         torch = self.torch
         p = getattr(f, "params", {}) or {}
         self.alpha = float(p.get("alpha", 0.0))
@@ -110,19 +255,23 @@ class ShardedJacobian(_ShardedColumns):
             self.b_t = torch.from_numpy(np.ascontiguousarray(p["b"], dtype=np.float64)).to(self.dev)
             self.A_a = ctx.wrap(self.A_t.data_ptr(), self.A_t.numel(), keepalive=self.A_t)
             self.b_a = ctx.wrap(self.b_t.data_ptr(), self.b_t.numel(), keepalive=self.b_t)
-        self.y_t = torch.zeros(self.m, dtype=torch.float64, device=self.dev)
-        self.y_a = ctx.wrap(self.y_t.data_ptr(), self.m, keepalive=self.y_t)
+        self.y_t, self.y_a = self._vector(0, self.m)
 
     def sweep(self):
         c = self.ctx
-        c.check(c.lib.fdb_jacobian_chunked(c.h, self.fid, self.x_a.h, self.m, self.N, self.A_a.h if self.A_a else None, self.m,
-                                           self.b_a.h if self.b_a else None, self.alpha, self.plan["chunk_lo"], self.plan["chunk_hi"],
-                                           self.J_a.h, self.m, self.y_a.h))
+        self._sweep_begin()
+        try:
+            c.check(c.lib.fdb_jacobian_chunked(c.h, self.fid, self.x_a.h, self.m, self.N, self.A_a.h if self.A_a else None, self.m,
+                                               self.b_a.h if self.b_a else None, self.alpha, self.plan["chunk_lo"], self.plan["chunk_hi"],
+                                               self.J_a.h, self.m, self.y_a.h))
+        finally:
+            self._sweep_end()
 
     def values(self):
-        """y = value.(ydual): taken from the rank owning the last chunk (src/jacobian.jl:229)."""
+        """y = value.(ydual): taken from the rank owning the last chunk (src/jacobian.jl:229); with the peer exchange
+        that rank's kernel has already stored it everywhere (valid after gather())."""
         import torch.distributed as dist
-        if self.world > 1:
+        if self.world > 1 and self.xch is None:
             dist.broadcast(self.y_t, src=owner_of_last_chunk(self.n, self.N, self.world), group=self.group)
         return self.y_t
 
@@ -131,28 +280,30 @@ class ShardedHessian(_ShardedColumns):
     """ForwardDiff.hessian!(result, f, x, cfg): outer chunks (column blocks of H) sharded over the ranks;
     every rank runs all inner chunks for its columns (src/hessian.jl:14-19)."""
 
-    def __init__(self, ctx, f, xlen, cfg=None, group=None):
+    def __init__(self, ctx, f, xlen, cfg=None, group=None, exchange="auto"):
         self.f = f
         self.cfg = cfg if cfg is not None else HessianConfig(f, np.empty(int(xlen)))
         self.fid = _catalogue_id(f, _lib.FN)
         if self.fid is None:
             raise _lib.UnsupportedOp("sharded Hessian needs a catalogue target")
-        self._setup(ctx, xlen, xlen, self.cfg.N, group)
-        torch = self.torch
-        self.g_t = torch.zeros(self.n, dtype=torch.float64, device=self.dev)
-        self.v_t = torch.zeros(1, dtype=torch.float64, device=self.dev)
-        self.g_a = ctx.wrap(self.g_t.data_ptr(), self.n, keepalive=self.g_t)
-        self.v_a = ctx.wrap(self.v_t.data_ptr(), 1, keepalive=self.v_t)
+        npad = -(-int(xlen) // 32) * 32
+        self._setup(ctx, xlen, xlen, self.cfg.N, group, exchange, extra=npad + 32)
+        self.g_t, self.g_a = self._vector(0, self.n)
+        self.v_t, self.v_a = self._vector(npad, 1)
 
     def sweep(self):
         c = self.ctx
-        c.check(c.lib.fdb_hessian_chunked(c.h, self.fid, self.x_a.h, self.N, self.plan["chunk_lo"], self.plan["chunk_hi"],
-                                          self.J_a.h, self.n, self.g_a.h, self.v_a.h))
+        self._sweep_begin()
+        try:
+            c.check(c.lib.fdb_hessian_chunked(c.h, self.fid, self.x_a.h, self.N, self.plan["chunk_lo"], self.plan["chunk_hi"],
+                                              self.J_a.h, self.n, self.g_a.h, self.v_a.h))
+        finally:
+            self._sweep_end()
 
     def value_and_gradient(self):
         """DiffResult value and gradient fall out of the last outer chunk's inner sweeps (src/hessian.jl:50-55)."""
         import torch.distributed as dist
-        if self.world > 1:
+        if self.world > 1 and self.xch is None:
             src = owner_of_last_chunk(self.n, self.N, self.world)
             dist.broadcast(self.g_t, src=src, group=self.group)
             dist.broadcast(self.v_t, src=src, group=self.group)
@@ -163,7 +314,7 @@ class ShardedGradient:
     """Reusable state for ForwardDiff.gradient!(out, f, x, cfg) sharded over the process group:
     device buffers are allocated once (like a GradientConfig's work buffers)."""
 
-    def __init__(self, ctx, f, xlen, cfg=None, group=None):
+    def __init__(self, ctx, f, xlen, cfg=None, group=None, exchange="auto"):
         import torch
         self.torch = torch
         self.ctx, self.f, self.n, self.group = ctx, f, int(xlen), group
@@ -177,23 +328,43 @@ class ShardedGradient:
         self.lay = slice_layout(self.n, self.N, self.world)
         dev = torch.device("cuda", ctx.device)
         self.x_t = torch.empty(self.n, dtype=torch.float64, device=dev)
-        # gathered buffer: rank r's slice sits at [r*per, (r+1)*per) == its absolute gradient positions
-        self.g_t = torch.zeros(max(self.lay["padded"], self.n), dtype=torch.float64, device=dev)
-        self.v_t = torch.zeros(1, dtype=torch.float64, device=dev)
         self.x_a = ctx.wrap(self.x_t.data_ptr(), self.n, keepalive=self.x_t)
-        self.g_a = ctx.wrap(self.g_t.data_ptr(), self.n, ld=self.g_t.numel(), keepalive=self.g_t)
-        self.v_a = ctx.wrap(self.v_t.data_ptr(), 1, keepalive=self.v_t)
         ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)     # kernels and NCCL on one stream
+        glen = -(-max(self.lay["padded"], self.n) // 32) * 32
+        self.xch = _make_exchange(ctx, glen + 32, group, exchange) if self.world > 1 or exchange == "p2p" else None
+        self.exchange = "p2p" if self.xch is not None else "nccl"
+        if self.xch is not None:
+            # gradient and value live in the arena every peer maps: the sweep kernel stores each entry everywhere
+            self.g_t, self.v_t = self.xch.torch_view(0, glen), self.xch.torch_view(glen, 1)
+            self.g_a, self.v_a = self.xch.view(0, self.n, ld=glen), self.xch.view(glen, 1, ld=32)
+        else:
+            # gathered buffer: rank r's slice sits at [r*per, (r+1)*per) == its absolute gradient positions
+            self.g_t = torch.zeros(glen, dtype=torch.float64, device=dev)
+            self.v_t = torch.zeros(1, dtype=torch.float64, device=dev)
+            self.g_a = ctx.wrap(self.g_t.data_ptr(), self.n, ld=self.g_t.numel(), keepalive=self.g_t)
+            self.v_a = ctx.wrap(self.v_t.data_ptr(), 1, keepalive=self.v_t)
 
     def sweep(self):
         """This rank's chunk sweeps (device-resident inputs); no host sync."""
         c = self.ctx
-        c.check(c.lib.fdb_gradient_chunked(c.h, self.fid, self.x_a.h, self.N, self.plan["chunk_lo"], self.plan["chunk_hi"],
-                                           self.g_a.h, self.v_a.h))
+        if self.xch is not None:
+            self.xch.barrier()          # peers have consumed the previous gradient before it is overwritten
+            self.xch.enable()
+        try:
+            c.check(c.lib.fdb_gradient_chunked(c.h, self.fid, self.x_a.h, self.N, self.plan["chunk_lo"], self.plan["chunk_hi"],
+                                               self.g_a.h, self.v_a.h))
+        finally:
+            if self.xch is not None:
+                self.xch.disable()
 
     def gather(self):
-        """All-gather the gradient slices (in place in g_t) and broadcast the value from the owner of the last chunk."""
+        """Complete gradient and value on every rank: a device-side barrier (p2p; the sweep kernel already stored
+        into every peer), or an all-gather of the slices plus a broadcast of the value from the owner of the last
+        chunk (nccl)."""
         import torch.distributed as dist
+        if self.xch is not None:
+            self.xch.barrier()
+            return
         if self.world > 1:
             per = self.lay["per"]
             mine = self.g_t[self.rank * per:(self.rank + 1) * per].clone()
@@ -210,3 +381,8 @@ class ShardedGradient:
             self.torch.cuda.current_stream().synchronize()
             return out_host_pinned
         return self.g_t[:self.n]
+
+    def close(self):
+        if self.xch is not None:
+            self.xch.close()
+            self.xch = None

@@ -270,6 +270,33 @@ int fdb_gradient_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, 
 int fdb_hessian_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, int N, int64_t chunk_lo,
                      int64_t chunk_hi, double* H_host, int64_t ldH, double* grad_host, double* value_host);
 
+/* ---- multi-GPU result exchange over NVLink peer memory ------------
+ * One process per GPU.  The reference's result (`result` of src/gradient.jl:141-152, the Jacobian of
+ * src/jacobian.jl:109-118, H of src/hessian.jl:14-71) must end up complete on every rank although each rank
+ * only sweeps its own chunk range.  Instead of an all-gather after the sweeps, every rank allocates a
+ * symmetric *arena* (same size everywhere), the ranks exchange its 64-byte CUDA IPC handle through whatever
+ * transport the host has (torch.distributed here, MPI.jl / NCCL.jl from Julia), and while an exchange is
+ * enabled on a context the whole-path drivers store every extracted entry (gradient slice, Jacobian/Hessian
+ * column block, y, value) into the local arena AND, from the same kernel, into every peer's arena at the same
+ * offset: the extraction is the gather.  All result arrays handed to a driver must then be views into the
+ * arena (fdb_exchange_view).  fdb_exchange_barrier is a device-side barrier over flag words in the arenas
+ * (enqueued on the context's stream, no host sync): call it after the sweeps (all peers' stores have landed)
+ * and before the next sweeps (all peers have consumed the previous result). */
+typedef struct fdb_exchange fdb_exchange;
+#define FDB_IPC_HANDLE_BYTES 64
+#define FDB_MAX_RANKS 8
+int fdb_exchange_create(fdb_ctx* ctx, int64_t n_doubles, int rank, int world, fdb_exchange** out);
+int fdb_exchange_handle(fdb_exchange* x, unsigned char handle[FDB_IPC_HANDLE_BYTES]);
+/* handles: world * FDB_IPC_HANDLE_BYTES bytes in rank order (this rank's own entry is ignored) */
+int fdb_exchange_connect(fdb_exchange* x, const unsigned char* handles);
+/* level-0 view of n doubles (plane stride ld >= n) at `offset` doubles into the local arena */
+int fdb_exchange_view(fdb_exchange* x, int64_t offset, int64_t n, int64_t ld, fdb_array** out);
+int fdb_exchange_enable(fdb_ctx* ctx, fdb_exchange* x_or_null);
+int fdb_exchange_barrier(fdb_exchange* x);
+/* number of barrier waits that gave up after the timeout (a peer never arrived); synchronises the stream */
+int fdb_exchange_timeouts(fdb_exchange* x, int64_t* count);
+int fdb_exchange_destroy(fdb_exchange* x);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------- */
 /* FP64 instruction-issue peak: a register-only chain of independent DMUL/DADD pairs;
  * returns achieved non-fused FP64 operations per second on this device. */

@@ -26,12 +26,24 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.cuda.set_stream(torch.cuda.Stream(dev))
     ctx = fdb200.Context(local)
+    for exchange in ("nccl", "p2p"):
+        check(ctx, rank, world, exchange)
+    if world > 1:
+        dist.barrier()
+    print(f"rank {rank}/{world}: sharded gradient / Jacobian / Hessian match the single-rank results (nccl and p2p exchange)", flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def check(ctx, rank, world, exchange):
+    """exchange="nccl": all-gather after the sweeps; "p2p": the sweep kernels store into every peer's arena."""
     rng = np.random.default_rng(3)
 
     # gradient: Ackley n = 100 003 (remainder chunk), Chunk{12}
     n, N = 100_003, 12
     x = rng.uniform(0.5, 1.5, n)
-    sg = fdb200.dist.ShardedGradient(ctx, F.ackley, n, fdb200.GradientConfig(F.ackley, x, fdb200.Chunk(N)))
+    sg = fdb200.dist.ShardedGradient(ctx, F.ackley, n, fdb200.GradientConfig(F.ackley, x, fdb200.Chunk(N)), exchange=exchange)
+    assert sg.exchange == exchange
     g = sg(torch.from_numpy(x).pin_memory()).cpu().numpy()
     ref = fdb200.GradientResult(x)
     fdb200.gradient_b(ref, F.ackley, x, fdb200.GradientConfig(F.ackley, x, fdb200.Chunk(N)), ctx=ctx)
@@ -42,7 +54,7 @@ def main():
     M = 2048; nb = 2 * M
     xb = np.concatenate([1 + np.sin(2 * np.pi * np.arange(1, M + 1) / (M + 1)), 3 * np.ones(M)])
     fb = F.brusselator.with_params(alpha=(M + 1) ** 2 / 50.0)
-    sj = fdb200.dist.ShardedJacobian(ctx, fb, nb, nb, fdb200.JacobianConfig(fb, xb, fdb200.Chunk(8), y=np.zeros(nb)))
+    sj = fdb200.dist.ShardedJacobian(ctx, fb, nb, nb, fdb200.JacobianConfig(fb, xb, fdb200.Chunk(8), y=np.zeros(nb)), exchange=exchange)
     sj.x_t.copy_(torch.from_numpy(xb)); sj.sweep()
     Jfull = sj.full_matrix(); yv = sj.values().cpu().numpy()
     yref = np.zeros(nb)
@@ -54,7 +66,7 @@ def main():
     m, k = 256, 160
     A = rng.uniform(-1, 1, (m, k)) / np.sqrt(k); b = rng.uniform(-1, 1, m); xt = rng.uniform(-1, 1, k)
     ft = F.tanh_affine.with_params(A=A, b=b)
-    st = fdb200.dist.ShardedJacobian(ctx, ft, k, m, fdb200.JacobianConfig(ft, xt, fdb200.Chunk(12)))
+    st = fdb200.dist.ShardedJacobian(ctx, ft, k, m, fdb200.JacobianConfig(ft, xt, fdb200.Chunk(12)), exchange=exchange)
     st.x_t.copy_(torch.from_numpy(xt)); st.sweep()
     Jt = st.full_matrix()
     Jtref = fdb200.jacobian(ft, xt, fdb200.JacobianConfig(ft, xt, fdb200.Chunk(12)), ctx=ctx, m=m)
@@ -63,18 +75,28 @@ def main():
     # Hessian: Rosenbrock n = 515, Chunk{8}
     nh = 515
     xh = rng.uniform(0.5, 1.5, nh)
-    sh = fdb200.dist.ShardedHessian(ctx, F.rosenbrock, nh, fdb200.HessianConfig(F.rosenbrock, xh, fdb200.Chunk(8)))
+    sh = fdb200.dist.ShardedHessian(ctx, F.rosenbrock, nh, fdb200.HessianConfig(F.rosenbrock, xh, fdb200.Chunk(8)), exchange=exchange)
     sh.x_t.copy_(torch.from_numpy(xh)); sh.sweep()
     H = sh.full_matrix(); v, gh = sh.value_and_gradient()
     href = fdb200.HessianResult(xh)
     fdb200.hessian_b(href, F.rosenbrock, xh, fdb200.HessianConfig(F.rosenbrock, xh, fdb200.Chunk(8)), ctx=ctx)
     assert np.array_equal(H, href.derivs[1]) and np.array_equal(gh.cpu().numpy(), href.derivs[0]) and v.item() == href.value
 
-    if world > 1:
-        dist.barrier()
-    print(f"rank {rank}/{world}: sharded gradient / Jacobian / Hessian match the single-rank results", flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    # a second sweep reuses the arenas (pre-sweep barrier protects the previous result) and must reproduce the first
+    sg.x_t.copy_(torch.from_numpy(x)); sg.sweep(); sg.gather()
+    assert np.array_equal(sg.g_t[:n].cpu().numpy(), ref.derivs[0])
+    if exchange == "p2p":
+        # with an exchange enabled a result outside the arena is refused, not silently left un-mirrored
+        sg.xch.enable()
+        try:
+            stray = ctx.zeros(n)
+            rc = ctx.lib.fdb_gradient_chunked(ctx.h, sg.fid, sg.x_a.h, N, 0, 1, stray.h, None)
+            assert rc != 0 and b"exchange arena" in ctx.lib.fdb_last_error(ctx.h)
+        finally:
+            sg.xch.disable()
+        assert sg.xch.timeouts() == 0 and sj.xch.timeouts() == 0
+    for s in (sg, sj, st, sh):
+        s.close()
 
 
 if __name__ == "__main__":
