@@ -265,12 +265,12 @@ __global__ void build_operand_dense_kernel(const double* __restrict__ x, int64_t
     for (int kk = 0; kk < N; kk++) col[(int64_t)(kk + 1) * ldb] = (j - start == kk && kk < cs) ? 1.0 : 0.0;
 }
 // epilogue: z = A*xdual .+ b ; y = tanh.(z) (DiffRules: val = tanh(v), deriv = 1 - val^2) ; J[:, start+k] = partials(y, k)
-template <bool NS, bool SHARE>
+template <bool NS, bool SHARE, bool MIR>
 __global__ void __launch_bounds__(256) tanh_affine_epilogue_kernel(const double* __restrict__ Y, int64_t ldy, int P, const double* __restrict__ A,
                                                                   int64_t lda, const double* __restrict__ b, int64_t m, int64_t n, int N,
                                                                   int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
                                                                   double* __restrict__ J, int64_t ldJ, double* __restrict__ yout,
-                                                                  const fdb_mirrors Mr) {
+                                                                  const __grid_constant__ fdb_mirrors Mr) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t cl = blockIdx.y, c = chunk_lo + cl;
     if (r >= m) return;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) tanh_affine_epilogue_kernel(const double*
         double p;
         if (SHARE) p = Yc[ldy] + A[r + (start + kk) * lda] * 1.0;   // shared zero lane + the one seeded column of the window
         else p = Yc[(int64_t)(kk + 1) * ldy];
-        mstore_cs(Mr, J + r + (start + kk) * ldJ, mulp<NS>(p, deriv));
+        mstore_cs<MIR>(Mr, J + r + (start + kk) * ldJ, mulp<NS>(p, deriv));
     }
     if (yout && last) mstore(Mr, &yout[r], val);
 }
@@ -312,11 +312,11 @@ int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_ar
     rc = launch_gemm(ctx, A->data, lda, Bop, ldb, Y, ldy, m, n, nc * P, share ? 2 : 0, ws, used_dmma, &ngemm); if (rc) return rc;
     dim3 ge((unsigned)cdiv(m, 256), (unsigned)nc);
     if (ctx->nansafe) {
-        if (share) tanh_affine_epilogue_kernel<true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
-        else tanh_affine_epilogue_kernel<true, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
+        if (share) { if (Mr.count) tanh_affine_epilogue_kernel<true, true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<true, true, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
+        else { if (Mr.count) tanh_affine_epilogue_kernel<true, false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<true, false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
     } else {
-        if (share) tanh_affine_epilogue_kernel<false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
-        else tanh_affine_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
+        if (share) { if (Mr.count) tanh_affine_epilogue_kernel<false, true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<false, true, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
+        else { if (Mr.count) tanh_affine_epilogue_kernel<false, false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<false, false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
     }
     return finish(ctx, 2 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma)");
 }
@@ -382,8 +382,8 @@ int mlp2_dmma(fdb_ctx* ctx, const fdb_array* A1, int64_t lda1, const fdb_array* 
     // second layer: dense partials -> DMMA contraction of A2 against all hidden planes of all chunks
     rc = launch_gemm(ctx, A2->data, lda2, H1, ldh, Z2, ldz, m, h, nc * P, 0, ws, nullptr, &n2); if (rc) return rc;
     dim3 ge((unsigned)cdiv(m, 256), (unsigned)nc);
-    if (ctx->nansafe) tanh_affine_epilogue_kernel<true, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
-    else tanh_affine_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr);
+    if (ctx->nansafe) { if (Mr.count) tanh_affine_epilogue_kernel<true, false, true><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<true, false, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
+    else { if (Mr.count) tanh_affine_epilogue_kernel<false, false, true><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<false, false, false><<<ge, 256, 0, ctx->stream>>>(Z2, ldz, P, A2->data, lda2, b2->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
     return finish(ctx, 3 + n1 + n2, "fdb_jacobian_mlp2_chunked");
 }
 

@@ -52,6 +52,31 @@ __global__ void exchange_barrier_kernel(PeerFlags P, int rank, int world, unsign
     }
 }
 
+// ---- store-bandwidth probe: the roofline denominator of the fused exchange -------------------------------
+// Every rank pushes the first n doubles of its arena into all peers at once.  VARIANT 0: element-major, each
+// thread repeats its 8-byte store for every peer in the order of `d` (what mstore does); 1: the same with
+// 16-byte stores; 2: peer-major, blockIdx.y picks the peer and the block streams a contiguous range to it.
+template <int VARIANT>
+__global__ void __launch_bounds__(256) exchange_probe_kernel(const double* __restrict__ src, int64_t n, const fdb_mirrors M) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (VARIANT == 0) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const double v = src[i];
+            for (int r = 0; r < M.count; r++) *reinterpret_cast<double*>(reinterpret_cast<char*>(const_cast<double*>(src + i)) + M.delta[r]) = v;
+        }
+    } else if (VARIANT == 1) {
+        for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i + 1 < n; i += stride * 2) {
+            const double2 v = *reinterpret_cast<const double2*>(src + i);
+            for (int r = 0; r < M.count; r++) *reinterpret_cast<double2*>(reinterpret_cast<char*>(const_cast<double*>(src + i)) + M.delta[r]) = v;
+        }
+    } else {
+        const int r = blockIdx.y;
+        char* dst = reinterpret_cast<char*>(const_cast<double*>(src)) + M.delta[r];
+        for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i + 1 < n; i += stride * 2)
+            *reinterpret_cast<double2*>(dst + i * 8) = *reinterpret_cast<const double2*>(src + i);
+    }
+}
+
 int mirrors_for(fdb_ctx* ctx, fdb_mirrors* m, const fdb_array* const* outs, int nouts, const char* what) {
     *m = fdb_mirrors();
     fdb_exchange* x = ctx->xch;
@@ -63,8 +88,11 @@ int mirrors_for(fdb_ctx* ctx, fdb_mirrors* m, const fdb_array* const* outs, int 
             return fail(ctx, FDB_ERR_BADARG, "%s: with a peer exchange enabled every result array must be a view of the exchange arena "
                                              "(fdb_exchange_view); output %d is not", what, i);
     }
-    for (int r = 0; r < x->world; r++)
-        if (r != x->rank) m->delta[m->count++] = (long long)(x->peer[r] - x->base);
+    // rank r visits its peers as r+1, r+2, ...: at any instant the ranks address different destinations
+    for (int k = 1; k < x->world; k++) {
+        const int r = (x->rank + k) % x->world;
+        m->delta[m->count++] = (long long)(x->peer[r] - x->base);
+    }
     return FDB_OK;
 }
 
@@ -149,6 +177,40 @@ extern "C" int fdb_exchange_barrier(fdb_exchange* x) {
     x->epoch++;
     exchange_barrier_kernel<<<1, 32, 0, ctx->stream>>>(P, x->rank, x->world, x->epoch, 20ull * 1000000000ull);
     return finish(ctx, 1, "fdb_exchange_barrier");
+}
+
+extern "C" int fdb_exchange_measure_store_bw(fdb_exchange* x, int64_t n_doubles, int variant, int rotate, double* gb_per_s) {
+    if (!x || !gb_per_s) return FDB_ERR_BADARG;
+    fdb_ctx* ctx = x->ctx;
+    if (!x->connected || x->world < 2) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_measure_store_bw: needs a connected exchange with peers");
+    if (n_doubles < 2 || (size_t)n_doubles * sizeof(double) > x->data_bytes || variant < 0 || variant > 2)
+        return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_measure_store_bw: bad size or variant");
+    fdb_mirrors M;
+    for (int k = 1; k < x->world; k++) {
+        const int r = rotate ? (x->rank + k) % x->world : (k - 1 < x->rank ? k - 1 : k);
+        M.delta[M.count++] = (long long)(x->peer[r] - x->base);
+    }
+    const bool was_async = ctx->async; ctx->async = true;
+    cudaEvent_t e0, e1;
+    FDB_CUDA(ctx, cudaEventCreate(&e0)); FDB_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    const double* src = reinterpret_cast<const double*>(x->base);
+    for (int rep = 0; rep < 4; rep++) {
+        int rc = fdb_exchange_barrier(x); if (rc) { ctx->async = was_async; return rc; }    // all ranks push at the same time
+        cudaEventRecord(e0, ctx->stream);
+        if (variant == 0) exchange_probe_kernel<0><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(src, n_doubles, M);
+        else if (variant == 1) exchange_probe_kernel<1><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(src, n_doubles, M);
+        else exchange_probe_kernel<2><<<dim3(ctx->sm_count * 2, M.count), 256, 0, ctx->stream>>>(src, n_doubles, M);
+        cudaEventRecord(e1, ctx->stream);
+        FDB_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+        ctx->launches++;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->async = was_async;
+    *gb_per_s = (double)n_doubles * 8.0 * M.count / (best * 1e-3) / 1e9;      // bytes this rank sent per second
+    return FDB_OK;
 }
 
 extern "C" int fdb_exchange_timeouts(fdb_exchange* x, int64_t* count) {

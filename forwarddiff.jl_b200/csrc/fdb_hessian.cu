@@ -50,7 +50,7 @@ template <class F, int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) hessian_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t outer_lo,
                                                                 int64_t nchunks_total, int lastchunksize, double* __restrict__ H,
                                                                 int64_t ldH, double* __restrict__ grad, double* __restrict__ value_out,
-                                                                const fdb_mirrors M) {
+                                                                const __grid_constant__ fdb_mirrors M) {
     typedef Dual<double, N, NS> DI;
     typedef Dual<DI, 1, NS> DG;
     typedef Dual<Dual<double, 1, NS>, 1, NS> DF;

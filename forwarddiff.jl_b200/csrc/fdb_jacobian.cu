@@ -9,6 +9,8 @@
 // block J[:, start .. start+chunksize) of the column-major result (fused extraction,
 // coalesced along rows, streaming stores).  Bound: the 8*m*n bytes of J that must be
 // written (HBM), DESIGN.md.
+#include <stdlib.h>
+
 #include "fdb_internal.h"
 #include "fdb_mirror.cuh"
 #include "fdb_targets.cuh"
@@ -37,18 +39,23 @@ FDB_DEV void brusselator_rows(const L& X, int64_t i, int64_t M, double al, D& du
     dv = (3.0 * u - pow2(u) * v) + al * lapv;
 }
 
-template <int N, bool NS, int THREADS, bool SHARE>
+template <int N, bool NS, int THREADS, bool SHARE, bool MIR>
 __global__ void __launch_bounds__(THREADS) brusselator_jacobian_kernel(const double* __restrict__ x, int64_t n, double alpha,
                                                                        int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
                                                                        double* __restrict__ J, int64_t ldJ, double* __restrict__ y,
-                                                                       const fdb_mirrors Mr) {
+                                                                       const unsigned nrb, const unsigned nch, const bool rowfast,
+                                                                       const __grid_constant__ fdb_mirrors Mr) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t M = n / 2;
-    const int64_t c = chunk_lo + blockIdx.x;
+    // 1-D grid of nch chunks x nrb row blocks.  rowfast: blocks in flight fill a few column groups top to bottom, so
+    // the write stream to the peers of an exchange walks memory in order (NVLink stores striding over the whole
+    // matrix ran at a third of the link rate); otherwise chunk fastest, which spreads local HBM writes best.
+    const int64_t c = chunk_lo + (rowfast ? blockIdx.x / nrb : blockIdx.x % nch);
+    const unsigned rb = rowfast ? blockIdx.x % nrb : blockIdx.x / nch;
     int64_t start; int chunksize;
     chunk_window(c, nchunks_total, lastchunksize, n, N, start, chunksize);
-    const int64_t i = (int64_t)blockIdx.y * THREADS + threadIdx.x;       // grid point
+    const int64_t i = (int64_t)rb * THREADS + threadIdx.x;               // grid point
     // warp-uniform: do rows w0..w0+31 read any seeded position?  they read u[w0-1..w0+32] and v[M + same]
     const int64_t w0 = i - (threadIdx.x & 31);
     const int64_t wend = start + chunksize;                               // window [start, wend)
@@ -63,14 +70,14 @@ __global__ void __launch_bounds__(THREADS) brusselator_jacobian_kernel(const dou
         brusselator_rows(ZeroLoader<1, NS>{x}, i, M, alpha, du, dv);
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < chunksize) { mstore_cs(Mr, Ju + k * ldJ, du.p[0]); mstore_cs(Mr, Jv + k * ldJ, dv.p[0]); }
+            if (k < chunksize) { mstore_cs<MIR>(Mr, Ju + k * ldJ, du.p[0]); mstore_cs<MIR>(Mr, Jv + k * ldJ, dv.p[0]); }
         if (write_y) { mstore(Mr, &y[i], du.v); mstore(Mr, &y[M + i], dv.v); }
     } else {
         D du, dv;
         brusselator_rows(SeedLoader<N, NS>{x, start, chunksize}, i, M, alpha, du, dv);
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < chunksize) { mstore_cs(Mr, Ju + k * ldJ, du.p[k]); mstore_cs(Mr, Jv + k * ldJ, dv.p[k]); }   // extract_jacobian_chunk!, jacobian.jl:109-118
+            if (k < chunksize) { mstore_cs<MIR>(Mr, Ju + k * ldJ, du.p[k]); mstore_cs<MIR>(Mr, Jv + k * ldJ, dv.p[k]); }   // extract_jacobian_chunk!, jacobian.jl:109-118
         if (write_y) { mstore(Mr, &y[i], du.v); mstore(Mr, &y[M + i], dv.v); }
     }
 }
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(THREADS) brusselator_jacobian_kernel(const dou
 // ---- test/JacobianTest.jl:23-31 target (n = 3, m = 4): one thread per chunk -------------------
 template <int N, bool NS>
 __global__ void jactest_jacobian_kernel(const double* __restrict__ x, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
-                                        double* __restrict__ J, int64_t ldJ, double* __restrict__ yout, const fdb_mirrors Mr) {
+                                        double* __restrict__ J, int64_t ldJ, double* __restrict__ yout, const __grid_constant__ fdb_mirrors Mr) {
     typedef Dual<double, N, NS> D;
     const int64_t c = chunk_lo + blockIdx.x;
     int64_t start; int chunksize;
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(THREADS) tanh_affine_jacobian_kernel(const dou
                                                                        const double* __restrict__ x, int64_t n, int64_t m,
                                                                        int64_t chunk_lo, int64_t chunk_hi, int64_t nchunks_total,
                                                                        int lastchunksize, double* __restrict__ J, int64_t ldJ,
-                                                                       double* __restrict__ yout, const fdb_mirrors Mr) {
+                                                                       double* __restrict__ yout, const __grid_constant__ fdb_mirrors Mr) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t r = (int64_t)blockIdx.y * THREADS + threadIdx.x;
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(THREADS) tanh_affine_jacobian_kernel(const dou
         D yv = tanh_v(z + bi);
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < csz[q]) mstore_cs(Mr, J + r + (start[q] + k) * ldJ, yv.p[k]);
+            if (k < csz[q]) mstore_cs<true>(Mr, J + r + (start[q] + k) * ldJ, yv.p[k]);
         if (yout && c == nchunks_total - 1) mstore(Mr, &yout[r], yv.v);
     }
 }
@@ -188,14 +195,17 @@ extern "C" int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, in
     switch (fn) {
         case FDB_JFN_BRUSSELATOR: {
             if (n % 2 != 0 || m != n) return fail(ctx, FDB_ERR_SHAPE, "brusselator needs x = [u; v] (even length) and m == n");
-            dim3 grid((unsigned)(chunk_hi - chunk_lo), (unsigned)cdiv(n / 2, T));
-            if (ctx->lane_sharing) {
-                FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-                    (brusselator_jacobian_kernel<NN, NS, T, true><<<grid, T, 0, ctx->stream>>>(x->data, n, alpha, chunk_lo, nchunks, lcs, J->data, ldJ, yp, Mr))));
-            } else {
-                FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-                    (brusselator_jacobian_kernel<NN, NS, T, false><<<grid, T, 0, ctx->stream>>>(x->data, n, alpha, chunk_lo, nchunks, lcs, J->data, ldJ, yp, Mr))));
-            }
+            const unsigned nrb = (unsigned)cdiv(n / 2, T);
+            if ((chunk_hi - chunk_lo) * (int64_t)nrb > 0x7fffffffLL) return fail(ctx, FDB_ERR_UNSUPPORTED, "brusselator: chunk range too large for one launch");
+            const unsigned nch = (unsigned)(chunk_hi - chunk_lo);
+            const unsigned grid = nch * nrb;
+            const char* env = getenv("FDB_JAC_ROWFAST");               // experiments only
+            const bool rowfast = env ? atoi(env) != 0 : Mr.count > 0;
+#define FDB_BRUSS(SH, MI) FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe, \
+                (brusselator_jacobian_kernel<NN, NS, T, SH, MI><<<grid, T, 0, ctx->stream>>>(x->data, n, alpha, chunk_lo, nchunks, lcs, J->data, ldJ, yp, nrb, nch, rowfast, Mr))))
+            if (ctx->lane_sharing) { if (Mr.count) { FDB_BRUSS(true, true); } else { FDB_BRUSS(true, false); } }
+            else { if (Mr.count) { FDB_BRUSS(false, true); } else { FDB_BRUSS(false, false); } }
+#undef FDB_BRUSS
             return finish(ctx, 1, "fdb_jacobian_chunked(brusselator)");
         }
         case FDB_JFN_JACTEST: {

@@ -7,18 +7,22 @@
 
 namespace fdb {
 
+// The mirrors travel as a __grid_constant__ kernel parameter, so delta[r] is an indexed constant-bank read
+// (no local-memory copy); the peer loops are not unrolled (they wait on NVLink, not on issue).
 __device__ __forceinline__ void mstore(const fdb_mirrors& M, double* p, double v) {
     *p = v;
+#pragma unroll 1
     for (int r = 0; r < M.count; r++) *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + M.delta[r]) = v;
 }
-// streaming (evict-first) local store for write-once result matrices
+// streaming (evict-first) local store for write-once result matrices.  MIR is a template flag in the
+// write-bound Jacobian kernels so that the single-GPU instantiation is exactly the plain store.
+template <bool MIR>
 __device__ __forceinline__ void mstore_cs(const fdb_mirrors& M, double* p, double v) {
     __stcs(p, v);
-    for (int r = 0; r < M.count; r++) *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + M.delta[r]) = v;
-}
-__device__ __forceinline__ void mstore2(const fdb_mirrors& M, double* p, double2 v) {
-    *reinterpret_cast<double2*>(p) = v;
-    for (int r = 0; r < M.count; r++) *reinterpret_cast<double2*>(reinterpret_cast<char*>(p) + M.delta[r]) = v;
+    if (MIR) {
+#pragma unroll 1
+        for (int r = 0; r < M.count; r++) *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + M.delta[r]) = v;
+    }
 }
 
 }  // namespace fdb

@@ -34,7 +34,7 @@ template <int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_constant__ Program P, const bool SHARE, const double* __restrict__ x, int64_t n,
                                                                    int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
                                                                    double* __restrict__ grad, double* __restrict__ value_out,
-                                                                   const fdb_mirrors M) {
+                                                                   const __grid_constant__ fdb_mirrors M) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t c = chunk_lo + blockIdx.x;

@@ -94,7 +94,7 @@ template <int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) program_hessian_kernel(const __grid_constant__ Program P, const double* __restrict__ x, int64_t n,
                                                                   int64_t outer_lo, int64_t nchunks_total, int lastchunksize,
                                                                   double* __restrict__ H, int64_t ldH, double* __restrict__ grad,
-                                                                  double* __restrict__ value_out, const fdb_mirrors M) {
+                                                                  double* __restrict__ value_out, const __grid_constant__ fdb_mirrors M) {
     typedef Dual<double, N, NS> DI;
     typedef Dual<DI, 1, NS> DG;
     typedef Dual<Dual<double, 1, NS>, 1, NS> DF;

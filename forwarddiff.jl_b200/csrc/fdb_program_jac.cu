@@ -6,18 +6,20 @@ namespace fdb {
 
 // elementwise / stencil array targets: y[i] = program(x[i .. i+halo]) for i in [0, n - halo);
 // J[i, start+k] = partials(y[i], k) -- the f(x)-form Jacobian chunk sweep (src/jacobian.jl:169-216)
-template <int N, bool NS, int THREADS>
+template <int N, bool NS, int THREADS, bool MIR>
 __global__ void __launch_bounds__(THREADS) program_jacobian_kernel(const __grid_constant__ Program P, const bool SHARE, const double* __restrict__ x, int64_t n,
                                                                    int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
                                                                    double* __restrict__ J, int64_t ldJ, double* __restrict__ yout,
-                                                                   const fdb_mirrors M) {
+                                                                   const unsigned nrb, const unsigned nch, const bool rowfast,
+                                                                   const __grid_constant__ fdb_mirrors M) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
-    const int64_t c = chunk_lo + blockIdx.x;
+    // 1-D grid; row block fastest when the stores also go to peers (see brusselator_jacobian_kernel)
+    const int64_t c = chunk_lo + (rowfast ? blockIdx.x / nrb : blockIdx.x % nch);
     const bool last = (c == nchunks_total - 1);
     const int chunksize = last ? lastchunksize : N;
     const int64_t start = last ? (n - lastchunksize) : c * N;
-    const int64_t i = (int64_t)blockIdx.y * THREADS + threadIdx.x;
+    const int64_t i = (int64_t)(rowfast ? blockIdx.x % nrb : blockIdx.x / nch) * THREADS + threadIdx.x;
     const int64_t m = n - P.halo;
     const int64_t w0 = i - (threadIdx.x & 31);
     const bool far = SHARE && ((w0 + 31 + P.halo < start) || (w0 >= start + chunksize));
@@ -27,7 +29,7 @@ __global__ void __launch_bounds__(THREADS) program_jacobian_kernel(const __grid_
         D1 acc1[PG_MAXK];
         pg_run_shared1<NS, THREADS>(P.term, P.n_term, P.consts, ZeroLoader<1, NS>{x}, i, rf1, acc1);
         D1 y; y.v = rf1[P.result_reg][0][threadIdx.x]; y.p[0] = rf1[P.result_reg][1][threadIdx.x];
-        for (int k = 0; k < chunksize; k++) mstore_cs(M, J + i + (start + k) * ldJ, y.p[0]);
+        for (int k = 0; k < chunksize; k++) mstore_cs<MIR>(M, J + i + (start + k) * ldJ, y.p[0]);
         if (yout && last) mstore(M, &yout[i], y.v);
     } else {
         D R[PG_MAXR]; D acc[1];
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(THREADS) program_jacobian_kernel(const __grid_
         const D y = R[P.result_reg];
 #pragma unroll
         for (int k = 0; k < N; k++)
-            if (k < chunksize) mstore_cs(M, J + i + (start + k) * ldJ, y.p[k]);
+            if (k < chunksize) mstore_cs<MIR>(M, J + i + (start + k) * ldJ, y.p[k]);
         if (yout && last) mstore(M, &yout[i], y.v);
     }
 }
@@ -63,12 +65,20 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
     if (chunk_lo < 0 || chunk_lo > chunk_hi || chunk_hi > nchunks) return fail(ctx, FDB_ERR_BADARG, "bad chunk range");
     if (chunk_lo == chunk_hi) return FDB_OK;
     constexpr int T = 128;
-    dim3 grid((unsigned)(chunk_hi - chunk_lo), (unsigned)cdiv(m, T));
+    const unsigned nrb = (unsigned)cdiv(m, T);
+    if ((chunk_hi - chunk_lo) * (int64_t)nrb > 0x7fffffffLL) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Jacobian: chunk range too large for one launch");
+    const unsigned nch = (unsigned)(chunk_hi - chunk_lo);
+    const unsigned grid = nch * nrb;
     double* yp = y ? y->data : nullptr;
     fdb_mirrors M;
     const fdb_array* outs[2] = {J, y};
     rc = mirrors_for(ctx, &M, outs, 2, "fdb_program_jacobian_chunked"); if (rc) return rc;
-    FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
-        (program_jacobian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, J->data, ldJ, yp, M))));
+    if (M.count) {
+        FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
+            (program_jacobian_kernel<NN, NS, T, true><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, J->data, ldJ, yp, nrb, nch, true, M))));
+    } else {
+        FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
+            (program_jacobian_kernel<NN, NS, T, false><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, J->data, ldJ, yp, nrb, nch, false, M))));
+    }
     return finish(ctx, 1, "fdb_program_jacobian_chunked");
 }

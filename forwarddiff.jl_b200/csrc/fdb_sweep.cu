@@ -33,7 +33,7 @@ template <class F, int N, bool NS, int THREADS, bool SHARE>
 __global__ void __launch_bounds__(THREADS) gradient_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo,
                                                                  int64_t nchunks_total, int lastchunksize,
                                                                  double* __restrict__ grad, double* __restrict__ value_out,
-                                                                 const fdb_mirrors M) {
+                                                                 const __grid_constant__ fdb_mirrors M) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
     const int64_t c = chunk_lo + blockIdx.x;                       // 0-based chunk number

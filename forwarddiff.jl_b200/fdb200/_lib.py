@@ -130,6 +130,7 @@ SIGNATURES = {
     "fdb_exchange_barrier": (C.c_int, [C.c_void_p]),
     "fdb_exchange_timeouts": (C.c_int, [C.c_void_p, C.POINTER(i64)]),
     "fdb_exchange_destroy": (C.c_int, [C.c_void_p]),
+    "fdb_exchange_measure_store_bw": (C.c_int, [C.c_void_p, i64, C.c_int, C.c_int, _dp]),
     "fdb_measure_fp64_peak": (C.c_int, [c_ctx, _dp, _dp]),
 }
 IPC_HANDLE_BYTES = 64

@@ -296,6 +296,10 @@ int fdb_exchange_barrier(fdb_exchange* x);
 /* number of barrier waits that gave up after the timeout (a peer never arrived); synchronises the stream */
 int fdb_exchange_timeouts(fdb_exchange* x, int64_t* count);
 int fdb_exchange_destroy(fdb_exchange* x);
+/* measurement helper (collective: every rank calls it): all ranks push the first n doubles of their arena into every
+ * peer at once; returns this rank's outgoing GB/s.  variant 0: 8-byte stores repeated per peer (what the drivers do),
+ * 1: 16-byte stores, 2: one peer per thread block.  rotate != 0: rank r visits peers r+1, r+2, ... */
+int fdb_exchange_measure_store_bw(fdb_exchange* x, int64_t n_doubles, int variant, int rotate, double* gb_per_s);
 
 /* ---- measurement helpers (bench.py) ---------------------------------------- */
 /* FP64 instruction-issue peak: a register-only chain of independent DMUL/DADD pairs;
