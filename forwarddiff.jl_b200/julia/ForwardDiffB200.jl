@@ -135,7 +135,7 @@ function chunk_mode_gradient!(result::B200Array{Float64}, f::F, x::B200Array{Flo
     value = B200Array{Float64}(undef, 1; ctx = x.ctx)
     check(x.ctx.h, ccall((:fdb_gradient_chunked, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
                          x.ctx.h, id, x.h, N, plan[][8], plan[][9], result.h, value.h))
-    return result                          # multi-rank: followed by the NCCL all-gather of the slices (INTEGRATION.md)
+    return result                          # multi-rank: see sharded_gradient! below (peer-memory exchange) or all-gather the slices
 end
 # Host Vectors: ForwardDiff.gradient!(out::Vector, f, x::Vector, cfg) for a catalogue f -> fdb_gradient_host
 function gradient_host!(out::Vector{Float64}, f, x::Vector{Float64}, ::Chunk{N}; ctx = context()) where {N}
@@ -196,5 +196,44 @@ seed_structured!(d::B200Array, x::B200Array, s::Symbol, rows, index, chunksize) 
 extract_gradient_chunk_structured!(res::B200Array, y::B200Array, s::Symbol, rows, index, chunksize) =
     check(res.ctx.h, ccall((:fdb_extract_gradient_chunk_structured, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Int64, Int64),
                            res.ctx.h, res.h, y.h, STRUCTURE[s], rows, index, chunksize))
+
+# ---- multi-GPU (one Julia process per GPU, e.g. under MPI): results completed on every rank by the peer-memory exchange ----
+# `allgather64(handle)::Vector{UInt8}` is the host's transport for the 64-byte IPC handles (e.g. MPI.Allgather).
+mutable struct PeerExchange
+    h::Ptr{Cvoid}
+    ctx::Context
+end
+function PeerExchange(ctx::Context, ndoubles::Integer, rank::Integer, world::Integer, allgather64)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx.h, ccall((:fdb_exchange_create, libfdb200), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Ref{Ptr{Cvoid}}), ctx.h, ndoubles, rank, world, r))
+    mine = Vector{UInt8}(undef, 64)
+    check(ctx.h, ccall((:fdb_exchange_handle, libfdb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}), r[], mine))
+    all = allgather64(mine)                                                        # world * 64 bytes, rank order
+    check(ctx.h, ccall((:fdb_exchange_connect, libfdb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}), r[], all))
+    return PeerExchange(r[], ctx)
+end
+function arena_view(x::PeerExchange, offset::Integer, n::Integer, ld::Integer = n)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(x.ctx.h, ccall((:fdb_exchange_view, libfdb200), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ref{Ptr{Cvoid}}), x.h, offset, n, ld, r))
+    return B200Array{Float64}(r[], n, x.ctx)
+end
+barrier(x::PeerExchange) = check(x.ctx.h, ccall((:fdb_exchange_barrier, libfdb200), Cint, (Ptr{Cvoid},), x.h))
+# chunk_mode_gradient! over this rank's chunk range; `result` and `value` are arena views, so on return (after the
+# second barrier) every rank holds the whole gradient (src/gradient.jl:141-155 across ranks)
+function sharded_gradient!(x::PeerExchange, result::B200Array{Float64}, value::B200Array{Float64}, fn_id, xs::B200Array{Float64}, ::Chunk{N},
+                           rank, world) where {N}
+    plan = Ref{NTuple{11,Int64}}()             # fdb_chunk_plan: fields 8, 9 = chunk_lo, chunk_hi
+    ccall((:fdb_plan_chunks, libfdb200), Cint, (Int64, Cint, Cint, Cint, Ptr{Cvoid}), length(xs), N, rank, world, plan)
+    barrier(x)                                                                     # peers have consumed the previous result
+    check(x.ctx.h, ccall((:fdb_exchange_enable, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.h, x.h))
+    try
+        check(x.ctx.h, ccall((:fdb_gradient_chunked, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                             x.ctx.h, fn_id, xs.h, N, plan[][8], plan[][9], result.h, value.h))
+    finally
+        ccall((:fdb_exchange_enable, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.h, C_NULL)
+    end
+    barrier(x)                                                                     # every peer's stores have landed here
+    return result
+end
 
 end # module
