@@ -368,16 +368,25 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
     ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["ackley"], x.h, CHUNK, 0, -1, g.h, v.h)), reps=2)
     out["ackley_gradient_c2"] = {"evals_per_s": 1e3 / ms, "ms": ms}
     # the same Rosenbrock written as an ordinary callable on the device Dual array (broadcast + sum), flattened into
-    # an op-program and interpreted per thread: what an arbitrary user f costs on the batched sweep
+    # an op-program: what an arbitrary user f costs on the batched sweep -- through the kernel specialised for it at
+    # run time (NVRTC instantiation of the sweep kernel template for the generated functor; the first call compiles,
+    # the timed calls hit the cache) and through the per-thread interpreter
     from fdb200 import trace
     from fdb200.api import _i32p
     prog = trace.trace_scalar(F.rosenbrock_generic, N_ELEMS)
     cp = prog.consts.ctypes.data_as(C_DP)
-    ms = t(lambda: ctx.check(lib.fdb_program_gradient_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi), cp,
-                                                              prog.consts.size, prog.n_acc, prog.halo, prog.result_reg, x.h, CHUNK, 0, 8192,
-                                                              g.h, v.h)), reps=2)
-    out["rosenbrock_gradient_generic_callable_op_program"] = {"evals_per_s": 1.0 / (ms * 1e-3 * 83334 / 8192), "timed": "8192 of 83334 chunks, scaled",
-                                                              "instructions": int(len(prog.term))}
+    run_prog = lambda hi: ctx.check(lib.fdb_program_gradient_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi), cp,
+                                                                     prog.consts.size, prog.n_acc, prog.halo, prog.result_reg, x.h, CHUNK, 0, hi,
+                                                                     g.h, v.h))
+    t0 = time.perf_counter(); run_prog(1); ctx.sync(); compile_s = time.perf_counter() - t0
+    ms = t(lambda: run_prog(-1), reps=2)
+    st = ctx.jit_stats()
+    out["rosenbrock_gradient_generic_callable_specialised"] = {"evals_per_s": 1e3 / ms, "ms": ms, "first_call_s": compile_s,
+                                                               "instructions": int(len(prog.term)), "jit": {k: st[k] for k in ("compiled", "cache_hits", "failures")}}
+    ctx.set_jit(False)
+    ms = t(lambda: run_prog(8192), reps=2)
+    ctx.set_jit(True)
+    out["rosenbrock_gradient_generic_callable_interpreted"] = {"evals_per_s": 1.0 / (ms * 1e-3 * 83334 / 8192), "timed": "8192 of 83334 chunks, scaled"}
     # C1: n = 10 000, Chunk{10} (the reference's published 0.2825 s case, docs/src/user/advanced.md:70-72)
     x1 = ctx.array(rng.random(10_000)); g1 = ctx.zeros(10_000)
     ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["rosenbrock"], x1.h, 10, 0, -1, g1.h, v.h)), reps=5)

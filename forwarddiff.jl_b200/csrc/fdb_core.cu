@@ -200,6 +200,7 @@ extern "C" int fdb_shutdown(fdb_ctx* ctx) {
     if (!ctx) return FDB_ERR_BADARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    jit_release(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->counter) cudaFree(ctx->counter);

@@ -14,8 +14,13 @@
 // The value type V is `double` or, for Hessians, another Dual<double,N,NS>
 // (Dual{T,Dual{T,V,N},N} with one tag on both levels, src/config.jl:198-201).
 #pragma once
+#ifndef __CUDACC_RTC__     // NVRTC (fdb_jit.cu) has the device math built in and no host headers
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
+#else
+typedef long long int64_t;
+#endif
 
 namespace fdb {
 

@@ -1,0 +1,130 @@
+// fdb_hessian_kernel.cuh -- the batched nested-dual Hessian kernel (see fdb_hessian.cu), as a header so that the
+// run-time specialiser (fdb_jit.cu) instantiates the same code for a user function's generated functor.
+#pragma once
+#include "fdb_mirror.cuh"
+#include "fdb_targets.cuh"
+
+namespace fdb {
+
+// far-from-both-windows loader: Dual{Dual{1},1} with all partials zero
+template <bool NS> struct FFLoader {
+    typedef Dual<Dual<double, 1, NS>, 1, NS> DO;
+    const double* x;
+    FDB_DEV DO operator()(int64_t i) const {
+        DO d; d.v.v = x[i]; d.v.p[0] = 0.0; d.p[0].v = 0.0; d.p[0].p[0] = 0.0; return d;
+    }
+};
+// general loader for inner lane k: value = outer-seeded Dual{N}; the single inner partial lane
+// carries one(Dual{N}) iff pos is slot k of the inner window (src/apiutils.jl:125-143 with
+// Partials{N,Dual{T,V,N}} seeds, src/config.jl:225-226)
+template <int N, bool NS> struct NearLoader {
+    typedef Dual<double, N, NS> DI;
+    typedef Dual<DI, 1, NS> DO;
+    const double* x; int64_t ostart; int ocs; int64_t istart; int ics; int k;
+    FDB_DEV DO operator()(int64_t pos) const {
+        DO d; d.v = seeded<N, NS>(x[pos], pos, ostart, ocs);
+        const bool hot = (pos - istart == k) && (k < ics);
+        d.p[0].v = hot ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++) d.p[0].p[j] = 0.0;
+        return d;
+    }
+};
+
+template <class F, int N, bool NS, int THREADS>
+FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t outer_lo,
+                                                                int64_t nchunks_total, int lastchunksize, double* __restrict__ H,
+                                                                int64_t ldH, double* __restrict__ grad, double* __restrict__ value_out,
+                                                                const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> DI;
+    typedef Dual<DI, 1, NS> DG;
+    typedef Dual<Dual<double, 1, NS>, 1, NS> DF;
+    constexpr int MAXNEAR = 2 * (N + F::HALO);
+    __shared__ double s_p[MAXNEAR][N][N + 1];   // per near term, per inner lane k: partials(y,k) as Dual{N}
+    __shared__ double s_v[MAXNEAR][N + 1];      // per near term: value(y) as Dual{N}
+    __shared__ double s_ff[4];
+    __shared__ double s_red[THREADS / 32][4];
+
+    const int64_t ci = blockIdx.x, co = outer_lo + blockIdx.y;
+    const bool ilast = (ci == nchunks_total - 1), olast = (co == nchunks_total - 1);
+    const int ics = ilast ? lastchunksize : N, ocs = olast ? lastchunksize : N;
+    const int64_t istart = ilast ? n - lastchunksize : ci * N;
+    const int64_t ostart = olast ? n - lastchunksize : co * N;
+    const int64_t nt = F::nterms(n);
+
+    // near-term ranges (terms reading a seeded position): A for the inner window, B for the outer
+    int64_t a0 = istart - F::HALO, a1 = istart + ics, b0 = ostart - F::HALO, b1 = ostart + ocs;
+    if (a0 < 0) a0 = 0; if (b0 < 0) b0 = 0; if (a1 > nt) a1 = nt; if (b1 > nt) b1 = nt;
+    if (a1 < a0) a1 = a0; if (b1 < b0) b1 = b0;
+    if (b0 <= a1 && a0 <= b1) { a0 = a0 < b0 ? a0 : b0; a1 = a1 > b1 ? a1 : b1; b0 = b1 = a1; }   // merge overlapping ranges
+    const int na = (int)(a1 - a0), nb = (int)(b1 - b0), nnear = na + nb;
+
+    // ---- phase 1: terms far from both windows, four shared lanes --------------------------------
+    DF accff[1]; accff[0].v.v = 0.0; accff[0].v.p[0] = 0.0; accff[0].p[0].v = 0.0; accff[0].p[0].p[0] = 0.0;
+    FFLoader<NS> xf{x};
+    for (int64_t i = threadIdx.x; i < nt; i += THREADS) {
+        const bool near = (i >= a0 && i < a1) || (i >= b0 && i < b1);
+        if (!near) F::term(xf, i, n, accff);
+    }
+    {
+        double r[4] = {accff[0].v.v, accff[0].v.p[0], accff[0].p[0].v, accff[0].p[0].p[0]};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) r[q] = r[q] + shfl_down_d(r[q], off);
+            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][q] = r[q];
+        }
+    }
+    // ---- phase 2: near terms, one work item per (term, inner lane k) ------------------------------
+    for (int w = threadIdx.x; w < nnear * N; w += THREADS) {
+        const int t = w / N, k = w - t * N;
+        const int64_t i = t < na ? a0 + t : b0 + (t - na);
+        NearLoader<N, NS> xn{x, ostart, ocs, istart, ics, k};
+        DG acc[1];
+        acc[0].v.v = 0.0; acc[0].p[0].v = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++) { acc[0].v.p[j] = 0.0; acc[0].p[0].p[j] = 0.0; }
+        F::term(xn, i, n, acc);
+        s_p[t][k][0] = acc[0].p[0].v;
+#pragma unroll
+        for (int j = 0; j < N; j++) s_p[t][k][j + 1] = acc[0].p[0].p[j];
+        if (k == 0) {
+            s_v[t][0] = acc[0].v.v;
+#pragma unroll
+            for (int j = 0; j < N; j++) s_v[t][j + 1] = acc[0].v.p[j];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+        for (int wq = 0; wq < THREADS / 32; wq++) s = s + s_red[wq][threadIdx.x];
+        s_ff[threadIdx.x] = s;
+    }
+    __syncthreads();
+    // ---- phase 3: fold and store (fused extract_gradient_chunk! + extract_jacobian_chunk!) --------
+    // lanes: s_ff[0] = value.value, [1] = value.outer-partial, [2] = inner-partial.value, [3] = inner-partial.outer-partial
+    for (int e = threadIdx.x; e < N * (N + 1); e += THREADS) {
+        const int k = e / (N + 1), j = e - k * (N + 1);     // j = 0: value of partials(y,k); j >= 1: outer partial j
+        if (k >= ics) continue;
+        double s = 0.0;
+        for (int t = 0; t < nnear; t++) s = s + s_p[t][k][j];
+        s = s + (j == 0 ? s_ff[2] : s_ff[3]);
+        if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
+        else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
+    }
+    if (threadIdx.x == 0 && olast && ilast && value_out) {
+        double s = 0.0;
+        for (int t = 0; t < nnear; t++) s = s + s_v[t][0];
+        mstore(M, value_out, s + s_ff[0]);
+    }
+}
+
+template <class F, int N, bool NS, int THREADS>
+__global__ void __launch_bounds__(THREADS) hessian_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t outer_lo,
+                                                                int64_t nchunks_total, int lastchunksize, double* __restrict__ H,
+                                                                int64_t ldH, double* __restrict__ grad, double* __restrict__ value_out,
+                                                                const __grid_constant__ fdb_mirrors M) {
+    hessian_sweep_body<F, N, NS, THREADS>(x, n, outer_lo, nchunks_total, lastchunksize, H, ldH, grad, value_out, M);
+}
+
+}  // namespace fdb

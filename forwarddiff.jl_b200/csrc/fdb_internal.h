@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/fdb200.h"
+#include "fdb_mirror.cuh"
 
 struct fdb_ctx {
     int device = 0;
@@ -29,14 +30,9 @@ struct fdb_ctx {
     double* pinned = nullptr;
     size_t pinned_bytes = 0;
     struct fdb_exchange* xch = nullptr;   // enabled peer-memory result exchange (fdb_exchange.cu), or null
+    struct fdb_jit_cache* jit = nullptr;  // kernels specialised at run time for op-programs (fdb_jit.cu)
+    bool use_jit = true;
     std::string err;
-};
-
-// byte offsets from the local exchange arena to every peer's arena; passed by value to the driver kernels,
-// which repeat each result store at p + delta[r] (fdb_mirror.cuh).  count == 0: single rank / exchange off.
-struct fdb_mirrors {
-    int count = 0;
-    long long delta[FDB_MAX_RANKS - 1] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 struct fdb_array {
@@ -96,6 +92,10 @@ int mirrors_for(fdb_ctx* ctx, fdb_mirrors* m, const fdb_array* const* outs, int 
 int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_array* b, const fdb_array* x, int64_t m, int N, int64_t lo,
                      int64_t hi, int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ, double* yout, bool* used_dmma, const fdb_mirrors& Mr);
 bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k);
+
+// fdb_jit.cu
+void jit_release(fdb_ctx* ctx);
+int jit_launch(fdb_ctx* ctx, void* fn, unsigned gridx, unsigned gridy, unsigned threads, void** args, const char* what);
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -3,7 +3,16 @@
 // offset of every peer's arena over NVLink: extract_gradient_chunk! / extract_jacobian_chunk!
 // (src/gradient.jl:74-81, src/jacobian.jl:109-118) double as the all-gather.
 #pragma once
-#include "fdb_internal.h"
+#ifndef FDB_MAX_RANKS
+#define FDB_MAX_RANKS 8      /* include/fdb200.h */
+#endif
+
+// byte offsets from the local exchange arena to every peer's arena; passed by value to the driver kernels,
+// which repeat each result store at p + delta[r].  count == 0: single rank / exchange off.
+struct fdb_mirrors {
+    int count = 0;
+    long long delta[FDB_MAX_RANKS - 1] = {0, 0, 0, 0, 0, 0, 0};
+};
 
 namespace fdb {
 

@@ -163,6 +163,16 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
     fdb_mirrors M;
     const fdb_array* outs[2] = {grad, value_dev};
     rc = mirrors_for(ctx, &M, outs, 2, "fdb_program_gradient_chunked"); if (rc) return rc;
+    {   // specialised kernel for this program (fdb_jit.cu): the catalogue sweep kernel instantiated for the user's functor
+        void* fn = nullptr;
+        if (jit_get(ctx, 0, P, N, ctx->nansafe, ctx->lane_sharing, false, &fn) == FDB_OK) {
+            const double* xp = x->data; int64_t nn = n, lo = chunk_lo, nc = nchunks; int lcs = (int)p.lastchunksize;
+            double* gp = grad->data;
+            void* args[] = {&xp, &nn, &lo, &nc, &lcs, &gp, &vout, &M};
+            rc = jit_launch(ctx, fn, grid, 1, 256, args, "fdb_program_gradient_chunked(specialised)"); if (rc) return rc;
+            return finish(ctx, 1, "fdb_program_gradient_chunked(specialised)");
+        }
+    }
     int nregs = 1;
     for (int i = 0; i < n_term; i++) { const int d = term_prog[4 * i + 1]; if ((term_prog[4 * i] >> 6) != PK_ACC && d + 1 > nregs) nregs = d + 1; }
     const size_t smem = (size_t)nregs * 2 * PG_VEC * T * sizeof(double);

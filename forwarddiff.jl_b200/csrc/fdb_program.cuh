@@ -228,6 +228,9 @@ struct SumK {   // block_combine policy: K sum accumulators
 };
 
 
+// fdb_jit.cu: the kernel specialised for this program (kind 0 gradient, 1 Jacobian, 2 Hessian), or non-zero
+int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share, bool mir, void** fn);
+
 int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, const int32_t* epi, int n_epi, const double* consts,
                   int n_consts, int n_acc, int halo, int result_reg, bool array_form);
 

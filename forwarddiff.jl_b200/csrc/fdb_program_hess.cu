@@ -214,6 +214,15 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
     fdb_mirrors M;
     const fdb_array* outs[3] = {H, grad, value_dev};
     { int mrc = mirrors_for(ctx, &M, outs, 3, "fdb_program_hessian_chunked"); if (mrc) return mrc; }
+    {   // specialised kernel for this program (fdb_jit.cu): hessian_sweep_body instantiated for the user's functor
+        void* fn = nullptr;
+        if (jit_get(ctx, 2, P, N, ctx->nansafe, false, false, &fn) == FDB_OK) {
+            const double* xp = x->data; int64_t nn = n, lo = chunk_lo, nc = nchunks, ld = ldH; int lcs = (int)p.lastchunksize;
+            void* args[] = {&xp, &nn, &lo, &nc, &lcs, &Hp, &ld, &gp, &vp, &M};
+            rc = jit_launch(ctx, fn, grid.x, grid.y, T, args, "fdb_program_hessian_chunked(specialised)"); if (rc) return rc;
+            return finish(ctx, 1, "fdb_program_hessian_chunked(specialised)");
+        }
+    }
     FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
         (program_hessian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, Hp, ldH, gp, vp, M))));
     return finish(ctx, 1, "fdb_program_hessian_chunked");

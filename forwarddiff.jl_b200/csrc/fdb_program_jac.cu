@@ -73,6 +73,17 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
     fdb_mirrors M;
     const fdb_array* outs[2] = {J, y};
     rc = mirrors_for(ctx, &M, outs, 2, "fdb_program_jacobian_chunked"); if (rc) return rc;
+    {   // specialised kernel for this program (fdb_jit.cu)
+        void* fn = nullptr;
+        if (jit_get(ctx, 1, P, N, ctx->nansafe, false, M.count > 0, &fn) == FDB_OK) {
+            bool share = ctx->lane_sharing, rowfast = M.count > 0;
+            const double* xp = x->data; int64_t nn = n, lo = chunk_lo, nc = nchunks, ld = ldJ; int lcs = (int)p.lastchunksize;
+            double* Jp = J->data; unsigned nrb_ = nrb, nch_ = nch;
+            void* args[] = {&share, &xp, &nn, &lo, &nc, &lcs, &Jp, &ld, &yp, &nrb_, &nch_, &rowfast, &M};
+            rc = jit_launch(ctx, fn, grid, 1, T, args, "fdb_program_jacobian_chunked(specialised)"); if (rc) return rc;
+            return finish(ctx, 1, "fdb_program_jacobian_chunked(specialised)");
+        }
+    }
     if (M.count) {
         FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
             (program_jacobian_kernel<NN, NS, T, true><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, J->data, ldJ, yp, nrb, nch, true, M))));

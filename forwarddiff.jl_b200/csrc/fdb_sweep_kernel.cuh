@@ -1,0 +1,87 @@
+// fdb_sweep_kernel.cuh -- the batched chunk-mode gradient kernel (see fdb_sweep.cu), as a header so that the
+// run-time specialiser (fdb_jit.cu) instantiates the very same code for a user function's generated functor.
+#pragma once
+#include "fdb_mirror.cuh"
+#include "fdb_targets.cuh"
+
+namespace fdb {
+
+// SHARE = lane sharing.  A term whose inputs all lie outside the seeded window sees
+// Duals with N identical (zero) partial lanes, so its N partial lanes are N copies of
+// one IEEE computation.  With SHARE the kernel evaluates such terms on Dual{1}
+// (value + one representative partial lane) into a separate accumulator and adds the
+// representative lane to all N lanes at the end; results are bit-identical lane by lane
+// (including NaN/Inf propagation, since the representative lane is really computed),
+// only the summation order changes, which the reduction tolerance already covers.
+// Every term of f is still evaluated in every chunk.  SHARE=false evaluates all N
+// lanes for every term (bench.py reports both).
+template <class F, int N, bool NS, int THREADS, bool SHARE>
+FDB_DEV void gradient_sweep_body(const double* __restrict__ x, int64_t n, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
+                                 double* __restrict__ grad, double* __restrict__ value_out, const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> D;
+    typedef Dual<double, 1, NS> D1;
+    const int64_t c = chunk_lo + blockIdx.x;                       // 0-based chunk number
+    const bool last = (c == nchunks_total - 1);
+    const int chunksize = last ? lastchunksize : N;               // src/gradient.jl:123
+    const int64_t start = last ? (n - lastchunksize) : c * N;     // lastchunkindex-1, src/gradient.jl:124
+    SeedLoader<N, NS> xs{x, start, chunksize};
+    ZeroLoader<1, NS> xz{x};
+    D acc[F::K];
+    D1 acc1[F::K];
+    D like; like.v = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) like.p[k] = 0.0;
+    D1 like1; like1.v = 0.0; like1.p[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < F::K; k++) { acc[k] = F::init(k, like); acc1[k] = F::init(k, like1); }
+    const int64_t nt = F::nterms(n);
+    if (SHARE) {
+        // iterations [0,itA) and [itB,nit) touch no seeded position anywhere in the block
+        const int64_t nit = (nt + THREADS - 1) / THREADS;
+        int64_t itA = (start - F::HALO) / THREADS; if (itA < 0) itA = 0; if (itA > nit) itA = nit;
+        int64_t itB = (start + chunksize + THREADS - 1) / THREADS; if (itB > nit) itB = nit; if (itB < itA) itB = itA;
+#pragma unroll 4
+        for (int64_t it = 0; it < itA; it++) F::term(xz, it * THREADS + threadIdx.x, n, acc1);
+        for (int64_t it = itA; it < itB; it++) {
+            const int64_t i = it * THREADS + threadIdx.x;
+            if (i < nt) F::term(xs, i, n, acc);
+        }
+        const int64_t full = nt / THREADS;      // iterations whose every lane is a valid term
+#pragma unroll 4
+        for (int64_t it = itB; it < full; it++) F::term(xz, it * THREADS + threadIdx.x, n, acc1);
+        for (int64_t it = (itB > full ? itB : full); it < nit; it++) {
+            const int64_t i = it * THREADS + threadIdx.x;
+            if (i < nt) F::term(xz, i, n, acc1);
+        }
+        // fold the shared accumulator into all N lanes
+#pragma unroll
+        for (int k = 0; k < F::K; k++) {
+            D e; e.v = acc1[k].v;
+#pragma unroll
+            for (int j = 0; j < N; j++) e.p[j] = acc1[k].p[0];
+            // for K > 1 or non-additive combines the neutral value lane must not be counted twice:
+            // acc[k] started from init, acc1[k] too; combine(init, z) == z for sum and prod.
+            acc[k] = F::combine(k, acc[k], e);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < nt; i += THREADS) F::term(xs, i, n, acc);
+    }
+    block_combine<F, D, THREADS>(acc);
+    if (threadIdx.x == 0) {
+        D y = F::finalize(acc, n);
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (k < chunksize) mstore(M, &grad[start + k], y.p[k]);   // extract_gradient_chunk!, src/gradient.jl:74-81 (+ peers)
+        if (last && value_out) mstore(M, value_out, y.v);          // extract_value!, src/gradient.jl:155
+    }
+}
+
+template <class F, int N, bool NS, int THREADS, bool SHARE>
+__global__ void __launch_bounds__(THREADS) gradient_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo,
+                                                                 int64_t nchunks_total, int lastchunksize,
+                                                                 double* __restrict__ grad, double* __restrict__ value_out,
+                                                                 const __grid_constant__ fdb_mirrors M) {
+    gradient_sweep_body<F, N, NS, THREADS, SHARE>(x, n, chunk_lo, nchunks_total, lastchunksize, grad, value_out, M);
+}
+
+}  // namespace fdb

@@ -63,6 +63,16 @@ class Context:
     def set_lane_sharing(self, flag):
         self.check(self.lib.fdb_set_lane_sharing(self.h, int(flag)))
 
+    def set_jit(self, flag):
+        """Run-time specialisation of the op-program kernels (fdb_jit.cu); False = per-thread interpreter."""
+        self.check(self.lib.fdb_set_jit(self.h, int(flag)))
+
+    def jit_stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self.check(self.lib.fdb_jit_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        log = self.lib.fdb_jit_last_log(self.h)
+        return dict(compiled=a.value, cache_hits=b.value, failures=c.value, last_log=log.decode() if log else "")
+
     def set_stream(self, cuda_stream_ptr):
         self.check(self.lib.fdb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 

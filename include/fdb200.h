@@ -262,6 +262,20 @@ int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_te
                                 const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* H, int64_t ldH,
                                 fdb_array* grad, fdb_array* value_dev);
 
+/* Run-time specialisation (fdb_jit.cu).  Julia compiles f for Vector{Dual{T,Float64,N}} when gradient(f, x, cfg) first
+ * runs; likewise the fdb_program_* drivers turn the op-program into a functor and instantiate the library's sweep kernel
+ * templates for it with NVRTC (sm_100a, -fmad=false), caching the result per context.  1 (default): specialise when
+ * libnvrtc is installed, otherwise (and with 0) the program is interpreted per thread.  Same results either way up to
+ * the order of the reduction. */
+int fdb_set_jit(fdb_ctx* ctx, int enabled);
+int fdb_jit_stats(fdb_ctx* ctx, int64_t* compiled, int64_t* cache_hits, int64_t* failures);
+const char* fdb_jit_last_log(fdb_ctx* ctx);   /* NVRTC log of the last failed specialisation ("" if none) */
+/* host-only (no GPU, no context): generate and compile the specialised kernel of a program; kind 0 gradient,
+ * 1 Jacobian, 2 Hessian.  Returns 0 and the cubin size, or the NVRTC log in `log`. */
+int fdb_jit_compile_check(int kind, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi, const double* consts,
+                          int n_consts, int n_acc, int halo, int result_reg, int N, int nansafe, int lane_sharing, char* log,
+                          int64_t log_capacity, int64_t* cubin_bytes);
+
 /* ---- host-buffer entry points (what ForwardDiff.gradient!(out, f, x, cfg) with
  * host Vectors binds to): upload x, run the sweeps, download the result slice.  grad_host has
  * xlen entries; only the entries of the requested chunks are written. ------------ */

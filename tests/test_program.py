@@ -36,9 +36,42 @@ def test_tracer_rejects_what_the_interpreter_cannot_run():
 
 
 # ---- GPU parity ---------------------------------------------------------------------------------------
+@pytest.fixture(params=["specialised", "interpreted"])
+def mode(request, ctx):
+    """Every op-program test runs twice: through the kernel specialised at run time for the traced f (fdb_jit.cu)
+    and through the per-thread interpreter.  The specialised run must really have used a specialised kernel."""
+    jit = request.param == "specialised"
+    ctx.set_jit(jit)
+    before = ctx.jit_stats()
+    yield request.param
+    after = ctx.jit_stats()
+    ctx.set_jit(True)
+    assert after["failures"] == before["failures"], after["last_log"]
+    used = (after["compiled"] + after["cache_hits"]) - (before["compiled"] + before["cache_hits"])
+    assert (used > 0) == jit
+
+
+def test_specialised_kernels_compile_on_the_host():
+    """NVRTC needs no GPU: the functor generated for a traced f and the sweep kernel templates compile for sm_100a."""
+    import ctypes as C
+    from fdb200.api import _i32p
+    lib = fdb200._lib.load()
+    dp = C.POINTER(C.c_double)
+    jac = trace.trace_array(lambda xd: fdb200.tanh(xd[1:] * xd[:-1]) + 2.0 ** xd[:-1], 50)
+    for kind, prog, N in ((0, trace.trace_scalar(F.rosenbrock_generic, 100), 12), (0, trace.trace_scalar(F.ackley_generic, 100), 7),
+                          (2, trace.trace_scalar(F.rosenbrock_generic, 100), 8), (1, jac, 5)):
+        log = C.create_string_buffer(1 << 16); nbytes = C.c_int64()
+        rc = lib.fdb_jit_compile_check(kind, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
+                                       prog.consts.ctypes.data_as(dp) if prog.consts.size else None, prog.consts.size, prog.n_acc,
+                                       prog.halo, prog.result_reg, N, 0, 1, log, len(log), C.byref(nbytes))
+        assert rc == 0 and nbytes.value > 1000, log.value.decode()
+    bad = np.array([[7 << 6, 0, 0, 0]], dtype=np.int32)                 # unknown instruction kind
+    assert lib.fdb_jit_compile_check(0, _i32p(bad), 1, None, 0, None, 0, 1, 0, 0, 4, 0, 1, None, 0, None) != 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("N", [1, 4, 7, 12])
-def test_program_gradient_vs_oracle_and_loop(ctx, oracle, N):
+def test_program_gradient_vs_oracle_and_loop(ctx, oracle, N, mode):
     for n in (13, 257, 1003):
         x = np.random.default_rng(n).uniform(0.5, 1.5, n)
         for gen, fn in ((F.rosenbrock_generic, "rosenbrock"), (F.ackley_generic, "ackley"), (F.sumsq_generic, "sumsq")):
@@ -55,7 +88,7 @@ def test_program_gradient_vs_oracle_and_loop(ctx, oracle, N):
 
 
 @pytest.mark.gpu
-def test_program_gradient_lane_sharing_chunk_ranges_and_fallback(ctx, oracle):
+def test_program_gradient_lane_sharing_chunk_ranges_and_fallback(ctx, oracle, mode):
     n, N = 1000, 12
     x = np.random.default_rng(4).uniform(0.5, 1.5, n)
     cfg = fdb200.GradientConfig(F.rosenbrock_generic, x, fdb200.Chunk(N))
@@ -92,7 +125,7 @@ def test_program_gradient_lane_sharing_chunk_ranges_and_fallback(ctx, oracle):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("N", [1, 6, 12])
-def test_program_jacobian_elementwise_and_stencil(ctx, N):
+def test_program_jacobian_elementwise_and_stencil(ctx, N, mode):
     n = 61
     x = np.random.default_rng(6).uniform(0.5, 1.5, n)
 
@@ -155,7 +188,7 @@ def test_chunk_cursor_follows_the_reference_bookkeeping(ctx):
 # ---- Hessians of flattened user functions (fdb_program_hess.cu) ------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("N", [1, 3, 8, 12])
-def test_program_hessian_vs_oracle_and_finite_differences(ctx, oracle, N):
+def test_program_hessian_vs_oracle_and_finite_differences(ctx, oracle, N, mode):
     for n in (13, 60):
         x = np.random.default_rng(n).uniform(0.5, 1.5, n)
         for gen, fn in ((F.rosenbrock_generic, "rosenbrock"), (F.sumsq_generic, "sumsq")):

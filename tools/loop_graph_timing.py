@@ -13,9 +13,11 @@ for n, N in ((10_000, 10), (100_000, 12)):
     for name, f in (("rosenbrock_generic", F.rosenbrock_generic), ("ackley_generic", F.ackley_generic)):
         cfg = fdb200.GradientConfig(f, x, fdb200.Chunk(N))
         out = {}
-        for mode, kw in (("eager", dict(fuse=False, graph=False)), ("graph", dict(fuse=False, graph=True)), ("op-program", dict(fuse=True))):
+        for mode, kw in (("eager", dict(fuse=False, graph=False)), ("graph", dict(fuse=False, graph=True)), ("op-program interpreted", dict(fuse=True, jit=False)), ("op-program specialised", dict(fuse=True, jit=True))):
             if mode == "eager" and n > 10_000:
                 continue
+            if "jit" in kw:
+                ctx.set_jit(kw.pop("jit"))
             fdb200.gradient(f, x, cfg, ctx=ctx, **kw)
             t0 = time.perf_counter(); g = fdb200.gradient(f, x, cfg, ctx=ctx, **kw); out[mode] = (time.perf_counter() - t0, g)
         base = out.get("graph")[1]
