@@ -318,10 +318,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks}
 
     if world == 1 and not args.no_cpu_baseline:
-        v, dt, nchunks = cpu_oracle_rate(400, 1)
+        v, dt, nchunks = cpu_oracle_rate(1200, 1)
         line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": 1, "kind": "port",
-                                "sample": f"400 consecutive chunk sweeps of {nchunks} (n={N_ELEMS}, Chunk{{12}}) in {dt:.1f} s on 1 core, "
-                                          "scaled by nchunks/400; oracle.cpp (C++ restatement of src/gradient.jl:114-159 on AoS Duals, "
+                                "sample": f"1200 consecutive chunk sweeps of {nchunks} (n={N_ELEMS}, Chunk{{12}}) in {dt:.1f} s on 1 core, "
+                                          "scaled by nchunks/1200; oracle.cpp (C++ restatement of src/gradient.jl:114-159 on AoS Duals, "
                                           "g++ -O3 -march=x86-64-v3, no FMA contraction); Julia not installed (JULIA_NUM_THREADS n/a); "
                                           "the reference is single-threaded by design (docs/src/user/upgrade.md:39-50)"}
     if world == 1 and not args.no_extras:
