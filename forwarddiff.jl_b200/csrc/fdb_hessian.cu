@@ -56,6 +56,7 @@ extern "C" int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int
     if (nchunks > 2147483647LL || chunk_hi - chunk_lo > 65535) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_hessian_chunked: more than 65535 outer chunks per call");
     switch (fn) {
         case FDB_FN_ROSENBROCK: return hessian_launch<Rosenbrock>(ctx, x, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, H, ldH, grad, value_dev, "fdb_hessian_chunked(rosenbrock)");
+        case FDB_FN_ACKLEY: return hessian_launch<Ackley>(ctx, x, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, H, ldH, grad, value_dev, "fdb_hessian_chunked(ackley)");
         case FDB_FN_SUMSQ: return hessian_launch<SumSq>(ctx, x, N, chunk_lo, chunk_hi, nchunks, (int)p.lastchunksize, H, ldH, grad, value_dev, "fdb_hessian_chunked(sumsq)");
     }
     return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_hessian_chunked: target %d has no nested-dual kernel (additive targets only)", fn);

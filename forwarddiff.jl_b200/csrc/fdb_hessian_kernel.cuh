@@ -119,12 +119,144 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
     }
 }
 
+// ---- general form: K sum accumulators and arithmetic after the reductions (F::finalize), e.g. Ackley ---------------
+// Same two-level lane sharing as above, but the block first assembles the K reduced accumulators as FULL nested duals
+// Dual{Dual{N},N} -- far terms contribute their four shared lanes, near terms their per-inner-lane Dual{Dual{N},1}
+// results, folded in term order -- and one thread then runs F::finalize on them (scalar nested-dual arithmetic, once
+// per block), exactly the Dual{T,Dual{T,V,N},N} evaluation of the tail of f in the reference (src/hessian.jl:14-19).
+// Near terms are processed in rounds of R terms so that the staging buffer stays under 40 KB for any K.
+template <class F, int N, bool NS, int THREADS>
+FDB_DEV void hessian_general_body(const double* __restrict__ x, int64_t n, int64_t outer_lo, int64_t nchunks_total, int lastchunksize,
+                                  double* __restrict__ H, int64_t ldH, double* __restrict__ grad, double* __restrict__ value_out,
+                                  const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> DI;
+    typedef Dual<DI, 1, NS> DG;
+    typedef Dual<DI, N, NS> DN;
+    typedef Dual<Dual<double, 1, NS>, 1, NS> DF;
+    constexpr int K = F::K;
+    constexpr int LANES = (N + 1) * (N + 1);                       // [a][b]: a = inner index (0 = value), b = outer index
+    constexpr int RCAP = (40 * 1024) / (K * (N + 1) * (N + 1) * 8);
+    constexpr int RT = THREADS / N;
+    constexpr int R = RCAP < 1 ? 1 : (RCAP < RT ? RCAP : RT);      // near terms per round
+    __shared__ double s_stage[K][R][N + 1][N + 1];                  // [kk][t][a][b] of one round (a = 0 row written by lane k = 0)
+    __shared__ double s_acc[K][N + 1][N + 1];                       // running fold, later the assembled accumulators
+    __shared__ double s_ff[K][4];
+    __shared__ double s_red[THREADS / 32][K][4];
+
+    const int64_t ci = blockIdx.x, co = outer_lo + blockIdx.y;
+    const bool ilast = (ci == nchunks_total - 1), olast = (co == nchunks_total - 1);
+    const int ics = ilast ? lastchunksize : N, ocs = olast ? lastchunksize : N;
+    const int64_t istart = ilast ? n - lastchunksize : ci * N;
+    const int64_t ostart = olast ? n - lastchunksize : co * N;
+    const int64_t nt = F::nterms(n);
+    int64_t a0 = istart - F::HALO, a1 = istart + ics, b0 = ostart - F::HALO, b1 = ostart + ocs;
+    if (a0 < 0) a0 = 0; if (b0 < 0) b0 = 0; if (a1 > nt) a1 = nt; if (b1 > nt) b1 = nt;
+    if (a1 < a0) a1 = a0; if (b1 < b0) b1 = b0;
+    if (b0 <= a1 && a0 <= b1) { a0 = a0 < b0 ? a0 : b0; a1 = a1 > b1 ? a1 : b1; b0 = b1 = a1; }
+    const int na = (int)(a1 - a0), nb = (int)(b1 - b0), nnear = na + nb;
+
+    // phase 1: far terms on four shared lanes per accumulator
+    DF accff[K];
+#pragma unroll
+    for (int kk = 0; kk < K; kk++) { accff[kk].v.v = 0.0; accff[kk].v.p[0] = 0.0; accff[kk].p[0].v = 0.0; accff[kk].p[0].p[0] = 0.0; }
+    FFLoader<NS> xf{x};
+    for (int64_t i = threadIdx.x; i < nt; i += THREADS) {
+        const bool near = (i >= a0 && i < a1) || (i >= b0 && i < b1);
+        if (!near) F::term(xf, i, n, accff);
+    }
+#pragma unroll
+    for (int kk = 0; kk < K; kk++) {
+        double r[4] = {accff[kk].v.v, accff[kk].v.p[0], accff[kk].p[0].v, accff[kk].p[0].p[0]};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) r[q] = r[q] + shfl_down_d(r[q], off);
+            if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][kk][q] = r[q];
+        }
+    }
+    for (int e = threadIdx.x; e < K * LANES; e += THREADS) (&s_acc[0][0][0])[e] = 0.0;
+    __syncthreads();
+    if (threadIdx.x < K * 4) {
+        const int kk = threadIdx.x / 4, q = threadIdx.x % 4;
+        double s = 0.0;
+        for (int wq = 0; wq < THREADS / 32; wq++) s = s + s_red[wq][kk][q];
+        s_ff[kk][q] = s;
+    }
+    // phase 2: near terms, R per round; work item = (term of the round, inner lane k)
+    for (int t0 = 0; t0 < nnear; t0 += R) {
+        const int rt = (nnear - t0 < R) ? nnear - t0 : R;
+        if (threadIdx.x < rt * N) {
+            const int tl = threadIdx.x / N, k = threadIdx.x - tl * N, t = t0 + tl;
+            const int64_t i = t < na ? a0 + t : b0 + (t - na);
+            NearLoader<N, NS> xn{x, ostart, ocs, istart, ics, k};
+            DG acc[K];
+#pragma unroll
+            for (int kk = 0; kk < K; kk++) {
+                acc[kk].v.v = 0.0; acc[kk].p[0].v = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; j++) { acc[kk].v.p[j] = 0.0; acc[kk].p[0].p[j] = 0.0; }
+            }
+            F::term(xn, i, n, acc);
+#pragma unroll
+            for (int kk = 0; kk < K; kk++) {
+                s_stage[kk][tl][k + 1][0] = acc[kk].p[0].v;
+#pragma unroll
+                for (int j = 0; j < N; j++) s_stage[kk][tl][k + 1][j + 1] = acc[kk].p[0].p[j];
+                if (k == 0) {
+                    s_stage[kk][tl][0][0] = acc[kk].v.v;
+#pragma unroll
+                    for (int j = 0; j < N; j++) s_stage[kk][tl][0][j + 1] = acc[kk].v.p[j];
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < K * LANES; e += THREADS) {        // fold this round in term order
+            const int kk = e / LANES, ab = e - kk * LANES;
+            double s = (&s_acc[kk][0][0])[ab];
+            for (int tl = 0; tl < rt; tl++) s = s + (&s_stage[kk][tl][0][0])[ab];
+            (&s_acc[kk][0][0])[ab] = s;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // phase 3: add the shared far lanes, finalize on the full nested duals, store
+    if (threadIdx.x == 0) {
+        DN accn[K];
+#pragma unroll 1
+        for (int kk = 0; kk < K; kk++) {
+            accn[kk].v.v = s_acc[kk][0][0] + s_ff[kk][0];
+            for (int j = 0; j < N; j++) accn[kk].v.p[j] = s_acc[kk][0][j + 1] + s_ff[kk][1];
+            for (int k = 0; k < N; k++) {
+                accn[kk].p[k].v = s_acc[kk][k + 1][0] + s_ff[kk][2];
+                for (int j = 0; j < N; j++) accn[kk].p[k].p[j] = s_acc[kk][k + 1][j + 1] + s_ff[kk][3];
+            }
+        }
+        const DN y = F::finalize(accn, n);
+        s_acc[0][0][0] = y.v.v;
+        for (int j = 0; j < N; j++) s_acc[0][0][j + 1] = y.v.p[j];
+        for (int k = 0; k < N; k++) {
+            s_acc[0][k + 1][0] = y.p[k].v;
+            for (int j = 0; j < N; j++) s_acc[0][k + 1][j + 1] = y.p[k].p[j];
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * (N + 1); e += THREADS) {
+        const int k = e / (N + 1), j = e - k * (N + 1);
+        if (k >= ics) continue;
+        const double s = s_acc[0][k + 1][j];
+        if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
+        else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
+    }
+    if (threadIdx.x == 0 && olast && ilast && value_out) mstore(M, value_out, s_acc[0][0][0]);
+}
+
 template <class F, int N, bool NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) hessian_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t outer_lo,
                                                                 int64_t nchunks_total, int lastchunksize, double* __restrict__ H,
                                                                 int64_t ldH, double* __restrict__ grad, double* __restrict__ value_out,
                                                                 const __grid_constant__ fdb_mirrors M) {
-    hessian_sweep_body<F, N, NS, THREADS>(x, n, outer_lo, nchunks_total, lastchunksize, H, ldH, grad, value_out, M);
+    if constexpr (F::PLAIN_SUM) hessian_sweep_body<F, N, NS, THREADS>(x, n, outer_lo, nchunks_total, lastchunksize, H, ldH, grad, value_out, M);
+    else hessian_general_body<F, N, NS, THREADS>(x, n, outer_lo, nchunks_total, lastchunksize, H, ldH, grad, value_out, M);
 }
 
 }  // namespace fdb

@@ -154,6 +154,7 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
     }
     const int K = P.n_acc > 0 ? P.n_acc : 1;
     s += "struct UserFn {\n";
+    s += std::string("    static constexpr bool PLAIN_SUM = ") + ((P.n_epi == 0 && K == 1 && P.result_reg == 0) ? "true" : "false") + ";\n";
     s += "    static constexpr int K = " + std::to_string(K) + ";\n    static constexpr int HALO = " + std::to_string(P.halo) + ";\n";
     s += "    static __device__ int64_t nterms(int64_t n) { return n > HALO ? n - HALO : 0; }\n";
     s += "    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }\n";
@@ -185,7 +186,8 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
         s += "extern \"C\" __global__ void __launch_bounds__(128) fdb_user_kernel(const double* __restrict__ x, int64_t n, int64_t outer_lo,\n"
              "        int64_t nchunks_total, int lastchunksize, double* __restrict__ H, int64_t ldH, double* __restrict__ grad,\n"
              "        double* __restrict__ value_out, const __grid_constant__ fdb_mirrors M) {\n"
-             "    fdb::hessian_sweep_body<" + targs + ", 128>(x, n, outer_lo, nchunks_total, lastchunksize, H, ldH, grad, value_out, M);\n}\n";
+             "    if constexpr (fdb::UserFn::PLAIN_SUM) fdb::hessian_sweep_body<" + targs + ", 128>(x, n, outer_lo, nchunks_total, lastchunksize, H, ldH, grad, value_out, M);\n"
+             "    else fdb::hessian_general_body<" + targs + ", 128>(x, n, outer_lo, nchunks_total, lastchunksize, H, ldH, grad, value_out, M);\n}\n";
     }
     return s;
 }

@@ -182,9 +182,10 @@ __global__ void __launch_bounds__(THREADS) program_hessian_kernel(const __grid_c
 
 using namespace fdb;
 
-extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const double* consts, int n_consts, int halo,
-                                           const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* H, int64_t ldH,
-                                           fdb_array* grad, fdb_array* value_dev) {
+extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi,
+                                           const double* consts, int n_consts, int n_acc, int halo, int result_reg, const fdb_array* x, int N,
+                                           int64_t chunk_lo, int64_t chunk_hi, fdb_array* H, int64_t ldH, fdb_array* grad,
+                                           fdb_array* value_dev) {
     if (!ctx || !x) return fail(ctx, FDB_ERR_BADARG, "fdb_program_hessian_chunked: null argument");
     if (x->level != 0 || (H && H->level != 0) || (grad && grad->level != 0) || (value_dev && value_dev->level != 0))
         return fail(ctx, FDB_ERR_BADARG, "x, H, grad, value must be plain arrays");
@@ -195,13 +196,17 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
     if (grad && grad->n != n) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: gradient result has %lld entries, x has %lld", (long long)grad->n, (long long)n);
     if (halo > PH_MAXHALO) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: stencil reach %d > %d", halo, PH_MAXHALO);
     Program P;
-    int rc = build_program(ctx, P, term_prog, n_term, nullptr, 0, consts, n_consts, 1, halo, 0, false); if (rc) return rc;
-    for (int i = 0; i < n_term; i++) {                 // rules that exist one dual level up
-        const int kind = P.term[i][0] >> 6, code = P.term[i][0] & 63;
-        const bool ok = (kind == PK_LOADX) || (kind == PK_ACC) || (kind == PK_MOV) || (kind == PK_UNARY && code <= FDB_POW3) ||
-                        ((kind == PK_DD || kind == PK_DC || kind == PK_CD) && code <= FDB_DIV);
-        if (!ok) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: instruction %d uses an op without a nested-dual rule", i);
-    }
+    int rc = build_program(ctx, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, false); if (rc) return rc;
+    for (int part = 0; part < 2; part++)
+        for (int i = 0; i < (part ? n_epi : n_term); i++) {                 // rules that exist one dual level up
+            const short* ins = part ? P.epi[i] : P.term[i];
+            const int kind = ins[0] >> 6, code = ins[0] & 63;
+            const bool ok = (kind == PK_LOADX) || (kind == PK_ACC) || (kind == PK_MOV) || (kind == PK_UNARY && code <= FDB_POW3) ||
+                            ((kind == PK_DD || kind == PK_DC || kind == PK_CD) && code <= FDB_DIV);
+            if (!ok) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: instruction %d uses an op without a nested-dual rule", i);
+        }
+    // f = one plain sum of terms: both executors.  K sums + arithmetic after the reductions: the specialised kernel only
+    const bool plain = (n_epi == 0 && n_acc == 1 && result_reg == 0);
     Plan p = make_plan(n, N);
     const int64_t nchunks = (n == N) ? 1 : p.nchunks;
     if (chunk_hi < 0) chunk_hi = nchunks;
@@ -223,6 +228,9 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
             return finish(ctx, 1, "fdb_program_hessian_chunked(specialised)");
         }
     }
+    if (!plain)
+        return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: arithmetic after the reduction needs the run-time specialised kernel (%s)",
+                    ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
         (program_hessian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, Hp, ldH, gp, vp, M))));
     return finish(ctx, 1, "fdb_program_hessian_chunked");

@@ -45,6 +45,7 @@ template <int N, bool NS> struct ZeroLoader {
 // a and b are Duals with zero partials, so `a - x[i]` is Dual-Dual and `b*(..)` is
 // Dual*Dual.
 struct Rosenbrock {
+    static constexpr bool PLAIN_SUM = true;   // f = sum of the terms: one accumulator, combine = +, finalize = identity
     static constexpr int K = 1;
     static constexpr int HALO = 1;   // term i reads positions i .. i+HALO
     static __host__ __device__ int64_t nterms(int64_t n) { return n > 0 ? n - 1 : 0; }
@@ -64,6 +65,7 @@ struct Rosenbrock {
 //   sum_cos += cos(c*x_i); sum_sqrs += x_i^2;
 //   -a*exp(b*sqrt(len_recip*sum_sqrs)) - exp(len_recip*sum_cos) + a + e
 struct Ackley {
+    static constexpr bool PLAIN_SUM = false;
     static constexpr int K = 2;
     static constexpr int HALO = 0;   // acc[0] = sum_cos, acc[1] = sum_sqrs
     static __host__ __device__ int64_t nterms(int64_t n) { return n; }
@@ -84,6 +86,7 @@ struct Ackley {
 
 // ---- sum(x.^2) ---------------------------------------------------------------------
 struct SumSq {
+    static constexpr bool PLAIN_SUM = true;
     static constexpr int K = 1;
     static constexpr int HALO = 0;
     static __host__ __device__ int64_t nterms(int64_t n) { return n; }
@@ -97,6 +100,7 @@ struct SumSq {
 
 // ---- prod(x) -------------------------------------------------------------------------
 struct ProdAll {
+    static constexpr bool PLAIN_SUM = false;
     static constexpr int K = 1;
     static constexpr int HALO = 0;
     static __host__ __device__ int64_t nterms(int64_t n) { return n; }
@@ -110,6 +114,7 @@ struct ProdAll {
 
 // ---- plain sum / prod of an array (fdb_reduce) -----------------------------------------
 struct SumAll {
+    static constexpr bool PLAIN_SUM = true;
     static constexpr int K = 1;
     static constexpr int HALO = 0;
     static __host__ __device__ int64_t nterms(int64_t n) { return n; }

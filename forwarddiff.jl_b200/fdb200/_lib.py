@@ -118,8 +118,8 @@ SIGNATURES = {
                                                C.c_int, C.c_int, C.c_int, c_arr, C.c_int, i64, i64, c_arr, c_arr]),
     "fdb_program_jacobian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, C.c_int, c_arr,
                                                C.c_int, i64, i64, c_arr, i64, c_arr]),
-    "fdb_program_hessian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, c_arr, C.c_int, i64, i64,
-                                              c_arr, i64, c_arr, c_arr]),
+    "fdb_program_hessian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int,
+                                              C.c_int, C.c_int, C.c_int, c_arr, C.c_int, i64, i64, c_arr, i64, c_arr, c_arr]),
     "fdb_set_jit": (C.c_int, [c_ctx, C.c_int]),
     "fdb_jit_stats": (C.c_int, [c_ctx, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "fdb_jit_last_log": (C.c_char_p, [c_ctx]),

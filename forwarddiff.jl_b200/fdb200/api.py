@@ -359,14 +359,13 @@ def _program_hessian(ctx, result, H, f, x, N, lo, hi):
     """hessian(f, x, cfg) of a user f flattened into an op-program (fdb_program_hessian_chunked)."""
     n = _length(x)
     prog = _try_trace("scalar", f, n)
-    if prog is None or prog.n_acc != 1 or len(prog.epi) != 0:
-        raise _lib.UnsupportedOp("hessian: f must be a catalogue target or flatten to a single sum of terms "
-                                 "(no prod, no arithmetic after the reduction)")
+    if prog is None:
+        raise _lib.UnsupportedOp("hessian: f must be a catalogue target or flatten to sums of elementwise terms (no prod, no strided views)")
     xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
     Hd = B200Array.alloc(ctx, n * n); gd = B200Array.alloc(ctx, n); vd = B200Array.alloc(ctx, 1)
-    ctx.check(ctx.lib.fdb_program_hessian_chunked(ctx.h, _i32p(prog.term), len(prog.term),
+    ctx.check(ctx.lib.fdb_program_hessian_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
                                                   prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
-                                                  prog.halo, xd.h, N, lo, hi, Hd.h, n, gd.h, vd.h))
+                                                  prog.n_acc, prog.halo, prog.result_reg, xd.h, N, lo, hi, Hd.h, n, gd.h, vd.h))
     nchunks = 1 if n == N else chunk_plan(n, N)["nchunks"]
     last = hi < 0 or hi == nchunks
     c0, c1 = lo * N, (n if last else hi * N)

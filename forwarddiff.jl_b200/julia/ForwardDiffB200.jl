@@ -162,8 +162,10 @@ end
 function program_hessian!(H::B200Array{Float64}, grad::B200Array{Float64}, p::Program, x::B200Array{Float64}, ::Chunk{N}; lo = 0, hi = -1) where {N}
     value = B200Array{Float64}(undef, 1; ctx = x.ctx)
     GC.@preserve p check(x.ctx.h, ccall((:fdb_program_hessian_chunked, libfdb200), Cint,
-        (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Float64}, Cint, Cint, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
-        x.ctx.h, p.term, size(p.term, 2), p.consts, length(p.consts), p.halo, x.h, N, lo, hi, H.h, length(x), grad.h, value.h))
+        (Ptr{Cvoid}, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Ptr{Float64}, Cint, Cint, Cint, Cint, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64,
+         Ptr{Cvoid}, Ptr{Cvoid}),
+        x.ctx.h, p.term, size(p.term, 2), p.epi, size(p.epi, 2), p.consts, length(p.consts), p.n_acc, p.halo, p.result_reg, x.h, N, lo, hi,
+        H.h, length(x), grad.h, value.h))
     return H, grad, value
 end
 

@@ -256,11 +256,13 @@ int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, int n_instr,
                                  int result_reg, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* J,
                                  int64_t ldJ, fdb_array* y);
 
-/* hessian(f, x, cfg) of a flattened f = sum_i term(x[i .. i+halo]) (one accumulator, no epilogue; ops with a
- * nested-dual rule: + - * / neg, literal powers, exp log sin cos tanh sqrt abs abs2 inv).  Outer chunks [lo, hi). */
-int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const double* consts, int n_consts, int halo,
-                                const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* H, int64_t ldH,
-                                fdb_array* grad, fdb_array* value_dev);
+/* hessian(f, x, cfg) of a flattened f (same program form as fdb_program_gradient_chunked; ops with a nested-dual rule:
+ * + - * / neg, literal powers, exp log sin cos tanh sqrt abs abs2 inv).  Outer chunks [lo, hi).  f = one plain sum of terms
+ * (n_acc = 1, no epilogue) runs on either executor; several sums and arithmetic after the reductions (e.g. Ackley) need the
+ * run-time specialised kernel, which finalizes on full Dual{Dual{N},N} numbers (FDB_ERR_UNSUPPORTED otherwise). */
+int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi,
+                                const double* consts, int n_consts, int n_acc, int halo, int result_reg, const fdb_array* x, int N,
+                                int64_t chunk_lo, int64_t chunk_hi, fdb_array* H, int64_t ldH, fdb_array* grad, fdb_array* value_dev);
 
 /* Run-time specialisation (fdb_jit.cu).  Julia compiles f for Vector{Dual{T,Float64,N}} when gradient(f, x, cfg) first
  * runs; likewise the fdb_program_* drivers turn the op-program into a functor and instantiate the library's sweep kernel

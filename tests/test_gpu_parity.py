@@ -513,7 +513,7 @@ def test_hessian_vs_oracle(ctx, oracle, N):
         if N not in (1, 2, 3, 4, 5, 6, 7, 8, 12):
             continue                                # oracle instantiates nested duals for these N only
         x = np.random.default_rng(n).uniform(0.5, 1.5, n)
-        for fn in ("rosenbrock", "sumsq"):
+        for fn in ("rosenbrock", "sumsq", "ackley"):   # ackley: two sums + exp/sqrt after the reductions (nested-dual finalize)
             res = fdb200.HessianResult(x)
             target = getattr(F, fn)
             fdb200.hessian_b(res, target, x, fdb200.HessianConfig(target, x, fdb200.Chunk(N)), ctx=ctx)
