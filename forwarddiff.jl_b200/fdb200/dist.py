@@ -331,12 +331,18 @@ class ShardedGradient:
         self.x_a = ctx.wrap(self.x_t.data_ptr(), self.n, keepalive=self.x_t)
         ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)     # kernels and NCCL on one stream
         glen = -(-max(self.lay["padded"], self.n) // 32) * 32
-        self.xch = _make_exchange(ctx, glen + 32, group, exchange) if self.world > 1 or exchange == "p2p" else None
+        slot = glen + 32                                               # one result: gradient | value
+        self.xch = _make_exchange(ctx, 2 * slot, group, exchange) if self.world > 1 or exchange == "p2p" else None
         self.exchange = "p2p" if self.xch is not None else "nccl"
         if self.xch is not None:
-            # gradient and value live in the arena every peer maps: the sweep kernel stores each entry everywhere
-            self.g_t, self.v_t = self.xch.torch_view(0, glen), self.xch.torch_view(glen, 1)
-            self.g_a, self.v_a = self.xch.view(0, self.n, ld=glen), self.xch.view(glen, 1, ld=32)
+            # Gradient and value live in the arena every peer maps: the sweep kernel stores each entry everywhere.
+            # Two result slots used alternately: a peer overwrites slot s again only two sweeps later, after the
+            # barrier that follows the sweep in between -- which this rank reaches only after it has consumed slot s.
+            # So ONE barrier per sweep (after it) is enough; no barrier before the sweep.
+            self._slots = [(self.xch.torch_view(b * slot, glen), self.xch.torch_view(b * slot + glen, 1),
+                            self.xch.view(b * slot, self.n, ld=glen), self.xch.view(b * slot + glen, 1, ld=32)) for b in (0, 1)]
+            self._cur = 1
+            self.g_t, self.v_t, self.g_a, self.v_a = self._slots[self._cur]
         else:
             # gathered buffer: rank r's slice sits at [r*per, (r+1)*per) == its absolute gradient positions
             self.g_t = torch.zeros(glen, dtype=torch.float64, device=dev)
@@ -345,10 +351,12 @@ class ShardedGradient:
             self.v_a = ctx.wrap(self.v_t.data_ptr(), 1, keepalive=self.v_t)
 
     def sweep(self):
-        """This rank's chunk sweeps (device-resident inputs); no host sync."""
+        """This rank's chunk sweeps (device-resident inputs); no host sync.  With the peer exchange the result of
+        this sweep is in `g_t` / `v_t` (which alternate between the two arena slots) after `gather()`."""
         c = self.ctx
         if self.xch is not None:
-            self.xch.barrier()          # peers have consumed the previous gradient before it is overwritten
+            self._cur ^= 1
+            self.g_t, self.v_t, self.g_a, self.v_a = self._slots[self._cur]
             self.xch.enable()
         try:
             c.check(c.lib.fdb_gradient_chunked(c.h, self.fid, self.x_a.h, self.N, self.plan["chunk_lo"], self.plan["chunk_hi"],
