@@ -2,7 +2,7 @@
 """Run one BASELINE.json configuration a few times (for ncu captures and quick timing).
 
     python tools/run_config.py c3 [--reps 3] [--no-share] [--no-dmma]
-configs: c1 c2 c2ackley c3 c4 c5 generic
+configs: c1 c2 c2ackley c2traced c3 c4 c5 c5ackley generic
 """
 import argparse
 import os
@@ -34,6 +34,21 @@ def main():
         x = ctx.array(rng.random(n)); g = ctx.zeros(n)
         fid = FN["ackley"] if a.config == "c2ackley" else FN["rosenbrock"]
         fn = lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid, x.h, N, 0, -1, g.h, v.h))
+    elif a.config == "c2traced":
+        # C2 written as a plain callable, traced into an op-program and run by the kernel specialised for it (fdb_jit.cu)
+        from fdb200 import trace, functions as F
+        from fdb200.api import _i32p
+        import ctypes as C
+        n, N = 1_000_000, 12
+        x = ctx.array(rng.random(n)); g = ctx.zeros(n)
+        prog = trace.trace_scalar(F.rosenbrock_generic, n)
+        cp = prog.consts.ctypes.data_as(C.POINTER(C.c_double))
+        fn = lambda: ctx.check(lib.fdb_program_gradient_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi), cp,
+                                                                prog.consts.size, prog.n_acc, prog.halo, prog.result_reg, x.h, N, 0, -1, g.h, v.h))
+    elif a.config == "c5ackley":
+        n = 2048
+        x = ctx.array(rng.random(n)); H = ctx.zeros(n * n); g = ctx.zeros(n)
+        fn = lambda: ctx.check(lib.fdb_hessian_chunked(ctx.h, FN["ackley"], x.h, 8, 0, -1, H.h, n, g.h, v.h))
     elif a.config == "c3":
         m = 8192
         A = ctx.array(rng.uniform(-1, 1, m * m) / np.sqrt(m)); b = ctx.array(rng.uniform(-1, 1, m)); x = ctx.array(rng.uniform(-1, 1, m))
