@@ -32,6 +32,10 @@ struct fdb_ctx {
     struct fdb_exchange* xch = nullptr;   // enabled peer-memory result exchange (fdb_exchange.cu), or null
     struct fdb_jit_cache* jit = nullptr;  // kernels specialised at run time for op-programs (fdb_jit.cu)
     bool use_jit = true;
+    // plain Float64 arrays an op-program reads next to x (closed-over data of the user's f): fdb_program_bind_params
+    const double* prm_ptr[FDB_MAX_PARAMS] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t prm_len[FDB_MAX_PARAMS] = {0, 0, 0, 0};
+    int n_prm = 0;
     std::string err;
 };
 
@@ -95,7 +99,7 @@ bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k);
 
 // fdb_jit.cu
 void jit_release(fdb_ctx* ctx);
-int jit_launch(fdb_ctx* ctx, void* fn, unsigned gridx, unsigned gridy, unsigned threads, void** args, const char* what);
+int jit_launch(fdb_ctx* ctx, void* entry, unsigned gridx, unsigned gridy, unsigned threads, void** args, const char* what);
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -27,7 +27,7 @@
 #include "../build/fdb_rtc_headers.inc"
 
 struct fdb_jit_cache {
-    struct Entry { CUmodule mod; CUfunction fn; };
+    struct Entry { CUmodule mod; CUfunction fn; CUdeviceptr prm; };   // prm: the module's fdb_prm[] (parameter array pointers)
     std::unordered_map<std::string, Entry> map;
     int64_t compiled = 0, hits = 0, failures = 0;
     std::string last_log;
@@ -72,6 +72,8 @@ struct Driver {
     CUresult (*ModuleUnload)(CUmodule) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
+    CUresult (*MemcpyHtoDAsync)(CUdeviceptr, const void*, size_t, CUstream) = nullptr;
     bool ok = false;
 };
 static Driver& driver() {
@@ -82,6 +84,7 @@ static Driver& driver() {
 #define FDB_DRV(field, sym) if (cudaGetDriverEntryPoint(sym, (void**)&d.field, cudaEnableDefault, &q) != cudaSuccess || !d.field) return;
         FDB_DRV(ModuleLoadData, "cuModuleLoadData") FDB_DRV(ModuleGetFunction, "cuModuleGetFunction")
         FDB_DRV(ModuleUnload, "cuModuleUnload") FDB_DRV(LaunchKernel, "cuLaunchKernel") FDB_DRV(GetErrorString, "cuGetErrorString")
+        FDB_DRV(ModuleGetGlobal, "cuModuleGetGlobal") FDB_DRV(MemcpyHtoDAsync, "cuMemcpyHtoDAsync")
 #undef FDB_DRV
         d.ok = true;
     });
@@ -129,6 +132,8 @@ static std::string emit_part(const short (*code)[4], int n) {
             case PK_DD: s += R(dst) + " = " + binary_expr(c, R(a), R(b)) + ";"; break;
             case PK_DC: s += R(dst) + " = " + binary_expr(c, R(a), C(b)) + ";"; break;
             case PK_CD: s += R(dst) + " = " + binary_expr(c, C(a), R(b)) + ";"; break;
+            case PK_DP: s += R(dst) + " = " + binary_expr(c, R(a), "fdb_prm[" + std::to_string(b) + "][i]") + ";"; break;
+            case PK_PD: s += R(dst) + " = " + binary_expr(c, "fdb_prm[" + std::to_string(a) + "][i]", R(b)) + ";"; break;
             case PK_ACC: s += "acc[" + std::to_string(dst) + "] = acc[" + std::to_string(dst) + "] + " + R(a) + ";"; break;
             default: s += R(dst) + " = " + R(a) + ";"; break;
         }
@@ -153,6 +158,8 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
         s += buf;
     }
     const int K = P.n_acc > 0 ? P.n_acc : 1;
+    // closed-over data arrays of the user's f: pointers uploaded into the module before each launch (jit_launch)
+    s += "__constant__ const double* fdb_prm[" + std::to_string(FDB_MAX_PARAMS) + "];\n";
     s += "struct UserFn {\n";
     s += std::string("    static constexpr bool PLAIN_SUM = ") + ((P.n_epi == 0 && K == 1 && P.result_reg == 0) ? "true" : "false") + ";\n";
     s += "    static constexpr int K = " + std::to_string(K) + ";\n    static constexpr int HALO = " + std::to_string(P.halo) + ";\n";
@@ -229,6 +236,7 @@ static std::string cache_key(int kind, const Program& P, int N, bool ns, bool sh
 // the specialised kernel for (kind, P, N, ...): from the context's cache, or compiled now.  A non-zero return means
 // "not available" (the caller interprets instead); the reason is kept in the cache's log.
 int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share, bool mir, void** fn) {
+    *fn = nullptr;
     if (!ctx->use_jit) return FDB_ERR_UNSUPPORTED;
     if (!ctx->jit) ctx->jit = new fdb_jit_cache();
     fdb_jit_cache& J = *ctx->jit;
@@ -236,8 +244,8 @@ int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share
     if (kind != JIT_JACOBIAN) mir = false;
     const std::string key = cache_key(kind, P, N, ns, share, mir);
     auto it = J.map.find(key);
-    if (it != J.map.end()) { J.hits++; *fn = it->second.fn; return it->second.fn ? FDB_OK : FDB_ERR_UNSUPPORTED; }
-    fdb_jit_cache::Entry e{nullptr, nullptr};
+    if (it != J.map.end()) { J.hits++; *fn = it->second.fn ? &it->second : nullptr; return it->second.fn ? FDB_OK : FDB_ERR_UNSUPPORTED; }
+    fdb_jit_cache::Entry e{nullptr, nullptr, 0};
     Driver& d = driver();
     std::vector<char> cubin;
     std::string log;
@@ -248,6 +256,8 @@ int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share
         cudaFree(0);                                   // the runtime's primary context is current for the driver calls
         CUresult cr = d.ModuleLoadData(&e.mod, cubin.data());
         if (cr == CUDA_SUCCESS) cr = d.ModuleGetFunction(&e.fn, e.mod, "fdb_user_kernel");
+        size_t pb = 0;
+        if (cr == CUDA_SUCCESS) cr = d.ModuleGetGlobal(&e.prm, &pb, e.mod, "fdb_prm");
         if (cr != CUDA_SUCCESS) {
             const char* es = nullptr; d.GetErrorString(cr, &es);
             log = std::string("cuModuleLoadData/GetFunction: ") + (es ? es : "?");
@@ -256,14 +266,18 @@ int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share
         }
     }
     if (rc == FDB_OK) J.compiled++; else { J.failures++; J.last_log = log; }
-    J.map.emplace(key, e);                             // failures are cached too: no recompilation per call
-    *fn = e.fn;
+    auto ins = J.map.emplace(key, e);                  // failures are cached too: no recompilation per call
+    *fn = e.fn ? &ins.first->second : nullptr;         // (node addresses of an unordered_map are stable)
     return rc;
 }
 
-int jit_launch(fdb_ctx* ctx, void* fn, unsigned gridx, unsigned gridy, unsigned threads, void** args, const char* what) {
+int jit_launch(fdb_ctx* ctx, void* entry, unsigned gridx, unsigned gridy, unsigned threads, void** args, const char* what) {
     Driver& d = driver();
-    CUresult cr = d.LaunchKernel((CUfunction)fn, gridx, gridy, 1, threads, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
+    fdb_jit_cache::Entry* e = static_cast<fdb_jit_cache::Entry*>(entry);
+    CUresult cr = CUDA_SUCCESS;
+    if (ctx->n_prm > 0)      // stream-ordered, so a launch already queued keeps the pointers it was given
+        cr = d.MemcpyHtoDAsync(e->prm, ctx->prm_ptr, sizeof(const double*) * FDB_MAX_PARAMS, (CUstream)ctx->stream);
+    if (cr == CUDA_SUCCESS) cr = d.LaunchKernel(e->fn, gridx, gridy, 1, threads, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
     if (cr != CUDA_SUCCESS) {
         const char* es = nullptr; d.GetErrorString(cr, &es);
         return fail(ctx, FDB_ERR_CUDA, "%s: cuLaunchKernel: %s", what, es ? es : "?");
@@ -300,11 +314,11 @@ extern "C" int fdb_jit_stats(fdb_ctx* ctx, int64_t* compiled, int64_t* cache_hit
 extern "C" const char* fdb_jit_last_log(fdb_ctx* ctx) { return (ctx && ctx->jit) ? ctx->jit->last_log.c_str() : ""; }
 
 extern "C" int fdb_jit_compile_check(int kind, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi, const double* consts,
-                                     int n_consts, int n_acc, int halo, int result_reg, int N, int nansafe, int lane_sharing, char* log,
-                                     int64_t log_capacity, int64_t* cubin_bytes) {
+                                     int n_consts, int n_acc, int halo, int result_reg, int n_params, int N, int nansafe, int lane_sharing,
+                                     char* log, int64_t log_capacity, int64_t* cubin_bytes) {
     if (kind < JIT_GRADIENT || kind > JIT_HESSIAN || N < 1 || N > FDB_MAX_CHUNK) return FDB_ERR_BADARG;
     Program P;
-    int rc = build_program(nullptr, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, kind == JIT_JACOBIAN);
+    int rc = build_program(nullptr, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, kind == JIT_JACOBIAN, n_params);
     std::vector<char> cubin;
     std::string lg;
     if (rc == FDB_OK) rc = compile_source(make_source(kind, P, N, nansafe != 0, lane_sharing != 0, false), cubin, lg);

@@ -108,19 +108,22 @@ static int launch_program_gradient(fdb_ctx* ctx, unsigned grid, size_t smem, con
 }
 
 int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, const int32_t* epi, int n_epi, const double* consts,
-                         int n_consts, int n_acc, int halo, int result_reg, bool array_form) {
+                         int n_consts, int n_acc, int halo, int result_reg, bool array_form, int n_params) {
     if (n_term < 0 || n_term > PG_MAXI || n_epi < 0 || n_epi > PG_MAXI || n_consts < 0 || n_consts > PG_MAXC || n_acc < 0 || n_acc > PG_MAXK ||
         halo < 0 || result_reg < 0 || result_reg >= PG_MAXR || (n_term && !term) || (n_epi && !epi) || (n_consts && !consts))
         return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program exceeds interpreter limits (%d instr, %d consts, %d registers, %d accumulators)",
                     PG_MAXI, PG_MAXC, PG_MAXR, PG_MAXK);
     memset(&P, 0, sizeof P);
     P.n_term = n_term; P.n_epi = n_epi; P.n_acc = n_acc; P.halo = halo; P.result_reg = result_reg;
+    int used_params = 0;
     for (int part = 0; part < 2; part++) {
         const int32_t* src = part ? epi : term; const int cnt = part ? n_epi : n_term;
         for (int i = 0; i < cnt; i++) {
             const int op = src[4 * i], dst = src[4 * i + 1], a = src[4 * i + 2], b = src[4 * i + 3];
             const int kind = op >> 6, code = op & 63;
-            bool ok = dst >= 0 && dst < PG_MAXR && kind >= PK_LOADX && kind <= PK_MOV;
+            bool ok = dst >= 0 && dst < PG_MAXR && kind >= PK_LOADX && kind <= PK_PD;
+            if (kind == PK_DP) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < PG_MAXR && b >= 0 && b < n_params; if (b + 1 > used_params) used_params = b + 1; }
+            if (kind == PK_PD) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < n_params && b >= 0 && b < PG_MAXR; if (a + 1 > used_params) used_params = a + 1; }
             if (kind == PK_LOADX) ok = ok && !part && b >= 0 && b <= halo;
             if (kind == PK_UNARY) ok = ok && code >= FDB_NEG && code <= FDB_CBRT && a >= 0 && a < PG_MAXR;
             if (kind == PK_DD) ok = ok && code >= FDB_ADD && code <= FDB_HYPOT && a >= 0 && a < PG_MAXR && b >= 0 && b < PG_MAXR;
@@ -134,6 +137,17 @@ int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, con
         }
     }
     for (int i = 0; i < n_consts; i++) P.consts[i] = consts[i];
+    P.n_params = used_params;
+    return FDB_OK;
+}
+
+int check_params(fdb_ctx* ctx, const Program& P, int64_t nterms, const char* what) {
+    if (P.n_params > ctx->n_prm)
+        return fail(ctx, FDB_ERR_BADARG, "%s: the program reads %d parameter arrays, %d are bound (fdb_program_bind_params)", what, P.n_params, ctx->n_prm);
+    for (int k = 0; k < P.n_params; k++)
+        if (ctx->prm_len[k] < nterms)
+            return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: parameter array %d has %lld entries, the broadcast has %lld", k,
+                        (long long)ctx->prm_len[k], (long long)nterms);
     return FDB_OK;
 }
 
@@ -151,7 +165,8 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
     if (N < 1 || N > FDB_MAX_CHUNK) return fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", N);
     if (n < N) return fail(ctx, FDB_ERR_CHUNK, "chunk size cannot be greater than ForwardDiff.structural_length(x) (%d > %lld)", N, (long long)n);
     Program P;
-    int rc = build_program(ctx, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, false); if (rc) return rc;
+    int rc = build_program(ctx, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, false, ctx->n_prm); if (rc) return rc;
+    rc = check_params(ctx, P, x->n - halo, "fdb_program_gradient_chunked"); if (rc) return rc;
     Plan p = make_plan(n, N);
     const int64_t nchunks = (n == N) ? 1 : p.nchunks;
     if (chunk_hi < 0) chunk_hi = nchunks;
@@ -173,6 +188,8 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
             return finish(ctx, 1, "fdb_program_gradient_chunked(specialised)");
         }
     }
+    if (P.n_params) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters needs the run-time specialised kernel (%s)",
+                                ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     int nregs = 1;
     for (int i = 0; i < n_term; i++) { const int d = term_prog[4 * i + 1]; if ((term_prog[4 * i] >> 6) != PK_ACC && d + 1 > nregs) nregs = d + 1; }
     const size_t smem = (size_t)nregs * 2 * PG_VEC * T * sizeof(double);
@@ -182,3 +199,15 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
     return finish(ctx, 1, "fdb_program_gradient_chunked");
 }
 
+extern "C" int fdb_program_bind_params(fdb_ctx* ctx, int count, const fdb_array* const* arrays) {
+    if (!ctx || count < 0 || count > FDB_MAX_PARAMS || (count && !arrays))
+        return fail(ctx, FDB_ERR_BADARG, "fdb_program_bind_params: 0..%d plain arrays", FDB_MAX_PARAMS);
+    for (int k = 0; k < count; k++)
+        if (!arrays[k] || arrays[k]->level != 0) return fail(ctx, FDB_ERR_BADARG, "fdb_program_bind_params: parameter %d must be a plain (level-0) array", k);
+    ctx->n_prm = count;
+    for (int k = 0; k < FDB_MAX_PARAMS; k++) {
+        ctx->prm_ptr[k] = k < count ? arrays[k]->data : nullptr;
+        ctx->prm_len[k] = k < count ? arrays[k]->n : 0;
+    }
+    return FDB_OK;
+}

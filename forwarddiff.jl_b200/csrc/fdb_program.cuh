@@ -16,13 +16,14 @@ constexpr int PG_MAXK = 4;       // sum accumulators
 constexpr int PG_VEC = 4;        // terms per thread per decoded instruction on the lane-shared path
 
 struct Program {
-    int n_term, n_epi, n_acc, halo, result_reg, pad;
+    int n_term, n_epi, n_acc, halo, result_reg, n_params;
     short term[PG_MAXI][4];      // {op, dst, a, b}
     short epi[PG_MAXI][4];
     double consts[PG_MAXC];
 };
 
-enum { PK_LOADX = 0, PK_UNARY = 1, PK_DD = 2, PK_DC = 3, PK_CD = 4, PK_ACC = 5, PK_MOV = 6 };
+enum { PK_LOADX = 0, PK_UNARY = 1, PK_DD = 2, PK_DC = 3, PK_CD = 4, PK_ACC = 5, PK_MOV = 6,
+       PK_DP = 7, PK_PD = 8 };   // Dual (x) param[b][i], param[a][i] (x) Dual: specialised kernels only (fdb_jit.cu)
 
 template <int N, bool NS> FDB_DEV Dual<double, N, NS> pg_unary(int code, const Dual<double, N, NS>& x) {
     switch (code) {
@@ -230,8 +231,10 @@ struct SumK {   // block_combine policy: K sum accumulators
 
 // fdb_jit.cu: the kernel specialised for this program (kind 0 gradient, 1 Jacobian, 2 Hessian), or non-zero
 int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share, bool mir, void** fn);
+// the bound parameter arrays cover `nterms` entries each (and there are as many as the program reads)
+int check_params(fdb_ctx* ctx, const Program& P, int64_t nterms, const char* what);
 
 int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, const int32_t* epi, int n_epi, const double* consts,
-                  int n_consts, int n_acc, int halo, int result_reg, bool array_form);
+                  int n_consts, int n_acc, int halo, int result_reg, bool array_form, int n_params);
 
 }  // namespace fdb

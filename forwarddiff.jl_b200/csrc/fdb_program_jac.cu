@@ -58,7 +58,8 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
     if (ldJ < m || J->n < ldJ * (n - 1) + m) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: Jacobian result must hold %lld x %lld", (long long)m, (long long)n);
     if (y && y->n != m) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: y has %lld entries, f(x) has %lld", (long long)y->n, (long long)m);
     Program P;
-    int rc = build_program(ctx, P, prog, n_instr, nullptr, 0, consts, n_consts, 0, halo, result_reg, true); if (rc) return rc;
+    int rc = build_program(ctx, P, prog, n_instr, nullptr, 0, consts, n_consts, 0, halo, result_reg, true, ctx->n_prm); if (rc) return rc;
+    rc = check_params(ctx, P, m, "fdb_program_jacobian_chunked"); if (rc) return rc;
     Plan p = make_plan(n, N);
     const int64_t nchunks = (n == N) ? 1 : p.nchunks;
     if (chunk_hi < 0) chunk_hi = nchunks;
@@ -84,6 +85,8 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
             return finish(ctx, 1, "fdb_program_jacobian_chunked(specialised)");
         }
     }
+    if (P.n_params) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters needs the run-time specialised kernel (%s)",
+                                ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     if (M.count) {
         FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
             (program_jacobian_kernel<NN, NS, T, true><<<grid, T, 0, ctx->stream>>>(P, ctx->lane_sharing, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, J->data, ldJ, yp, nrb, nch, true, M))));

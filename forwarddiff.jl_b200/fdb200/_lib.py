@@ -124,7 +124,8 @@ SIGNATURES = {
     "fdb_jit_stats": (C.c_int, [c_ctx, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
     "fdb_jit_last_log": (C.c_char_p, [c_ctx]),
     "fdb_jit_compile_check": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, C.c_int,
-                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, i64, C.POINTER(i64)]),
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, i64, C.POINTER(i64)]),
+    "fdb_program_bind_params": (C.c_int, [c_ctx, C.c_int, C.POINTER(C.c_void_p)]),
     "fdb_gradient_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, C.c_int, i64, i64, _dp, _dp]),
     "fdb_hessian_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, C.c_int, i64, i64, _dp, i64, _dp, _dp]),
     "fdb_exchange_create": (C.c_int, [c_ctx, i64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

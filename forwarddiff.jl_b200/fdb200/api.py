@@ -268,6 +268,29 @@ def _i32p(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32)) if a.size else None
 
 
+class _bound_params:
+    """Upload the data arrays a traced f closes over and bind them for the program call (fdb_program_bind_params)."""
+
+    def __init__(self, ctx, prog):
+        self.ctx, self.arrays = ctx, [ctx.array(a) for a in prog.params]
+
+    def __enter__(self):
+        if self.arrays:
+            hs = (C.c_void_p * len(self.arrays))(*[a.h for a in self.arrays])
+            self.ctx.check(self.ctx.lib.fdb_program_bind_params(self.ctx.h, len(self.arrays), hs))
+        return self
+
+    def __exit__(self, *exc):
+        if self.arrays:
+            self.ctx.lib.fdb_program_bind_params(self.ctx.h, 0, None)
+        return False
+
+
+def _usable(ctx, prog):
+    """A program with data arrays runs on the specialised kernels only; without them f takes the reference loop."""
+    return prog is not None and (not prog.params or ctx.jit_enabled())
+
+
 def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True, graph=True):
     """ForwardDiff.gradient(f, x, cfg, Val{check}()) (src/gradient.jl:16-24)."""
     if isinstance(x, _Structured):
@@ -305,7 +328,7 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
         value = _fused_gradient(ctx, fid, x, N, lo, hi, out)
     else:
         prog = _try_trace("scalar", f, n) if fuse else None
-        if prog is not None:
+        if _usable(ctx, prog):
             value = _program_gradient(ctx, prog, x, N, lo, hi, out)
         else:
             value = _loop_gradient(ctx, f, x, cfg, lo, hi, out, graph)
@@ -361,11 +384,14 @@ def _program_hessian(ctx, result, H, f, x, N, lo, hi):
     prog = _try_trace("scalar", f, n)
     if prog is None:
         raise _lib.UnsupportedOp("hessian: f must be a catalogue target or flatten to sums of elementwise terms (no prod, no strided views)")
+    if prog.params and not ctx.jit_enabled():
+        raise _lib.UnsupportedOp("hessian: a function with data arrays needs the run-time specialised kernel")
     xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
     Hd = B200Array.alloc(ctx, n * n); gd = B200Array.alloc(ctx, n); vd = B200Array.alloc(ctx, 1)
-    ctx.check(ctx.lib.fdb_program_hessian_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
-                                                  prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
-                                                  prog.n_acc, prog.halo, prog.result_reg, xd.h, N, lo, hi, Hd.h, n, gd.h, vd.h))
+    with _bound_params(ctx, prog):
+        ctx.check(ctx.lib.fdb_program_hessian_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
+                                                      prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
+                                                      prog.n_acc, prog.halo, prog.result_reg, xd.h, N, lo, hi, Hd.h, n, gd.h, vd.h))
     nchunks = 1 if n == N else chunk_plan(n, N)["nchunks"]
     last = hi < 0 or hi == nchunks
     c0, c1 = lo * N, (n if last else hi * N)
@@ -382,9 +408,10 @@ def _program_gradient(ctx, prog, x, N, lo, hi, out):
     xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
     res = out if isinstance(out, _DeviceArray) else B200Array.alloc(ctx, xd.n)
     val = B200Array.alloc(ctx, 1)
-    ctx.check(lib.fdb_program_gradient_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
-                                               prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
-                                               prog.n_acc, prog.halo, prog.result_reg, xd.h, N, lo, hi, res.h, val.h))
+    with _bound_params(ctx, prog):
+        ctx.check(lib.fdb_program_gradient_chunked(ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
+                                                   prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
+                                                   prog.n_acc, prog.halo, prog.result_reg, xd.h, N, lo, hi, res.h, val.h))
     nchunks = 1 if xd.n == N else chunk_plan(xd.n, N)["nchunks"]
     lo_e, hi_e = lo * N, (xd.n if (hi < 0 or hi == nchunks) else hi * N)
     if res is not out:
@@ -525,7 +552,7 @@ def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None
         return _mlp2_jacobian(ctx, result, out, f, x, N, lo, hi)
     if fid is None:
         prog = _try_trace("array", f, n) if (fuse and y is None) else None
-        if prog is not None:
+        if _usable(ctx, prog):
             return _program_jacobian(ctx, prog, result, out, x, N, lo, hi)
         return _loop_jacobian(ctx, result, out, f, x, cfg, y, lo, hi)
     params = params or getattr(f, "params", {}) or {}
@@ -591,9 +618,10 @@ def _program_jacobian(ctx, prog, result, out, x, N, lo, hi):
             raise DimensionMismatch(f"Jacobian result has shape {out.shape}, expected {(m, n)}")
         Jd = B200Array.alloc(ctx, m * n)
     yd = B200Array.alloc(ctx, m)
-    ctx.check(lib.fdb_program_jacobian_chunked(ctx.h, _i32p(prog.term), len(prog.term),
-                                               prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
-                                               prog.halo, prog.result_reg, xd.h, N, lo, hi, Jd.h, m, yd.h))
+    with _bound_params(ctx, prog):
+        ctx.check(lib.fdb_program_jacobian_chunked(ctx.h, _i32p(prog.term), len(prog.term),
+                                                   prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
+                                                   prog.halo, prog.result_reg, xd.h, N, lo, hi, Jd.h, m, yd.h))
     nchunks = 1 if n == N else chunk_plan(n, N)["nchunks"]
     last = hi < 0 or hi == nchunks
     if Jd is not out:

@@ -65,7 +65,22 @@ class Context:
 
     def set_jit(self, flag):
         """Run-time specialisation of the op-program kernels (fdb_jit.cu); False = per-thread interpreter."""
+        self._jit = bool(flag)
         self.check(self.lib.fdb_set_jit(self.h, int(flag)))
+
+    def jit_enabled(self):
+        return getattr(self, "_jit", True)
+
+    def data_array(self, host):
+        """Device copy of a NumPy data array used inside f on the materialised path (cached by identity while a
+        gradient / jacobian call runs, so the chunk loop uploads it once)."""
+        cache = self.__dict__.setdefault("_data_cache", {})
+        hit = cache.get(id(host))
+        if hit is None or hit[0] is not host:
+            if len(cache) > 64:
+                cache.clear()
+            hit = cache[id(host)] = (host, self.array(np.ascontiguousarray(host, dtype=np.float64).ravel()))
+        return hit[1]
 
     def jit_stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
@@ -244,6 +259,7 @@ class B200Array(_DeviceArray):
 
 class B200DualArray(_DeviceArray):
     """Vector{Dual{T,Float64,N}} (level 1) or Vector{Dual{T,Dual{T,Float64,N},N}} (level 2), SoA planes."""
+    __array_ufunc__ = None          # `ndarray * xdual` defers to xdual.__rmul__ (Real (x) Dual broadcast)
 
     @classmethod
     def alloc(cls, ctx, n, N, level=1):
@@ -297,6 +313,8 @@ class B200DualArray(_DeviceArray):
             out = self._out()
             ctx.check(lib.fdb_map2_scalar(ctx.h, OP2[op], out.h, self.h, float(other), int(reverse)))
             return out
+        if isinstance(other, np.ndarray) and other.ndim == 1:        # closed-over data: Vector{Float64} .(op) Vector{Dual}
+            return self._map2(op, ctx.data_array(other), reverse)
         return NotImplemented
 
     def __add__(self, o): return self._map2("add", o)

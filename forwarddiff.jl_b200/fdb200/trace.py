@@ -3,16 +3,17 @@
 The Julia shim would do this by walking the `Broadcasted` tree of `f`'s broadcast expressions
 (a custom BroadcastStyle); here the same flattening is done by calling `f` once on a symbolic array
 whose operators record instead of compute.  Supported shape: elementwise src/dual.jl arithmetic on
-unit-stride views `x[a:b]` of the input (all of one common length), `sum()` reductions of such arrays,
-and scalar Dual arithmetic on the reduced values.  Anything else raises TraceError and the caller
+unit-stride views `x[a:b]` of the input (all of one common length), NumPy arrays the function closes over
+(data: `w * x**2` -- they become array parameters read at the term index, with the Real (x) Dual rules), `sum()`
+reductions of such arrays, and scalar Dual arithmetic on the reduced values.  Anything else raises TraceError and the caller
 falls back to the reference chunk loop on materialised device duals.
 """
 import numpy as np
 
 from ._lib import OP1, OP2
 
-K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC, K_MOV = range(7)
-MAX_INSTR, MAX_CONST, MAX_REG, MAX_ACC = 48, 24, 12, 4
+K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC, K_MOV, K_DP, K_PD = range(9)
+MAX_INSTR, MAX_CONST, MAX_REG, MAX_ACC, MAX_PARAMS = 48, 24, 12, 4, 4
 
 
 class TraceError(Exception):
@@ -33,6 +34,7 @@ class _Node:
 
 class _Sym:
     """Common operator plumbing of the symbolic array (stage 'term') and symbolic scalar (stage 'scalar')."""
+    __array_ufunc__ = None          # `ndarray * sym` defers to sym.__rmul__ instead of broadcasting over an object
 
     def __init__(self, tr, node, length):
         self.tr, self.node, self.n = tr, node, length
@@ -61,9 +63,29 @@ class _Sym:
                 raise TraceError(f"{op} needs two Dual operands")
             kind = K_CD if reverse else K_DC
             return self._like(_Node(self.tr, kind, code, (self.node,), const=float(other), stage=self.node.stage))
+        if isinstance(other, np.ndarray):
+            return self._map2_param(code, op, other, reverse)
         self._check(other)
         a, b = (other.node, self.node) if reverse else (self.node, other.node)
         return self._like(_Node(self.tr, K_DD, code, (a, b), stage=self.node.stage))
+
+    def _map2_param(self, code, op, arr, reverse):
+        """A closed-over data array: Dual (x) Real elementwise, the array read at the term index."""
+        if not isinstance(self, TArray) or code > OP2["pow"]:
+            raise TraceError(f"{op} with a data array is not expressible")
+        if arr.ndim != 1 or arr.size != self.n:
+            from ._lib import DimensionMismatch
+            raise DimensionMismatch(f"arrays could not be broadcast to a common size ({self.n} vs {arr.shape})")
+        tr = self.tr
+        for k, a in enumerate(tr.params):
+            if a is arr:
+                break
+        else:
+            if len(tr.params) >= MAX_PARAMS:
+                raise TraceError("too many data arrays")
+            tr.params.append(arr)
+            k = len(tr.params) - 1
+        return self._like(_Node(tr, K_PD if reverse else K_DP, code, (self.node,), const=k, stage=self.node.stage))
 
     def __add__(self, o): return self._map2("add", o)
     def __radd__(self, o): return self._map2("add", o, True)
@@ -118,7 +140,7 @@ class TArray(_Sym):
 class _Trace:
     def __init__(self, n):
         self.n = n
-        self.nodes, self.accs, self.term_lengths = [], [], set()
+        self.nodes, self.accs, self.term_lengths, self.params = [], [], set(), []
 
 
 def _emit(tr, roots, stage, preloaded):
@@ -174,6 +196,10 @@ def _emit(tr, roots, stage, preloaded):
             instrs.append(((K_DC << 6) | nd.op, dst, srcs[0], cidx(nd.const)))
         elif nd.kind == K_CD:
             instrs.append(((K_CD << 6) | nd.op, dst, cidx(nd.const), srcs[0]))
+        elif nd.kind == K_DP:
+            instrs.append(((K_DP << 6) | nd.op, dst, srcs[0], int(nd.const)))
+        elif nd.kind == K_PD:
+            instrs.append(((K_PD << 6) | nd.op, dst, int(nd.const), srcs[0]))
         else:
             raise TraceError("unexpected node in stage " + stage)
         if len(instrs) > MAX_INSTR:
@@ -184,11 +210,12 @@ def _emit(tr, roots, stage, preloaded):
 class Program:
     """term/epilogue instruction arrays + constants, ready for fdb_program_*_chunked."""
 
-    def __init__(self, term, epi, consts, n_acc, halo, result_reg, out_len):
+    def __init__(self, term, epi, consts, n_acc, halo, result_reg, out_len, params=()):
         self.term = np.asarray(term, dtype=np.int32).reshape(-1, 4)
         self.epi = np.asarray(epi, dtype=np.int32).reshape(-1, 4)
         self.consts = np.asarray(consts, dtype=np.float64)
         self.n_acc, self.halo, self.result_reg, self.out_len = n_acc, halo, result_reg, out_len
+        self.params = [np.ascontiguousarray(a, dtype=np.float64) for a in params]     # data arrays, one entry per term
 
 
 def _common_halo(tr, lengths):
@@ -219,7 +246,7 @@ def trace_scalar(f, n):
         raise TraceError("program too long")
     pre = {nd.id: nd.op for nd in tr.nodes if nd.kind == K_ACC}
     epi, ereg = _emit(tr, [y.node], "scalar", pre)
-    return Program(term, epi, tr.consts, len(tr.accs), halo, ereg[y.node.id], 1)
+    return Program(term, epi, tr.consts, len(tr.accs), halo, ereg[y.node.id], 1, tr.params)
 
 
 def trace_array(f, n):
@@ -234,4 +261,4 @@ def trace_array(f, n):
         raise TraceError("reductions inside an array-valued f need two passes")
     L, halo = _common_halo(tr, {y.n})
     term, reg = _emit(tr, [y.node], "term", {})
-    return Program(term, [], tr.consts, 0, halo, reg[y.node.id], L)
+    return Program(term, [], tr.consts, 0, halo, reg[y.node.id], L, tr.params)

@@ -264,6 +264,13 @@ int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_te
                                 const double* consts, int n_consts, int n_acc, int halo, int result_reg, const fdb_array* x, int N,
                                 int64_t chunk_lo, int64_t chunk_hi, fdb_array* H, int64_t ldH, fdb_array* grad, fdb_array* value_dev);
 
+/* Data arrays the user's f closes over (`f(x) = sum(w .* x.^2)`): up to FDB_MAX_PARAMS plain Float64 device arrays, read at the
+ * term index i by the program instructions of kind 7 (Dual (x) param[b][i], Real-on-the-right rules of src/dual.jl) and 8
+ * (param[a][i] (x) Dual).  Each must hold at least xlen - halo entries.  They stay bound until rebound; count = 0 unbinds.
+ * Programs with array parameters run on the specialised kernels only. */
+#define FDB_MAX_PARAMS 4
+int fdb_program_bind_params(fdb_ctx* ctx, int count, const fdb_array* const* arrays);
+
 /* Run-time specialisation (fdb_jit.cu).  Julia compiles f for Vector{Dual{T,Float64,N}} when gradient(f, x, cfg) first
  * runs; likewise the fdb_program_* drivers turn the op-program into a functor and instantiate the library's sweep kernel
  * templates for it with NVRTC (sm_100a, -fmad=false), caching the result per context.  1 (default): specialise when
@@ -275,8 +282,8 @@ const char* fdb_jit_last_log(fdb_ctx* ctx);   /* NVRTC log of the last failed sp
 /* host-only (no GPU, no context): generate and compile the specialised kernel of a program; kind 0 gradient,
  * 1 Jacobian, 2 Hessian.  Returns 0 and the cubin size, or the NVRTC log in `log`. */
 int fdb_jit_compile_check(int kind, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi, const double* consts,
-                          int n_consts, int n_acc, int halo, int result_reg, int N, int nansafe, int lane_sharing, char* log,
-                          int64_t log_capacity, int64_t* cubin_bytes);
+                          int n_consts, int n_acc, int halo, int result_reg, int n_params, int N, int nansafe, int lane_sharing,
+                          char* log, int64_t log_capacity, int64_t* cubin_bytes);
 
 /* ---- host-buffer entry points (what ForwardDiff.gradient!(out, f, x, cfg) with
  * host Vectors binds to): upload x, run the sweeps, download the result slice.  grad_host has

@@ -58,15 +58,19 @@ def test_specialised_kernels_compile_on_the_host():
     lib = fdb200._lib.load()
     dp = C.POINTER(C.c_double)
     jac = trace.trace_array(lambda xd: fdb200.tanh(xd[1:] * xd[:-1]) + 2.0 ** xd[:-1], 50)
+    w = np.linspace(1.0, 2.0, 99)
+    data = trace.trace_scalar(lambda xd: (w * (xd[1:] - xd[:-1]) ** 2 / (1.0 + w)).sum(), 100)     # closes over a data array
+    assert len(data.params) == 2            # w and the host-evaluated 1.0 + w
     for kind, prog, N in ((0, trace.trace_scalar(F.rosenbrock_generic, 100), 12), (0, trace.trace_scalar(F.ackley_generic, 100), 7),
-                          (2, trace.trace_scalar(F.rosenbrock_generic, 100), 8), (1, jac, 5)):
+                          (2, trace.trace_scalar(F.rosenbrock_generic, 100), 8), (1, jac, 5), (0, data, 6), (2, data, 4),
+                          (2, trace.trace_scalar(F.ackley_generic, 100), 8)):
         log = C.create_string_buffer(1 << 16); nbytes = C.c_int64()
         rc = lib.fdb_jit_compile_check(kind, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
                                        prog.consts.ctypes.data_as(dp) if prog.consts.size else None, prog.consts.size, prog.n_acc,
-                                       prog.halo, prog.result_reg, N, 0, 1, log, len(log), C.byref(nbytes))
+                                       prog.halo, prog.result_reg, len(prog.params), N, 0, 1, log, len(log), C.byref(nbytes))
         assert rc == 0 and nbytes.value > 1000, log.value.decode()
     bad = np.array([[7 << 6, 0, 0, 0]], dtype=np.int32)                 # unknown instruction kind
-    assert lib.fdb_jit_compile_check(0, _i32p(bad), 1, None, 0, None, 0, 1, 0, 0, 4, 0, 1, None, 0, None) != 0
+    assert lib.fdb_jit_compile_check(0, _i32p(bad), 1, None, 0, None, 0, 1, 0, 0, 0, 4, 0, 1, None, 0, None) != 0
 
 
 @pytest.mark.gpu
@@ -147,6 +151,48 @@ def test_program_jacobian_elementwise_and_stencil(ctx, N, mode):
         expect[i, i + 2] = 1.0; expect[i, i + 1] = -2.0; expect[i, i] = 2.0 * x[i]
     assert np.array_equal(res.derivs[0], expect)
     assert np.allclose(res.value, x[2:] - 2.0 * x[1:-1] + x[:-2] ** 2, rtol=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 5, 12])
+def test_functions_closing_over_data_arrays(ctx, N, mode):
+    """f(x) = sum(w .* (x[2:end] .- x[1:end-1]).^2 ./ (1 .+ w)) + sum((x .- d).^2): NumPy arrays inside f become array
+    parameters of the program (Real (x) Dual rules).  Specialised kernels only; with the interpreter f takes the reference
+    loop on materialised duals, which handles Vector{Float64} .(op) Vector{Dual} through fdb_map2."""
+    n = 101
+    rng = np.random.default_rng(8)
+    x, w, d = rng.uniform(0.5, 1.5, n), rng.uniform(1.0, 2.0, n - 1), rng.uniform(0.0, 1.0, n)
+
+    def f(xd):
+        return (w * (xd[1:] - xd[:-1]) ** 2 / (1.0 + w)).sum() + ((xd - d) ** 2).sum()
+
+    c = w / (1.0 + w)
+    g_ref = 2.0 * (x - d)
+    g_ref[1:] += 2.0 * c * (x[1:] - x[:-1]); g_ref[:-1] -= 2.0 * c * (x[1:] - x[:-1])
+    H_ref = 2.0 * np.eye(n)
+    for i in range(n - 1):
+        H_ref[i, i] += 2 * c[i]; H_ref[i + 1, i + 1] += 2 * c[i]; H_ref[i, i + 1] -= 2 * c[i]; H_ref[i + 1, i] -= 2 * c[i]
+    res = fdb200.GradientResult(x)
+    fdb200.gradient_b(res, f, x, fdb200.GradientConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+    assert np.allclose(res.derivs[0], g_ref, rtol=1e-12, atol=1e-13)
+    assert res.value == pytest.approx((c * (x[1:] - x[:-1]) ** 2).sum() + ((x - d) ** 2).sum(), rel=1e-13)
+    gl = fdb200.gradient(f, x, fdb200.GradientConfig(f, x, fdb200.Chunk(N)), ctx=ctx, fuse=False)          # reference loop
+    assert np.allclose(res.derivs[0], gl, rtol=1e-12, atol=1e-13)
+
+    def fa(xd):
+        return d[:-1] * xd[1:] - xd[:-1] / w + w ** 2.0
+
+    J = fdb200.jacobian(fa, x, fdb200.JacobianConfig(fa, x, fdb200.Chunk(N)), ctx=ctx)
+    J_ref = np.zeros((n - 1, n))
+    for i in range(n - 1):
+        J_ref[i, i + 1] = d[i]; J_ref[i, i] = -1.0 / w[i]
+    assert np.allclose(J, J_ref, rtol=1e-15, atol=0)
+    if mode == "specialised":
+        H = fdb200.hessian(f, x, fdb200.HessianConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+        assert np.allclose(H, H_ref, rtol=1e-12, atol=1e-13)
+    else:
+        with pytest.raises(fdb200.UnsupportedOp):
+            fdb200.hessian(f, x, fdb200.HessianConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
 
 
 # ---- the reference loop as a replayed CUDA graph (fdb_graph.cu) ------------------------------------------
