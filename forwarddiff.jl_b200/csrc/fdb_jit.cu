@@ -150,7 +150,10 @@ static std::string decl_regs() {
 enum { JIT_GRADIENT = 0, JIT_JACOBIAN = 1, JIT_HESSIAN = 2 };
 
 static std::string make_source(int kind, const Program& P, int N, bool ns, bool share, bool mir) {
-    std::string s = "#include \"fdb_sweep_kernel.cuh\"\n#include \"fdb_hessian_kernel.cuh\"\n#include \"fdb_jac_kernel.cuh\"\nnamespace fdb {\n";
+    std::string s = "#include \"fdb_sweep_kernel.cuh\"\n#include \"fdb_hessian_kernel.cuh\"\n#include \"fdb_jac_kernel.cuh\"\n";
+    // closed-over data arrays of the user's f: pointers uploaded into the module before each launch (jit_launch)
+    s += "extern \"C\" { __constant__ const double* fdb_prm[" + std::to_string(FDB_MAX_PARAMS) + "]; }\n";
+    s += "namespace fdb {\n";
     char buf[96];
     for (int i = 0; i < PG_MAXC; i++) {            // constants by bit pattern: exact for every double including Inf/NaN
         long long bits; memcpy(&bits, &P.consts[i], 8);
@@ -158,8 +161,6 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
         s += buf;
     }
     const int K = P.n_acc > 0 ? P.n_acc : 1;
-    // closed-over data arrays of the user's f: pointers uploaded into the module before each launch (jit_launch)
-    s += "__constant__ const double* fdb_prm[" + std::to_string(FDB_MAX_PARAMS) + "];\n";
     s += "struct UserFn {\n";
     s += std::string("    static constexpr bool PLAIN_SUM = ") + ((P.n_epi == 0 && K == 1 && P.result_reg == 0) ? "true" : "false") + ";\n";
     s += "    static constexpr int K = " + std::to_string(K) + ";\n    static constexpr int HALO = " + std::to_string(P.halo) + ";\n";
@@ -257,7 +258,7 @@ int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share
         CUresult cr = d.ModuleLoadData(&e.mod, cubin.data());
         if (cr == CUDA_SUCCESS) cr = d.ModuleGetFunction(&e.fn, e.mod, "fdb_user_kernel");
         size_t pb = 0;
-        if (cr == CUDA_SUCCESS) cr = d.ModuleGetGlobal(&e.prm, &pb, e.mod, "fdb_prm");
+        if (cr == CUDA_SUCCESS && P.n_params > 0) cr = d.ModuleGetGlobal(&e.prm, &pb, e.mod, "fdb_prm");
         if (cr != CUDA_SUCCESS) {
             const char* es = nullptr; d.GetErrorString(cr, &es);
             log = std::string("cuModuleLoadData/GetFunction: ") + (es ? es : "?");
@@ -275,7 +276,7 @@ int jit_launch(fdb_ctx* ctx, void* entry, unsigned gridx, unsigned gridy, unsign
     Driver& d = driver();
     fdb_jit_cache::Entry* e = static_cast<fdb_jit_cache::Entry*>(entry);
     CUresult cr = CUDA_SUCCESS;
-    if (ctx->n_prm > 0)      // stream-ordered, so a launch already queued keeps the pointers it was given
+    if (ctx->n_prm > 0 && e->prm)      // stream-ordered, so a launch already queued keeps the pointers it was given
         cr = d.MemcpyHtoDAsync(e->prm, ctx->prm_ptr, sizeof(const double*) * FDB_MAX_PARAMS, (CUstream)ctx->stream);
     if (cr == CUDA_SUCCESS) cr = d.LaunchKernel(e->fn, gridx, gridy, 1, threads, 1, 1, 0, (CUstream)ctx->stream, args, nullptr);
     if (cr != CUDA_SUCCESS) {
