@@ -72,15 +72,20 @@ class Context:
         return getattr(self, "_jit", True)
 
     def data_array(self, host):
-        """Device copy of a NumPy data array used inside f on the materialised path (cached by identity while a
-        gradient / jacobian call runs, so the chunk loop uploads it once)."""
+        """Device copy of a NumPy data array used inside f on the materialised path.  Cached by content, so the chunk
+        loop uploads it once and the captured iteration of the graph-replayed loop (where f runs again and temporaries
+        like `1.0 + w` are new objects) finds the copy made by the eager first chunk instead of uploading mid-capture."""
         cache = self.__dict__.setdefault("_data_cache", {})
-        hit = cache.get(id(host))
-        if hit is None or hit[0] is not host:
+        flat = np.ascontiguousarray(host, dtype=np.float64).ravel()
+        key = (flat.size, hash(flat.tobytes()))
+        hit = cache.get(key)
+        if hit is None:
+            if self._capturing:
+                raise FdbError("a data array was first seen while the chunk loop was being captured")
             if len(cache) > 64:
                 cache.clear()
-            hit = cache[id(host)] = (host, self.array(np.ascontiguousarray(host, dtype=np.float64).ravel()))
-        return hit[1]
+            hit = cache[key] = self.array(flat)
+        return hit
 
     def jit_stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
