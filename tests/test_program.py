@@ -156,31 +156,34 @@ def test_program_jacobian_elementwise_and_stencil(ctx, N, mode):
 @pytest.mark.gpu
 @pytest.mark.parametrize("N", [1, 5, 12])
 def test_functions_closing_over_data_arrays(ctx, N, mode):
-    """f(x) = sum(w .* (x[2:end] .- x[1:end-1]).^2 ./ (1 .+ w)) + sum((x .- d).^2): NumPy arrays inside f become array
+    """f(x) = sum(w .* (x[2:end] .- x[1:end-1]).^2 ./ (1 .+ w)) + sum((x[1:end-1] .- d).^2): NumPy arrays inside f become array
     parameters of the program (Real (x) Dual rules).  Specialised kernels only; with the interpreter f takes the reference
     loop on materialised duals, which handles Vector{Float64} .(op) Vector{Dual} through fdb_map2."""
     n = 101
     rng = np.random.default_rng(8)
-    x, w, d = rng.uniform(0.5, 1.5, n), rng.uniform(1.0, 2.0, n - 1), rng.uniform(0.0, 1.0, n)
+    x, w, d = rng.uniform(0.5, 1.5, n), rng.uniform(1.0, 2.0, n - 1), rng.uniform(0.0, 1.0, n - 1)
 
     def f(xd):
-        return (w * (xd[1:] - xd[:-1]) ** 2 / (1.0 + w)).sum() + ((xd - d) ** 2).sum()
+        return (w * (xd[1:] - xd[:-1]) ** 2 / (1.0 + w)).sum() + ((xd[:-1] - d) ** 2).sum()
 
+    from fdb200 import trace
+    assert len(trace.trace_scalar(f, n).params) == 3                 # w, 1.0 + w (evaluated on the host), d
     c = w / (1.0 + w)
-    g_ref = 2.0 * (x - d)
+    g_ref = np.zeros(n)
+    g_ref[:-1] += 2.0 * (x[:-1] - d)
     g_ref[1:] += 2.0 * c * (x[1:] - x[:-1]); g_ref[:-1] -= 2.0 * c * (x[1:] - x[:-1])
-    H_ref = 2.0 * np.eye(n)
+    H_ref = 2.0 * np.eye(n); H_ref[-1, -1] = 0.0
     for i in range(n - 1):
         H_ref[i, i] += 2 * c[i]; H_ref[i + 1, i + 1] += 2 * c[i]; H_ref[i, i + 1] -= 2 * c[i]; H_ref[i + 1, i] -= 2 * c[i]
     res = fdb200.GradientResult(x)
     fdb200.gradient_b(res, f, x, fdb200.GradientConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
     assert np.allclose(res.derivs[0], g_ref, rtol=1e-12, atol=1e-13)
-    assert res.value == pytest.approx((c * (x[1:] - x[:-1]) ** 2).sum() + ((x - d) ** 2).sum(), rel=1e-13)
+    assert res.value == pytest.approx((c * (x[1:] - x[:-1]) ** 2).sum() + ((x[:-1] - d) ** 2).sum(), rel=1e-13)
     gl = fdb200.gradient(f, x, fdb200.GradientConfig(f, x, fdb200.Chunk(N)), ctx=ctx, fuse=False)          # reference loop
     assert np.allclose(res.derivs[0], gl, rtol=1e-12, atol=1e-13)
 
     def fa(xd):
-        return d[:-1] * xd[1:] - xd[:-1] / w + w ** 2.0
+        return d * xd[1:] - xd[:-1] / w + w ** 2.0
 
     J = fdb200.jacobian(fa, x, fdb200.JacobianConfig(fa, x, fdb200.Chunk(N)), ctx=ctx)
     J_ref = np.zeros((n - 1, n))
