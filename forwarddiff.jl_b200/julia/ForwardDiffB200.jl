@@ -151,6 +151,9 @@ end
 struct Program
     term::Matrix{Int32}; epi::Matrix{Int32}; consts::Vector{Float64}; n_acc::Int; halo::Int; result_reg::Int
 end
+# data arrays the flattened f closes over (program instruction kinds 7 / 8): bound for the following program_* calls
+bind_params!(ctx::Context, arrays::Vector{B200Array{Float64}}) =
+    check(ctx.h, ccall((:fdb_program_bind_params, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}), ctx.h, length(arrays), [a.h for a in arrays]))
 function program_gradient!(result::B200Array{Float64}, p::Program, x::B200Array{Float64}, ::Chunk{N}; lo = 0, hi = -1) where {N}
     value = B200Array{Float64}(undef, 1; ctx = x.ctx)
     GC.@preserve p check(x.ctx.h, ccall((:fdb_program_gradient_chunked, libfdb200), Cint,
