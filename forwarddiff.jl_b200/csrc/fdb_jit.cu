@@ -122,11 +122,13 @@ static std::string C(int c) { return "c" + std::to_string(c); }
 // one statement per instruction, the same evaluation order as pg_run (fdb_program.cuh)
 static std::string emit_part(const short (*code)[4], int n) {
     std::string s;
+    int close_at = -1;
     for (int pc = 0; pc < n; pc++) {
         const int op = code[pc][0], dst = code[pc][1], a = code[pc][2], b = code[pc][3];
         const int kind = op >> 6, c = op & 63;
         s += "        ";
         switch (kind) {
+            case PK_GUARD: s += "if (i + " + std::to_string(a) + " < n) {"; close_at = pc + b; break;
             case PK_LOADX: s += R(dst) + " = x(i + " + std::to_string(b) + ");"; break;
             case PK_UNARY: s += R(dst) + " = " + (c == FDB_NEG ? "-" + R(a) : std::string(unary_fn(c)) + "(" + R(a) + ")") + ";"; break;
             case PK_DD: s += R(dst) + " = " + binary_expr(c, R(a), R(b)) + ";"; break;
@@ -138,6 +140,7 @@ static std::string emit_part(const short (*code)[4], int n) {
             default: s += R(dst) + " = " + R(a) + ";"; break;
         }
         s += "\n";
+        if (pc == close_at) { s += "        }\n"; close_at = -1; }
     }
     return s;
 }
@@ -164,11 +167,11 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
     s += "struct UserFn {\n";
     s += std::string("    static constexpr bool PLAIN_SUM = ") + ((P.n_epi == 0 && K == 1 && P.result_reg == 0) ? "true" : "false") + ";\n";
     s += "    static constexpr int K = " + std::to_string(K) + ";\n    static constexpr int HALO = " + std::to_string(P.halo) + ";\n";
-    s += "    static __device__ int64_t nterms(int64_t n) { return n > HALO ? n - HALO : 0; }\n";
+    s += "    static __device__ int64_t nterms(int64_t n) { return n > " + std::to_string(P.term_halo) + " ? n - " + std::to_string(P.term_halo) + " : 0; }\n";
     s += "    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }\n";
     s += "    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }\n";
     // term: the user's broadcast body for one i, adding into the sum accumulators
-    s += "    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t, D (&acc)[K]) {\n" + decl_regs() +
+    s += "    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t n, D (&acc)[K]) {\n" + decl_regs() +
          emit_part(P.term, P.n_term) + "    }\n";
     // finalize: scalar Dual arithmetic after the reductions; registers 0..K-1 start as the reduced accumulators
     s += "    template <class D> static FDB_DEV D finalize(const D (&acc)[K], int64_t) {\n" + decl_regs();

@@ -116,12 +116,26 @@ int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, con
     memset(&P, 0, sizeof P);
     P.n_term = n_term; P.n_epi = n_epi; P.n_acc = n_acc; P.halo = halo; P.result_reg = result_reg;
     int used_params = 0;
+    P.term_halo = halo;
+    for (int k = 0; k < FDB_MAX_PARAMS; k++) P.prm_halo[k] = (short)halo;
+    int guard_left = 0, guard_h = halo, min_guard = halo;
+    bool unguarded_reads = false;
     for (int part = 0; part < 2; part++) {
         const int32_t* src = part ? epi : term; const int cnt = part ? n_epi : n_term;
         for (int i = 0; i < cnt; i++) {
             const int op = src[4 * i], dst = src[4 * i + 1], a = src[4 * i + 2], b = src[4 * i + 3];
             const int kind = op >> 6, code = op & 63;
-            bool ok = dst >= 0 && dst < PG_MAXR && kind >= PK_LOADX && kind <= PK_PD;
+            bool ok = dst >= 0 && dst < PG_MAXR && kind >= PK_LOADX && kind <= PK_GUARD;
+            if (kind == PK_GUARD) {
+                ok = !part && !array_form && guard_left == 0 && a >= 0 && a <= halo && b >= 1 && i + b <= n_term - 1;
+                if (ok) { guard_left = b + 1; guard_h = a; P.has_guard = 1; if (a < min_guard) min_guard = a; }
+            }
+            const int h_here = (!part && guard_left > 0 && kind != PK_GUARD) ? guard_h : halo;
+            if (!part && kind != PK_GUARD && guard_left == 0 && (kind == PK_LOADX || kind == PK_ACC || kind == PK_DP || kind == PK_PD)) unguarded_reads = true;
+            if (kind == PK_LOADX && !part) ok = ok && b <= h_here;
+            if (kind == PK_DP && b >= 0 && b < FDB_MAX_PARAMS && h_here < P.prm_halo[b]) P.prm_halo[b] = (short)h_here;
+            if (kind == PK_PD && a >= 0 && a < FDB_MAX_PARAMS && h_here < P.prm_halo[a]) P.prm_halo[a] = (short)h_here;
+            if (guard_left > 0) guard_left--;
             if (kind == PK_DP) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < PG_MAXR && b >= 0 && b < n_params; if (b + 1 > used_params) used_params = b + 1; }
             if (kind == PK_PD) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < n_params && b >= 0 && b < PG_MAXR; if (a + 1 > used_params) used_params = a + 1; }
             if (kind == PK_LOADX) ok = ok && !part && b >= 0 && b <= halo;
@@ -138,16 +152,20 @@ int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, con
     }
     for (int i = 0; i < n_consts; i++) P.consts[i] = consts[i];
     P.n_params = used_params;
+    if (P.has_guard) {
+        if (unguarded_reads) return fail(ctx, FDB_ERR_BADARG, "op-program: with guards every term instruction must belong to a guarded group");
+        P.term_halo = min_guard;
+    }
     return FDB_OK;
 }
 
-int check_params(fdb_ctx* ctx, const Program& P, int64_t nterms, const char* what) {
+int check_params(fdb_ctx* ctx, const Program& P, int64_t xlen, const char* what) {
     if (P.n_params > ctx->n_prm)
         return fail(ctx, FDB_ERR_BADARG, "%s: the program reads %d parameter arrays, %d are bound (fdb_program_bind_params)", what, P.n_params, ctx->n_prm);
     for (int k = 0; k < P.n_params; k++)
-        if (ctx->prm_len[k] < nterms)
+        if (ctx->prm_len[k] < xlen - P.prm_halo[k])
             return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: parameter array %d has %lld entries, the broadcast has %lld", k,
-                        (long long)ctx->prm_len[k], (long long)nterms);
+                        (long long)ctx->prm_len[k], (long long)(xlen - P.prm_halo[k]));
     return FDB_OK;
 }
 
@@ -166,7 +184,7 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
     if (n < N) return fail(ctx, FDB_ERR_CHUNK, "chunk size cannot be greater than ForwardDiff.structural_length(x) (%d > %lld)", N, (long long)n);
     Program P;
     int rc = build_program(ctx, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, false, ctx->n_prm); if (rc) return rc;
-    rc = check_params(ctx, P, x->n - halo, "fdb_program_gradient_chunked"); if (rc) return rc;
+    rc = check_params(ctx, P, x->n, "fdb_program_gradient_chunked"); if (rc) return rc;
     Plan p = make_plan(n, N);
     const int64_t nchunks = (n == N) ? 1 : p.nchunks;
     if (chunk_hi < 0) chunk_hi = nchunks;
@@ -188,7 +206,7 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
             return finish(ctx, 1, "fdb_program_gradient_chunked(specialised)");
         }
     }
-    if (P.n_params) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters needs the run-time specialised kernel (%s)",
+    if (P.n_params || P.has_guard) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters or reductions of different lengths needs the run-time specialised kernel (%s)",
                                 ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     int nregs = 1;
     for (int i = 0; i < n_term; i++) { const int d = term_prog[4 * i + 1]; if ((term_prog[4 * i] >> 6) != PK_ACC && d + 1 > nregs) nregs = d + 1; }

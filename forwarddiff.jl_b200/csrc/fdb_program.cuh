@@ -9,7 +9,7 @@
 
 namespace fdb {
 
-constexpr int PG_MAXI = 48;      // instructions per program part
+constexpr int PG_MAXI = 96;      // instructions per program part
 constexpr int PG_MAXC = 24;      // Float64 constants
 constexpr int PG_MAXR = 12;      // virtual Dual registers
 constexpr int PG_MAXK = 4;       // sum accumulators
@@ -17,13 +17,16 @@ constexpr int PG_VEC = 4;        // terms per thread per decoded instruction on 
 
 struct Program {
     int n_term, n_epi, n_acc, halo, result_reg, n_params;
+    int term_halo, has_guard;    // terms run for i in [0, n - term_halo); guards restrict groups whose views are shorter
+    short prm_halo[FDB_MAX_PARAMS];   // parameter k is read for i < n - prm_halo[k]
     short term[PG_MAXI][4];      // {op, dst, a, b}
     short epi[PG_MAXI][4];
     double consts[PG_MAXC];
 };
 
 enum { PK_LOADX = 0, PK_UNARY = 1, PK_DD = 2, PK_DC = 3, PK_CD = 4, PK_ACC = 5, PK_MOV = 6,
-       PK_DP = 7, PK_PD = 8 };   // Dual (x) param[b][i], param[a][i] (x) Dual: specialised kernels only (fdb_jit.cu)
+       PK_DP = 7, PK_PD = 8,     // Dual (x) param[b][i], param[a][i] (x) Dual: specialised kernels only (fdb_jit.cu)
+       PK_GUARD = 9 };           // the next b instructions run only while i + a < n (a reduction over a shorter view); ditto
 
 template <int N, bool NS> FDB_DEV Dual<double, N, NS> pg_unary(int code, const Dual<double, N, NS>& x) {
     switch (code) {
@@ -232,7 +235,7 @@ struct SumK {   // block_combine policy: K sum accumulators
 // fdb_jit.cu: the kernel specialised for this program (kind 0 gradient, 1 Jacobian, 2 Hessian), or non-zero
 int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share, bool mir, void** fn);
 // the bound parameter arrays cover `nterms` entries each (and there are as many as the program reads)
-int check_params(fdb_ctx* ctx, const Program& P, int64_t nterms, const char* what);
+int check_params(fdb_ctx* ctx, const Program& P, int64_t xlen, const char* what);
 
 int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, const int32_t* epi, int n_epi, const double* consts,
                   int n_consts, int n_acc, int halo, int result_reg, bool array_form, int n_params);

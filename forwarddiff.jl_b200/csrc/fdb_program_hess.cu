@@ -197,17 +197,17 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
     if (halo > PH_MAXHALO) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: stencil reach %d > %d", halo, PH_MAXHALO);
     Program P;
     int rc = build_program(ctx, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, false, ctx->n_prm); if (rc) return rc;
-    rc = check_params(ctx, P, n - halo, "fdb_program_hessian_chunked"); if (rc) return rc;
+    rc = check_params(ctx, P, n, "fdb_program_hessian_chunked"); if (rc) return rc;
     for (int part = 0; part < 2; part++)
         for (int i = 0; i < (part ? n_epi : n_term); i++) {                 // rules that exist one dual level up
             const short* ins = part ? P.epi[i] : P.term[i];
             const int kind = ins[0] >> 6, code = ins[0] & 63;
-            const bool ok = (kind == PK_LOADX) || (kind == PK_ACC) || (kind == PK_MOV) || (kind == PK_UNARY && code <= FDB_POW3) ||
+            const bool ok = (kind == PK_LOADX) || (kind == PK_ACC) || (kind == PK_MOV) || (kind == PK_GUARD) || (kind == PK_UNARY && code <= FDB_POW3) ||
                             ((kind == PK_DD || kind == PK_DC || kind == PK_CD || kind == PK_DP || kind == PK_PD) && code <= FDB_DIV);
             if (!ok) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: instruction %d uses an op without a nested-dual rule", i);
         }
     // f = one plain sum of terms: both executors.  K sums + arithmetic after the reductions: the specialised kernel only
-    const bool plain = (n_epi == 0 && n_acc == 1 && result_reg == 0 && P.n_params == 0);
+    const bool plain = (n_epi == 0 && n_acc == 1 && result_reg == 0 && P.n_params == 0 && !P.has_guard);
     Plan p = make_plan(n, N);
     const int64_t nchunks = (n == N) ? 1 : p.nchunks;
     if (chunk_hi < 0) chunk_hi = nchunks;

@@ -59,7 +59,7 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
     if (y && y->n != m) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: y has %lld entries, f(x) has %lld", (long long)y->n, (long long)m);
     Program P;
     int rc = build_program(ctx, P, prog, n_instr, nullptr, 0, consts, n_consts, 0, halo, result_reg, true, ctx->n_prm); if (rc) return rc;
-    rc = check_params(ctx, P, m, "fdb_program_jacobian_chunked"); if (rc) return rc;
+    rc = check_params(ctx, P, n, "fdb_program_jacobian_chunked"); if (rc) return rc;
     Plan p = make_plan(n, N);
     const int64_t nchunks = (n == N) ? 1 : p.nchunks;
     if (chunk_hi < 0) chunk_hi = nchunks;

@@ -287,8 +287,9 @@ class _bound_params:
 
 
 def _usable(ctx, prog):
-    """A program with data arrays runs on the specialised kernels only; without them f takes the reference loop."""
-    return prog is not None and (not prog.params or ctx.jit_enabled())
+    """A program with data arrays or reductions of different lengths runs on the specialised kernels only; without them
+    f takes the reference loop."""
+    return prog is not None and (not prog.needs_jit or ctx.jit_enabled())
 
 
 def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True, graph=True):
@@ -384,8 +385,8 @@ def _program_hessian(ctx, result, H, f, x, N, lo, hi):
     prog = _try_trace("scalar", f, n)
     if prog is None:
         raise _lib.UnsupportedOp("hessian: f must be a catalogue target or flatten to sums of elementwise terms (no prod, no strided views)")
-    if prog.params and not ctx.jit_enabled():
-        raise _lib.UnsupportedOp("hessian: a function with data arrays needs the run-time specialised kernel")
+    if prog.needs_jit and not ctx.jit_enabled():
+        raise _lib.UnsupportedOp("hessian: a function with data arrays or reductions of different lengths needs the run-time specialised kernel")
     xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
     Hd = B200Array.alloc(ctx, n * n); gd = B200Array.alloc(ctx, n); vd = B200Array.alloc(ctx, 1)
     with _bound_params(ctx, prog):

@@ -12,8 +12,8 @@ import numpy as np
 
 from ._lib import OP1, OP2
 
-K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC, K_MOV, K_DP, K_PD = range(9)
-MAX_INSTR, MAX_CONST, MAX_REG, MAX_ACC, MAX_PARAMS = 48, 24, 12, 4, 4
+K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC, K_MOV, K_DP, K_PD, K_GUARD = range(10)
+MAX_INSTR, MAX_CONST, MAX_REG, MAX_ACC, MAX_PARAMS = 96, 24, 12, 4, 4
 
 
 class TraceError(Exception):
@@ -129,6 +129,7 @@ class TArray(_Sym):
         if len(tr.accs) >= MAX_ACC:
             raise TraceError("too many reductions")
         tr.accs.append(self.node)
+        tr.acc_lengths.append(self.n)
         tr.term_lengths.add(self.n)
         node = _Node(tr, K_ACC, len(tr.accs) - 1, (), stage="scalar")
         return TScalar(tr, node, 1)
@@ -140,7 +141,7 @@ class TArray(_Sym):
 class _Trace:
     def __init__(self, n):
         self.n = n
-        self.nodes, self.accs, self.term_lengths, self.params = [], [], set(), []
+        self.nodes, self.accs, self.acc_lengths, self.term_lengths, self.params = [], [], [], set(), []
 
 
 def _emit(tr, roots, stage, preloaded):
@@ -216,6 +217,8 @@ class Program:
         self.consts = np.asarray(consts, dtype=np.float64)
         self.n_acc, self.halo, self.result_reg, self.out_len = n_acc, halo, result_reg, out_len
         self.params = [np.ascontiguousarray(a, dtype=np.float64) for a in params]     # data arrays, one entry per term
+        # data arrays and guarded groups exist only in the run-time specialised kernels, not in the interpreter
+        self.needs_jit = bool(self.params) or bool(self.term.size and np.any((self.term[:, 0] >> 6) == K_GUARD))
 
 
 def _common_halo(tr, lengths):
@@ -237,11 +240,25 @@ def trace_scalar(f, n):
     y = f(x)
     if not isinstance(y, TScalar):
         raise TraceError("f did not return a reduced scalar")
-    L, halo = _common_halo(tr, set(tr.term_lengths))
-    # term part: evaluate every accumulated expression, then ACC
-    term, reg = _emit(tr, tr.accs, "term", {})
-    for k, nd in enumerate(tr.accs):
-        term.append((K_ACC << 6, k, reg[nd.id], 0))
+    if len(tr.term_lengths) == 1:
+        L, halo = _common_halo(tr, set(tr.term_lengths))
+        # term part: evaluate every accumulated expression, then ACC
+        term, reg = _emit(tr, tr.accs, "term", {})
+        for k, nd in enumerate(tr.accs):
+            term.append((K_ACC << 6, k, reg[nd.id], 0))
+    else:
+        # reductions over views of different lengths (sum(g.(x[2:end], x[1:end-1])) + sum(h.(x))): one guarded group per
+        # reduction, term i of group k runs while i + halo_k < n (specialised kernels only)
+        if not tr.accs or min(tr.acc_lengths) < 0 or max(tr.acc_lengths) > tr.n:
+            raise TraceError("view outside the input")
+        term, halo = [], tr.n - min(tr.acc_lengths)
+        for k, (nd, L) in enumerate(zip(tr.accs, tr.acc_lengths)):
+            group, reg = _emit(tr, [nd], "term", {})
+            if any((ins[0] >> 6) == K_LOADX and ins[3] > tr.n - L for ins in group):
+                raise TraceError("view outside the input")
+            group.append((K_ACC << 6, k, reg[nd.id], 0))
+            term.append((K_GUARD << 6, 0, tr.n - L, len(group)))
+            term += group
     if len(term) > MAX_INSTR:
         raise TraceError("program too long")
     pre = {nd.id: nd.op for nd in tr.nodes if nd.kind == K_ACC}

@@ -182,6 +182,28 @@ def test_functions_closing_over_data_arrays(ctx, N, mode):
     gl = fdb200.gradient(f, x, fdb200.GradientConfig(f, x, fdb200.Chunk(N)), ctx=ctx, fuse=False)          # reference loop
     assert np.allclose(res.derivs[0], gl, rtol=1e-12, atol=1e-13)
 
+    # reductions over views of different lengths: one guarded group per reduction
+    d2 = rng.uniform(0.0, 1.0, n)
+
+    def f2(xd):
+        return (w * (xd[1:] - xd[:-1]) ** 2).sum() + ((xd - d2) ** 2).sum() * 0.5 + fdb200.exp(xd[2:] * 0.1).sum()
+
+    g2_ref = (x - d2).copy()
+    g2_ref[1:] += 2.0 * w * (x[1:] - x[:-1]); g2_ref[:-1] -= 2.0 * w * (x[1:] - x[:-1])
+    g2_ref[2:] += 0.1 * np.exp(0.1 * x[2:])
+    res2 = fdb200.GradientResult(x)
+    fdb200.gradient_b(res2, f2, x, fdb200.GradientConfig(f2, x, fdb200.Chunk(N)), ctx=ctx)
+    assert np.allclose(res2.derivs[0], g2_ref, rtol=1e-12, atol=1e-13)
+    assert res2.value == pytest.approx((w * (x[1:] - x[:-1]) ** 2).sum() + 0.5 * ((x - d2) ** 2).sum() + np.exp(0.1 * x[2:]).sum(), rel=1e-13)
+    if mode == "specialised":
+        assert trace.trace_scalar(f2, n).needs_jit
+        H2 = fdb200.hessian(f2, x, fdb200.HessianConfig(f2, x, fdb200.Chunk(N)), ctx=ctx)
+        H2_ref = np.eye(n)
+        for i in range(n - 1):
+            H2_ref[i, i] += 2 * w[i]; H2_ref[i + 1, i + 1] += 2 * w[i]; H2_ref[i, i + 1] -= 2 * w[i]; H2_ref[i + 1, i] -= 2 * w[i]
+        H2_ref[np.arange(2, n), np.arange(2, n)] += 0.01 * np.exp(0.1 * x[2:])
+        assert np.allclose(H2, H2_ref, rtol=1e-12, atol=1e-13)
+
     def fa(xd):
         return d * xd[1:] - xd[:-1] / w + w ** 2.0
 
