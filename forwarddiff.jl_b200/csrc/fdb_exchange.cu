@@ -196,13 +196,18 @@ extern "C" int fdb_exchange_measure_store_bw(fdb_exchange* x, int64_t n_doubles,
     float best = 1e30f;
     const double* src = reinterpret_cast<const double*>(x->base);
     for (int rep = 0; rep < 4; rep++) {
-        int rc = fdb_exchange_barrier(x); if (rc) { ctx->async = was_async; return rc; }    // all ranks push at the same time
+        int rc = fdb_exchange_barrier(x);                                                    // all ranks push at the same time
+        if (rc) { ctx->async = was_async; cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
         cudaEventRecord(e0, ctx->stream);
         if (variant == 0) exchange_probe_kernel<0><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(src, n_doubles, M);
         else if (variant == 1) exchange_probe_kernel<1><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(src, n_doubles, M);
         else exchange_probe_kernel<2><<<dim3(ctx->sm_count * 2, M.count), 256, 0, ctx->stream>>>(src, n_doubles, M);
         cudaEventRecord(e1, ctx->stream);
-        FDB_CUDA(ctx, cudaEventSynchronize(e1));
+        cudaError_t ce = cudaEventSynchronize(e1);
+        if (ce != cudaSuccess) {
+            ctx->async = was_async; cudaEventDestroy(e0); cudaEventDestroy(e1);
+            return fail(ctx, FDB_ERR_CUDA, "fdb_exchange_measure_store_bw: %s", cudaGetErrorString(ce));
+        }
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0 && ms < best) best = ms;
         ctx->launches++;

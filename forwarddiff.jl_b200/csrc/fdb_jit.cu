@@ -251,6 +251,11 @@ int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share
     if (it != J.map.end()) { J.hits++; *fn = it->second.fn ? &it->second : nullptr; return it->second.fn ? FDB_OK : FDB_ERR_UNSUPPORTED; }
     fdb_jit_cache::Entry e{nullptr, nullptr, 0};
     Driver& d = driver();
+    if (J.map.size() >= 512) {                         // e.g. a caller that changes a literal constant on every call
+        cudaStreamSynchronize(ctx->stream);            // nothing queued may still run a module that is about to go
+        for (auto& kv : J.map) if (kv.second.mod && d.ok) d.ModuleUnload(kv.second.mod);
+        J.map.clear();
+    }
     std::vector<char> cubin;
     std::string log;
     int rc = d.ok ? compile_source(make_source(kind, P, N, ns, share, mir), cubin, log) : FDB_ERR_UNSUPPORTED;
