@@ -17,6 +17,19 @@ def test_sharded_drivers_single_rank():
     assert "match the single-rank results" in out.stdout
 
 
+def test_sharded_drivers_two_ranks_peer_memory_exchange():
+    """Two processes, two GPUs: the sweep kernels store into the peer's arena (fdb_exchange_*), checked bit for bit
+    against the single-rank results, and against the NCCL all-gather path.  Skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    port = str(29700 + os.getpid() % 200)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", port, os.path.join(ROOT, "tools", "check_sharded.py")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("match the single-rank results") == 2
+
+
 def test_c_abi_demo_runs_from_plain_c(tmp_path):
     """examples/c_abi_demo.c: the reference's golden vectors through the C ABI from a C program."""
     libdir = os.path.join(ROOT, "forwarddiff.jl_b200", "lib")

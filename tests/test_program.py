@@ -51,6 +51,29 @@ def mode(request, ctx):
     assert (used > 0) == jit
 
 
+def test_tracer_data_arrays_and_reductions_of_different_lengths():
+    n = 20
+    w, d = np.linspace(1.0, 2.0, n - 1), np.linspace(0.0, 1.0, n)
+    K_DP, K_PD, K_GUARD = trace.K_DP, trace.K_PD, trace.K_GUARD
+    p = trace.trace_scalar(lambda x: (w * (x[1:] - x[:-1]) ** 2).sum(), n)
+    kinds = [int(i[0]) >> 6 for i in p.term]
+    assert K_PD in kinds and K_GUARD not in kinds and len(p.params) == 1 and np.array_equal(p.params[0], w)
+    assert p.halo == 1 and p.needs_jit
+    # the same array used twice is one parameter; an expression of data only is evaluated on the host into another
+    p = trace.trace_scalar(lambda x: (w * x[1:] + x[:-1] / w - (w * w) * x[1:]).sum(), n)
+    assert len(p.params) == 2
+    # sums over views of different lengths: one guarded group per reduction, group k runs while i + halo_k < n
+    p = trace.trace_scalar(lambda x: ((x[1:] - x[:-1]) ** 2).sum() + ((x - d) ** 2).sum() + (x[2:] * 3.0).sum(), n)
+    guards = [(int(i[2]), int(i[3])) for i in p.term if (int(i[0]) >> 6) == K_GUARD]
+    assert [g[0] for g in guards] == [1, 0, 2] and p.halo == 2 and p.n_acc == 3 and p.needs_jit
+    assert sum(g[1] + 1 for g in guards) == len(p.term)                    # every instruction belongs to a group
+    with pytest.raises(fdb200.DimensionMismatch):
+        trace.trace_scalar(lambda x: (w * x).sum(), n)                     # w has n - 1 entries
+    with pytest.raises(trace.TraceError):
+        trace.trace_scalar(lambda x: fdb200.maximum(x, d).sum(), n)        # max with a data array has no Real rule here
+    assert not trace.trace_scalar(F.rosenbrock_generic, n).needs_jit
+
+
 def test_specialised_kernels_compile_on_the_host():
     """NVRTC needs no GPU: the functor generated for a traced f and the sweep kernel templates compile for sm_100a."""
     import ctypes as C
