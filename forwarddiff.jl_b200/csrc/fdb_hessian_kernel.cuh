@@ -122,8 +122,9 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
 // ---- general form: K sum accumulators and arithmetic after the reductions (F::finalize), e.g. Ackley ---------------
 // Same two-level lane sharing as above, but the block first assembles the K reduced accumulators as FULL nested duals
 // Dual{Dual{N},N} -- far terms contribute their four shared lanes, near terms their per-inner-lane Dual{Dual{N},1}
-// results, folded in term order -- and one thread then runs F::finalize on them (scalar nested-dual arithmetic, once
-// per block), exactly the Dual{T,Dual{T,V,N},N} evaluation of the tail of f in the reference (src/hessian.jl:14-19).
+// results, folded in term order -- and then runs F::finalize on them (scalar nested-dual arithmetic, once per block,
+// one thread per inner partial lane), the Dual{T,Dual{T,V,N},N} evaluation of the tail of f in the reference
+// (src/hessian.jl:14-19).
 // Near terms are processed in rounds of R terms so that the staging buffer stays under 40 KB for any K.
 template <class F, int N, bool NS, int THREADS>
 FDB_DEV void hessian_general_body(const double* __restrict__ x, int64_t n, int64_t outer_lo, int64_t nchunks_total, int lastchunksize,
@@ -131,7 +132,6 @@ FDB_DEV void hessian_general_body(const double* __restrict__ x, int64_t n, int64
                                   const fdb_mirrors& M) {
     typedef Dual<double, N, NS> DI;
     typedef Dual<DI, 1, NS> DG;
-    typedef Dual<DI, N, NS> DN;
     typedef Dual<Dual<double, 1, NS>, 1, NS> DF;
     constexpr int K = F::K;
     constexpr int LANES = (N + 1) * (N + 1);                       // [a][b]: a = inner index (0 = value), b = outer index
@@ -219,35 +219,34 @@ FDB_DEV void hessian_general_body(const double* __restrict__ x, int64_t n, int64
         __syncthreads();
     }
     __syncthreads();
-    // phase 3: add the shared far lanes, finalize on the full nested duals, store
-    if (threadIdx.x == 0) {
-        DN accn[K];
-#pragma unroll 1
+    // phase 3: add the shared far lanes, finalize, store.  A Dual{Dual{N},N} is N independent Dual{Dual{N},1} numbers
+    // sharing their value part (the inner partial lanes never interact), so thread k runs F::finalize on the
+    // accumulators restricted to inner lane k -- N threads in parallel on 2(N+1)-lane numbers instead of one thread on
+    // (N+1)^2 lanes -- and stores row istart+k of the block: value(partials(y,k)) -> gradient, partials(partials(y,k),j) -> H.
+    if (threadIdx.x < N) {
+        const int k = threadIdx.x;
+        DG accg[K];
+#pragma unroll
         for (int kk = 0; kk < K; kk++) {
-            accn[kk].v.v = s_acc[kk][0][0] + s_ff[kk][0];
-            for (int j = 0; j < N; j++) accn[kk].v.p[j] = s_acc[kk][0][j + 1] + s_ff[kk][1];
-            for (int k = 0; k < N; k++) {
-                accn[kk].p[k].v = s_acc[kk][k + 1][0] + s_ff[kk][2];
-                for (int j = 0; j < N; j++) accn[kk].p[k].p[j] = s_acc[kk][k + 1][j + 1] + s_ff[kk][3];
+            accg[kk].v.v = s_acc[kk][0][0] + s_ff[kk][0];
+            accg[kk].p[0].v = s_acc[kk][k + 1][0] + s_ff[kk][2];
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                accg[kk].v.p[j] = s_acc[kk][0][j + 1] + s_ff[kk][1];
+                accg[kk].p[0].p[j] = s_acc[kk][k + 1][j + 1] + s_ff[kk][3];
             }
         }
-        const DN y = F::finalize(accn, n);
-        s_acc[0][0][0] = y.v.v;
-        for (int j = 0; j < N; j++) s_acc[0][0][j + 1] = y.v.p[j];
-        for (int k = 0; k < N; k++) {
-            s_acc[0][k + 1][0] = y.p[k].v;
-            for (int j = 0; j < N; j++) s_acc[0][k + 1][j + 1] = y.p[k].p[j];
+        const DG y = F::finalize(accg, n);
+        if (k < ics) {
+            if (olast && grad) mstore(M, &grad[istart + k], y.p[0].v);
+            if (H) {
+#pragma unroll
+                for (int j = 0; j < N; j++)
+                    if (j < ocs) mstore(M, &H[(istart + k) + (ostart + j) * ldH], y.p[0].p[j]);
+            }
         }
+        if (k == 0 && olast && ilast && value_out) mstore(M, value_out, y.v.v);
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < N * (N + 1); e += THREADS) {
-        const int k = e / (N + 1), j = e - k * (N + 1);
-        if (k >= ics) continue;
-        const double s = s_acc[0][k + 1][j];
-        if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
-        else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
-    }
-    if (threadIdx.x == 0 && olast && ilast && value_out) mstore(M, value_out, s_acc[0][0][0]);
 }
 
 template <class F, int N, bool NS, int THREADS>
