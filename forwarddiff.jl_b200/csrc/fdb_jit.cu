@@ -120,15 +120,16 @@ static std::string R(int r) { return "r" + std::to_string(r); }
 static std::string C(int c) { return "c" + std::to_string(c); }
 
 // one statement per instruction, the same evaluation order as pg_run (fdb_program.cuh)
-static std::string emit_part(const short (*code)[4], int n) {
+static std::string emit_part(const short (*code)[4], int n, int from = 0) {
     std::string s;
     int close_at = -1;
-    for (int pc = 0; pc < n; pc++) {
+    for (int pc = from; pc < n; pc++) {
         const int op = code[pc][0], dst = code[pc][1], a = code[pc][2], b = code[pc][3];
         const int kind = op >> 6, c = op & 63;
         s += "        ";
         switch (kind) {
             case PK_GUARD: s += "if (i + " + std::to_string(a) + " < n) {"; close_at = pc + b; break;
+            case PK_LOADS: s += R(dst) + " = S[" + std::to_string(a) + "];"; break;
             case PK_LOADX: s += R(dst) + " = x(i + " + std::to_string(b) + ");"; break;
             case PK_UNARY: s += R(dst) + " = " + (c == FDB_NEG ? "-" + R(a) : std::string(unary_fn(c)) + "(" + R(a) + ")") + ";"; break;
             case PK_DD: s += R(dst) + " = " + binary_expr(c, R(a), R(b)) + ";"; break;
@@ -170,23 +171,45 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
     s += "    static __device__ int64_t nterms(int64_t n) { return n > " + std::to_string(P.term_halo) + " ? n - " + std::to_string(P.term_halo) + " : 0; }\n";
     s += "    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }\n";
     s += "    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }\n";
-    // term: the user's broadcast body for one i, adding into the sum accumulators
+    int st1 = -1, st2 = -1;                         // positions of the stage markers of a two-pass program
+    for (int pc = 0; pc < P.n_term; pc++)
+        if ((P.term[pc][0] >> 6) == PK_STAGE) { if (P.term[pc][2] == 1) st1 = pc; else st2 = pc; }
+    s += std::string("    static constexpr bool TWO_PASS = ") + (P.two_pass ? "true" : "false") + ";\n";
+    s += "    static constexpr int NSCAL = " + std::to_string(PG_MAXR) + ";\n";
+    // term: the user's broadcast body for one i, adding into the sum accumulators (pass 1 of a two-pass program)
     s += "    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t n, D (&acc)[K]) {\n" + decl_regs() +
-         emit_part(P.term, P.n_term) + "    }\n";
+         emit_part(P.term, P.two_pass ? st1 : P.n_term) + "    }\n";
+    if (P.two_pass) {
+        // finalize1: scalar Dual code on the pass-1 sums; the whole register file is published as S
+        s += "    template <class D> static FDB_DEV void finalize1(const D (&acc)[K], D* S) {\n" + decl_regs();
+        for (int k = 0; k < P.k1 && k < PG_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
+        s += emit_part(P.term, st2, st1 + 1);
+        for (int r = 0; r < PG_MAXR; r++) s += "        S[" + std::to_string(r) + "] = " + R(r) + ";\n";
+        s += "    }\n";
+        // term2: the second broadcast, reading x and the scalars S
+        s += "    template <class D, class L> static FDB_DEV void term2(const L& x, int64_t i, int64_t n, const D* S, D (&acc)[K]) {\n" + decl_regs() +
+             emit_part(P.term, P.n_term, st2 + 1) + "    }\n";
+        // finalize2: registers k1..K-1 start as the pass-2 sums
+        s += "    template <class D> static FDB_DEV D finalize2(const D (&acc)[K], const D* S, int64_t) {\n" + decl_regs();
+        for (int k = P.k1; k < K && k < PG_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
+        s += emit_part(P.epi, P.n_epi) + "        return " + R(P.result_reg) + ";\n    }\n";
+    }
     // finalize: scalar Dual arithmetic after the reductions; registers 0..K-1 start as the reduced accumulators
     s += "    template <class D> static FDB_DEV D finalize(const D (&acc)[K], int64_t) {\n" + decl_regs();
     for (int k = 0; k < K && k < PG_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
-    s += emit_part(P.epi, P.n_epi) + "        return " + R(P.result_reg) + ";\n    }\n";
+    s += (P.two_pass ? std::string() : emit_part(P.epi, P.n_epi)) + "        return " + R(P.result_reg) + ";\n    }\n";
     // apply: array-valued form, y[i] = result register after the term part
-    s += "    template <class D, class L> static FDB_DEV D apply(const L& x, int64_t i) {\n        D acc[K];\n" + decl_regs() +
-         emit_part(P.term, P.n_term) + "        (void)acc;\n        return " + R(P.result_reg) + ";\n    }\n";
+    if (!P.two_pass)
+        s += "    template <class D, class L> static FDB_DEV D apply(const L& x, int64_t i) {\n        D acc[K];\n        const int64_t n = 0; (void)n;\n" + decl_regs() +
+             emit_part(P.term, P.n_term) + "        (void)acc;\n        return " + R(P.result_reg) + ";\n    }\n";
     s += "};\n}  // namespace fdb\n";
     const std::string targs = "fdb::UserFn, " + std::to_string(N) + ", " + (ns ? "true" : "false");
     if (kind == JIT_GRADIENT) {
         s += "extern \"C\" __global__ void __launch_bounds__(256) fdb_user_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo,\n"
              "        int64_t nchunks_total, int lastchunksize, double* __restrict__ grad, double* __restrict__ value_out,\n"
              "        const __grid_constant__ fdb_mirrors M) {\n"
-             "    fdb::gradient_sweep_body<" + targs + ", 256, " + (share ? "true" : "false") + ">(x, n, chunk_lo, nchunks_total, lastchunksize, grad, value_out, M);\n}\n";
+             "    fdb::" + std::string(P.two_pass ? "gradient_sweep2_body<" : "gradient_sweep_body<") + targs + ", 256, " + (share ? "true" : "false") +
+             ">(x, n, chunk_lo, nchunks_total, lastchunksize, grad, value_out, M);\n}\n";
     } else if (kind == JIT_JACOBIAN) {
         s += "extern \"C\" __global__ void __launch_bounds__(128) fdb_user_kernel(const bool share, const double* __restrict__ x, int64_t n,\n"
              "        int64_t chunk_lo, int64_t nchunks_total, int lastchunksize, double* __restrict__ J, int64_t ldJ, double* __restrict__ yout,\n"

@@ -118,14 +118,21 @@ int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, con
     int used_params = 0;
     P.term_halo = halo;
     for (int k = 0; k < FDB_MAX_PARAMS; k++) P.prm_halo[k] = (short)halo;
-    int guard_left = 0, guard_h = halo, min_guard = halo;
+    int guard_left = 0, guard_h = halo, min_guard = halo, stage = 0, max_acc = -1;
     bool unguarded_reads = false;
     for (int part = 0; part < 2; part++) {
         const int32_t* src = part ? epi : term; const int cnt = part ? n_epi : n_term;
         for (int i = 0; i < cnt; i++) {
             const int op = src[4 * i], dst = src[4 * i + 1], a = src[4 * i + 2], b = src[4 * i + 3];
             const int kind = op >> 6, code = op & 63;
-            bool ok = dst >= 0 && dst < PG_MAXR && kind >= PK_LOADX && kind <= PK_GUARD;
+            bool ok = dst >= 0 && dst < PG_MAXR && kind >= PK_LOADX && kind <= PK_LOADS;
+            if (kind == PK_STAGE) {
+                ok = !part && !array_form && guard_left == 0 && a == stage + 1 && a <= 2;
+                if (ok) { stage = a; P.two_pass = 1; if (a == 1) P.k1 = max_acc + 1; }
+            }
+            if (kind == PK_LOADS) ok = ok && a >= 0 && a < PG_MAXR && P.two_pass && (part || stage == 2);
+            if (!part && stage == 1 && (kind == PK_LOADX || kind == PK_ACC || kind == PK_DP || kind == PK_PD || kind == PK_GUARD)) ok = false;   // scalar code only
+            if (kind == PK_ACC && dst > max_acc) max_acc = dst;
             if (kind == PK_GUARD) {
                 ok = !part && !array_form && guard_left == 0 && a >= 0 && a <= halo && b >= 1 && i + b <= n_term - 1;
                 if (ok) { guard_left = b + 1; guard_h = a; P.has_guard = 1; if (a < min_guard) min_guard = a; }
@@ -152,6 +159,8 @@ int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, con
     }
     for (int i = 0; i < n_consts; i++) P.consts[i] = consts[i];
     P.n_params = used_params;
+    if (P.two_pass && (stage != 2 || P.has_guard))
+        return fail(ctx, FDB_ERR_BADARG, "op-program: a two-pass program needs both stage markers and no guarded groups");
     if (P.has_guard) {
         if (unguarded_reads) return fail(ctx, FDB_ERR_BADARG, "op-program: with guards every term instruction must belong to a guarded group");
         P.term_halo = min_guard;
@@ -206,7 +215,7 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
             return finish(ctx, 1, "fdb_program_gradient_chunked(specialised)");
         }
     }
-    if (P.n_params || P.has_guard) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters or reductions of different lengths needs the run-time specialised kernel (%s)",
+    if (P.n_params || P.has_guard || P.two_pass) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters, reductions of different lengths or two passes needs the run-time specialised kernel (%s)",
                                 ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     int nregs = 1;
     for (int i = 0; i < n_term; i++) { const int d = term_prog[4 * i + 1]; if ((term_prog[4 * i] >> 6) != PK_ACC && d + 1 > nregs) nregs = d + 1; }

@@ -18,6 +18,7 @@ constexpr int PG_VEC = 4;        // terms per thread per decoded instruction on 
 struct Program {
     int n_term, n_epi, n_acc, halo, result_reg, n_params;
     int term_halo, has_guard;    // terms run for i in [0, n - term_halo); guards restrict groups whose views are shorter
+    int two_pass, k1;            // PK_STAGE markers split the term part into term1 | epilogue1 | term2; accumulators [0, k1) belong to pass 1
     short prm_halo[FDB_MAX_PARAMS];   // parameter k is read for i < n - prm_halo[k]
     short term[PG_MAXI][4];      // {op, dst, a, b}
     short epi[PG_MAXI][4];
@@ -26,7 +27,10 @@ struct Program {
 
 enum { PK_LOADX = 0, PK_UNARY = 1, PK_DD = 2, PK_DC = 3, PK_CD = 4, PK_ACC = 5, PK_MOV = 6,
        PK_DP = 7, PK_PD = 8,     // Dual (x) param[b][i], param[a][i] (x) Dual: specialised kernels only (fdb_jit.cu)
-       PK_GUARD = 9 };           // the next b instructions run only while i + a < n (a reduction over a shorter view); ditto
+       PK_GUARD = 9,             // the next b instructions run only while i + a < n (a reduction over a shorter view); ditto
+       PK_STAGE = 10,            // a = 1: the first-stage epilogue follows (scalar Dual code on the pass-1 sums); a = 2: the
+                                 // second-stage terms follow (they may read the epilogue's registers with PK_LOADS); ditto
+       PK_LOADS = 11 };          // R[dst] = S[a], S = the register file as the first-stage epilogue left it
 
 template <int N, bool NS> FDB_DEV Dual<double, N, NS> pg_unary(int code, const Dual<double, N, NS>& x) {
     switch (code) {

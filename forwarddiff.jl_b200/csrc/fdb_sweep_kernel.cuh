@@ -15,18 +15,13 @@ namespace fdb {
 // only the summation order changes, which the reduction tolerance already covers.
 // Every term of f is still evaluated in every chunk.  SHARE=false evaluates all N
 // lanes for every term (bench.py reports both).
+// pass over all terms of f for the chunk window [start, start+chunksize): this thread's partial accumulators
 template <class F, int N, bool NS, int THREADS, bool SHARE>
-FDB_DEV void gradient_sweep_body(const double* __restrict__ x, int64_t n, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
-                                 double* __restrict__ grad, double* __restrict__ value_out, const fdb_mirrors& M) {
+FDB_DEV void sweep_terms(const double* __restrict__ x, int64_t n, int64_t start, int chunksize, Dual<double, N, NS> (&acc)[F::K]) {
     typedef Dual<double, N, NS> D;
     typedef Dual<double, 1, NS> D1;
-    const int64_t c = chunk_lo + blockIdx.x;                       // 0-based chunk number
-    const bool last = (c == nchunks_total - 1);
-    const int chunksize = last ? lastchunksize : N;               // src/gradient.jl:123
-    const int64_t start = last ? (n - lastchunksize) : c * N;     // lastchunkindex-1, src/gradient.jl:124
     SeedLoader<N, NS> xs{x, start, chunksize};
     ZeroLoader<1, NS> xz{x};
-    D acc[F::K];
     D1 acc1[F::K];
     D like; like.v = 0.0;
 #pragma unroll
@@ -66,6 +61,19 @@ FDB_DEV void gradient_sweep_body(const double* __restrict__ x, int64_t n, int64_
     } else {
         for (int64_t i = threadIdx.x; i < nt; i += THREADS) F::term(xs, i, n, acc);
     }
+}
+
+template <class F, int N, bool NS, int THREADS, bool SHARE>
+FDB_DEV void gradient_sweep_body(const double* __restrict__ x, int64_t n, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
+                                 double* __restrict__ grad, double* __restrict__ value_out, const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> D;
+    typedef Dual<double, 1, NS> D1;
+    const int64_t c = chunk_lo + blockIdx.x;                       // 0-based chunk number
+    const bool last = (c == nchunks_total - 1);
+    const int chunksize = last ? lastchunksize : N;               // src/gradient.jl:123
+    const int64_t start = last ? (n - lastchunksize) : c * N;     // lastchunkindex-1, src/gradient.jl:124
+    D acc[F::K];
+    sweep_terms<F, N, NS, THREADS, SHARE>(x, n, start, chunksize, acc);
     block_combine<F, D, THREADS>(acc);
     if (threadIdx.x == 0) {
         D y = F::finalize(acc, n);
@@ -73,6 +81,44 @@ FDB_DEV void gradient_sweep_body(const double* __restrict__ x, int64_t n, int64_
         for (int k = 0; k < N; k++)
             if (k < chunksize) mstore(M, &grad[start + k], y.p[k]);   // extract_gradient_chunk!, src/gradient.jl:74-81 (+ peers)
         if (last && value_out) mstore(M, value_out, y.v);          // extract_value!, src/gradient.jl:155
+    }
+}
+
+// Two-pass form: f uses a reduced value inside a second broadcast -- sum((x .- mean(x)).^2), log(sum(exp.(x .- m))) ...
+// Pass 1 is the sweep above (lane sharing included) over the first-stage terms; thread 0 runs F::finalize1 on the reduced
+// Duals and publishes the resulting scalar Duals S (dense partials: every lane of the window contributes) in shared
+// memory; pass 2 evaluates the second-stage terms, which read S, on all N lanes for every term (no sharing: S is not a
+// zero-partial operand); F::finalize2 closes.  Used by specialised op-programs only (fdb_jit.cu).
+template <class F, int N, bool NS, int THREADS, bool SHARE>
+FDB_DEV void gradient_sweep2_body(const double* __restrict__ x, int64_t n, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
+                                  double* __restrict__ grad, double* __restrict__ value_out, const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> D;
+    typedef Dual<double, 1, NS> D1;
+    const int64_t c = chunk_lo + blockIdx.x;                       // 0-based chunk number
+    const bool last = (c == nchunks_total - 1);
+    const int chunksize = last ? lastchunksize : N;               // src/gradient.jl:123
+    const int64_t start = last ? (n - lastchunksize) : c * N;     // lastchunkindex-1, src/gradient.jl:124
+    __shared__ D s_S[F::NSCAL];
+    D acc[F::K];
+    sweep_terms<F, N, NS, THREADS, SHARE>(x, n, start, chunksize, acc);
+    block_combine<F, D, THREADS>(acc);
+    if (threadIdx.x == 0) F::finalize1(acc, s_S);
+    __syncthreads();
+    D like; like.v = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) like.p[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < F::K; k++) acc[k] = F::init(k, like);
+    SeedLoader<N, NS> xs{x, start, chunksize};
+    const int64_t nt = F::nterms(n);
+    for (int64_t i = threadIdx.x; i < nt; i += THREADS) F::term2(xs, i, n, s_S, acc);
+    block_combine<F, D, THREADS>(acc);
+    if (threadIdx.x == 0) {
+        D y = F::finalize2(acc, s_S, n);
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (k < chunksize) mstore(M, &grad[start + k], y.p[k]);
+        if (last && value_out) mstore(M, value_out, y.v);
     }
 }
 

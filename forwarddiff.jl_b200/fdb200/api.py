@@ -185,7 +185,9 @@ class DiffResult:
 
 
 def GradientResult(x):
-    return DiffResult(0.0, np.zeros(_length(x)))
+    """DiffResults.GradientResult(x): the gradient has the shape of x (a Matrix input gives a Matrix gradient)."""
+    shape = np.shape(x) if isinstance(x, np.ndarray) and x.ndim > 1 else (_length(x),)
+    return DiffResult(0.0, np.zeros(shape, order="F"))
 
 
 def JacobianResult(y, x):
@@ -296,7 +298,10 @@ def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True, graph
     """ForwardDiff.gradient(f, x, cfg, Val{check}()) (src/gradient.jl:16-24)."""
     if isinstance(x, _Structured):
         return gradient_b(None, f, x, cfg, check, ctx)
-    result = np.zeros(_length(x)) if not isinstance(x, _DeviceArray) else x.similar()
+    if isinstance(x, np.ndarray) and x.ndim > 1:
+        result = np.zeros(x.shape, order="F")
+    else:
+        result = np.zeros(_length(x)) if not isinstance(x, _DeviceArray) else x.similar()
     return gradient_b(result, f, x, cfg, check, ctx, chunks, fuse, graph)
 
 
@@ -311,6 +316,26 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
         checktag(cfg.tag, f, x)
     if isinstance(x, _Structured):
         return _structured_gradient(_ctx_of(x, ctx), result, f, x, cfg)
+    if isinstance(x, np.ndarray) and x.ndim > 1:
+        # an N-d input is seeded in linear-index (column-major) order (structural_eachindex, src/apiutils.jl:44-47);
+        # f sees vec(x) and the gradient comes back in the shape of x
+        out = result.derivs[0] if isinstance(result, DiffResult) else result
+        if np.shape(out) != x.shape:
+            raise DimensionMismatch(f"gradient result has shape {np.shape(out)}, x has {x.shape}")
+        flat = DiffResult(0.0, np.zeros(x.size))
+        gradient_b(flat, f, x.ravel(order="F"), cfg, check, ctx, chunks, fuse, graph)
+        if chunks is None:
+            out[...] = flat.derivs[0].reshape(x.shape, order="F")
+        else:                                                       # only the entries of the requested chunks are written
+            p = chunk_plan(x.size, cfg.N)
+            e0, e1 = chunks[0] * cfg.N, (x.size if chunks[1] < 0 or chunks[1] >= p["nchunks"] else chunks[1] * cfg.N)
+            view = out.reshape(-1, order="F") if out.flags.f_contiguous else None
+            if view is None:
+                raise FdbError("gradient!: an N-d result must be column-major when a chunk range is given")
+            view[e0:e1] = flat.derivs[0][e0:e1]
+        if isinstance(result, DiffResult):
+            result.value = flat.value
+        return result
     n = _length(x)
     out = result.derivs[0] if isinstance(result, DiffResult) else result
     if _length(out) != n:

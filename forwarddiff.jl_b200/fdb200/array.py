@@ -346,6 +346,14 @@ class B200DualArray(_DeviceArray):
     def prod(self):
         return self._reduce("prod")
 
+    def mean(self):
+        """Statistics.mean: sum(x) / length(x)"""
+        return self.sum() / self.n
+
+    def dot(self, other):
+        """LinearAlgebra.dot of real vectors: sum(x .* y)"""
+        return (self * other).sum()
+
     def _reduce(self, op):
         out = B200DualArray.alloc(self.ctx, 1, self.N, 1)
         self.ctx.check(self.ctx.lib.fdb_reduce(self.ctx.h, REDOP[op], out.h, self.h))
@@ -384,6 +392,11 @@ def atan2(y, x):
 
 def hypot(x, y):
     return x._map2("hypot", y)
+
+
+def dot(a, b):
+    """dot(a, b) where at least one operand is a Dual array (or a symbolic array while f is being flattened)."""
+    return a.dot(b) if hasattr(a, "dot") and not isinstance(a, np.ndarray) else b.dot(a)
 
 
 def fma(x, y, z):

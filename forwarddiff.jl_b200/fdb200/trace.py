@@ -5,14 +5,15 @@ The Julia shim would do this by walking the `Broadcasted` tree of `f`'s broadcas
 whose operators record instead of compute.  Supported shape: elementwise src/dual.jl arithmetic on
 unit-stride views `x[a:b]` of the input (all of one common length), NumPy arrays the function closes over
 (data: `w * x**2` -- they become array parameters read at the term index, with the Real (x) Dual rules), `sum()`
-reductions of such arrays, and scalar Dual arithmetic on the reduced values.  Anything else raises TraceError and the caller
+reductions of such arrays, scalar Dual arithmetic on the reduced values, and ONE re-entry of reduced values into a
+second broadcast (`sum((x .- mean(x)).^2)`: a two-pass program -- stage levels term -> scalar -> term2 -> scalar2).  Anything else raises TraceError and the caller
 falls back to the reference chunk loop on materialised device duals.
 """
 import numpy as np
 
 from ._lib import OP1, OP2
 
-K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC, K_MOV, K_DP, K_PD, K_GUARD = range(10)
+K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC, K_MOV, K_DP, K_PD, K_GUARD, K_STAGE, K_LOADS = range(12)
 MAX_INSTR, MAX_CONST, MAX_REG, MAX_ACC, MAX_PARAMS = 96, 24, 12, 4, 4
 
 
@@ -32,8 +33,11 @@ class _Node:
         tr.nodes.append(self)
 
 
+_LEVEL = {"term": 0, "scalar": 1, "term2": 2, "scalar2": 3}
+
+
 class _Sym:
-    """Common operator plumbing of the symbolic array (stage 'term') and symbolic scalar (stage 'scalar')."""
+    """Common operator plumbing of the symbolic array (stages 'term', 'term2') and symbolic scalar ('scalar', 'scalar2')."""
     __array_ufunc__ = None          # `ndarray * sym` defers to sym.__rmul__ instead of broadcasting over an object
 
     def __init__(self, tr, node, length):
@@ -46,7 +50,7 @@ class _Sym:
         if not isinstance(other, _Sym) or other.tr is not self.tr:
             raise TraceError("operand is not part of this trace")
         if type(other) is not type(self):
-            raise TraceError("mixing reduced scalars and arrays inside one broadcast needs two passes")
+            raise TraceError("operand kinds differ")
         if other.n != self.n:
             from ._lib import DimensionMismatch
             raise DimensionMismatch(f"arrays could not be broadcast to a common size ({self.n} vs {other.n})")
@@ -65,9 +69,19 @@ class _Sym:
             return self._like(_Node(self.tr, kind, code, (self.node,), const=float(other), stage=self.node.stage))
         if isinstance(other, np.ndarray):
             return self._map2_param(code, op, other, reverse)
+        if isinstance(self, TScalar) and isinstance(other, TArray):
+            return other._map2(op, self, not reverse)
+        if isinstance(self, TArray) and isinstance(other, TScalar) and other.tr is self.tr:
+            # a reduced value re-enters a broadcast: Vector{Dual} .(op) Dual -> second pass
+            if _LEVEL[other.node.stage] != 1:
+                raise TraceError("only one re-entry of reduced values into a broadcast (two passes) is supported")
+            a, b = (other.node, self.node) if reverse else (self.node, other.node)
+            return self._like(_Node(self.tr, K_DD, code, (a, b), stage="term2"))
         self._check(other)
         a, b = (other.node, self.node) if reverse else (self.node, other.node)
-        return self._like(_Node(self.tr, K_DD, code, (a, b), stage=self.node.stage))
+        lvl = max(_LEVEL[a.stage], _LEVEL[b.stage])
+        stage = {0: "term", 1: "scalar", 2: "term2", 3: "scalar2"}[lvl]
+        return self._like(_Node(self.tr, K_DD, code, (a, b), stage=stage))
 
     def _map2_param(self, code, op, arr, reverse):
         """A closed-over data array: Dual (x) Real elementwise, the array read at the term index."""
@@ -131,8 +145,17 @@ class TArray(_Sym):
         tr.accs.append(self.node)
         tr.acc_lengths.append(self.n)
         tr.term_lengths.add(self.n)
-        node = _Node(tr, K_ACC, len(tr.accs) - 1, (), stage="scalar")
+        node = _Node(tr, K_ACC, len(tr.accs) - 1, (), stage="scalar" if _LEVEL[self.node.stage] == 0 else "scalar2")
+        tr.acc_nodes.append(node)
         return TScalar(tr, node, 1)
+
+    def mean(self):
+        """Statistics.mean: sum(x) / length(x) (Dual / Int, src/dual.jl:538)."""
+        return self.sum() / self.n
+
+    def dot(self, other):
+        """LinearAlgebra.dot of two real vectors: sum of elementwise products."""
+        return (self * other).sum()
 
     def prod(self):
         raise TraceError("prod is not an additive reduction")
@@ -141,15 +164,23 @@ class TArray(_Sym):
 class _Trace:
     def __init__(self, n):
         self.n = n
-        self.nodes, self.accs, self.acc_lengths, self.term_lengths, self.params = [], [], [], set(), []
+        self.nodes, self.accs, self.acc_lengths, self.term_lengths, self.params, self.acc_nodes = [], [], [], set(), [], []
 
 
-def _emit(tr, roots, stage, preloaded):
-    """Linearise the DAG reachable from `roots` (restricted to `stage`) into instructions with register reuse."""
+def _emit(tr, roots, stage, preloaded, sreg=None):
+    """Linearise the DAG reachable from `roots` (restricted to `stage`, a name or a set of names) into instructions with
+    register reuse.  `sreg` maps first-stage scalar nodes to their slot in S: such operands are fetched with LOADS."""
     order, seen = [], set()
+    stages = {stage} if isinstance(stage, str) else set(stage)
+    stage = "/".join(sorted(stages))
 
     def visit(nd):
-        if nd.id in seen or nd.stage != stage:
+        if nd.id in seen:
+            return
+        if nd.stage not in stages:
+            if sreg is not None and nd.id in sreg:          # value published by the first-stage epilogue
+                seen.add(nd.id)
+                order.append(nd)
             return
         seen.add(nd.id)
         for a in nd.args:
@@ -179,15 +210,18 @@ def _emit(tr, roots, stage, preloaded):
     for pos, nd in enumerate(order):
         if nd.id in reg:                         # preloaded accumulator register
             continue
-        srcs = [reg[a.id] for a in nd.args]
-        for a in nd.args:                        # release operands whose last use is this instruction
+        foreign = nd.stage not in stages
+        srcs = [] if foreign else [reg[a.id] for a in nd.args]
+        for a in (() if foreign else nd.args):   # release operands whose last use is this instruction
             if last_use.get(a.id) == pos and a.id in reg and reg[a.id] not in free and a.id not in preloaded:
                 free.append(reg[a.id])
         if not free:
             raise TraceError("expression needs more than %d live Dual registers" % MAX_REG)
         dst = free.pop()
         reg[nd.id] = dst
-        if nd.kind == K_LOADX:
+        if nd.stage not in stages:
+            instrs.append((K_LOADS << 6, dst, sreg[nd.id], 0))
+        elif nd.kind == K_LOADX:
             instrs.append((K_LOADX << 6, dst, 0, int(nd.const)))
         elif nd.kind == K_UNARY:
             instrs.append(((K_UNARY << 6) | nd.op, dst, srcs[0], 0))
@@ -218,7 +252,9 @@ class Program:
         self.n_acc, self.halo, self.result_reg, self.out_len = n_acc, halo, result_reg, out_len
         self.params = [np.ascontiguousarray(a, dtype=np.float64) for a in params]     # data arrays, one entry per term
         # data arrays and guarded groups exist only in the run-time specialised kernels, not in the interpreter
-        self.needs_jit = bool(self.params) or bool(self.term.size and np.any((self.term[:, 0] >> 6) == K_GUARD))
+        kinds = (self.term[:, 0] >> 6) if self.term.size else np.zeros(0, dtype=np.int32)
+        self.two_pass = bool(np.any(kinds == K_STAGE))
+        self.needs_jit = bool(self.params) or bool(np.any(kinds == K_GUARD)) or self.two_pass
 
 
 def _common_halo(tr, lengths):
@@ -240,6 +276,8 @@ def trace_scalar(f, n):
     y = f(x)
     if not isinstance(y, TScalar):
         raise TraceError("f did not return a reduced scalar")
+    if any(_LEVEL[nd.stage] >= 2 for nd in tr.accs):
+        return _two_pass_program(tr, y)
     if len(tr.term_lengths) == 1:
         L, halo = _common_halo(tr, set(tr.term_lengths))
         # term part: evaluate every accumulated expression, then ACC
@@ -263,6 +301,45 @@ def trace_scalar(f, n):
         raise TraceError("program too long")
     pre = {nd.id: nd.op for nd in tr.nodes if nd.kind == K_ACC}
     epi, ereg = _emit(tr, [y.node], "scalar", pre)
+    return Program(term, epi, tr.consts, len(tr.accs), halo, ereg[y.node.id], 1, tr.params)
+
+
+def _two_pass_program(tr, y):
+    """term1 | STAGE 1 | epilogue1 | STAGE 2 | term2 in the term part, the final epilogue in the epilogue part.
+    Pass-1 sums take the accumulator indices [0, K1), pass-2 sums [K1, K)."""
+    L, halo = _common_halo(tr, set(tr.term_lengths))
+    first = [k for k, nd in enumerate(tr.accs) if _LEVEL[nd.stage] == 0]
+    second = [k for k, nd in enumerate(tr.accs) if _LEVEL[nd.stage] == 2]
+    for new, old in enumerate(first + second):                     # renumber: pass-1 accumulators first
+        tr.acc_nodes[old].op = new
+    K1 = len(first)
+    term, reg = _emit(tr, [tr.accs[k] for k in first], "term", {})
+    for k in first:
+        term.append((K_ACC << 6, tr.acc_nodes[k].op, reg[tr.accs[k].id], 0))
+    # first-stage scalars needed later: operands of second-pass nodes and of the final epilogue
+    late = [nd for nd in tr.nodes if _LEVEL[nd.stage] >= 2]
+    needed, seen = [], set()
+    for nd in late:
+        for a in nd.args:
+            if _LEVEL[a.stage] == 1 and a.id not in seen:
+                seen.add(a.id)
+                needed.append(a)
+    if _LEVEL[y.node.stage] == 1:
+        raise TraceError("the second pass does not contribute to the result")
+    pre1 = {tr.acc_nodes[k].id: tr.acc_nodes[k].op for k in first}
+    epi1, sreg = _emit(tr, needed, "scalar", pre1)
+    sreg = {nd.id: sreg[nd.id] for nd in needed}
+    term.append((K_STAGE << 6, 0, 1, 0))
+    term += epi1
+    term.append((K_STAGE << 6, 0, 2, 0))
+    term2, reg2 = _emit(tr, [tr.accs[k] for k in second], {"term", "term2"}, {}, sreg)
+    term += term2
+    for k in second:
+        term.append((K_ACC << 6, tr.acc_nodes[k].op, reg2[tr.accs[k].id], 0))
+    if len(term) > MAX_INSTR:
+        raise TraceError("program too long")
+    pre2 = {tr.acc_nodes[k].id: tr.acc_nodes[k].op for k in second}
+    epi, ereg = _emit(tr, [y.node], "scalar2", pre2, sreg)
     return Program(term, epi, tr.consts, len(tr.accs), halo, ereg[y.node.id], 1, tr.params)
 
 

@@ -523,6 +523,22 @@ def test_hessian_vs_oracle(ctx, oracle, N):
             assert res.value == pytest.approx(v_ref, rel=RED_RTOL)
 
 
+def test_matrix_input_is_seeded_in_linear_index_order(ctx, oracle):
+    """gradient(f, x::Matrix): structural positions follow the linear (column-major) index and the gradient has the shape
+    of x (src/apiutils.jl:44-47; the reference tests call gradient on matrices throughout test/GradientTest.jl)."""
+    X = np.random.default_rng(9).uniform(0.5, 1.5, (7, 5))
+    flat = X.ravel(order="F")
+    g_ref, v_ref = oracle.gradient("rosenbrock", flat, 4)
+    G = fdb200.gradient(F.rosenbrock, X, fdb200.GradientConfig(F.rosenbrock, X, fdb200.Chunk(4)), ctx=ctx)
+    assert G.shape == X.shape and np.allclose(G, g_ref.reshape(X.shape, order="F"), rtol=RED_RTOL, atol=1e-13)
+    res = fdb200.GradientResult(X)
+    fdb200.gradient_b(res, F.rosenbrock_generic, X, fdb200.GradientConfig(F.rosenbrock_generic, X, fdb200.Chunk(4)), ctx=ctx)
+    assert res.derivs[0].shape == X.shape and np.allclose(res.derivs[0].ravel(order="F"), g_ref, rtol=1e-11, atol=1e-12)
+    assert res.value == pytest.approx(v_ref, rel=1e-12)
+    with pytest.raises(fdb200.DimensionMismatch):
+        fdb200.gradient_b(np.zeros((5, 7)), F.rosenbrock, X, fdb200.GradientConfig(F.rosenbrock, X, fdb200.Chunk(4)), ctx=ctx)
+
+
 def test_hessian_chunk_ranges_and_chunk_size_independence(ctx):
     n = 200
     x = np.random.default_rng(5).uniform(0.5, 1.5, n)

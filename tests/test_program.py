@@ -23,8 +23,7 @@ def test_tracer_flattens_rosenbrock_and_ackley():
 def test_tracer_rejects_what_the_interpreter_cannot_run():
     with pytest.raises(trace.TraceError):
         trace.trace_scalar(F.prod_generic, 10)                       # not an additive reduction
-    with pytest.raises(trace.TraceError):
-        trace.trace_scalar(lambda x: (x * x.sum()).sum(), 10)        # reduced value inside a broadcast: two passes
+    assert trace.trace_scalar(lambda x: (x * x.sum()).sum(), 10).two_pass    # reduced value inside a broadcast: two passes
     with pytest.raises(trace.TraceError):
         trace.trace_scalar(lambda x: x * 2.0, 10)                    # not a scalar
     with pytest.raises(fdb200.DimensionMismatch):
@@ -72,6 +71,18 @@ def test_tracer_data_arrays_and_reductions_of_different_lengths():
     with pytest.raises(trace.TraceError):
         trace.trace_scalar(lambda x: fdb200.maximum(x, d).sum(), n)        # max with a data array has no Real rule here
     assert not trace.trace_scalar(F.rosenbrock_generic, n).needs_jit
+    # a reduced value re-entering a broadcast: term1 | STAGE 1 | epilogue1 | STAGE 2 | term2, pass-1 sums numbered first
+    p = trace.trace_scalar(lambda x: ((x - x.mean()) ** 2).sum() + (x * 2.0).sum(), n)
+    kinds = [int(i[0]) >> 6 for i in p.term]
+    assert p.two_pass and kinds.count(trace.K_STAGE) == 2 and trace.K_LOADS in kinds and p.n_acc == 3
+    st1, st2 = [i for i, k in enumerate(kinds) if k == trace.K_STAGE]
+    assert sorted(int(i[1]) for i in p.term[:st1] if (int(i[0]) >> 6) == trace.K_ACC) == [0, 1]      # pass-1 sums: 0, 1
+    assert [int(i[1]) for i in p.term[st2:] if (int(i[0]) >> 6) == trace.K_ACC] == [2]                 # pass-2 sum: 2
+    with pytest.raises(trace.TraceError):                                    # a second re-entry would need a third pass
+        trace.trace_scalar(lambda x: ((x - ((x - x.mean()) ** 2).sum()) ** 2).sum(), n)
+    # mean and dot are sums: dot with a data vector is one Real (x) Dual multiply per term
+    p = trace.trace_scalar(lambda x: fdb200.dot(d, x) + (x ** 2).mean(), n)
+    assert p.n_acc == 2 and len(p.params) == 1 and 1.0 * n in p.consts.tolist()
 
 
 def test_specialised_kernels_compile_on_the_host():
@@ -227,6 +238,12 @@ def test_functions_closing_over_data_arrays(ctx, N, mode):
         H2_ref[np.arange(2, n), np.arange(2, n)] += 0.01 * np.exp(0.1 * x[2:])
         assert np.allclose(H2, H2_ref, rtol=1e-12, atol=1e-13)
 
+    def f3(xd):
+        return fdb200.dot(d2, xd) + (xd ** 2).mean()
+
+    g3 = fdb200.gradient(f3, x, fdb200.GradientConfig(f3, x, fdb200.Chunk(N)), ctx=ctx)
+    assert np.allclose(g3, d2 + 2.0 * x / n, rtol=1e-13, atol=0)
+
     def fa(xd):
         return d * xd[1:] - xd[:-1] / w + w ** 2.0
 
@@ -241,6 +258,40 @@ def test_functions_closing_over_data_arrays(ctx, N, mode):
     else:
         with pytest.raises(fdb200.UnsupportedOp):
             fdb200.hessian(f, x, fdb200.HessianConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 4, 12])
+def test_reduced_values_reentering_a_broadcast_two_pass(ctx, N, mode):
+    """var(x) = sum((x .- mean(x)).^2) / (n - 1) and logsumexp with a reduced shift: the reduced Dual re-enters a second
+    broadcast, so the program has two passes (specialised kernel: gradient_sweep2_body); with the interpreter the same f
+    takes the reference loop (Vector{Dual} .- Dual through fdb_map2's broadcast of a 1-element array)."""
+    n = 203
+    x = np.random.default_rng(12).uniform(-1.0, 2.0, n)
+
+    def var(xd):
+        m = xd.mean()
+        return ((xd - m) ** 2).sum() / (len(xd) - 1)
+
+    def lse(xd):
+        m = xd.mean()
+        return fdb200.log(fdb200.exp(xd - m).sum()) + m
+
+    from fdb200 import trace
+    assert trace.trace_scalar(var, n).two_pass and trace.trace_scalar(lse, n).two_pass
+    res = fdb200.GradientResult(x)
+    fdb200.gradient_b(res, var, x, fdb200.GradientConfig(var, x, fdb200.Chunk(N)), ctx=ctx)
+    assert np.allclose(res.derivs[0], 2.0 * (x - x.mean()) / (n - 1), rtol=1e-11, atol=1e-14)
+    assert res.value == pytest.approx(x.var(ddof=1), rel=1e-13)
+    res = fdb200.GradientResult(x)
+    fdb200.gradient_b(res, lse, x, fdb200.GradientConfig(lse, x, fdb200.Chunk(N)), ctx=ctx)
+    e = np.exp(x - x.max())
+    assert np.allclose(res.derivs[0], e / e.sum(), rtol=1e-11, atol=1e-15)        # softmax
+    assert res.value == pytest.approx(np.log(np.exp(x - x.max()).sum()) + x.max(), rel=1e-13)
+    gl = fdb200.gradient(lse, x, fdb200.GradientConfig(lse, x, fdb200.Chunk(N)), ctx=ctx, fuse=False)
+    assert np.allclose(res.derivs[0], gl, rtol=1e-11, atol=1e-15)
+    with pytest.raises(fdb200.UnsupportedOp):
+        fdb200.hessian(var, x, fdb200.HessianConfig(var, x, fdb200.Chunk(N)), ctx=ctx)
 
 
 # ---- the reference loop as a replayed CUDA graph (fdb_graph.cu) ------------------------------------------
