@@ -236,7 +236,7 @@ int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t
 
 /* ---- op-programs: fused broadcast trees for an arbitrary user f -----------------------------
  * What Julia's `Broadcasted` tree + `sum` gives for a user function is flattened by the host into a small
- * program (no JIT): instructions are 4 int32 words {op, dst, a, b} with op = kind*64 + code,
+ * program: instructions are 4 int32 words {op, dst, a, b} with op = kind*64 + code,
  *   kind 0 LOADX  dst <- seeded Dual of x[i + b]            (term part only; 0 <= b <= halo)
  *   kind 1 UNARY  dst <- code(a)                            code = fdb_op1
  *   kind 2 DD     dst <- a (code) b                         code = fdb_op2, both Dual registers
@@ -244,8 +244,18 @@ int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t
  *   kind 4 CD     dst <- consts[a] (code) b                 Real (op) Dual
  *   kind 5 ACC    accumulator dst += a                      (`sum`; term part only)
  *   kind 6 MOV    dst <- a
+ * and, executed by the run-time specialised kernels only (fdb_set_jit; the interpreter answers FDB_ERR_UNSUPPORTED):
+ *   kind 7 DP     dst <- a (code) param[b][i]               Dual (op) data array (fdb_program_bind_params)
+ *   kind 8 PD     dst <- param[a][i] (code) b               data array (op) Dual
+ *   kind 9 GUARD  the next b instructions run only while i + a < n    (a reduction over a shorter view; every term
+ *                 instruction of a program with guards belongs to a guarded group; terms run for i in [0, n - min a))
+ *   kind 10 STAGE a = 1: the first-stage epilogue follows (scalar code on accumulators 0..K1-1, K1 = number of
+ *                 accumulators used so far); a = 2: the second-stage terms follow.  term1 | STAGE 1 | epilogue1 |
+ *                 STAGE 2 | term2: a reduced Dual re-enters a second broadcast (sum((x .- mean(x)).^2)); gradients only
+ *   kind 11 LOADS dst <- S[a], S = the register file as the first-stage epilogue left it (term2 and final epilogue;
+ *                 there registers K1..n_acc-1 are preloaded with the second-stage accumulators)
  * The term part runs for every i in [0, n - halo); the epilogue part runs once per chunk with registers
- * 0..n_acc-1 preloaded with the reduced accumulators; `result_reg` holds f(xdual).  Limits: 48 instructions
+ * 0..n_acc-1 preloaded with the reduced accumulators; `result_reg` holds f(xdual).  Limits: 96 instructions
  * per part, 24 constants, 12 registers, 4 accumulators (FDB_ERR_UNSUPPORTED beyond).  Same chunk-range
  * semantics as fdb_gradient_chunked / fdb_jacobian_chunked.  The Jacobian form evaluates
  * y[i] = program(x[i .. i+halo]), i in [0, n - halo) (elementwise / stencil array functions). */
