@@ -166,6 +166,7 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
     }
     const int K = P.n_acc > 0 ? P.n_acc : 1;
     s += "struct UserFn {\n";
+    s += std::string("    static constexpr bool PURE_X = ") + ((P.n_params == 0 && !P.has_guard) ? "true" : "false") + ";\n";
     s += std::string("    static constexpr bool PLAIN_SUM = ") + ((P.n_epi == 0 && K == 1 && P.result_reg == 0) ? "true" : "false") + ";\n";
     s += "    static constexpr int K = " + std::to_string(K) + ";\n    static constexpr int HALO = " + std::to_string(P.halo) + ";\n";
     s += "    static __device__ int64_t nterms(int64_t n) { return n > " + std::to_string(P.term_halo) + " ? n - " + std::to_string(P.term_halo) + " : 0; }\n";

@@ -231,6 +231,7 @@ __device__ __noinline__ void pg_run_shared_vec(const short (*code)[4], int ninst
 
 struct SumK {   // block_combine policy: K sum accumulators
     static constexpr int K = PG_MAXK;
+    static constexpr bool PURE_X = false;
     template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }
     template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }
 };

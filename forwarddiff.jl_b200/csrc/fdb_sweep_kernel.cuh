@@ -15,6 +15,60 @@ namespace fdb {
 // only the summation order changes, which the reduction tolerance already covers.
 // Every term of f is still evaluated in every chunk.  SHARE=false evaluates all N
 // lanes for every term (bench.py reports both).
+// A term's inputs held in registers: the far loops below fetch x for the NEXT group of terms before they evaluate the
+// current group, so the L2 latency of the x stream (x is L2-resident, every block re-reads all of it: ncu showed as many
+// long-scoreboard stalls as FP64-pipe stalls) is hidden behind FP64 work of the same warp.  The functor is called with the
+// literal term index 0, so x(0 + b) becomes register v[b]; only functors whose term depends on i through x(i + b) alone
+// (F::PURE_X) take this path.
+template <int H, bool NS> struct RegLoader {
+    double v[H + 1];
+    FDB_DEV void fetch(const double* __restrict__ x, int64_t i) {
+#pragma unroll
+        for (int b = 0; b <= H; b++) v[b] = x[i + b];
+    }
+    FDB_DEV Dual<double, 1, NS> operator()(int64_t j) const {
+        Dual<double, 1, NS> d; d.v = v[j]; d.p[0] = 0.0; return d;
+    }
+};
+
+// far terms of iterations [it0, it1) (term index = it * THREADS + threadIdx.x, all valid), Dual{1} accumulators
+template <class F, bool NS, int THREADS>
+FDB_DEV void far_range(const double* __restrict__ x, int64_t n, int64_t it0, int64_t it1, Dual<double, 1, NS> (&acc1)[F::K]) {
+    constexpr int U = 4;
+    const int64_t t = threadIdx.x;
+    int64_t it = it0;
+    if constexpr (F::PURE_X) {
+        RegLoader<F::HALO, NS> a[U], b[U];
+        if (it + U <= it1) {
+#pragma unroll
+            for (int u = 0; u < U; u++) a[u].fetch(x, (it + u) * THREADS + t);
+        }
+        // two groups per trip: while group A is evaluated group B's loads are in flight, and vice versa
+        for (; it + 3 * U <= it1; it += 2 * U) {
+#pragma unroll
+            for (int u = 0; u < U; u++) b[u].fetch(x, (it + U + u) * THREADS + t);
+#pragma unroll
+            for (int u = 0; u < U; u++) F::term(a[u], (int64_t)0, n, acc1);
+#pragma unroll
+            for (int u = 0; u < U; u++) a[u].fetch(x, (it + 2 * U + u) * THREADS + t);
+#pragma unroll
+            for (int u = 0; u < U; u++) F::term(b[u], (int64_t)0, n, acc1);
+        }
+        if (it + U <= it1) {                       // group A is loaded and not yet evaluated
+#pragma unroll
+            for (int u = 0; u < U; u++) F::term(a[u], (int64_t)0, n, acc1);
+            it += U;
+        }
+    }
+    ZeroLoader<1, NS> xz{x};
+    if constexpr (!F::PURE_X) {
+#pragma unroll 4
+        for (; it < it1; it++) F::term(xz, it * THREADS + t, n, acc1);
+    } else {
+        for (; it < it1; it++) F::term(xz, it * THREADS + t, n, acc1);
+    }
+}
+
 // pass over all terms of f for the chunk window [start, start+chunksize): this thread's partial accumulators
 template <class F, int N, bool NS, int THREADS, bool SHARE>
 FDB_DEV void sweep_terms(const double* __restrict__ x, int64_t n, int64_t start, int chunksize, Dual<double, N, NS> (&acc)[F::K]) {
@@ -35,15 +89,13 @@ FDB_DEV void sweep_terms(const double* __restrict__ x, int64_t n, int64_t start,
         const int64_t nit = (nt + THREADS - 1) / THREADS;
         int64_t itA = (start - F::HALO) / THREADS; if (itA < 0) itA = 0; if (itA > nit) itA = nit;
         int64_t itB = (start + chunksize + THREADS - 1) / THREADS; if (itB > nit) itB = nit; if (itB < itA) itB = itA;
-#pragma unroll 4
-        for (int64_t it = 0; it < itA; it++) F::term(xz, it * THREADS + threadIdx.x, n, acc1);
+        far_range<F, NS, THREADS>(x, n, 0, itA, acc1);
         for (int64_t it = itA; it < itB; it++) {
             const int64_t i = it * THREADS + threadIdx.x;
             if (i < nt) F::term(xs, i, n, acc);
         }
         const int64_t full = nt / THREADS;      // iterations whose every lane is a valid term
-#pragma unroll 4
-        for (int64_t it = itB; it < full; it++) F::term(xz, it * THREADS + threadIdx.x, n, acc1);
+        far_range<F, NS, THREADS>(x, n, itB, full, acc1);
         for (int64_t it = (itB > full ? itB : full); it < nit; it++) {
             const int64_t i = it * THREADS + threadIdx.x;
             if (i < nt) F::term(xz, i, n, acc1);

@@ -46,6 +46,7 @@ template <int N, bool NS> struct ZeroLoader {
 // Dual*Dual.
 struct Rosenbrock {
     static constexpr bool PLAIN_SUM = true;   // f = sum of the terms: one accumulator, combine = +, finalize = identity
+    static constexpr bool PURE_X = true;      // term(x, i, ...) depends on i only through x(i + b), 0 <= b <= HALO
     static constexpr int K = 1;
     static constexpr int HALO = 1;   // term i reads positions i .. i+HALO
     static __host__ __device__ int64_t nterms(int64_t n) { return n > 0 ? n - 1 : 0; }
@@ -66,6 +67,7 @@ struct Rosenbrock {
 //   -a*exp(b*sqrt(len_recip*sum_sqrs)) - exp(len_recip*sum_cos) + a + e
 struct Ackley {
     static constexpr bool PLAIN_SUM = false;
+    static constexpr bool PURE_X = true;
     static constexpr int K = 2;
     static constexpr int HALO = 0;   // acc[0] = sum_cos, acc[1] = sum_sqrs
     static __host__ __device__ int64_t nterms(int64_t n) { return n; }
@@ -87,6 +89,7 @@ struct Ackley {
 // ---- sum(x.^2) ---------------------------------------------------------------------
 struct SumSq {
     static constexpr bool PLAIN_SUM = true;
+    static constexpr bool PURE_X = true;
     static constexpr int K = 1;
     static constexpr int HALO = 0;
     static __host__ __device__ int64_t nterms(int64_t n) { return n; }
@@ -101,6 +104,7 @@ struct SumSq {
 // ---- prod(x) -------------------------------------------------------------------------
 struct ProdAll {
     static constexpr bool PLAIN_SUM = false;
+    static constexpr bool PURE_X = true;
     static constexpr int K = 1;
     static constexpr int HALO = 0;
     static __host__ __device__ int64_t nterms(int64_t n) { return n; }
@@ -115,6 +119,7 @@ struct ProdAll {
 // ---- plain sum / prod of an array (fdb_reduce) -----------------------------------------
 struct SumAll {
     static constexpr bool PLAIN_SUM = true;
+    static constexpr bool PURE_X = true;
     static constexpr int K = 1;
     static constexpr int HALO = 0;
     static __host__ __device__ int64_t nterms(int64_t n) { return n; }
