@@ -290,8 +290,8 @@ def main():
     roofline = {"bound": "fp64", "kernel": "gradient_sweep_kernel<Rosenbrock,12,false,256,true>",
                 "achieved": achieved, "peak": dp_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (dp_peak / 1e12),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one full C2 launch, ncu --set full
-                # (profiles/r01_sweep_rosenbrock_raw.csv): x read once, the 8 MB gradient still in L2
-                "traffic": 8.094e6 if my_chunks == 83334 else None,
+                # (profiles/r01_sweep_rosenbrock_pipelined_raw.csv): x read once, the 8 MB gradient still in L2
+                "traffic": 8.165e6 if my_chunks == 83334 else None,
                 "peak_source": "fdb_measure_fp64_peak: non-fused DMUL/DADD issue rate measured live on this GPU "
                                "(MEASURED_PEAKS.json has no FP64 figure); FMA peak %.1f TFLOP/s" % (2 * dfma_peak / 1e12),
                 "algorithmic": f"{DP_OPS_PER_TERM_SHARED} FP64 ops per term per chunk sweep x {N_ELEMS - 1} terms x {my_chunks} chunks "
