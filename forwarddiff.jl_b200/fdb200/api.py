@@ -354,9 +354,14 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
         value = _fused_gradient(ctx, fid, x, N, lo, hi, out)
     else:
         prog = _try_trace("scalar", f, n) if fuse else None
+        value, done = None, False
         if _usable(ctx, prog):
-            value = _program_gradient(ctx, prog, x, N, lo, hi, out)
-        else:
+            try:
+                value, done = _program_gradient(ctx, prog, x, N, lo, hi, out), True
+            except _lib.UnsupportedOp:
+                if not prog.needs_jit:                  # only "libnvrtc is not installed" is recoverable: take the loop
+                    raise
+        if not done:
             value = _loop_gradient(ctx, f, x, cfg, lo, hi, out, graph)
     if isinstance(result, DiffResult) and value is not None:
         result.value = value
@@ -579,7 +584,11 @@ def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None
     if fid is None:
         prog = _try_trace("array", f, n) if (fuse and y is None) else None
         if _usable(ctx, prog):
-            return _program_jacobian(ctx, prog, result, out, x, N, lo, hi)
+            try:
+                return _program_jacobian(ctx, prog, result, out, x, N, lo, hi)
+            except _lib.UnsupportedOp:
+                if not prog.needs_jit:
+                    raise
         return _loop_jacobian(ctx, result, out, f, x, cfg, y, lo, hi)
     params = params or getattr(f, "params", {}) or {}
     host = not isinstance(x, _DeviceArray)
