@@ -116,6 +116,38 @@ def cpu_oracle_rate(sample_chunks, threads):
     return 1.0 / (dt * nchunks / done), dt, nchunks
 
 
+def reference_cpp_rate(ctx):
+    """The reference's OWN native benchmark (benchmarks/cpp: gradient<rosenbrock<Dual5>>, n = 12 000, the shape it ships with),
+    built from /root/reference into oracle/_ref, against the same gradient through the library: kind "reference"."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    if not orc.RefBench.available():
+        return None
+    import fdb200
+    rb = orc.RefBench()
+    n, K = 12_000, 5
+    x = np.random.default_rng(11).random(n)
+    rb.gradient("rosenbrock", x, K)
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        g_ref = rb.gradient("rosenbrock", x, K)
+    cpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    xd, gd, vd = ctx.array(x), ctx.zeros(n), ctx.zeros(1)
+    run = lambda: ctx.check(ctx.lib.fdb_gradient_chunked(ctx.h, fdb200._lib.FN["rosenbrock"], xd.h, K, 0, -1, gd.h, vd.h))
+    run(); ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run()
+    ctx.sync()
+    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    g = gd.numpy()
+    return {"kind": "reference", "workload": "benchmarks/cpp gradient<rosenbrock<Dual5>>, n = 12000 (2400 chunk sweeps)", "cores": 1,
+            "reference_cpp_ms": cpu_ms, "fdb200_ms": gpu_ms, "speedup": cpu_ms / gpu_ms,
+            "max_rel_diff": float(np.max(np.abs(g - g_ref) / np.maximum(np.abs(g_ref), 1e-300))),
+            "build": "g++ -std=c++11 -O2 on the reference's own sources (oracle/Makefile target ref)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -324,6 +356,13 @@ def main():
                                           "scaled by nchunks/1200; oracle.cpp (C++ restatement of src/gradient.jl:114-159 on AoS Duals, "
                                           "g++ -O3 -march=x86-64-v3, no FMA contraction); Julia not installed (JULIA_NUM_THREADS n/a); "
                                           "the reference is single-threaded by design (docs/src/user/upgrade.md:39-50)"}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = reference_cpp_rate(ctx)
+            if r is not None:
+                line["cpu_baseline_reference_cpp"] = r
+        except Exception as e:
+            line["cpu_baseline_reference_cpp"] = {"error": repr(e)}
     if world == 1 and not args.no_extras:
         try:
             line["extra"] = extras(ctx, torch, dev, flush, hbm_peak, dp_peak)
