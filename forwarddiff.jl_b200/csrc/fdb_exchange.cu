@@ -218,6 +218,23 @@ extern "C" int fdb_exchange_measure_store_bw(fdb_exchange* x, int64_t n_doubles,
     return FDB_OK;
 }
 
+// all-gather / broadcast for data the drivers did not mirror themselves (e.g. results of the materialised loop path):
+// copy [offset, offset+count) of the local arena to the same place in every peer's arena.
+extern "C" int fdb_exchange_push(fdb_exchange* x, int64_t offset, int64_t count) {
+    if (!x) return FDB_ERR_BADARG;
+    fdb_ctx* ctx = x->ctx;
+    if (!x->connected) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_push: not connected");
+    if (offset < 0 || count < 0 || (size_t)(offset + count) * sizeof(double) > x->data_bytes)
+        return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_push: [%lld, %lld) outside the arena", (long long)offset, (long long)(offset + count));
+    if (x->world == 1 || count == 0) return FDB_OK;
+    fdb_mirrors M;
+    for (int k = 1; k < x->world; k++) M.delta[M.count++] = (long long)(x->peer[(x->rank + k) % x->world] - x->base);
+    const double* src = reinterpret_cast<const double*>(x->base) + offset;
+    int64_t blocks = cdiv(count, 256 * 4); if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8; if (blocks < 1) blocks = 1;
+    exchange_probe_kernel<0><<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, count, M);
+    return finish(ctx, 1, "fdb_exchange_push");
+}
+
 extern "C" int fdb_exchange_timeouts(fdb_exchange* x, int64_t* count) {
     if (!x || !count) return FDB_ERR_BADARG;
     unsigned v = 0;

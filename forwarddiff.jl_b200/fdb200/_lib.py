@@ -134,6 +134,7 @@ SIGNATURES = {
     "fdb_exchange_view": (C.c_int, [C.c_void_p, i64, i64, i64, C.POINTER(c_arr)]),
     "fdb_exchange_enable": (C.c_int, [c_ctx, C.c_void_p]),
     "fdb_exchange_barrier": (C.c_int, [C.c_void_p]),
+    "fdb_exchange_push": (C.c_int, [C.c_void_p, i64, i64]),
     "fdb_exchange_timeouts": (C.c_int, [C.c_void_p, C.POINTER(i64)]),
     "fdb_exchange_destroy": (C.c_int, [C.c_void_p]),
     "fdb_exchange_measure_store_bw": (C.c_int, [C.c_void_p, i64, C.c_int, C.c_int, _dp]),

@@ -112,6 +112,10 @@ class PeerExchange:
     def disable(self):
         self.ctx.check(self.ctx.lib.fdb_exchange_enable(self.ctx.h, None))
 
+    def push(self, offset, count):
+        """Copy [offset, offset+count) of the local arena into every peer's arena (all-gather / broadcast building block)."""
+        self.ctx.check(self.ctx.lib.fdb_exchange_push(self.h, int(offset), int(count)))
+
     def barrier(self):
         """Device-side barrier on the context's stream (no host synchronisation)."""
         self.ctx.check(self.ctx.lib.fdb_exchange_barrier(self.h))

@@ -326,6 +326,9 @@ int fdb_exchange_connect(fdb_exchange* x, const unsigned char* handles);
 int fdb_exchange_view(fdb_exchange* x, int64_t offset, int64_t n, int64_t ld, fdb_array** out);
 int fdb_exchange_enable(fdb_ctx* ctx, fdb_exchange* x_or_null);
 int fdb_exchange_barrier(fdb_exchange* x);
+/* all-gather / broadcast of arena data the drivers did not mirror themselves: copy [offset, offset+count) doubles of the local
+ * arena to the same place in every peer's arena (every rank pushing its slice + a barrier = all-gather; one rank = broadcast) */
+int fdb_exchange_push(fdb_exchange* x, int64_t offset, int64_t count);
 /* number of barrier waits that gave up after the timeout (a peer never arrived); synchronises the stream */
 int fdb_exchange_timeouts(fdb_exchange* x, int64_t* count);
 int fdb_exchange_destroy(fdb_exchange* x);

@@ -95,6 +95,16 @@ def check(ctx, rank, world, exchange):
         finally:
             sg.xch.disable()
         assert sg.xch.timeouts() == 0 and sj.xch.timeouts() == 0
+    if exchange == "p2p":
+        # all-gather of data no driver mirrored: every rank fills its slice of a fresh arena, pushes it, barrier
+        per = 1000
+        xa = fdb200.dist.PeerExchange(ctx, per * world)
+        mine = xa.torch_view(rank * per, per)
+        mine.copy_(torch.arange(per, dtype=torch.float64, device=mine.device) + 1000.0 * rank)
+        xa.push(rank * per, per); xa.barrier()
+        allv = xa.torch_view(0, per * world).cpu().numpy()
+        assert np.array_equal(allv, np.concatenate([np.arange(per) + 1000.0 * r for r in range(world)]))
+        xa.close()
     for s in (sg, sj, st, sh):
         s.close()
 
