@@ -97,7 +97,9 @@ def test_specialised_kernels_compile_on_the_host():
     assert len(data.params) == 2            # w and the host-evaluated 1.0 + w
     for kind, prog, N in ((0, trace.trace_scalar(F.rosenbrock_generic, 100), 12), (0, trace.trace_scalar(F.ackley_generic, 100), 7),
                           (2, trace.trace_scalar(F.rosenbrock_generic, 100), 8), (1, jac, 5), (0, data, 6), (2, data, 4),
-                          (2, trace.trace_scalar(F.ackley_generic, 100), 8)):
+                          (2, trace.trace_scalar(F.ackley_generic, 100), 8),
+                          (0, trace.trace_scalar(lambda xd: ((xd - xd.mean()) ** 2).sum() / 99.0, 100), 12),                 # two passes
+                          (0, trace.trace_scalar(lambda xd: ((xd[1:] - xd[:-1]) ** 2).sum() + (xd * xd).sum(), 100), 3)):  # guards
         log = C.create_string_buffer(1 << 16); nbytes = C.c_int64()
         rc = lib.fdb_jit_compile_check(kind, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
                                        prog.consts.ctypes.data_as(dp) if prog.consts.size else None, prog.consts.size, prog.n_acc,
