@@ -108,6 +108,11 @@ def _length(x):
     return x.n if isinstance(x, _DeviceArray) else int(np.asarray(x).size)
 
 
+def _vec(x):
+    """vec(x): an N-d input is differentiated in linear-index (column-major) order, src/apiutils.jl:44-47."""
+    return x.ravel(order="F") if isinstance(x, np.ndarray) and x.ndim > 1 else x
+
+
 def _ctx_of(x, ctx=None):
     if ctx is not None:
         return ctx
@@ -547,6 +552,7 @@ def _loop_gradient(ctx, f, x, cfg, lo, hi, out, graph=True):
 def jacobian(f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=None, m=None, fuse=True):
     """ForwardDiff.jacobian(f, x, cfg) and, with `y`, jacobian(f!, y, x, cfg) (src/jacobian.jl:18-44).
     Returns the dense column-major length(y) x length(x) matrix (jacobian.jl:221)."""
+    x = _vec(x)
     n = _length(x)
     ylen = _length(y) if y is not None else (m if m is not None else getattr(f, "output_length", lambda n: None)(n))
     fp = getattr(f, "params", None) or {}
@@ -568,6 +574,7 @@ def jacobian(f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=N
 
 def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None, chunks=None, fuse=True):
     """ForwardDiff.jacobian!(result, f, x, cfg) / jacobian!(result, f!, y, x, cfg) (src/jacobian.jl:57-87)."""
+    x = _vec(x)
     cfg = cfg if cfg is not None else JacobianConfig(f, x, y=y)
     if check:
         checktag(cfg.tag, f, x)
@@ -743,7 +750,8 @@ def _loop_jacobian(ctx, result, out, f, x, cfg, y, lo, hi):
 # hessian
 # ---------------------------------------------------------------------------
 def hessian(f, x, cfg=None, check=True, ctx=None, chunks=None):
-    """ForwardDiff.hessian(f, x, cfg) (src/hessian.jl:14-19)."""
+    """ForwardDiff.hessian(f, x, cfg) (src/hessian.jl:14-19); for an N-d x the Hessian is over vec(x)."""
+    x = _vec(x)
     n = _length(x)
     result = np.zeros((n, n), order="F")
     return hessian_b(result, f, x, cfg, check, ctx, chunks)
@@ -751,6 +759,7 @@ def hessian(f, x, cfg=None, check=True, ctx=None, chunks=None):
 
 def hessian_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None):
     """ForwardDiff.hessian!(result, f, x, cfg) for an array or a HessianResult (src/hessian.jl:31-37,66-71)."""
+    x = _vec(x)
     cfg = cfg if cfg is not None else HessianConfig(f, x)
     if check:
         checktag(cfg.tag, f, x)

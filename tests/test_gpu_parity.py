@@ -537,6 +537,13 @@ def test_matrix_input_is_seeded_in_linear_index_order(ctx, oracle):
     assert res.value == pytest.approx(v_ref, rel=1e-12)
     with pytest.raises(fdb200.DimensionMismatch):
         fdb200.gradient_b(np.zeros((5, 7)), F.rosenbrock, X, fdb200.GradientConfig(F.rosenbrock, X, fdb200.Chunk(4)), ctx=ctx)
+    # hessian / jacobian of a matrix input are over vec(x)
+    H = fdb200.hessian(F.rosenbrock, X, fdb200.HessianConfig(F.rosenbrock, X, fdb200.Chunk(5)), ctx=ctx)
+    H_ref, _, _ = oracle.hessian("rosenbrock", flat, 5)
+    assert H.shape == (35, 35) and np.allclose(H, H_ref, rtol=RED_RTOL, atol=1e-12)
+    fsq = lambda xd: xd ** 2 * 3.0
+    J = fdb200.jacobian(fsq, X, fdb200.JacobianConfig(fsq, X, fdb200.Chunk(4)), ctx=ctx)
+    assert np.array_equal(J, np.diag(6.0 * flat))
 
 
 def test_hessian_chunk_ranges_and_chunk_size_independence(ctx):
