@@ -370,6 +370,10 @@ def test_program_hessian_vs_oracle_and_finite_differences(ctx, oracle, N, mode):
     fd = np.array([[(fv(x + h * E[i] + h * E[j]) - fv(x + h * E[i] - h * E[j]) - fv(x - h * E[i] + h * E[j]) + fv(x - h * E[i] - h * E[j])) / (4 * h * h)
                     for j in range(n)] for i in range(n)])
     assert np.allclose(H, fd, atol=2e-2 * max(1.0, np.abs(H).max()) * 1e-2 + 1e-4)      # Calculus.hessian-style tolerance (HessianTest.jl:65-88)
+    if N == 1:      # test/MiscTest.jl:183: hessian(t -> abs(t[1])^2, [0.0]) == 2 pins abs'(0) = +1 through the nested rule
+        fa0 = lambda xd: (fdb200.abs_(xd) ** 2).sum()
+        x0 = np.array([0.0])
+        assert fdb200.hessian(fa0, x0, fdb200.HessianConfig(fa0, x0, fdb200.Chunk(1)), ctx=ctx)[0, 0] == 2.0
     # arithmetic after the reductions (Ackley: two sums, then exp / sqrt on Dual{Dual{N},N}): the specialised kernel
     # finalizes on full nested duals; the interpreter has no such path and says so
     if mode == "specialised":
