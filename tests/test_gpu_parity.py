@@ -523,6 +523,21 @@ def test_hessian_vs_oracle(ctx, oracle, N):
             assert res.value == pytest.approx(v_ref, rel=RED_RTOL)
 
 
+@pytest.mark.parametrize("N", [1, 2, 3, 4])
+def test_readme_example_gradient(ctx, N):
+    """README.md:26-45: f(x) = sin(x[1]) + prod(x[2:end]) at x = [pi/4, 2, 3, 4] -> [0.7071067811865476, 12, 8, 6].
+    Written with views instead of scalar indexing; prod keeps it on the reference chunk loop over device Dual arrays."""
+    x = np.array([np.pi / 4, 2.0, 3.0, 4.0])
+
+    def f(xd):
+        return fdb200.sin(xd[:1]).sum() + xd[1:].prod()
+
+    res = fdb200.GradientResult(x)
+    fdb200.gradient_b(res, f, x, fdb200.GradientConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+    assert np.allclose(res.derivs[0], [0.7071067811865476, 12.0, 8.0, 6.0], rtol=1e-15, atol=0)
+    assert res.value == pytest.approx(np.sin(np.pi / 4) + 24.0, rel=1e-15)
+
+
 def test_matrix_input_is_seeded_in_linear_index_order(ctx, oracle):
     """gradient(f, x::Matrix): structural positions follow the linear (column-major) index and the gradient has the shape
     of x (src/apiutils.jl:44-47; the reference tests call gradient on matrices throughout test/GradientTest.jl)."""
