@@ -85,6 +85,51 @@ def test_tracer_data_arrays_and_reductions_of_different_lengths():
     assert p.n_acc == 2 and len(p.params) == 1 and 1.0 * n in p.consts.tolist()
 
 
+def test_programs_mean_what_the_reference_evaluator_says(oracle):
+    """tests/program_ref.py evaluates a traced program with full dual numbers in NumPy: the tracer and the instruction
+    encoding (guards, stage markers, data arrays, accumulator numbering) checked on the CPU against closed forms and
+    against the oracle's chunk-mode gradients."""
+    import program_ref
+    n = 23
+    rng = np.random.default_rng(21)
+    x, w, d = rng.uniform(0.5, 1.5, n), rng.uniform(1.0, 2.0, n - 1), rng.uniform(0.0, 1.0, n)
+    for gen, name in ((F.rosenbrock_generic, "rosenbrock"), (F.ackley_generic, "ackley"), (F.sumsq_generic, "sumsq")):
+        v, g = program_ref.evaluate(trace.trace_scalar(gen, n), x)
+        g_ref, v_ref = oracle.gradient(name, x, 4)
+        assert np.allclose(g, g_ref, rtol=1e-12, atol=1e-13) and v == pytest.approx(v_ref, rel=1e-13), name
+    # data arrays + reductions of different lengths (guarded groups)
+    f = lambda xd: (w * (xd[1:] - xd[:-1]) ** 2).sum() + 0.5 * ((xd - d) ** 2).sum() + fdb200.exp(xd[2:] * 0.1).sum()
+    v, g = program_ref.evaluate(trace.trace_scalar(f, n), x)
+    g_ref = (x - d).copy()
+    g_ref[1:] += 2.0 * w * (x[1:] - x[:-1]); g_ref[:-1] -= 2.0 * w * (x[1:] - x[:-1]); g_ref[2:] += 0.1 * np.exp(0.1 * x[2:])
+    assert np.allclose(g, g_ref, rtol=1e-13, atol=1e-14)
+    assert v == pytest.approx((w * (x[1:] - x[:-1]) ** 2).sum() + 0.5 * ((x - d) ** 2).sum() + np.exp(0.1 * x[2:]).sum(), rel=1e-14)
+    # two passes: variance, and logsumexp with a reduced shift (gradient = softmax)
+    v, g = program_ref.evaluate(trace.trace_scalar(lambda xd: ((xd - xd.mean()) ** 2).sum() / (len(xd) - 1), n), x)
+    assert v == pytest.approx(x.var(ddof=1), rel=1e-13) and np.allclose(g, 2.0 * (x - x.mean()) / (n - 1), rtol=1e-12, atol=1e-15)
+    lse = lambda xd: fdb200.log(fdb200.exp(xd - xd.mean()).sum()) + xd.mean()
+    v, g = program_ref.evaluate(trace.trace_scalar(lse, n), x)
+    e = np.exp(x - x.max())
+    assert np.allclose(g, e / e.sum(), rtol=1e-12, atol=1e-16) and v == pytest.approx(np.log(e.sum()) + x.max(), rel=1e-13)
+    # array-valued (Jacobian) form with a stencil and a data array
+    y, J = program_ref.evaluate(trace.trace_array(lambda xd: d[:-2] * xd[2:] - 2.0 * xd[1:-1] + xd[:-2] ** 2, n), x)
+    J_ref = np.zeros((n - 2, n))
+    for i in range(n - 2):
+        J_ref[i, i + 2] = d[i]; J_ref[i, i + 1] = -2.0; J_ref[i, i] = 2.0 * x[i]
+    assert np.allclose(J, J_ref, rtol=1e-15, atol=0) and np.allclose(y, d[:-2] * x[2:] - 2.0 * x[1:-1] + x[:-2] ** 2, rtol=1e-15)
+    # every op family through one function, against central differences (the reference's own 3e-5 tolerance)
+    def fall(xd):
+        u = fdb200.tanh(xd[:-1]) * fdb200.log1p(xd[1:]) + 2.0 / xd[:-1] - (xd[1:] ** 2.5) / 3.0 + fdb200.atan(xd[:-1]) * fdb200.cbrt(xd[1:])
+        return (fdb200.maximum(u, xd[1:]) ** 3).sum() + fdb200.sqrt((xd ** 2).sum())
+    def fnum(z):
+        u = np.tanh(z[:-1]) * np.log1p(z[1:]) + 2.0 / z[:-1] - z[1:] ** 2.5 / 3.0 + np.arctan(z[:-1]) * np.cbrt(z[1:])
+        return (np.maximum(u, z[1:]) ** 3).sum() + np.sqrt((z ** 2).sum())
+    v, g = program_ref.evaluate(trace.trace_scalar(fall, n), x)
+    h = 1e-6
+    fd = np.array([(fnum(x + h * np.eye(n)[i]) - fnum(x - h * np.eye(n)[i])) / (2 * h) for i in range(n)])
+    assert v == pytest.approx(fnum(x), rel=1e-13) and np.allclose(g, fd, atol=3e-5)
+
+
 def test_specialised_kernels_compile_on_the_host():
     """NVRTC needs no GPU: the functor generated for a traced f and the sweep kernel templates compile for sm_100a."""
     import ctypes as C
