@@ -30,6 +30,20 @@ def test_library_exports_every_declared_symbol():
     assert fdb200._lib.load().fdb_version().decode().startswith("fdb200")
 
 
+def test_sweep_kernel_has_no_contracted_multiply_adds():
+    """The reference never contracts a*b + c (src/partials.jl:222-224 are separate operations), so the library is built
+    with -fmad=false: the SASS of the C2 gradient sweep kernel must hold DMUL and DADD only, no DFMA."""
+    import shutil
+    if not shutil.which("cuobjdump") or not shutil.which("nm"):
+        pytest.skip("cuobjdump / nm not available")
+    syms = subprocess.run(["nm", fdb200.LIB_PATH], capture_output=True, text=True).stdout.split()
+    names = [t for t in syms if "gradient_sweep_kernelINS_10RosenbrockELi12ELb0ELi256ELb1" in t and t.startswith("_ZN3fdb")]
+    assert names, "kernel symbol not found"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", names[0], fdb200.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert sass.count("DMUL") > 100 and sass.count("DADD") > 100
+    assert "DFMA" not in sass
+
+
 def test_no_cpu_fallback_without_gpu():
     n = C.c_int(-1)
     rc = fdb200._lib.load().fdb_device_count(C.byref(n))
