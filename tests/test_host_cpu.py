@@ -44,6 +44,24 @@ def test_sweep_kernel_has_no_contracted_multiply_adds():
     assert "DFMA" not in sass
 
 
+def test_tensor_core_and_tma_instructions_are_in_the_library():
+    """SASS evidence that needs no GPU: the FP64 contraction kernel issues DMMA and is fed by TMA (UTMALDG tensor loads,
+    UBLKCP bulk copies, mbarrier SYNCS); the pipelined reduction streams with UBLKCP as well."""
+    import shutil
+    if not shutil.which("cuobjdump") or not shutil.which("nm"):
+        pytest.skip("cuobjdump / nm not available")
+    syms = subprocess.run(["nm", fdb200.LIB_PATH], capture_output=True, text=True).stdout.split()
+
+    def sass(fragment):
+        name = next(t for t in syms if t.startswith("_ZN3fdb") and fragment in t)
+        return subprocess.run(["cuobjdump", "-sass", "-fun", name, fdb200.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+
+    gemm = sass("dmma_gemm_kernel")
+    assert "DMMA" in gemm and "UTMALDG" in gemm and "UBLKCP" in gemm and "SYNCS" in gemm
+    red = sass("mapreduce_tma_kernel")
+    assert "UBLKCP" in red and "SYNCS" in red
+
+
 def test_no_cpu_fallback_without_gpu():
     n = C.c_int(-1)
     rc = fdb200._lib.load().fdb_device_count(C.byref(n))
