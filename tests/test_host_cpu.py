@@ -122,6 +122,35 @@ def test_rank_chunk_ranges_partition_the_chunks(n, N, world):
     assert 0 <= fdb200.dist.owner_of_last_chunk(n, N, world) < world
 
 
+def test_chunk_plan_properties_random():
+    """Property test of fdb_plan_chunks (hypothesis): for any n >= N the ranks' chunk ranges are contiguous, disjoint and
+    cover every chunk; every structural position is seeded by exactly one chunk (the last chunk starts at n - lastchunksize,
+    src/gradient.jl:121-125); the bookkeeping identities of the reference hold."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 12), st.integers(0, 5_000_000), st.integers(1, 8))
+    def check(N, extra, world):
+        n = N + extra
+        plans = [fdb200.chunk_plan(n, N, r, world) for r in range(world)]
+        p = plans[0]
+        assert p["remainder"] == n % N and p["lastchunksize"] == (N if n % N == 0 else n % N)
+        assert p["lastchunkindex"] == n - p["lastchunksize"] + 1
+        assert p["nchunks"] == p["middle_hi"] + 1 == -(-n // N)
+        pos = 0
+        for q in plans:
+            assert q["chunk_lo"] == min(pos, p["nchunks"]) or q["chunk_lo"] == q["chunk_hi"] == p["nchunks"]
+            assert q["elem_lo"] == min(q["chunk_lo"] * N, n) and q["elem_hi"] == min(q["chunk_hi"] * N, n)
+            pos = q["chunk_hi"]
+        assert pos == p["nchunks"] and plans[-1]["elem_hi"] == n or any(q["chunk_hi"] == p["nchunks"] for q in plans)
+        assert sum(q["elem_hi"] - q["elem_lo"] for q in plans) == n          # every position belongs to exactly one rank
+        lay = fdb200.dist.slice_layout(n, N, world)
+        assert lay["per"] % N == 0 and lay["per"] * world >= n
+        assert all(q["elem_hi"] - q["elem_lo"] <= lay["per"] for q in plans)
+
+    check()
+
+
 def test_structural_index_sets(oracle):
     lib = fdb200._lib.load()
     for name, kind in fdb200._lib.STRUCTURE.items():
