@@ -130,6 +130,88 @@ def test_programs_mean_what_the_reference_evaluator_says(oracle):
     assert v == pytest.approx(fnum(x), rel=1e-13) and np.allclose(g, fd, atol=3e-5)
 
 
+def test_random_expression_trees_trace_to_equivalent_programs():
+    """Property test (hypothesis): random broadcast expression DAGs over x[1:], x[:-1], constants and a data array are traced,
+    and the program -- whatever instruction order and register reuse the tracer chose -- must evaluate (program_ref) to the
+    same value and gradient as the expression applied directly to NumPy dual numbers."""
+    import program_ref
+    from hypothesis import assume, given, settings, strategies as st
+
+    class ND:                                   # NumPy dual array with the operators a user function uses
+        __array_ufunc__ = None
+
+        def __init__(self, d):
+            self.d = d
+
+        def __getitem__(self, sl):
+            return ND(program_ref.D(self.d.v[sl], self.d.g[sl]))
+
+        def _lift(self, o):
+            m, k = self.d.v.size, self.d.g.shape[1]
+            if isinstance(o, ND):
+                return o.d
+            if isinstance(o, np.ndarray):
+                return program_ref.D(o, np.zeros((m, k)))
+            return program_ref.D.const(o, m, k)
+
+        def _b(self, op, o, rev=False):
+            a, b = (self._lift(o), self.d) if rev else (self.d, self._lift(o))
+            return ND(program_ref.binary(op, a, b))
+
+        def __add__(self, o): return self._b("add", o)
+        def __radd__(self, o): return self._b("add", o, True)
+        def __sub__(self, o): return self._b("sub", o)
+        def __rsub__(self, o): return self._b("sub", o, True)
+        def __mul__(self, o): return self._b("mul", o)
+        def __rmul__(self, o): return self._b("mul", o, True)
+        def __truediv__(self, o): return self._b("div", o)
+        def __neg__(self): return ND(program_ref.unary("neg", self.d))
+        def __pow__(self, k): return ND(program_ref.unary(f"pow{k}", self.d))
+        def _trace_unary(self, op): return ND(program_ref.unary(op, self.d))      # the hook fdb200.sin etc. dispatch on
+        def sum(self): return ND(program_ref.D(self.d.v.sum(keepdims=True), self.d.g.sum(axis=0, keepdims=True)))
+
+    n = 9
+    w = np.linspace(0.5, 1.5, n - 1)
+    unary = {"sin": fdb200.sin, "cos": fdb200.cos, "tanh": fdb200.tanh, "atan": fdb200.atan, "abs2": fdb200.abs2, "neg": lambda t: -t,
+             "pow2": lambda t: t ** 2, "pow3": lambda t: t ** 3}
+    leaf = st.sampled_from(["a", "b"])
+    expr = st.recursive(leaf, lambda kids: st.one_of(
+        st.tuples(st.just("un"), st.sampled_from(sorted(unary)), kids),
+        st.tuples(st.just("bin"), st.sampled_from(["add", "sub", "mul"]), kids, kids),
+        st.tuples(st.just("con"), st.sampled_from(["add", "sub", "mul", "div", "rsub"]), kids, st.sampled_from([0.5, 2.0, -1.5, 3.0])),
+        st.tuples(st.just("dat"), st.sampled_from(["mul", "add", "rsub"]), kids)), max_leaves=8)
+
+    def build(e, X):
+        if e == "a": return X[:-1]
+        if e == "b": return X[1:]
+        if e[0] == "un": return unary[e[1]](build(e[2], X))
+        if e[0] == "bin":
+            l, r = build(e[2], X), build(e[3], X)
+            return l + r if e[1] == "add" else (l - r if e[1] == "sub" else l * r)
+        if e[0] == "con":
+            t, c = build(e[2], X), e[3]
+            return {"add": lambda: t + c, "sub": lambda: t - c, "mul": lambda: c * t, "div": lambda: t / c, "rsub": lambda: c - t}[e[1]]()
+        t = build(e[2], X)
+        return {"mul": lambda: w * t, "add": lambda: t + w, "rsub": lambda: w - t}[e[1]]()
+
+    @settings(max_examples=120, deadline=None)
+    @given(expr, expr, st.integers(0, 10_000))
+    def check(e1, e2, seed):
+        x = np.random.default_rng(seed).uniform(0.5, 1.5, n)
+        f = lambda X: build(e1, X).sum() * 0.5 + fdb200.tanh(build(e2, X).sum())
+        try:
+            prog = trace.trace_scalar(f, n)
+        except trace.TraceError:                    # e.g. more than 12 live registers: such an f takes the reference loop
+            assume(False)
+        v, g = program_ref.evaluate(prog, x)
+        ref = f(ND(program_ref.D(x, np.eye(n)))).d
+        assert np.isfinite(v)
+        assert v == pytest.approx(float(ref.v[0]), rel=1e-12, abs=1e-12)
+        assert np.allclose(g, ref.g[0], rtol=1e-11, atol=1e-11 * max(1.0, np.abs(ref.g).max()))
+
+    check()
+
+
 def test_specialised_kernels_compile_on_the_host():
     """NVRTC needs no GPU: the functor generated for a traced f and the sweep kernel templates compile for sm_100a."""
     import ctypes as C
