@@ -211,6 +211,27 @@ def test_random_expression_trees_trace_to_equivalent_programs():
 
     check()
 
+    # and the functor text generated for such programs always compiles (NVRTC, host only; a handful of examples)
+    import ctypes as C
+    from fdb200.api import _i32p
+    lib = fdb200._lib.load()
+
+    @settings(max_examples=6, deadline=None)
+    @given(expr, expr)
+    def compiles(e1, e2):
+        f = lambda X: build(e1, X).sum() * 0.5 + fdb200.tanh(build(e2, X).sum())
+        try:
+            prog = trace.trace_scalar(f, n)
+        except trace.TraceError:
+            assume(False)
+        log = C.create_string_buffer(1 << 15); nbytes = C.c_int64()
+        rc = lib.fdb_jit_compile_check(0, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
+                                       prog.consts.ctypes.data_as(C.POINTER(C.c_double)) if prog.consts.size else None, prog.consts.size,
+                                       prog.n_acc, prog.halo, prog.result_reg, len(prog.params), 5, 0, 1, log, len(log), C.byref(nbytes))
+        assert rc == 0 and nbytes.value > 1000, log.value.decode()
+
+    compiles()
+
 
 def test_specialised_kernels_compile_on_the_host():
     """NVRTC needs no GPU: the functor generated for a traced f and the sweep kernel templates compile for sm_100a."""
