@@ -523,6 +523,21 @@ def test_hessian_vs_oracle(ctx, oracle, N):
             assert res.value == pytest.approx(v_ref, rel=RED_RTOL)
 
 
+def test_gradients_match_vectors_generated_by_the_reference_cpp_program(ctx):
+    """The device path against outputs of the reference's own benchmarks/cpp program (tests/golden/refcpp_vectors.json,
+    generated from /root/reference by tests/golden/make_refcpp_vectors.py): Rosenbrock and Ackley, chunk sizes 1..5."""
+    import json
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refcpp_vectors.json")))
+    x = np.array([float.fromhex(h) for h in fx["x"]])
+    for case in fx["cases"]:
+        target = getattr(F, case["fn"])
+        g_ref = np.array([float.fromhex(h) for h in case["gradient"]])
+        res = fdb200.GradientResult(x)
+        fdb200.gradient_b(res, target, x, fdb200.GradientConfig(target, x, fdb200.Chunk(case["chunk"])), ctx=ctx)
+        assert np.allclose(res.derivs[0], g_ref, rtol=RED_RTOL, atol=1e-12 * np.abs(g_ref).max()), (case["fn"], case["chunk"])
+        assert res.value == pytest.approx(float.fromhex(fx["value_" + case["fn"]]), rel=RED_RTOL)
+
+
 @pytest.mark.parametrize("N", [1, 2, 3, 4])
 def test_readme_example_gradient(ctx, N):
     """README.md:26-45: f(x) = sin(x[1]) + prod(x[2:end]) at x = [pi/4, 2, 3, 4] -> [0.7071067811865476, 12, 8, 6].

@@ -276,3 +276,19 @@ def test_against_reference_cpp_program(oracle):
         # Rosenbrock: the C++ toy uses plain-double constants (a*t2*t2), the Julia definition Dual constants
         assert np.allclose(ref.gradient("rosenbrock", x, K), oracle.gradient("rosenbrock", x, K)[0], rtol=1e-13, atol=1e-13)
     assert ref.value("ackley", x) == oracle.value("ackley", x)
+
+
+def test_oracle_matches_vectors_generated_by_the_reference_cpp_program(oracle):
+    """tests/golden/refcpp_vectors.json holds outputs of the reference's own benchmarks/cpp program (generated by
+    tests/golden/make_refcpp_vectors.py from /root/reference).  The reference's C++ functions use plain double constants and
+    a sequential sum, so the oracle agrees to the last bits for Rosenbrock and Ackley, chunk sizes 1..5."""
+    import json
+    import os
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refcpp_vectors.json")))
+    x = np.array([float.fromhex(h) for h in fx["x"]])
+    for case in fx["cases"]:
+        g_ref = np.array([float.fromhex(h) for h in case["gradient"]])
+        g, v = oracle.gradient(case["fn"], x, case["chunk"])
+        assert np.allclose(g, g_ref, rtol=1e-13, atol=1e-15), (case["fn"], case["chunk"])
+        assert v == pytest.approx(float.fromhex(fx["value_" + case["fn"]]), rel=1e-14)
+
