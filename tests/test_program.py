@@ -194,15 +194,26 @@ def test_random_expression_trees_trace_to_equivalent_programs():
         t = build(e[2], X)
         return {"mul": lambda: w * t, "add": lambda: t + w, "rsub": lambda: w - t}[e[1]]()
 
-    @settings(max_examples=120, deadline=None)
-    @given(expr, expr, st.integers(0, 10_000))
-    def check(e1, e2, seed):
+    def shape_of(kind, e1, e2):
+        if kind == "plain":                     # two reductions + scalar arithmetic after them
+            return lambda X: build(e1, X).sum() * 0.5 + fdb200.tanh(build(e2, X).sum())
+        if kind == "lengths":                   # reductions over views of different lengths: guarded groups
+            return lambda X: build(e1, X).sum() + (X * 2.0 - 1.0).sum() * 0.25 + fdb200.sin(X[2:]).sum()
+        # a reduced value re-enters a broadcast: two passes
+        return lambda X: ((build(e1, X) - build(e2, X).mean()) ** 2).sum() / 3.0 + build(e2, X).sum()
+
+    ND.mean = lambda self: self.sum() / self.d.v.size
+
+    @settings(max_examples=150, deadline=None)
+    @given(expr, expr, st.integers(0, 10_000), st.sampled_from(["plain", "lengths", "twopass"]))
+    def check(e1, e2, seed, kind):
         x = np.random.default_rng(seed).uniform(0.5, 1.5, n)
-        f = lambda X: build(e1, X).sum() * 0.5 + fdb200.tanh(build(e2, X).sum())
+        f = shape_of(kind, e1, e2)
         try:
             prog = trace.trace_scalar(f, n)
         except trace.TraceError:                    # e.g. more than 12 live registers: such an f takes the reference loop
             assume(False)
+        assert prog.two_pass == (kind == "twopass") and (kind != "lengths" or prog.needs_jit)
         v, g = program_ref.evaluate(prog, x)
         ref = f(ND(program_ref.D(x, np.eye(n)))).d
         assert np.isfinite(v)
@@ -216,10 +227,10 @@ def test_random_expression_trees_trace_to_equivalent_programs():
     from fdb200.api import _i32p
     lib = fdb200._lib.load()
 
-    @settings(max_examples=6, deadline=None)
-    @given(expr, expr)
-    def compiles(e1, e2):
-        f = lambda X: build(e1, X).sum() * 0.5 + fdb200.tanh(build(e2, X).sum())
+    @settings(max_examples=9, deadline=None)
+    @given(expr, expr, st.sampled_from(["plain", "lengths", "twopass"]))
+    def compiles(e1, e2, kind):
+        f = shape_of(kind, e1, e2)
         try:
             prog = trace.trace_scalar(f, n)
         except trace.TraceError:
