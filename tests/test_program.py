@@ -455,6 +455,63 @@ def test_reduced_values_reentering_a_broadcast_two_pass(ctx, N, mode):
         fdb200.hessian(var, x, fdb200.HessianConfig(var, x, fdb200.Chunk(N)), ctx=ctx)
 
 
+@pytest.mark.gpu
+def test_random_programs_on_the_device_match_the_reference_evaluator(ctx):
+    """Random broadcast expressions (plain, guarded and two-pass shapes, with a data array) through the specialised kernels
+    and, where it can run them, the interpreter -- against tests/program_ref.py on the same traced program."""
+    import program_ref
+    rng = np.random.default_rng(77)
+    n = 47
+    w = rng.uniform(0.5, 1.5, n - 1)
+    un = [fdb200.sin, fdb200.cos, fdb200.tanh, fdb200.atan, fdb200.abs2, lambda t: -t, lambda t: t ** 2, lambda t: t ** 3]
+
+    def rand_expr(depth):
+        r = rng.integers(0, 6 if depth > 0 else 2)
+        if r == 0: return lambda X: X[:-1]
+        if r == 1: return lambda X: X[1:]
+        if r == 2:
+            u, e = un[rng.integers(len(un))], rand_expr(depth - 1)
+            return lambda X: u(e(X))
+        if r == 3:
+            a, b, k = rand_expr(depth - 1), rand_expr(depth - 1), rng.integers(3)
+            return lambda X: (a(X) + b(X)) if k == 0 else ((a(X) - b(X)) if k == 1 else a(X) * b(X))
+        if r == 4:
+            e, c, k = rand_expr(depth - 1), float(rng.choice([0.5, 2.0, -1.5])), rng.integers(3)
+            return lambda X: (c * e(X)) if k == 0 else ((e(X) / c) if k == 1 else c - e(X))
+        e, k = rand_expr(depth - 1), rng.integers(2)
+        return lambda X: (w * e(X)) if k == 0 else (e(X) + w)
+
+    checked = 0
+    for trial in range(24):
+        e1, e2, kind, N = rand_expr(3), rand_expr(2), ("plain", "lengths", "twopass")[trial % 3], int(rng.choice([1, 3, 5, 12]))
+        if kind == "plain":
+            f = lambda X: e1(X).sum() * 0.5 + fdb200.tanh(e2(X).sum())
+        elif kind == "lengths":
+            f = lambda X: e1(X).sum() + (X * 2.0 - 1.0).sum() * 0.25 + fdb200.sin(X[2:]).sum()
+        else:
+            f = lambda X: ((e1(X) - e2(X).mean()) ** 2).sum() / 3.0 + e2(X).sum()
+        x = rng.uniform(0.5, 1.5, n)
+        try:
+            prog = trace.trace_scalar(f, n)
+        except trace.TraceError:
+            continue
+        v_ref, g_ref = program_ref.evaluate(prog, x)
+        scale = max(1.0, np.abs(g_ref).max())
+        for jit in (True, False):
+            if not jit and prog.needs_jit:
+                continue
+            ctx.set_jit(jit)
+            try:
+                res = fdb200.GradientResult(x)
+                fdb200.gradient_b(res, f, x, fdb200.GradientConfig(f, x, fdb200.Chunk(N)), ctx=ctx)
+            finally:
+                ctx.set_jit(True)
+            assert np.allclose(res.derivs[0], g_ref, rtol=1e-10, atol=1e-11 * scale), (trial, kind, N, jit)
+            assert res.value == pytest.approx(v_ref, rel=1e-11, abs=1e-11), (trial, kind, N, jit)
+            checked += 1
+    assert checked >= 20 and ctx.jit_stats()["failures"] == 0
+
+
 # ---- the reference loop as a replayed CUDA graph (fdb_graph.cu) ------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("N", [1, 5, 12])
