@@ -172,6 +172,86 @@ function program_hessian!(H::B200Array{Float64}, grad::B200Array{Float64}, p::Pr
     return H, grad, value
 end
 
+# ---- flattening a user f: the Julia twin of fdb200/trace.py (its basic form: one term part + scalar epilogue) ------------
+# f is called once on a TraceArray; broadcasting over TraceArrays records nodes instead of computing (BroadcastStyle below),
+# `sum` closes a reduction.  The recorded DAG is linearised into {op,dst,a,b} words exactly as trace.py:_emit does
+# (post-order, registers released at last use).  Guards, data arrays and the two-pass form follow trace.py the same way.
+const K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC = 0, 1, 2, 3, 4, 5
+const OP1 = Dict(:- => 1, :exp => 2, :log => 3, :sin => 4, :cos => 5, :tanh => 6, :sqrt => 7, :abs => 8, :abs2 => 9, :inv => 10)
+const OP2 = Dict(:+ => 1, :- => 2, :* => 3, :/ => 4, :^ => 5, :max => 6, :min => 7)
+mutable struct TNode; kind::Int; op::Int; args::Vector{TNode}; c::Float64; scalar::Bool; end
+struct TraceArray <: AbstractVector{Float64}; node::TNode; n::Int; accs::Vector{TNode}; end      # a view x[a:b] or a broadcast result
+struct TraceScalar; node::TNode; accs::Vector{TNode}; end                                       # sum(...) and scalar math on it
+Base.size(t::TraceArray) = (t.n,)
+Base.getindex(t::TraceArray, r::UnitRange) =                                                     # views directly on the input only
+    TraceArray(TNode(K_LOADX, 0, TNode[], t.node.c + first(r) - 1, false), length(r), t.accs)
+struct B200TraceStyle <: Broadcast.AbstractArrayStyle{1} end
+Base.BroadcastStyle(::Type{TraceArray}) = B200TraceStyle()
+B200TraceStyle(::Val{1}) = B200TraceStyle()
+function Base.copy(bc::Broadcast.Broadcasted{B200TraceStyle})                                    # x .op y -> a node, nothing computed
+    args = map(a -> a isa Broadcast.Broadcasted ? copy(a) : a, bc.args)
+    arr = args[findfirst(a -> a isa TraceArray, args)]
+    f = nameof(bc.f)
+    if length(args) == 1
+        return TraceArray(TNode(K_UNARY, OP1[f], [args[1].node], 0.0, false), arr.n, arr.accs)
+    elseif args[1] isa TraceArray && args[2] isa TraceArray
+        return TraceArray(TNode(K_DD, OP2[f], [args[1].node, args[2].node], 0.0, false), arr.n, arr.accs)
+    elseif args[1] isa TraceArray                                                                # Dual (op) Real, src/dual.jl Real methods
+        return TraceArray(TNode(K_DC, OP2[f], [args[1].node], Float64(args[2]), false), arr.n, arr.accs)
+    else
+        return TraceArray(TNode(K_CD, OP2[f], [args[2].node], Float64(args[1]), false), arr.n, arr.accs)
+    end
+end
+function Base.sum(t::TraceArray)
+    push!(t.accs, t.node)
+    return TraceScalar(TNode(K_ACC, length(t.accs) - 1, TNode[], 0.0, true), t.accs)
+end
+for (f, code) in ((:+, 1), (:-, 2), (:*, 3), (:/, 4))
+    @eval Base.$f(a::TraceScalar, b::TraceScalar) = TraceScalar(TNode(K_DD, $code, [a.node, b.node], 0.0, true), a.accs)
+    @eval Base.$f(a::TraceScalar, b::Real) = TraceScalar(TNode(K_DC, $code, [a.node], Float64(b), true), a.accs)
+    @eval Base.$f(a::Real, b::TraceScalar) = TraceScalar(TNode(K_CD, $code, [b.node], Float64(a), true), b.accs)
+end
+for (f, code) in ((:exp, 2), (:log, 3), (:sqrt, 7))
+    @eval Base.$f(a::TraceScalar) = TraceScalar(TNode(K_UNARY, $code, [a.node], 0.0, true), a.accs)
+end
+# linearise the nodes reachable from `roots` with the given scalar-ness into instruction words (trace.py:_emit)
+function emit(roots::Vector{TNode}, scalar::Bool, preloaded::Dict{TNode,Int}, consts::Vector{Float64})
+    order = TNode[]; seen = Set{TNode}()
+    visit(nd) = (nd in seen || nd.scalar != scalar) ? nothing : (push!(seen, nd); foreach(visit, nd.args); push!(order, nd))
+    foreach(visit, roots)
+    lastuse = Dict{TNode,Int}(); for (pos, nd) in enumerate(order), a in nd.args; lastuse[a] = pos; end
+    reg = copy(preloaded); free = [r for r in 11:-1:0 if !(r in values(reg))]; words = Int32[]
+    cidx(v) = (i = findfirst(==(v), consts); i === nothing ? (push!(consts, v); length(consts) - 1) : i - 1)
+    for (pos, nd) in enumerate(order)
+        haskey(reg, nd) && continue
+        srcs = [reg[a] for a in nd.args]
+        for a in nd.args; get(lastuse, a, 0) == pos && !haskey(preloaded, a) && push!(free, reg[a]); end
+        dst = pop!(free); reg[nd] = dst
+        w = nd.kind == K_LOADX ? (K_LOADX << 6, dst, 0, Int(nd.c)) :
+            nd.kind == K_UNARY ? ((K_UNARY << 6) | nd.op, dst, srcs[1], 0) :
+            nd.kind == K_DD ? ((K_DD << 6) | nd.op, dst, srcs[1], srcs[2]) :
+            nd.kind == K_DC ? ((K_DC << 6) | nd.op, dst, srcs[1], cidx(nd.c)) : ((K_CD << 6) | nd.op, dst, cidx(nd.c), srcs[1])
+        append!(words, Int32.(collect(w)))
+    end
+    return words, reg
+end
+function trace_scalar(f, n::Integer)
+    accs = TNode[]
+    y = f(TraceArray(TNode(K_LOADX, 0, TNode[], 0.0, false), n, accs))::TraceScalar
+    consts = Float64[]
+    term, reg = emit(accs, false, Dict{TNode,Int}(), consts)
+    for (k, nd) in enumerate(accs); append!(term, Int32[K_ACC << 6, k - 1, reg[nd], 0]); end
+    pre = Dict{TNode,Int}(); collectacc(nd) = (nd.kind == K_ACC && (pre[nd] = nd.op); foreach(collectacc, nd.args)); collectacc(y.node)
+    epi, ereg = emit([y.node], true, pre, consts)
+    halo = maximum(Int(term[4i]) for i in 1:length(term) ÷ 4 if term[4i - 3] >> 6 == K_LOADX; init = 0)
+    return Program(reshape(term, 4, :), reshape(epi, 4, :), consts, length(accs), halo, ereg[y.node])
+end
+# ForwardDiff.gradient!(result, f, x::B200Array, cfg) for a non-catalogue f: flatten once, one batched launch
+function chunk_mode_gradient_traced!(result::B200Array{Float64}, f::F, x::B200Array{Float64}, cfg::GradientConfig{T,V,N}) where {F,T,V,N}
+    p = trace_scalar(f, length(x))
+    return first(program_gradient!(result, p, x, Chunk{N}()))
+end
+
 # ---- the generic chunk loop as a replayed CUDA graph (fdb_graph.cu): chunk_mode_gradient! for a B200Array when f is an
 # arbitrary Julia function of B200Array{<:Dual} (every array op inside f is a ccall recorded by stream capture) ----------
 function chunk_mode_gradient_graph!(result::B200Array{Float64}, f::F, x::B200Array{Float64}, cfg::GradientConfig{T,V,N}) where {F,T,V,N}
