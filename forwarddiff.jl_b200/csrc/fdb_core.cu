@@ -197,14 +197,17 @@ extern "C" int fdb_init(int device, fdb_ctx** out) {
 }
 
 extern "C" int fdb_shutdown(fdb_ctx* ctx) {
+    FDB_ENTER(ctx);
     if (!ctx) return FDB_ERR_BADARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     jit_release(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->hostws) cudaFree(ctx->hostws);
     if (ctx->counter) cudaFree(ctx->counter);
     if (ctx->cursor) cudaFree(ctx->cursor);
+    if (ctx->xch_timeout_flag) cudaFreeHost(ctx->xch_timeout_flag);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FDB_OK;
@@ -213,15 +216,17 @@ extern "C" int fdb_shutdown(fdb_ctx* ctx) {
 extern "C" const char* fdb_last_error(fdb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
 
 extern "C" int fdb_sync(fdb_ctx* ctx) {
+    FDB_ENTER(ctx);
     if (!ctx) return FDB_ERR_BADARG;
     FDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return FDB_OK;
+    return check_poison(ctx, "fdb_sync");
 }
 extern "C" int fdb_set_async(fdb_ctx* ctx, int async) { if (!ctx) return FDB_ERR_BADARG; ctx->async = async != 0; return FDB_OK; }
 extern "C" int fdb_set_nansafe(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->nansafe = en != 0; return FDB_OK; }
 extern "C" int fdb_set_lane_sharing(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->lane_sharing = en != 0; return FDB_OK; }
 extern "C" int fdb_set_dmma(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->use_dmma = en != 0; return FDB_OK; }
 extern "C" int fdb_set_stream(fdb_ctx* ctx, void* s) {
+    FDB_ENTER(ctx);
     if (!ctx) return FDB_ERR_BADARG;
     cudaStreamSynchronize(ctx->stream);
     if (s == nullptr) {
@@ -245,6 +250,7 @@ static int check_level(fdb_ctx* ctx, int N, int level) {
 }
 
 extern "C" int fdb_array_alloc(fdb_ctx* ctx, int64_t n, int N, int level, fdb_array** out) {
+    FDB_ENTER(ctx);
     if (!ctx || !out || n < 0) return fail(ctx, FDB_ERR_BADARG, "fdb_array_alloc: bad argument");
     int rc = check_level(ctx, N, level); if (rc) return rc;
     fdb_array* a = new fdb_array();
@@ -267,6 +273,7 @@ extern "C" int fdb_array_wrap(fdb_ctx* ctx, double* ptr, int64_t n, int64_t ld, 
     return FDB_OK;
 }
 extern "C" int fdb_array_free(fdb_array* a) {
+    FDB_ENTER(a ? a->ctx : nullptr);
     if (!a) return FDB_ERR_BADARG;
     if (a->ctx->capturing && a->owned)     // freeing synchronises the stream, which is illegal during graph capture
         return fail(a->ctx, FDB_ERR_BADARG, "fdb_array_free: arrays allocated while a graph is captured must outlive the graph");
@@ -280,6 +287,7 @@ extern "C" int fdb_array_info(const fdb_array* a, int64_t* n, int* N, int* level
     return FDB_OK;
 }
 extern "C" int fdb_upload_values(fdb_array* a, const double* host) {
+    FDB_ENTER(a ? a->ctx : nullptr);
     if (!a || !host) return FDB_ERR_BADARG;
     fdb_ctx* ctx = a->ctx;
     FDB_CUDA(ctx, cudaMemcpyAsync(a->data, host, (size_t)a->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -287,13 +295,15 @@ extern "C" int fdb_upload_values(fdb_array* a, const double* host) {
     return FDB_OK;
 }
 extern "C" int fdb_download_values(const fdb_array* a, double* host) {
+    FDB_ENTER(a ? a->ctx : nullptr);
     if (!a || !host) return FDB_ERR_BADARG;
     fdb_ctx* ctx = a->ctx;
     FDB_CUDA(ctx, cudaMemcpyAsync(host, a->data, (size_t)a->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return FDB_OK;
+    return check_poison(ctx, "fdb_download_values");
 }
 extern "C" int fdb_upload_duals_aos(fdb_array* a, const double* host) {
+    FDB_ENTER(a ? a->ctx : nullptr);
     if (!a || !host) return FDB_ERR_BADARG;
     fdb_ctx* ctx = a->ctx; int P = a->planes();
     if (a->n == 0) return FDB_OK;
@@ -307,6 +317,7 @@ extern "C" int fdb_upload_duals_aos(fdb_array* a, const double* host) {
     return FDB_OK;
 }
 extern "C" int fdb_download_duals_aos(const fdb_array* a, double* host) {
+    FDB_ENTER(a ? a->ctx : nullptr);
     if (!a || !host) return FDB_ERR_BADARG;
     fdb_ctx* ctx = a->ctx; int P = a->planes();
     if (a->n == 0) return FDB_OK;
@@ -317,9 +328,10 @@ extern "C" int fdb_download_duals_aos(const fdb_array* a, double* host) {
     rc = finish(ctx, 1, "soa_to_aos"); if (rc) return rc;
     FDB_CUDA(ctx, cudaMemcpyAsync(host, ctx->scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     FDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return FDB_OK;
+    return check_poison(ctx, "fdb_download_duals_aos");
 }
 extern "C" int fdb_copy(fdb_array* dst, const fdb_array* src) {
+    FDB_ENTER(dst ? dst->ctx : nullptr);
     if (!dst || !src) return FDB_ERR_BADARG;
     fdb_ctx* ctx = dst->ctx;
     if (dst->n != src->n || dst->planes() != src->planes()) return fail(ctx, FDB_ERR_SHAPE, "fdb_copy: shape mismatch");
@@ -406,9 +418,11 @@ static int seed_zero_impl(fdb_ctx* ctx, fdb_array* d, const fdb_array* x, int st
 }
 
 extern "C" int fdb_seed(fdb_ctx* ctx, fdb_array* d, const fdb_array* x, int64_t index, int64_t chunksize) {
+    FDB_ENTER(ctx);
     return seed_impl(ctx, d, x, FDB_DENSE, d ? d->n : 0, d ? d->n : 0, index, chunksize);
 }
 extern "C" int fdb_seed_zero(fdb_ctx* ctx, fdb_array* d, const fdb_array* x, int64_t index, int64_t count) {
+    FDB_ENTER(ctx);
     return seed_zero_impl(ctx, d, x, FDB_DENSE, d ? d->n : 0, d ? d->n : 0, index, count);
 }
 static int check_structure(fdb_ctx* ctx, const fdb_array* d, int structure, int64_t rows) {
@@ -419,17 +433,20 @@ static int check_structure(fdb_ctx* ctx, const fdb_array* d, int structure, int6
 }
 extern "C" int fdb_seed_structured(fdb_ctx* ctx, fdb_array* d, const fdb_array* x, int structure, int64_t rows,
                                    int64_t index, int64_t chunksize) {
+    FDB_ENTER(ctx);
     int rc = check_structure(ctx, d, structure, rows); if (rc) return rc;
     return seed_impl(ctx, d, x, structure, rows, fdb_structural_length(structure, rows), index, chunksize);
 }
 extern "C" int fdb_seed_zero_structured(fdb_ctx* ctx, fdb_array* d, const fdb_array* x, int structure, int64_t rows,
                                         int64_t index, int64_t count) {
+    FDB_ENTER(ctx);
     int rc = check_structure(ctx, d, structure, rows); if (rc) return rc;
     return seed_zero_impl(ctx, d, x, structure, rows, fdb_structural_length(structure, rows), index, count);
 }
 
 extern "C" int fdb_extract_gradient_chunk_structured(fdb_ctx* ctx, fdb_array* res, const fdb_array* y, int structure, int64_t rows,
                                                      int64_t index, int64_t chunksize) {
+    FDB_ENTER(ctx);
     if (!ctx || !res || !y) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient_chunk: null argument");
     if (y->level < 1 || res->level != y->level - 1) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient_chunk: result must be one level below ydual");
     if (y->n != 1)   // GRAD_ERROR, src/gradient.jl:88-91
@@ -437,6 +454,9 @@ extern "C" int fdb_extract_gradient_chunk_structured(fdb_ctx* ctx, fdb_array* re
     if (structure < 0 || structure > 3) return fail(ctx, FDB_ERR_BADARG, "unknown structure %d", structure);
     if (structure != FDB_DENSE && res->n != rows * rows) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: structured result needs rows*rows storage");
     if (chunksize > y->N) return fail(ctx, FDB_ERR_BADARG, "chunksize > N");
+    if (index < 1) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient_chunk: index %lld < 1 (1-based structural position)", (long long)index);
+    if (res->level == 1 && res->N != y->N)     // nested: the partials are Dual{T,V,N} themselves and must carry the same N (config.jl:198-201)
+        return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient_chunk: nested chunk sizes differ (result N=%d, ydual N=%d)", res->N, y->N);
     if (chunksize <= 0) return FDB_OK;
     int PB = res->planes();
     int64_t total = chunksize * PB;
@@ -446,9 +466,11 @@ extern "C" int fdb_extract_gradient_chunk_structured(fdb_ctx* ctx, fdb_array* re
     return finish(ctx, 1, "fdb_extract_gradient_chunk");
 }
 extern "C" int fdb_extract_gradient_chunk(fdb_ctx* ctx, fdb_array* res, const fdb_array* y, int64_t index, int64_t chunksize) {
+    FDB_ENTER(ctx);
     return fdb_extract_gradient_chunk_structured(ctx, res, y, FDB_DENSE, res ? res->n : 0, index, chunksize);
 }
 extern "C" int fdb_fill(fdb_ctx* ctx, fdb_array* a, double value) {
+    FDB_ENTER(ctx);
     // fill!(a, value) on every plane (used to zero the off-structure entries of structured work buffers)
     if (!ctx || !a) return fail(ctx, FDB_ERR_BADARG, "fdb_fill: null argument");
     if (value != 0.0) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_fill: only zero fill is implemented");
@@ -458,11 +480,13 @@ extern "C" int fdb_fill(fdb_ctx* ctx, fdb_array* a, double value) {
     return FDB_OK;
 }
 extern "C" int fdb_extract_gradient(fdb_ctx* ctx, fdb_array* res, const fdb_array* y) {
+    FDB_ENTER(ctx);
     if (!y) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient: null argument");
     return fdb_extract_gradient_chunk(ctx, res, y, 1, y->N);   // zip(1:npartials, idxs), src/gradient.jl:66-72
 }
 extern "C" int fdb_extract_jacobian_chunk(fdb_ctx* ctx, fdb_array* res, int64_t ldres, const fdb_array* y, int64_t index,
                                           int64_t chunksize) {
+    FDB_ENTER(ctx);
     if (!ctx || !res || !y) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_jacobian_chunk: null argument");
     if (y->level < 1 || res->level != y->level - 1) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_jacobian_chunk: result must be one level below ydual");
     if (chunksize > y->N || index < 1) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_jacobian_chunk: bad window");
@@ -476,9 +500,11 @@ extern "C" int fdb_extract_jacobian_chunk(fdb_ctx* ctx, fdb_array* res, int64_t 
     return finish(ctx, 1, "fdb_extract_jacobian_chunk");
 }
 extern "C" int fdb_extract_jacobian(fdb_ctx* ctx, fdb_array* res, int64_t ldres, const fdb_array* y, int64_t n) {
+    FDB_ENTER(ctx);
     return fdb_extract_jacobian_chunk(ctx, res, ldres, y, 1, n);
 }
 extern "C" int fdb_extract_value(fdb_ctx* ctx, fdb_array* out, const fdb_array* y) {
+    FDB_ENTER(ctx);
     if (!ctx || !out || !y) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_value: null argument");
     if (y->level < 1 || out->level != y->level - 1 || out->n != y->n) return fail(ctx, FDB_ERR_SHAPE, "fdb_extract_value: shape mismatch");
     if (y->n == 0) return FDB_OK;

@@ -218,11 +218,10 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
         if (nlaunch) *nlaunch = 1;
         return FDB_OK;
     }
-    static bool configured = false;
-    if (!configured) {
+    if (!ctx->dmma_configured) {       // a per-device attribute: every context (GPU) of the process sets it once
         cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
         if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(dmma_gemm_kernel): %s", cudaGetErrorString(e));
-        configured = true;
+        ctx->dmma_configured = true;
     }
     CUtensorMap tm;
     const cuuint64_t gdim[2] = {(cuuint64_t)m, (cuuint64_t)k};
@@ -395,6 +394,7 @@ using namespace fdb;
 extern "C" int fdb_jacobian_mlp2_chunked(fdb_ctx* ctx, const fdb_array* x, int64_t h, int64_t m, int N, const fdb_array* A1, int64_t lda1,
                                          const fdb_array* b1, const fdb_array* A2, int64_t lda2, const fdb_array* b2, int64_t chunk_lo,
                                          int64_t chunk_hi, fdb_array* J, int64_t ldJ, fdb_array* y) {
+    FDB_ENTER(ctx);
     if (!ctx || !x || !A1 || !b1 || !A2 || !b2 || !J) return fail(ctx, FDB_ERR_BADARG, "fdb_jacobian_mlp2_chunked: null argument");
     const fdb_array* all[] = {x, A1, b1, A2, b2, J};
     for (const fdb_array* a : all) if (a->level != 0) return fail(ctx, FDB_ERR_BADARG, "fdb_jacobian_mlp2_chunked: operands must be plain arrays");
@@ -419,6 +419,7 @@ extern "C" int fdb_jacobian_mlp2_chunked(fdb_ctx* ctx, const fdb_array* x, int64
 // C[m x ncols] = A[m x k] * B[k x ncols] on plain column-major arrays
 extern "C" int fdb_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t k, const fdb_array* B, int64_t ldb, int64_t ncols,
                           fdb_array* C, int64_t ldc) {
+    FDB_ENTER(ctx);
     if (!ctx || !A || !B || !C) return fail(ctx, FDB_ERR_BADARG, "fdb_matmul: null argument");
     if (A->level != 0 || B->level != 0 || C->level != 0) return fail(ctx, FDB_ERR_BADARG, "fdb_matmul: operands must be plain arrays");
     if (lda < m || ldb < k || ldc < m || A->n < lda * (k - 1) + m || B->n < ldb * (ncols - 1) + k || C->n < ldc * (ncols - 1) + m)
@@ -432,6 +433,7 @@ extern "C" int fdb_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t
 
 // ydual = A * xdual  (A: m x n plain column-major; xdual: n Duals; ydual: m Duals): the planes are the columns
 extern "C" int fdb_dual_matvec(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t n, const fdb_array* xdual, fdb_array* ydual) {
+    FDB_ENTER(ctx);
     if (!ctx || !A || !xdual || !ydual) return fail(ctx, FDB_ERR_BADARG, "fdb_dual_matvec: null argument");
     if (A->level != 0 || xdual->level < 1 || ydual->level != xdual->level || xdual->N != ydual->N)
         return fail(ctx, FDB_ERR_BADARG, "fdb_dual_matvec: A plain, xdual/ydual Dual arrays of the same type");

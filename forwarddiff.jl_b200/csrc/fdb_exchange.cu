@@ -11,16 +11,6 @@
 
 #include "fdb_internal.h"
 
-struct fdb_exchange {
-    fdb_ctx* ctx = nullptr;
-    char* base = nullptr;          // local arena: data | flag page
-    size_t data_bytes = 0;
-    int rank = 0, world = 1;
-    char* peer[FDB_MAX_RANKS] = {nullptr};   // peer[r] = rank r's arena mapped here (peer[rank] = base)
-    bool connected = false;
-    unsigned long long epoch = 0;
-};
-
 namespace fdb {
 
 static constexpr size_t FLAG_PAGE = 256;            // FDB_MAX_RANKS u64 arrival flags, then the timeout counter
@@ -33,7 +23,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 // thread r: tell rank r that this rank has arrived at `epoch`, then wait until rank r has.
-__global__ void exchange_barrier_kernel(PeerFlags P, int rank, int world, unsigned long long epoch, unsigned long long timeout_ns) {
+__global__ void exchange_barrier_kernel(PeerFlags P, int rank, int world, unsigned long long epoch, unsigned long long timeout_ns,
+                                        unsigned* host_flag) {
     const int r = threadIdx.x;
     if (r >= world || r == rank) return;
     __threadfence_system();       // everything this stream stored into peer arenas is ordered before the flag
@@ -46,6 +37,7 @@ __global__ void exchange_barrier_kernel(PeerFlags P, int rank, int world, unsign
         if (v >= epoch) break;
         if (globaltimer_ns() - t0 > timeout_ns) {      // a peer died: give up instead of hanging the GPU
             atomicAdd(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(P.flags[rank]) + TIMEOUT_OFF), 1u);
+            if (host_flag) { *reinterpret_cast<volatile unsigned*>(host_flag) = 1u; __threadfence_system(); }   // sticky, host-visible: check_poison
             break;
         }
         __nanosleep(200);
@@ -101,6 +93,7 @@ int mirrors_for(fdb_ctx* ctx, fdb_mirrors* m, const fdb_array* const* outs, int 
 using namespace fdb;
 
 extern "C" int fdb_exchange_create(fdb_ctx* ctx, int64_t n_doubles, int rank, int world, fdb_exchange** out) {
+    FDB_ENTER(ctx);
     if (!ctx || !out || n_doubles < 0) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_create: bad argument");
     if (world < 1 || world > FDB_MAX_RANKS || rank < 0 || rank >= world)
         return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_create: rank %d of %d (at most %d ranks, one NVSwitch domain)", rank, world, FDB_MAX_RANKS);
@@ -113,6 +106,11 @@ extern "C" int fdb_exchange_create(fdb_ctx* ctx, int64_t n_doubles, int rank, in
                                                   "cudaMalloc(%zu bytes): %s", x->data_bytes + FLAG_PAGE, cudaGetErrorString(e)); }
     e = cudaMemset(x->base, 0, x->data_bytes + FLAG_PAGE);
     if (e != cudaSuccess) { cudaFree(x->base); delete x; return fail(ctx, FDB_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
+    if (!ctx->xch_timeout_flag) {     // pinned, device-visible word: a barrier that gives up poisons the context (fdb_internal.h check_poison)
+        e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->xch_timeout_flag), 64, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e != cudaSuccess) { cudaFree(x->base); delete x; return fail(ctx, FDB_ERR_CUDA, "cudaHostAlloc: %s", cudaGetErrorString(e)); }
+        *ctx->xch_timeout_flag = 0;
+    }
     x->peer[rank] = x->base;
     x->connected = (world == 1);
     *out = x;
@@ -120,6 +118,7 @@ extern "C" int fdb_exchange_create(fdb_ctx* ctx, int64_t n_doubles, int rank, in
 }
 
 extern "C" int fdb_exchange_handle(fdb_exchange* x, unsigned char handle[FDB_IPC_HANDLE_BYTES]) {
+    FDB_ENTER(x ? x->ctx : nullptr);
     if (!x || !handle) return FDB_ERR_BADARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == FDB_IPC_HANDLE_BYTES, "IPC handle size");
     cudaIpcMemHandle_t h;
@@ -129,6 +128,7 @@ extern "C" int fdb_exchange_handle(fdb_exchange* x, unsigned char handle[FDB_IPC
 }
 
 extern "C" int fdb_exchange_connect(fdb_exchange* x, const unsigned char* handles) {
+    FDB_ENTER(x ? x->ctx : nullptr);
     if (!x || !handles) return FDB_ERR_BADARG;
     fdb_ctx* ctx = x->ctx;
     if (x->connected) return FDB_OK;
@@ -149,6 +149,46 @@ extern "C" int fdb_exchange_connect(fdb_exchange* x, const unsigned char* handle
     return FDB_OK;
 }
 
+// Single-process form of fdb_exchange_connect: the `world` exchanges live in THIS process, one per device (one Julia
+// session driving all GPUs).  CUDA IPC cannot open a handle in the process that exported it, and does not need to:
+// with peer access enabled both ways the arenas are directly addressable (unified virtual addressing), so the
+// peers' base pointers are linked as they are.
+extern "C" int fdb_exchange_connect_local(fdb_exchange* const* xs, int world) {
+    if (!xs || world < 1 || world > FDB_MAX_RANKS) return FDB_ERR_BADARG;
+    for (int r = 0; r < world; r++)
+        if (!xs[r] || xs[r]->world != world || xs[r]->rank != r) return fail(xs[0] ? xs[0]->ctx : nullptr, FDB_ERR_BADARG,
+            "fdb_exchange_connect_local: xs[%d] must be rank %d of %d", r, r, world);
+    for (int r = 0; r < world; r++)
+        if (xs[r]->data_bytes != xs[0]->data_bytes) return fail(xs[0]->ctx, FDB_ERR_BADARG, "fdb_exchange_connect_local: arenas must be symmetric");
+    int prev = 0; cudaGetDevice(&prev);
+    for (int r = 0; r < world; r++) {
+        fdb_ctx* ctx = xs[r]->ctx;
+        cudaSetDevice(ctx->device);
+        for (int q = 0; q < world; q++) {
+            if (q == r) continue;
+            const int pd = xs[q]->ctx->device;
+            if (pd == ctx->device) continue;                                        // two contexts on one GPU (tests): plain pointers
+            int can = 0; cudaDeviceCanAccessPeer(&can, ctx->device, pd);
+            if (!can) { cudaSetDevice(prev); return fail(ctx, FDB_ERR_CUDA, "device %d cannot map device %d's memory (no peer access)", ctx->device, pd); }
+            cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) { cudaSetDevice(prev); return fail(ctx, FDB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", ctx->device, pd, cudaGetErrorString(e)); }
+        }
+    }
+    cudaSetDevice(prev);
+    for (int r = 0; r < world; r++) {
+        for (int q = 0; q < world; q++) xs[r]->peer[q] = xs[q]->base;
+        xs[r]->connected = true; xs[r]->in_process = true;
+    }
+    return FDB_OK;
+}
+
+extern "C" int fdb_exchange_set_timeout(fdb_exchange* x, double seconds) {
+    if (!x || !(seconds > 0.0)) return FDB_ERR_BADARG;
+    x->timeout_ns = (unsigned long long)(seconds * 1e9);
+    return FDB_OK;
+}
+
 extern "C" int fdb_exchange_view(fdb_exchange* x, int64_t offset, int64_t n, int64_t ld, fdb_array** out) {
     if (!x || !out) return FDB_ERR_BADARG;
     if (offset < 0 || n < 0 || ld < n || (size_t)(offset + ld) * sizeof(double) > x->data_bytes)
@@ -158,6 +198,7 @@ extern "C" int fdb_exchange_view(fdb_exchange* x, int64_t offset, int64_t n, int
 }
 
 extern "C" int fdb_exchange_enable(fdb_ctx* ctx, fdb_exchange* x) {
+    FDB_ENTER(ctx);
     if (!ctx) return FDB_ERR_BADARG;
     if (x && x->ctx != ctx) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_enable: exchange belongs to another context");
     if (x && !x->connected) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_enable: call fdb_exchange_connect first");
@@ -166,6 +207,7 @@ extern "C" int fdb_exchange_enable(fdb_ctx* ctx, fdb_exchange* x) {
 }
 
 extern "C" int fdb_exchange_barrier(fdb_exchange* x) {
+    FDB_ENTER(x ? x->ctx : nullptr);
     if (!x) return FDB_ERR_BADARG;
     fdb_ctx* ctx = x->ctx;
     if (!x->connected) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_barrier: not connected");
@@ -175,11 +217,12 @@ extern "C" int fdb_exchange_barrier(fdb_exchange* x) {
     for (int r = 0; r < FDB_MAX_RANKS; r++)
         P.flags[r] = r < x->world ? reinterpret_cast<unsigned long long*>(x->peer[r] + x->data_bytes) : nullptr;
     x->epoch++;
-    exchange_barrier_kernel<<<1, 32, 0, ctx->stream>>>(P, x->rank, x->world, x->epoch, 20ull * 1000000000ull);
+    exchange_barrier_kernel<<<1, 32, 0, ctx->stream>>>(P, x->rank, x->world, x->epoch, x->timeout_ns, ctx->xch_timeout_flag);
     return finish(ctx, 1, "fdb_exchange_barrier");
 }
 
 extern "C" int fdb_exchange_measure_store_bw(fdb_exchange* x, int64_t n_doubles, int variant, int rotate, double* gb_per_s) {
+    FDB_ENTER(x ? x->ctx : nullptr);
     if (!x || !gb_per_s) return FDB_ERR_BADARG;
     fdb_ctx* ctx = x->ctx;
     if (!x->connected || x->world < 2) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_measure_store_bw: needs a connected exchange with peers");
@@ -221,6 +264,7 @@ extern "C" int fdb_exchange_measure_store_bw(fdb_exchange* x, int64_t n_doubles,
 // all-gather / broadcast for data the drivers did not mirror themselves (e.g. results of the materialised loop path):
 // copy [offset, offset+count) of the local arena to the same place in every peer's arena.
 extern "C" int fdb_exchange_push(fdb_exchange* x, int64_t offset, int64_t count) {
+    FDB_ENTER(x ? x->ctx : nullptr);
     if (!x) return FDB_ERR_BADARG;
     fdb_ctx* ctx = x->ctx;
     if (!x->connected) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_push: not connected");
@@ -236,6 +280,7 @@ extern "C" int fdb_exchange_push(fdb_exchange* x, int64_t offset, int64_t count)
 }
 
 extern "C" int fdb_exchange_timeouts(fdb_exchange* x, int64_t* count) {
+    FDB_ENTER(x ? x->ctx : nullptr);
     if (!x || !count) return FDB_ERR_BADARG;
     unsigned v = 0;
     FDB_CUDA(x->ctx, cudaMemcpyAsync(&v, x->base + x->data_bytes + TIMEOUT_OFF, sizeof v, cudaMemcpyDeviceToHost, x->ctx->stream));
@@ -245,12 +290,14 @@ extern "C" int fdb_exchange_timeouts(fdb_exchange* x, int64_t* count) {
 }
 
 extern "C" int fdb_exchange_destroy(fdb_exchange* x) {
+    FDB_ENTER(x ? x->ctx : nullptr);
     if (!x) return FDB_ERR_BADARG;
     fdb_ctx* ctx = x->ctx;
     if (ctx->xch == x) ctx->xch = nullptr;
     cudaStreamSynchronize(ctx->stream);
-    for (int r = 0; r < x->world; r++)
-        if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    if (!x->in_process)
+        for (int r = 0; r < x->world; r++)
+            if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);
     cudaFree(x->base);
     delete x;
     return FDB_OK;

@@ -88,18 +88,21 @@ static int check_pair(fdb_ctx* ctx, const fdb_array* d, const fdb_array* x, cons
 using namespace fdb;
 
 extern "C" int fdb_cursor_set(fdb_ctx* ctx, int64_t index, int64_t chunksize) {
+    FDB_ENTER(ctx);
     if (!ctx || index < 1 || chunksize < 0) return fail(ctx, FDB_ERR_BADARG, "fdb_cursor_set: bad argument");
     int rc = ensure_cursor(ctx); if (rc) return rc;
     cursor_set_kernel<<<1, 1, 0, ctx->stream>>>(ctx->cursor, index, chunksize);
     return finish(ctx, 1, "fdb_cursor_set");
 }
 extern "C" int fdb_cursor_advance(fdb_ctx* ctx, int64_t step, int64_t xlen) {
+    FDB_ENTER(ctx);
     if (!ctx || step < 1) return fail(ctx, FDB_ERR_BADARG, "fdb_cursor_advance: bad argument");
     int rc = ensure_cursor(ctx); if (rc) return rc;
     cursor_advance_kernel<<<1, 1, 0, ctx->stream>>>(ctx->cursor, step, xlen);
     return finish(ctx, 1, "fdb_cursor_advance");
 }
 extern "C" int fdb_cursor_get(fdb_ctx* ctx, int64_t* index, int64_t* chunksize) {
+    FDB_ENTER(ctx);
     if (!ctx) return FDB_ERR_BADARG;
     int rc = ensure_cursor(ctx); if (rc) return rc;
     int64_t h[2];
@@ -109,18 +112,21 @@ extern "C" int fdb_cursor_get(fdb_ctx* ctx, int64_t* index, int64_t* chunksize) 
     return FDB_OK;
 }
 extern "C" int fdb_seed_at_cursor(fdb_ctx* ctx, fdb_array* d, const fdb_array* x) {
+    FDB_ENTER(ctx);
     int rc = check_pair(ctx, d, x, "fdb_seed_at_cursor"); if (rc) return rc;
     const int PB = x->planes(), P = (d->N + 1) * PB;
     seed_at_cursor_kernel<<<(unsigned)cdiv((int64_t)d->N * P, 128), 128, 0, ctx->stream>>>(d->data, d->ld, x->data, x->ld, d->N, PB, d->n, ctx->cursor);
     return finish(ctx, 1, "fdb_seed_at_cursor");
 }
 extern "C" int fdb_seed_zero_at_cursor(fdb_ctx* ctx, fdb_array* d, const fdb_array* x) {
+    FDB_ENTER(ctx);
     int rc = check_pair(ctx, d, x, "fdb_seed_zero_at_cursor"); if (rc) return rc;
     const int PB = x->planes(), P = (d->N + 1) * PB;
     seed_zero_at_cursor_kernel<<<(unsigned)cdiv((int64_t)d->N * P, 128), 128, 0, ctx->stream>>>(d->data, d->ld, x->data, x->ld, d->N, PB, d->n, ctx->cursor);
     return finish(ctx, 1, "fdb_seed_zero_at_cursor");
 }
 extern "C" int fdb_extract_gradient_chunk_at_cursor(fdb_ctx* ctx, fdb_array* res, const fdb_array* y) {
+    FDB_ENTER(ctx);
     if (!ctx || !res || !y) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_gradient_chunk_at_cursor: null argument");
     if (y->level < 1 || res->level != y->level - 1) return fail(ctx, FDB_ERR_BADARG, "result must be one level below ydual");
     if (y->n != 1) return fail(ctx, FDB_ERR_SHAPE, "gradient(f, x) expects that f(x) is a real number. Perhaps you meant jacobian(f, x)?");
@@ -130,6 +136,7 @@ extern "C" int fdb_extract_gradient_chunk_at_cursor(fdb_ctx* ctx, fdb_array* res
     return finish(ctx, 1, "fdb_extract_gradient_chunk_at_cursor");
 }
 extern "C" int fdb_extract_jacobian_chunk_at_cursor(fdb_ctx* ctx, fdb_array* res, int64_t ldres, const fdb_array* y) {
+    FDB_ENTER(ctx);
     if (!ctx || !res || !y) return fail(ctx, FDB_ERR_BADARG, "fdb_extract_jacobian_chunk_at_cursor: null argument");
     if (y->level < 1 || res->level != y->level - 1) return fail(ctx, FDB_ERR_BADARG, "result must be one level below ydual");
     if (ldres < y->n) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: leading dimension smaller than length(ydual)");
@@ -142,6 +149,7 @@ extern "C" int fdb_extract_jacobian_chunk_at_cursor(fdb_ctx* ctx, fdb_array* res
 
 // ---- stream capture / replay ---------------------------------------------------------------------------------
 extern "C" int fdb_graph_begin(fdb_ctx* ctx) {
+    FDB_ENTER(ctx);
     if (!ctx) return FDB_ERR_BADARG;
     if (ctx->capturing) return fail(ctx, FDB_ERR_BADARG, "fdb_graph_begin: already capturing");
     int rc = ensure_cursor(ctx); if (rc) return rc;
@@ -154,11 +162,13 @@ extern "C" int fdb_graph_begin(fdb_ctx* ctx) {
     return FDB_OK;
 }
 extern "C" int fdb_graph_end(fdb_ctx* ctx, void** exec_out) {
+    FDB_ENTER(ctx);
     if (!ctx || !exec_out) return FDB_ERR_BADARG;
     if (!ctx->capturing) return fail(ctx, FDB_ERR_BADARG, "fdb_graph_end: not capturing");
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     ctx->capturing = false; ctx->async = ctx->saved_async;
+    if (e != cudaSuccess || !graph) cudaGetLastError();      // an invalidated capture (f synchronised / read device data) is not sticky: the eager loop can follow
     if (e != cudaSuccess || !graph) return fail(ctx, FDB_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, graph, 0);
@@ -168,6 +178,7 @@ extern "C" int fdb_graph_end(fdb_ctx* ctx, void** exec_out) {
     return FDB_OK;
 }
 extern "C" int fdb_graph_launch(fdb_ctx* ctx, void* exec, int64_t times) {
+    FDB_ENTER(ctx);
     if (!ctx || !exec || times < 0) return FDB_ERR_BADARG;
     for (int64_t i = 0; i < times; i++) FDB_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)exec, ctx->stream));
     if (!ctx->async) FDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

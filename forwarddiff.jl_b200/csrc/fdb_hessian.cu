@@ -40,6 +40,7 @@ using namespace fdb;
 
 extern "C" int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi,
                                    fdb_array* H, int64_t ldH, fdb_array* grad, fdb_array* value_dev) {
+    FDB_ENTER(ctx);
     if (!ctx || !x) return fail(ctx, FDB_ERR_BADARG, "fdb_hessian_chunked: null argument");
     if (x->level != 0 || (H && H->level != 0) || (grad && grad->level != 0) || (value_dev && value_dev->level != 0))
         return fail(ctx, FDB_ERR_BADARG, "fdb_hessian_chunked: x, H, grad, value must be plain arrays");
@@ -64,6 +65,7 @@ extern "C" int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int
 
 extern "C" int fdb_hessian_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, int N, int64_t chunk_lo, int64_t chunk_hi,
                                 double* H_host, int64_t ldH, double* grad_host, double* value_host) {
+    FDB_ENTER(ctx);
     if (!ctx || !x_host || !H_host) return fail(ctx, FDB_ERR_BADARG, "fdb_hessian_host: null argument");
     if (xlen == 0) { if (value_host) *value_host = 0.0; return FDB_OK; }
     if (N < 1 || N > FDB_MAX_CHUNK) return fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", N);

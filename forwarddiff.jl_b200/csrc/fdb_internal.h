@@ -29,9 +29,18 @@ struct fdb_ctx {
     bool saved_async = false;
     double* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // device staging of the *_host entry points that run drivers with their own scratch needs (fdb_multi.cu)
+    double* hostws = nullptr;
+    size_t hostws_bytes = 0;
     struct fdb_exchange* xch = nullptr;   // enabled peer-memory result exchange (fdb_exchange.cu), or null
     struct fdb_jit_cache* jit = nullptr;  // kernels specialised at run time for op-programs (fdb_jit.cu)
     bool use_jit = true;
+    bool dmma_configured = false;         // cudaFuncSetAttribute(dmma_gemm_kernel, ...) done on THIS device (per device, not per process)
+    struct fdb_multi* multi = nullptr;    // owning single-process multi-GPU group (fdb_multi.cu), or null
+    // sticky failure of an asynchronous step (a peer never reached an exchange barrier): reported by the next
+    // fdb_sync / synchronous call / fdb_exchange_* on this context; results produced since are invalid
+    unsigned* xch_timeout_flag = nullptr; // pinned host word the barrier kernel bumps when it gives up
+    bool poisoned = false;
     // plain Float64 arrays an op-program reads next to x (closed-over data of the user's f): fdb_program_bind_params
     const double* prm_ptr[FDB_MAX_PARAMS] = {nullptr, nullptr, nullptr, nullptr};
     int64_t prm_len[FDB_MAX_PARAMS] = {0, 0, 0, 0};
@@ -50,9 +59,38 @@ struct fdb_array {
     int planes() const { return level == 0 ? 1 : (level == 1 ? N + 1 : (N + 1) * (N + 1)); }
 };
 
+// symmetric result arena of one rank (fdb_exchange.cu)
+struct fdb_exchange {
+    fdb_ctx* ctx = nullptr;
+    char* base = nullptr;          // local arena: data | flag page
+    size_t data_bytes = 0;
+    int rank = 0, world = 1;
+    char* peer[FDB_MAX_RANKS] = {nullptr};   // peer[r] = rank r's arena mapped here (peer[rank] = base)
+    bool connected = false;
+    unsigned long long epoch = 0;
+    unsigned long long timeout_ns = 20ull * 1000000000ull;   // a barrier gives up after this long (fdb_exchange_set_timeout)
+    bool in_process = false;       // peers linked with cudaDeviceEnablePeerAccess inside one process (fdb_exchange_connect_local)
+};
+
 namespace fdb {
 
 extern thread_local std::string g_init_error;
+
+// Every extern "C" entry point runs with its context's device current and restores the caller's device on return:
+// several contexts (one per GPU) may live in one process, and a host framework (torch, CUDA.jl) may have switched devices.
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define FDB_ENTER(c) fdb::DeviceGuard fdb_device_guard__(fdb::device_of(c))
+
+inline int device_of(const fdb_ctx* c) { return c ? c->device : -1; }
 
 inline int fail(fdb_ctx* ctx, int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
 inline int fail(fdb_ctx* ctx, int code, const char* fmt, ...) {
@@ -73,6 +111,15 @@ inline int fail(fdb_ctx* ctx, int code, const char* fmt, ...) {
                              "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+// after a host synchronisation: did an exchange barrier on this context give up (dead / slow peer)?  Then every result
+// stored since is incomplete: the context stays poisoned and every later synchronising call reports it.
+inline int check_poison(fdb_ctx* ctx, const char* what) {
+    if (ctx->xch_timeout_flag && *(volatile unsigned*)ctx->xch_timeout_flag) ctx->poisoned = true;
+    if (ctx->poisoned)
+        return fail(ctx, FDB_ERR_CUDA, "%s: a peer never reached an exchange barrier (timeout); results since then are incomplete", what);
+    return FDB_OK;
+}
+
 // after a kernel launch: check the launch, count it, and drain the stream unless async
 inline int finish(fdb_ctx* ctx, int nlaunch, const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -81,6 +128,7 @@ inline int finish(fdb_ctx* ctx, int nlaunch, const char* what) {
     if (!ctx->async) {
         e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        return check_poison(ctx, what);
     }
     return FDB_OK;
 }
@@ -100,6 +148,13 @@ bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k);
 // fdb_jit.cu
 void jit_release(fdb_ctx* ctx);
 int jit_launch(fdb_ctx* ctx, void* entry, unsigned gridx, unsigned gridy, unsigned threads, void** args, const char* what);
+
+// cudaFuncSetAttribute is a per-device setting: remember per (kernel instantiation, device)
+inline bool first_use_on_device(unsigned long long& mask, int dev) {
+    const bool first = !((mask >> (dev & 63)) & 1ull);
+    mask |= 1ull << (dev & 63);
+    return first;
+}
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

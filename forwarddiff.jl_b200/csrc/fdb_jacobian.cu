@@ -171,6 +171,7 @@ using namespace fdb;
 extern "C" int fdb_jacobian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int64_t m, int N, const fdb_array* A, int64_t lda,
                                     const fdb_array* b, double alpha, int64_t chunk_lo, int64_t chunk_hi, fdb_array* J, int64_t ldJ,
                                     fdb_array* y) {
+    FDB_ENTER(ctx);
     if (!ctx || !x || !J) return fail(ctx, FDB_ERR_BADARG, "fdb_jacobian_chunked: null argument");
     if (x->level != 0 || J->level != 0 || (y && y->level != 0)) return fail(ctx, FDB_ERR_BADARG, "fdb_jacobian_chunked: x, J, y must be plain arrays");
     const int64_t n = x->n;

@@ -150,6 +150,7 @@ static int check_same(fdb_ctx* ctx, const fdb_array* out, const fdb_array* a, co
 }
 
 extern "C" int fdb_map1(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a) {
+    FDB_ENTER(ctx);
     int rc = check_same(ctx, out, a, "fdb_map1"); if (rc) return rc;
     if (op < FDB_NEG || op > FDB_CBRT) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map1: unknown op %d", op);
     if (out->n != a->n) return fail(ctx, FDB_ERR_SHAPE, "fdb_map1: DimensionMismatch");
@@ -162,6 +163,7 @@ extern "C" int fdb_map1(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a
 }
 
 extern "C" int fdb_map2(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a, const fdb_array* b) {
+    FDB_ENTER(ctx);
     if (!ctx || !out || !a || !b) return fail(ctx, FDB_ERR_BADARG, "fdb_map2: null argument");
     if (op < FDB_ADD || op > FDB_HYPOT) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map2: unknown op %d", op);
     if (out->level != 1 || a->level > 1 || b->level > 1 || (a->level == 0 && b->level == 0))
@@ -189,6 +191,7 @@ extern "C" int fdb_map2(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a
 }
 
 extern "C" int fdb_map2_scalar(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a, double s, int scalar_first) {
+    FDB_ENTER(ctx);
     int rc = check_same(ctx, out, a, "fdb_map2_scalar"); if (rc) return rc;
     if (op < FDB_ADD || op > FDB_POW) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map2_scalar: unknown op %d", op);
     if (out->n != a->n) return fail(ctx, FDB_ERR_SHAPE, "fdb_map2_scalar: DimensionMismatch");
@@ -206,6 +209,7 @@ extern "C" int fdb_map2_scalar(fdb_ctx* ctx, int op, fdb_array* out, const fdb_a
 }
 
 extern "C" int fdb_fma(fdb_ctx* ctx, int kind, fdb_array* out, const fdb_array* a, const fdb_array* b, const fdb_array* c, double s) {
+    FDB_ENTER(ctx);
     int rc = check_same(ctx, out, a, "fdb_fma"); if (rc) return rc;
     if (kind < 0 || kind > 2) return fail(ctx, FDB_ERR_BADARG, "fdb_fma: kind %d", kind);
     if ((kind != 2 && !b) || (kind != 1 && !c)) return fail(ctx, FDB_ERR_BADARG, "fdb_fma: missing operand");

@@ -96,12 +96,11 @@ __global__ void __launch_bounds__(THREADS) program_gradient_kernel(const __grid_
 template <int N, bool NS, int T>
 static int launch_program_gradient(fdb_ctx* ctx, unsigned grid, size_t smem, const Program& P, const double* x, int64_t n, int64_t chunk_lo,
                                    int64_t nchunks, int lcs, double* grad, double* vout, const fdb_mirrors& M) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;      // per device: several contexts (GPUs) may live in one process
+    if (first_use_on_device(configured, ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(program_gradient_kernel<N, NS, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(PG_MAXR * 2 * PG_VEC * T * sizeof(double)));
         if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(program_gradient_kernel): %s", cudaGetErrorString(e));
-        configured = true;
     }
     program_gradient_kernel<N, NS, T><<<grid, T, smem, ctx->stream>>>(P, ctx->lane_sharing, x, n, chunk_lo, nchunks, lcs, grad, vout, M);
     return FDB_OK;
@@ -185,6 +184,7 @@ using namespace fdb;
 extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi,
                                             const double* consts, int n_consts, int n_acc, int halo, int result_reg, const fdb_array* x, int N,
                                             int64_t chunk_lo, int64_t chunk_hi, fdb_array* grad, fdb_array* value_dev) {
+    FDB_ENTER(ctx);
     if (!ctx || !x || !grad) return fail(ctx, FDB_ERR_BADARG, "fdb_program_gradient_chunked: null argument");
     if (x->level != 0 || grad->level != 0 || (value_dev && value_dev->level != 0)) return fail(ctx, FDB_ERR_BADARG, "x, grad, value must be plain arrays");
     if (grad->n != x->n) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: gradient result has %lld entries, x has %lld", (long long)grad->n, (long long)x->n);
@@ -227,6 +227,7 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
 }
 
 extern "C" int fdb_program_bind_params(fdb_ctx* ctx, int count, const fdb_array* const* arrays) {
+    FDB_ENTER(ctx);
     if (!ctx || count < 0 || count > FDB_MAX_PARAMS || (count && !arrays))
         return fail(ctx, FDB_ERR_BADARG, "fdb_program_bind_params: 0..%d plain arrays", FDB_MAX_PARAMS);
     for (int k = 0; k < count; k++)

@@ -186,6 +186,7 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
                                            const double* consts, int n_consts, int n_acc, int halo, int result_reg, const fdb_array* x, int N,
                                            int64_t chunk_lo, int64_t chunk_hi, fdb_array* H, int64_t ldH, fdb_array* grad,
                                            fdb_array* value_dev) {
+    FDB_ENTER(ctx);
     if (!ctx || !x) return fail(ctx, FDB_ERR_BADARG, "fdb_program_hessian_chunked: null argument");
     if (x->level != 0 || (H && H->level != 0) || (grad && grad->level != 0) || (value_dev && value_dev->level != 0))
         return fail(ctx, FDB_ERR_BADARG, "x, H, grad, value must be plain arrays");

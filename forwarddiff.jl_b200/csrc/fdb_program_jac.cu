@@ -49,6 +49,7 @@ using namespace fdb;
 extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, int n_instr, const double* consts, int n_consts, int halo,
                                             int result_reg, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* J,
                                             int64_t ldJ, fdb_array* y) {
+    FDB_ENTER(ctx);
     if (!ctx || !x || !J) return fail(ctx, FDB_ERR_BADARG, "fdb_program_jacobian_chunked: null argument");
     if (x->level != 0 || J->level != 0 || (y && y->level != 0)) return fail(ctx, FDB_ERR_BADARG, "x, J, y must be plain arrays");
     const int64_t n = x->n, m = n - halo;

@@ -252,11 +252,10 @@ __global__ void __launch_bounds__(MR_THREADS) mapreduce_tma_kernel(const double*
 template <class F, int N, bool NS>
 static int mapreduce_tma_launch(fdb_ctx* ctx, fdb_array* out1, const fdb_array* a, int64_t ntiles) {
     const size_t smem = (size_t)MR_STAGES * (N + 1) * MR_ROW * 8 + 2 * MR_STAGES * 8 + 128;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;      // per device: several contexts (GPUs) may live in one process
+    if (first_use_on_device(configured, ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(mapreduce_tma_kernel<F, N, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(mapreduce_tma_kernel): %s", cudaGetErrorString(e));
-        configured = true;
     }
     int per_sm = (int)((220 * 1024) / smem); if (per_sm < 1) per_sm = 1; if (per_sm > 6) per_sm = 6;
     int64_t want = (int64_t)ctx->sm_count * per_sm;
@@ -309,12 +308,14 @@ static int check_reduce(fdb_ctx* ctx, fdb_array* out1, const fdb_array* a, const
     return FDB_OK;
 }
 extern "C" int fdb_reduce(fdb_ctx* ctx, int redop, fdb_array* out1, const fdb_array* a) {
+    FDB_ENTER(ctx);
     int rc = check_reduce(ctx, out1, a, "fdb_reduce"); if (rc) return rc;
     if (redop == FDB_SUM) return mapreduce_launch<SumAll>(ctx, out1, a, "fdb_reduce(sum)");
     if (redop == FDB_PROD) return mapreduce_launch<ProdAll>(ctx, out1, a, "fdb_reduce(prod)");
     return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_reduce: unknown reduction %d", redop);
 }
 extern "C" int fdb_eval_scalar_fn(fdb_ctx* ctx, int fn, fdb_array* out1, const fdb_array* xdual) {
+    FDB_ENTER(ctx);
     int rc = check_reduce(ctx, out1, xdual, "fdb_eval_scalar_fn"); if (rc) return rc;
     switch (fn) {
         case FDB_FN_ROSENBROCK: return mapreduce_launch<Rosenbrock>(ctx, out1, xdual, "fdb_eval_scalar_fn(rosenbrock)");

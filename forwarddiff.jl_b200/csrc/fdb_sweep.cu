@@ -46,6 +46,7 @@ using namespace fdb;
 
 extern "C" int fdb_gradient_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi,
                                     fdb_array* grad, fdb_array* value_dev) {
+    FDB_ENTER(ctx);
     if (!ctx || !x || !grad) return fail(ctx, FDB_ERR_BADARG, "fdb_gradient_chunked: null argument");
     if (x->level != 0 || grad->level != 0 || (value_dev && value_dev->level != 0))
         return fail(ctx, FDB_ERR_BADARG, "fdb_gradient_chunked: x, grad and value must be plain (level-0) arrays");
@@ -77,6 +78,7 @@ extern "C" int fdb_gradient_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, in
 // the sweeps, D2H of the gradient slice of the requested chunks (and the value).
 extern "C" int fdb_gradient_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, int N, int64_t chunk_lo,
                                  int64_t chunk_hi, double* grad_host, double* value_host) {
+    FDB_ENTER(ctx);
     if (!ctx || !x_host || !grad_host) return fail(ctx, FDB_ERR_BADARG, "fdb_gradient_host: null argument");
     if (xlen == 0) { if (value_host) *value_host = 0.0; return FDB_OK; }   // Chunk{0}: fill!(result, 0) on an empty result
     if (N < 1 || N > FDB_MAX_CHUNK) return fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", N);
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 }  // namespace fdb
 
 extern "C" int fdb_measure_fp64_peak(fdb_ctx* ctx, double* dp_ops_per_s, double* dfma_per_s) {
+    FDB_ENTER(ctx);
     if (!ctx) return FDB_ERR_BADARG;
     int rc = ensure_scratch(ctx, 4096); if (rc) return rc;
     cudaEvent_t e0, e1;

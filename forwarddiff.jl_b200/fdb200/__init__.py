@@ -11,8 +11,10 @@ from .array import (B200Array, B200DualArray, Context, abs2, abs_, acos, asin, a
                     expm1, fma, hypot, inv, log, log10, log1p, log2, maximum, minimum, sin, sinh, sqrt, tan, tanh)
 from .api import (Chunk, Diagonal, DiffResult, LowerTriangular, UpperTriangular, GradientConfig, GradientResult, HessianConfig, HessianResult, JacobianConfig,
                   JacobianResult, Tag, checktag, chunk_plan, default_context, gradient, gradient_b, hessian, hessian_b,
-                  jacobian, jacobian_b, pickchunksize)
+                  jacobian, jacobian_b, pickchunksize, SlowPathWarning)
 from . import functions
 from . import dist
+from . import multi
+from .multi import DeviceGroup
 
 __all__ = [n for n in dir() if not n.startswith("_")]

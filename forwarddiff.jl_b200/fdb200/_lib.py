@@ -128,6 +128,29 @@ SIGNATURES = {
     "fdb_program_bind_params": (C.c_int, [c_ctx, C.c_int, C.POINTER(C.c_void_p)]),
     "fdb_gradient_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, C.c_int, i64, i64, _dp, _dp]),
     "fdb_hessian_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, C.c_int, i64, i64, _dp, i64, _dp, _dp]),
+    "fdb_jacobian_host": (C.c_int, [c_ctx, C.c_int, _dp, i64, i64, C.c_int, _dp, i64, _dp, C.c_double, C.c_int, i64, i64, _dp, i64, _dp]),
+    "fdb_host_register": (C.c_int, [C.c_void_p, i64]),
+    "fdb_host_unregister": (C.c_int, [C.c_void_p]),
+    "fdb_multi_init": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "fdb_multi_shutdown": (C.c_int, [C.c_void_p]),
+    "fdb_multi_size": (C.c_int, [C.c_void_p]),
+    "fdb_multi_ctx": (c_ctx, [C.c_void_p, C.c_int]),
+    "fdb_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "fdb_multi_sync": (C.c_int, [C.c_void_p]),
+    "fdb_multi_gradient_host": (C.c_int, [C.c_void_p, C.c_int, _dp, i64, C.c_int, _dp, _dp]),
+    "fdb_multi_jacobian_host": (C.c_int, [C.c_void_p, C.c_int, _dp, i64, i64, C.c_int, _dp, i64, _dp, C.c_double, C.c_int, _dp, i64, _dp]),
+    "fdb_multi_hessian_host": (C.c_int, [C.c_void_p, C.c_int, _dp, i64, C.c_int, _dp, i64, _dp, _dp]),
+    "fdb_multi_exchange_create": (C.c_int, [C.c_void_p, i64, C.POINTER(C.c_void_p)]),
+    "fdb_multi_exchange_destroy": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fdb_multi_barrier": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "fdb_multi_upload": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), i64, _dp, i64]),
+    "fdb_multi_download": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, i64, _dp, i64]),
+    "fdb_multi_gradient_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, i64, i64, C.c_int, i64, i64]),
+    "fdb_multi_jacobian_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, i64, i64, i64, C.c_int, C.POINTER(C.c_void_p), i64,
+                                              C.POINTER(C.c_void_p), C.c_double, i64, i64, i64]),
+    "fdb_multi_hessian_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, i64, i64, C.c_int, i64, i64, i64, i64]),
+    "fdb_exchange_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "fdb_exchange_set_timeout": (C.c_int, [C.c_void_p, C.c_double]),
     "fdb_exchange_create": (C.c_int, [c_ctx, i64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "fdb_exchange_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
     "fdb_exchange_connect": (C.c_int, [C.c_void_p, C.c_char_p]),

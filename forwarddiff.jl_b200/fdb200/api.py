@@ -214,6 +214,12 @@ class _Config:
         self.tag = Tag(f) if tag is _DEFAULT else tag
         self.xlen = _length(x)
         self._duals = None           # allocated lazily: only the materialised path needs them
+        # which execution path the last call through this config took: "catalogue" (fused batched kernel of a catalogue
+        # target), "program:specialised" / "program:interpreted" (flattened f on the batched sweep), "loop:graph" /
+        # "loop:eager" (the reference chunk loop on materialised duals); trace_error: why f was not flattened
+        self.last_path = None
+        self.trace_error = None
+        self.capture_error = None
 
     @property
     def chunksize(self):
@@ -262,13 +268,36 @@ class HessianConfig(_Config):
 # ---------------------------------------------------------------------------
 # gradient
 # ---------------------------------------------------------------------------
+class SlowPathWarning(UserWarning):
+    """f could not be flattened into an op-program: the reference chunk loop runs on materialised device duals, one small
+    kernel per array statement per chunk (launch-bound; orders of magnitude slower than the batched sweep)."""
+
+
+_trace_failure = {}
+
+
 def _try_trace(kind, f, n):
-    """Flatten a non-catalogue callable into an op-program; None when its shape is not supported."""
+    """Flatten a non-catalogue callable into an op-program; None when its shape is not supported (the reason is kept
+    for `cfg.trace_error` / the SlowPathWarning)."""
     from . import trace
     try:
+        _trace_failure.pop(id(f), None)
         return (trace.trace_scalar if kind == "scalar" else trace.trace_array)(f, n)
-    except (trace.TraceError, TypeError, AttributeError, ValueError):
+    except (trace.TraceError, TypeError, AttributeError, ValueError) as e:
+        _trace_failure[id(f)] = f"{type(e).__name__}: {e}"
         return None
+
+
+def _warn_loop(what, f, n, N, cfg):
+    """The drop to the materialised loop is never silent: cfg.last_path / cfg.trace_error say what ran and why, and a
+    SlowPathWarning is issued when the loop is long enough to matter."""
+    import warnings
+    cfg.trace_error = _trace_failure.get(id(f))
+    nchunks = -(-n // N)
+    if nchunks >= 64:
+        warnings.warn(f"{what}: {getattr(f, '__name__', f)!r} runs on the materialised chunk loop ({nchunks} chunks x one kernel per "
+                      f"array statement) because it could not be flattened ({cfg.trace_error or 'fuse=False'}); see cfg.last_path",
+                      SlowPathWarning, stacklevel=4)
 
 
 def _i32p(a):
@@ -357,16 +386,23 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
     lo, hi = (0, -1) if chunks is None else chunks
     if fid is not None:
         value = _fused_gradient(ctx, fid, x, N, lo, hi, out)
+        cfg.last_path = "catalogue"
     else:
         prog = _try_trace("scalar", f, n) if fuse else None
         value, done = None, False
         if _usable(ctx, prog):
             try:
+                c0 = ctx.jit_stats()
                 value, done = _program_gradient(ctx, prog, x, N, lo, hi, out), True
+                c1 = ctx.jit_stats()
+                ran_jit = (c1["compiled"] + c1["cache_hits"]) > (c0["compiled"] + c0["cache_hits"])
+                cfg.last_path = "program:specialised" if ran_jit else "program:interpreted"
             except _lib.UnsupportedOp:
                 if not prog.needs_jit:                  # only "libnvrtc is not installed" is recoverable: take the loop
                     raise
         if not done:
+            cfg.last_path = "loop:eager"
+            _warn_loop("gradient", f, n, N, cfg)
             value = _loop_gradient(ctx, f, x, cfg, lo, hi, out, graph)
     if isinstance(result, DiffResult) and value is not None:
         result.value = value
@@ -465,10 +501,13 @@ def _fused_gradient(ctx, fid, x, N, lo, hi, out):
     xh = np.ascontiguousarray(x, dtype=np.float64).ravel()
     if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous):
         raise FdbError("gradient!: result must be a contiguous float64 array")
-    val = C.c_double(float("nan"))
+    val = C.c_double(0.0)
     ctx.check(lib.fdb_gradient_host(ctx.h, fid, xh.ctypes.data_as(_dp), xh.size, N, lo, hi,
                                     out.ctypes.data_as(_dp), C.byref(val)))
-    return None if np.isnan(val.value) and not (hi < 0) else val.value
+    # the value is written exactly when the range includes the last chunk (gradient.jl:155) -- decided from the plan,
+    # not from the number that came back (f(x) may legitimately be NaN)
+    nchunks = 1 if xh.size == N else chunk_plan(xh.size, N)["nchunks"]
+    return val.value if (hi < 0 or hi == nchunks) else None
 
 
 def _loop_gradient(ctx, f, x, cfg, lo, hi, out, graph=True):
@@ -500,26 +539,39 @@ def _loop_gradient(ctx, f, x, cfg, lo, hi, out, graph=True):
         if graph and full and nchunks >= 4:
             # first chunk eagerly (gradient.jl:133-138; it also sizes the library's scratch buffers), then ONE
             # iteration  seed! -> f -> extract -> unseed -> advance  captured at the device-resident chunk cursor
-            # and replayed for chunks 2..nchunks (the cursor's chunksize shrinks for the short last chunk)
+            # and replayed for chunks 2..nchunks (the cursor's chunksize shrinks for the short last chunk).
+            # Capture restrictions: f must only enqueue device work.  An f that reads device data back (`.numpy()`),
+            # synchronises, or takes host-side decisions from device values invalidates the capture; the capture is
+            # then abandoned and chunks 2.. run through the eager loop below, which handles any f.
             ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, 1, N))
             ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, N + 1, n - N))
             ydual = call_f()
             ctx.check(lib.fdb_extract_gradient_chunk(ctx.h, res.h, ydual.h, 1, N))
             ctx.check(lib.fdb_seed_zero(ctx.h, xdual.h, xd.h, 1, N))
             ctx.check(lib.fdb_cursor_set(ctx.h, N + 1, min(N, n - N)))
-            with ctx.capture() as cap:
-                ctx.check(lib.fdb_seed_at_cursor(ctx.h, xdual.h, xd.h))
-                ydual = call_f()
-                ctx.check(lib.fdb_extract_gradient_chunk_at_cursor(ctx.h, res.h, ydual.h))
-                ctx.check(lib.fdb_seed_zero_at_cursor(ctx.h, xdual.h, xd.h))
-                ctx.check(lib.fdb_cursor_advance(ctx.h, N, n))
-            cap.graph.launch(nchunks - 1)
-            ctx.sync()
-            value = float(ydual.numpy()[0, 0])
-            if res is not out:
-                out[...] = res.numpy().reshape(np.shape(out))
-            cap.graph.destroy()
-            return value
+            cap = None
+            try:
+                with ctx.capture() as cap:
+                    ctx.check(lib.fdb_seed_at_cursor(ctx.h, xdual.h, xd.h))
+                    ydual = call_f()
+                    ctx.check(lib.fdb_extract_gradient_chunk_at_cursor(ctx.h, res.h, ydual.h))
+                    ctx.check(lib.fdb_seed_zero_at_cursor(ctx.h, xdual.h, xd.h))
+                    ctx.check(lib.fdb_cursor_advance(ctx.h, N, n))
+            except DimensionMismatch:
+                raise
+            except (FdbError, RuntimeError, ValueError, TypeError) as e:
+                cap = None
+                cfg.capture_error = repr(e)
+            if cap is not None and cap.graph is not None:
+                cap.graph.launch(nchunks - 1)
+                ctx.sync()
+                value = float(ydual.numpy()[0, 0])
+                if res is not out:
+                    out[...] = res.numpy().reshape(np.shape(out))
+                cap.graph.destroy()
+                cfg.last_path = "loop:graph"
+                return value
+            lo, full = 1, False                                     # nothing of the abandoned capture ran: continue eagerly with chunk 2
         for c in range(lo, hi):
             c1 = c + 1
             if c1 == nchunks:                                       # final chunk, gradient.jl:150-152
@@ -587,16 +639,24 @@ def jacobian_b(result, f, x, cfg=None, check=True, ctx=None, y=None, params=None
     fid = _catalogue_id(f, _lib.JFN)
     lo, hi = (0, -1) if chunks is None else chunks
     if getattr(f, "fdb_catalogue", None) == "mlp2":
+        cfg.last_path = "catalogue"
         return _mlp2_jacobian(ctx, result, out, f, x, N, lo, hi)
     if fid is None:
         prog = _try_trace("array", f, n) if (fuse and y is None) else None
         if _usable(ctx, prog):
             try:
-                return _program_jacobian(ctx, prog, result, out, x, N, lo, hi)
+                c0 = ctx.jit_stats()
+                r = _program_jacobian(ctx, prog, result, out, x, N, lo, hi)
+                c1 = ctx.jit_stats()
+                cfg.last_path = "program:specialised" if (c1["compiled"] + c1["cache_hits"]) > (c0["compiled"] + c0["cache_hits"]) else "program:interpreted"
+                return r
             except _lib.UnsupportedOp:
                 if not prog.needs_jit:
                     raise
+        cfg.last_path = "loop:eager"
+        _warn_loop("jacobian", f, n, N, cfg)
         return _loop_jacobian(ctx, result, out, f, x, cfg, y, lo, hi)
+    cfg.last_path = "catalogue"
     params = params or getattr(f, "params", {}) or {}
     host = not isinstance(x, _DeviceArray)
     xd = ctx.array(x) if host else x
@@ -773,7 +833,9 @@ def hessian_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None):
     if H.shape != (n, n) or not H.flags.f_contiguous:
         raise DimensionMismatch("hessian!: result must be a column-major n x n float64 matrix")
     if fid is None:
+        cfg.last_path = "program:specialised" if ctx.jit_enabled() else "program:interpreted"
         return _program_hessian(ctx, result, H, f, x, N, lo, hi)
+    cfg.last_path = "catalogue"
     xh = np.ascontiguousarray(x.numpy() if isinstance(x, _DeviceArray) else x, dtype=np.float64).ravel()
     g = np.zeros(n)
     val = C.c_double(0.0)

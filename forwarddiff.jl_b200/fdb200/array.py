@@ -94,7 +94,15 @@ class Context:
         return dict(compiled=a.value, cache_hits=b.value, failures=c.value, last_log=log.decode() if log else "")
 
     def set_stream(self, cuda_stream_ptr):
-        self.check(self.lib.fdb_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+        """Run this context's kernels and copies on a caller-owned CUDA stream.  A handle of 0 -- what torch reports for
+        its default stream -- is the LEGACY DEFAULT STREAM and is passed as cudaStreamLegacy (0x1): the C ABI reserves
+        NULL for "go back to the context's own non-blocking stream" (use_own_stream()), which does not synchronise with
+        the default stream at all."""
+        ptr = int(cuda_stream_ptr or 0)
+        self.check(self.lib.fdb_set_stream(self.h, C.c_void_p(ptr if ptr != 0 else 1)))
+
+    def use_own_stream(self):
+        self.check(self.lib.fdb_set_stream(self.h, None))
 
     def stream(self):
         s = C.c_void_p()

@@ -178,6 +178,9 @@ class _ShardedColumns:
         per = self.lay["per"]
         self.x_t = torch.empty(self.n, dtype=torch.float64, device=self.dev)
         self.x_a = ctx.wrap(self.x_t.data_ptr(), self.n, keepalive=self.x_t)
+        # kernels, torch copies and NCCL on ONE stream.  torch's default stream has handle 0 = the legacy default stream;
+        # Context.set_stream passes that as cudaStreamLegacy (NULL would mean the context's own non-blocking stream,
+        # which does not order against torch's copies at all)
         ctx.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
         self.full = None
         self._mat = self.m * per * self.world                     # padded full matrix (whole chunks per rank)
@@ -220,8 +223,8 @@ class _ShardedColumns:
         or one all-gather of the padded column blocks (nccl)."""
         import torch.distributed as dist
         if self.xch is not None:
-            self.xch.barrier()
-            return self.full[: self.m * self.n]
+            self.xch.barrier()                    # asynchronous; a barrier that times out poisons the context: the next
+            return self.full[: self.m * self.n]   # ctx.sync() / download / full_matrix() raises instead of returning stale data
         per = self.lay["per"]
         if self.full is None:
             self.full = self.torch.empty(self.m * per * self.world, dtype=self.torch.float64, device=self.dev)
@@ -232,7 +235,9 @@ class _ShardedColumns:
         return self.full[: self.m * self.n]
 
     def full_matrix(self):
-        return self.gather().cpu().numpy().reshape((self.m, self.n), order="F")
+        host = self.gather().cpu().numpy().reshape((self.m, self.n), order="F")
+        self.ctx.sync()                           # raises if an exchange barrier gave up on a peer (the matrix would be stale)
+        return host
 
     def close(self):
         if self.xch is not None:
@@ -333,7 +338,7 @@ class ShardedGradient:
         dev = torch.device("cuda", ctx.device)
         self.x_t = torch.empty(self.n, dtype=torch.float64, device=dev)
         self.x_a = ctx.wrap(self.x_t.data_ptr(), self.n, keepalive=self.x_t)
-        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)     # kernels and NCCL on one stream
+        ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)     # kernels, copies and NCCL on one stream (0 = legacy default stream)
         glen = -(-max(self.lay["padded"], self.n) // 32) * 32
         slot = glen + 32                                               # one result: gradient | value
         self.xch = _make_exchange(ctx, 2 * slot, group, exchange) if self.world > 1 or exchange == "p2p" else None
@@ -391,6 +396,7 @@ class ShardedGradient:
         if out_host_pinned is not None:
             out_host_pinned.copy_(self.g_t[:self.n], non_blocking=True)
             self.torch.cuda.current_stream().synchronize()
+            self.ctx.sync()                       # raises if an exchange barrier gave up on a peer (the result would be stale)
             return out_host_pinned
         return self.g_t[:self.n]
 

@@ -22,9 +22,12 @@
  *    which is the reference's AoS field order (src/dual.jl:14-16,357-360);
  *  - host-side `*_aos` buffers use that AoS order: element e occupies
  *    doubles [e*P, (e+1)*P), P = number of planes;
- *  - one context per process and per GPU (one process per GPU); calls on a
- *    context are issued on its CUDA stream and are synchronous unless the
- *    context was put in async mode with fdb_set_async(ctx, 1);
+ *  - one context per GPU.  A process may own several contexts (one host process driving all
+ *    GPUs: fdb_multi_*), or there may be one process per GPU (fdb_exchange_* over CUDA IPC).
+ *    Every entry point makes its context's device current for the duration of the call and
+ *    restores the caller's.  Calls on a context are issued on its CUDA stream and are
+ *    synchronous unless the context was put in async mode with fdb_set_async(ctx, 1);
+ *  - a context is not re-entrant: one in-flight API call per context;
  *  - there is no CPU fallback: without a CUDA device fdb_init fails.
  */
 #ifndef FDB200_H
@@ -86,7 +89,10 @@ int fdb_shutdown(fdb_ctx* ctx);
 const char* fdb_last_error(fdb_ctx* ctx);          /* ctx may be NULL: last error of a failed fdb_init */
 int fdb_sync(fdb_ctx* ctx);
 int fdb_set_async(fdb_ctx* ctx, int async);       /* 1: calls return after enqueueing (benchmarks) */
-int fdb_set_stream(fdb_ctx* ctx, void* cuda_stream); /* adopt a caller-owned cudaStream_t (NULL = own stream) */
+/* adopt a caller-owned cudaStream_t.  NULL returns to the context's own (non-blocking) stream -- it does NOT mean the
+ * CUDA default stream: to run on the legacy default stream (what torch calls its default stream, handle 0) pass
+ * cudaStreamLegacy = (void*)0x1, for the per-thread default stream cudaStreamPerThread = (void*)0x2. */
+int fdb_set_stream(fdb_ctx* ctx, void* cuda_stream);
 int fdb_get_stream(fdb_ctx* ctx, void** cuda_stream);
 int fdb_set_nansafe(fdb_ctx* ctx, int enabled);   /* `nansafe_mode` preference, src/prelude.jl:1 */
 /* 1 (default): terms that touch no seeded position are evaluated on one representative
@@ -302,6 +308,59 @@ int fdb_gradient_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, 
                       int64_t chunk_hi, double* grad_host, double* value_host);
 int fdb_hessian_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, int N, int64_t chunk_lo,
                      int64_t chunk_hi, double* H_host, int64_t ldH, double* grad_host, double* value_host);
+/* jacobian!(result, f, x, cfg) / jacobian!(result, f!, y, x, cfg) on host arrays (src/jacobian.jl:57-87): J_host is
+ * column-major m x xlen (ldJ), only the columns of the requested chunks are written; y_host (may be NULL) receives
+ * value.(ydual) when the range includes the last chunk.  A_host (m x xlen, lda) / b_host are the target's parameters
+ * (NULL for targets without); reuse_params = 1: A and b are unchanged since the previous host call of the same shape
+ * on this context and are not uploaded again. */
+int fdb_jacobian_host(fdb_ctx* ctx, int fn, const double* x_host, int64_t xlen, int64_t m, int N, const double* A_host, int64_t lda,
+                      const double* b_host, double alpha, int reuse_params, int64_t chunk_lo, int64_t chunk_hi, double* J_host,
+                      int64_t ldJ, double* y_host);
+/* page-lock a caller-owned host buffer (x, a result) so that the copies of the host entry points are asynchronous and,
+ * with several devices, overlap (cudaHostRegister, portable) */
+int fdb_host_register(void* ptr, int64_t bytes);
+int fdb_host_unregister(void* ptr);
+
+/* ---- one host process, several GPUs ("one context drives all visible devices") ----------------
+ * What `ForwardDiff.gradient!(out, f, x, cfg)` (src/gradient.jl:35-44), `jacobian!` (src/jacobian.jl:57-87) and
+ * `hessian!` (src/hessian.jl:31-37) called from ONE Julia session bind to.  fdb_multi_init creates one context per
+ * device (ndev <= 0: all visible devices, at most FDB_MAX_RANKS; devices == NULL: 0..ndev-1).  Device i of n owns the
+ * contiguous chunk range fdb_plan_chunks(xlen, N, i, n) gives.
+ *   fdb_multi_*_host: inputs on the host, complete result on the host.  Every device's sweeps are launched before
+ *       the host waits for any; each device copies its own result slice (gradient entries / column block) straight
+ *       into the caller's buffer, so there is no inter-GPU traffic.
+ *   fdb_multi_*_resident: inputs and results live in symmetric exchange arenas (fdb_multi_exchange_create: one arena
+ *       per device, linked in-process with cudaDeviceEnablePeerAccess -- no CUDA IPC); arguments are offsets in
+ *       doubles into the arena (the same on every device; -1 = not wanted, for optional outputs).  The sweep kernels
+ *       store every extracted entry into every peer's arena and a device-side flag barrier follows: on return the
+ *       COMPLETE result is resident on every device.  Replicated inputs go in with fdb_multi_upload.
+ * Errors: the status of the first failing device; fdb_multi_last_error names the device. */
+typedef struct fdb_multi fdb_multi;
+int fdb_multi_init(int ndev, const int* devices, fdb_multi** out);
+int fdb_multi_shutdown(fdb_multi* g);
+int fdb_multi_size(const fdb_multi* g);
+fdb_ctx* fdb_multi_ctx(fdb_multi* g, int i);        /* per-device context: fdb_set_nansafe etc., fdb_array_alloc for parameters */
+const char* fdb_multi_last_error(fdb_multi* g);     /* g may be NULL: last error of a failed fdb_multi_init */
+int fdb_multi_sync(fdb_multi* g);
+int fdb_multi_gradient_host(fdb_multi* g, int fn, const double* x_host, int64_t xlen, int N, double* grad_host, double* value_host);
+int fdb_multi_jacobian_host(fdb_multi* g, int fn, const double* x_host, int64_t xlen, int64_t m, int N, const double* A_host, int64_t lda,
+                            const double* b_host, double alpha, int reuse_params, double* J_host, int64_t ldJ, double* y_host);
+int fdb_multi_hessian_host(fdb_multi* g, int fn, const double* x_host, int64_t xlen, int N, double* H_host, int64_t ldH, double* grad_host,
+                           double* value_host);
+struct fdb_exchange;
+int fdb_multi_exchange_create(fdb_multi* g, int64_t n_doubles, struct fdb_exchange** xs /* fdb_multi_size(g) entries */);
+int fdb_multi_exchange_destroy(fdb_multi* g, struct fdb_exchange** xs);
+int fdb_multi_barrier(fdb_multi* g, struct fdb_exchange* const* xs);
+int fdb_multi_upload(fdb_multi* g, struct fdb_exchange* const* xs, int64_t offset, const double* host, int64_t count);
+int fdb_multi_download(fdb_multi* g, struct fdb_exchange* const* xs, int device_index, int64_t offset, double* host, int64_t count);
+int fdb_multi_gradient_resident(fdb_multi* g, struct fdb_exchange* const* xs, int fn, int64_t x_off, int64_t xlen, int N, int64_t grad_off,
+                                int64_t value_off);
+/* A, b: one plain device array per device (allocated on fdb_multi_ctx(g, i)), or NULL */
+int fdb_multi_jacobian_resident(fdb_multi* g, struct fdb_exchange* const* xs, int fn, int64_t x_off, int64_t xlen, int64_t m, int N,
+                                const fdb_array* const* A, int64_t lda, const fdb_array* const* b, double alpha, int64_t J_off, int64_t ldJ,
+                                int64_t y_off);
+int fdb_multi_hessian_resident(fdb_multi* g, struct fdb_exchange* const* xs, int fn, int64_t x_off, int64_t xlen, int N, int64_t H_off,
+                               int64_t ldH, int64_t grad_off, int64_t value_off);
 
 /* ---- multi-GPU result exchange over NVLink peer memory ------------
  * One process per GPU.  The reference's result (`result` of src/gradient.jl:141-152, the Jacobian of
@@ -322,6 +381,12 @@ int fdb_exchange_create(fdb_ctx* ctx, int64_t n_doubles, int rank, int world, fd
 int fdb_exchange_handle(fdb_exchange* x, unsigned char handle[FDB_IPC_HANDLE_BYTES]);
 /* handles: world * FDB_IPC_HANDLE_BYTES bytes in rank order (this rank's own entry is ignored) */
 int fdb_exchange_connect(fdb_exchange* x, const unsigned char* handles);
+/* the same when all `world` exchanges belong to contexts of THIS process (xs[r] = rank r): peer access is enabled both
+ * ways and the arenas are linked directly -- CUDA IPC cannot open a handle in the process that exported it */
+int fdb_exchange_connect_local(fdb_exchange* const* xs, int world);
+/* a barrier that waits longer than this for a peer gives up (default 20 s), counts a timeout and POISONS the context:
+ * fdb_sync, every synchronous call and every download on it then fail -- results since the timeout are incomplete */
+int fdb_exchange_set_timeout(fdb_exchange* x, double seconds);
 /* level-0 view of n doubles (plane stride ld >= n) at `offset` doubles into the local arena */
 int fdb_exchange_view(fdb_exchange* x, int64_t offset, int64_t n, int64_t ld, fdb_array** out);
 int fdb_exchange_enable(fdb_ctx* ctx, fdb_exchange* x_or_null);

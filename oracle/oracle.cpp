@@ -633,7 +633,8 @@ void third_order_vector_mode(int fn, const double* x, double* T3) {
         case 3: { const int NN = 3; CALL; } break;  case 4: { const int NN = 4; CALL; } break;   \
         case 5: { const int NN = 5; CALL; } break;  case 6: { const int NN = 6; CALL; } break;   \
         case 7: { const int NN = 7; CALL; } break;  case 8: { const int NN = 8; CALL; } break;   \
-        case 12: { const int NN = 12; CALL; } break;                                       \
+        case 9: { const int NN = 9; CALL; } break;  case 10: { const int NN = 10; CALL; } break; \
+        case 11: { const int NN = 11; CALL; } break; case 12: { const int NN = 12; CALL; } break;\
         default: return -1;                                                                \
     }
 

@@ -322,7 +322,6 @@ def test_gradient_vs_oracle_all_chunk_sizes(ctx, oracle, fn, N):
 
 def test_gradient_lane_sharing_is_bit_identical(ctx):
     x = np.random.default_rng(2).uniform(0.5, 1.5, 5000)
-    x[100] = np.inf if False else x[100]
     for fn in (F.rosenbrock, F.ackley):
         cfg = fdb200.GradientConfig(fn, x, fdb200.Chunk(12))
         a = fdb200.gradient(fn, x, cfg, ctx=ctx)
@@ -510,8 +509,6 @@ def test_hessian_reference_golden(ctx):
 @pytest.mark.parametrize("N", list(range(1, 13)))
 def test_hessian_vs_oracle(ctx, oracle, N):
     for n in sorted({N, N + 1, 13, 100} - set(range(N))):
-        if N not in (1, 2, 3, 4, 5, 6, 7, 8, 12):
-            continue                                # oracle instantiates nested duals for these N only
         x = np.random.default_rng(n).uniform(0.5, 1.5, n)
         for fn in ("rosenbrock", "sumsq", "ackley"):   # ackley: two sums + exp/sqrt after the reductions (nested-dual finalize)
             res = fdb200.HessianResult(x)
