@@ -37,6 +37,10 @@ METRIC = "rosenbrock_gradient_evals_per_sec"
 # (SASS of gradient_sweep_kernel<Rosenbrock,12,false,256,true>: 9 DMUL + 11 DADD)
 DP_OPS_PER_TERM_SHARED = 20
 DP_OPS_PER_TERM_FULL = 133          # all 12 lanes: 120 in the term + 13 accumulate (lane sharing off)
+# FP64-pipe instructions (thread level) per element per chunk sweep / per term per chunk pair, measured with ncu on the C2 Ackley launch
+# and the C5 Hessian launch (profiles/r02_fp64_counts.md): sum of smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on / units
+ACKLEY_FP64_ISSUE_PER_TERM = 0.0    # filled in from the ncu capture (0 = not yet measured: roofline frac reads 0)
+HESSIAN_FP64_ISSUE_PER_TERM = 0.0
 
 
 def load_peaks():
@@ -306,6 +310,12 @@ def main():
 
     exchange = sg.exchange
     xch_timeouts = sg.xch.timeouts() if sg.xch is not None else 0
+    sharded = None
+    if world > 1 and not args.no_extras:
+        try:
+            sharded = extras_sharded(ctx, torch, dist, dev, rank, world, flush)       # collective: every rank takes part
+        except Exception as e:
+            sharded = {"error": repr(e)}
     if rank != 0:
         sg.close()
         if world > 1:
@@ -368,6 +378,8 @@ def main():
             line["extra"] = extras(ctx, torch, dev, flush, hbm_peak, dp_peak)
         except Exception as e:                                    # extras never invalidate the headline line
             line["extra"] = {"error": repr(e)}
+    if sharded is not None:
+        line["extra_sharded"] = sharded
     if world > 1 and exchange == "p2p":
         line["exchange_compare"] = {"p2p_fused_ms_per_step": ms_per_step, "nccl_allgather_ms_per_step": tot_nccl / K,
                                     "barrier_timeouts": int(xch_timeouts)}
@@ -377,10 +389,124 @@ def main():
         dist.destroy_process_group()
 
 
-def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
-    """Other BASELINE.json configs and the generic HBM-bound kernels, each timed with CUDA events (3 reps, L2 flushed)."""
+def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
+    """C3, C4 (the full 34.4 GB Jacobian) and C5 with their chunk sweeps sharded over the ranks (collective: every rank calls it).
+    Per config, ms per evaluation (median of the reps, max over ranks, CUDA events, L2 flushed between reps) for
+      sharded_resident : every rank sweeps its chunk range into its own column block, no exchange (the result stays sharded);
+      gathered_p2p     : the sweep kernels also store every entry into all peers' arenas over NVLink + device-side flag barrier
+                         (the complete matrix is resident on every rank);
+      gathered_nccl    : the sharded-resident sweep followed by one NCCL all-gather of the column blocks;
+    and a bit-for-bit check of sampled chunk column blocks (first / middle / last chunk, wherever they were computed) of both
+    gathered matrices against the same chunks recomputed on THIS rank alone."""
     import fdb200
     from fdb200 import functions as F
+    lib = ctx.lib
+    rng = np.random.default_rng(1)
+
+    def sync_all():
+        dist.barrier(); torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        fn(); sync_all()
+        ms = []
+        for _ in range(reps):
+            flush.zero_(); sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        tt = torch.tensor([float(np.median(ms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def all_ok(flag):
+        tt = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+        return bool(tt.item() > 0.5)
+
+    def check_columns(sh, recompute, nchunks, N, n, m):
+        """sampled chunks of the gathered matrix vs a single-rank recomputation, bit for bit"""
+        full = sh.gather()
+        torch.cuda.synchronize()
+        ok = True
+        for c in sorted({0, nchunks // 2, nchunks - 1}):
+            c0, c1 = c * N, min((c + 1) * N, n)
+            blk = torch.zeros(m * (c1 - c0), dtype=torch.float64, device=dev)
+            shifted = ctx.wrap(blk.data_ptr() - 8 * c0 * m, m * n, keepalive=blk)
+            recompute(c, shifted)
+            torch.cuda.synchronize()
+            ok = ok and bool(torch.equal(full[m * c0: m * c1], blk))
+        return all_ok(ok)
+
+    out = {}
+    configs = []
+    # C3: tanh.(A*x .+ b), n = m = 8192, Chunk{12}
+    m3 = 8192
+    A_h = (rng.uniform(-1, 1, m3 * m3) / np.sqrt(m3)).reshape((m3, m3), order="F"); b_h = rng.uniform(-1, 1, m3); x3 = rng.uniform(-1, 1, m3)
+    f3 = F.tanh_affine.with_params(A=A_h, b=b_h)
+    configs.append(("tanh_affine_jacobian_c3", "jac", f3, x3, m3, 12, 5,
+                    "per rank: DMMA contraction of its 683/W chunk sweeps (tile-count quantisation on 148 SMs) with the peer stores issued from the tile epilogue"))
+    # C4: Brusselator n = 65 536, Chunk{8}: 34.4 GB, every rank ends up holding all of it when gathered
+    M = 32768
+    xb = np.concatenate([1 + np.sin(2 * np.pi * np.arange(1, M + 1) / (M + 1)), 3 * np.ones(M)])
+    f4 = F.brusselator.with_params(alpha=(M + 1) ** 2 / 50.0)
+    configs.append(("brusselator_jacobian_c4", "jac", f4, xb, 2 * M, 8, 3,
+                    "gathered: each GPU's NVLink INGRESS of (W-1)/W of the 34.4 GB matrix; sharded-resident: HBM writes of 34.4/W GB"))
+    # C5: Rosenbrock Hessian n = 2048, Chunk{8}
+    xh = rng.random(2048)
+    configs.append(("rosenbrock_hessian_c5", "hess", F.rosenbrock, xh, 2048, 8, 10,
+                    "latency: 256/W outer chunks x 256 inner chunks of 2047 short terms per rank, then a 33.5 MB exchange"))
+
+    for name, kind, f, xhost, m, N, reps, limiting in configs:
+        n = xhost.size
+        nchunks = fdb200.chunk_plan(n, N)["nchunks"]
+        entry = {"ranks": world, "n": int(n), "chunk": N, "limiting_element": limiting}
+        res = {}
+        for mode in ("nccl", "p2p"):
+            try:
+                if kind == "jac":
+                    sh = fdb200.dist.ShardedJacobian(ctx, f, n, m, fdb200.JacobianConfig(f, xhost, fdb200.Chunk(N)), exchange=mode)
+                else:
+                    sh = fdb200.dist.ShardedHessian(ctx, f, n, fdb200.HessianConfig(f, xhost, fdb200.Chunk(N)), exchange=mode)
+            except Exception as e:
+                entry[f"gathered_{mode}_error"] = repr(e)
+                continue
+            sh.x_t.copy_(torch.from_numpy(xhost)); torch.cuda.synchronize()
+            if mode == "nccl":
+                res["sharded_resident_ms"] = timed(sh.sweep, reps)
+
+            def step():
+                sh.sweep(); sh.gather()
+            res[f"gathered_{mode}_ms"] = timed(step, reps)
+            if kind == "jac":
+                fid = sh.fid
+                rec = lambda c, arr: ctx.check(lib.fdb_jacobian_chunked(ctx.h, fid, sh.x_a.h, m, N, sh.A_a.h if sh.A_a else None, m,
+                                                                         sh.b_a.h if sh.b_a else None, sh.alpha, c, c + 1, arr.h, m, None))
+            else:
+                rec = lambda c, arr: ctx.check(lib.fdb_hessian_chunked(ctx.h, sh.fid, sh.x_a.h, N, c, c + 1, arr.h, n, None, None))
+            res[f"gathered_{mode}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
+            if sh.xch is not None:
+                res["barrier_timeouts"] = int(sh.xch.timeouts())
+            sh.close()
+            del sh
+            torch.cuda.empty_cache()
+        entry.update(res)
+        entry["result_bytes"] = 8 * int(m) * int(n)
+        if "gathered_p2p_ms" in res:
+            entry["gathered_p2p_ingress_GBps_per_gpu"] = 8.0 * m * n * (world - 1) / world / (res["gathered_p2p_ms"] * 1e-3) / 1e9
+        out[name] = entry
+    return out
+
+
+def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
+    """Other BASELINE.json configs and the generic HBM-bound kernels, each timed with CUDA events (L2 flushed between reps) and
+    each CHECKED, outside the timed region, against the CPU oracle on a sample of chunk sweeps (oracle/checks.py; the same
+    checks as tests/test_gpu_fullsize.py) or against a closed form: every entry carries `verified`."""
+    import fdb200
+    from fdb200 import functions as F
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import checks
+    import orc
+    o = orc.Oracle()
     lib = ctx.lib
     out = {}
 
@@ -395,17 +521,36 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
         return float(np.median(best))
 
     rng = np.random.default_rng(1)
-    # lane sharing off: all 12 lanes evaluated for every term of every chunk
-    x = ctx.array(rng.random(N_ELEMS)); g = ctx.zeros(N_ELEMS); v = ctx.zeros(1)
+    xs_host = rng.random(N_ELEMS)
+    x = ctx.array(xs_host); g = ctx.zeros(N_ELEMS); v = ctx.zeros(1)
     fid = fdb200._lib.FN
+    closed = checks.rosenbrock_closed_form(xs_host)
+    # lane sharing off: all 12 lanes evaluated for every term of every chunk
     ctx.set_lane_sharing(False)
     ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["rosenbrock"], x.h, CHUNK, 0, 8192, g.h, v.h)), reps=2)
     ctx.set_lane_sharing(True)
     full_s = ms * 1e-3 * 83334 / 8192
+    gh = g.numpy()[:8192 * CHUNK]
     out["rosenbrock_gradient_all_lanes"] = {"evals_per_s": 1.0 / full_s, "timed": "8192 of 83334 chunks, scaled",
-                                            "fp64_frac": DP_OPS_PER_TERM_FULL * (N_ELEMS - 1) * 8192 / (ms * 1e-3) / dp_peak}
+                                            "fp64_frac": DP_OPS_PER_TERM_FULL * (N_ELEMS - 1) * 8192 / (ms * 1e-3) / dp_peak,
+                                            "verified": {"ok": bool(np.allclose(gh, closed[:8192 * CHUNK], rtol=1e-12, atol=1e-11)),
+                                                         "against": "closed-form gradient, all 98304 entries of the timed chunk range"}}
+    # Ackley at C2's size.  Roofline: FP64 thread-level instructions of one launch, from the ncu capture of this kernel
+    # (profiles/r02_ackley_sweep_raw.csv: smsp__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on.sum; libdevice sincos is
+    # FP64 polynomial code, so they are all on the FP64 pipe), against the FP64 issue rate
     ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["ackley"], x.h, CHUNK, 0, -1, g.h, v.h)), reps=2)
-    out["ackley_gradient_c2"] = {"evals_per_s": 1e3 / ms, "ms": ms}
+    ga = g.numpy(); va = float(v.numpy()[0])
+    ver = checks.gradient_sample(o, "ackley", xs_host, CHUNK, ga, va)
+    ca = checks.ackley_closed_form(xs_host)
+    ver["closed_form_max_rel_err"] = float(np.max(np.abs(ga - ca)) / np.max(np.abs(ca)))
+    ver["ok"] = bool(ver["ok"] and ver["closed_form_max_rel_err"] <= 1e-12)
+    ack_issue = ACKLEY_FP64_ISSUE_PER_TERM * (N_ELEMS) * 83334 / (ms * 1e-3)
+    out["ackley_gradient_c2"] = {"evals_per_s": 1e3 / ms, "ms": ms, "verified": ver,
+                                 "roofline": {"bound": "fp64", "achieved": ack_issue / 1e12, "peak": dp_peak / 1e12, "unit": "T FP64 instr/s",
+                                              "frac": ack_issue / dp_peak,
+                                              "algorithmic": f"{ACKLEY_FP64_ISSUE_PER_TERM} FP64 pipe instructions (DADD+DMUL+DFMA, thread level) per element per chunk sweep "
+                                                             "(one sincos + x^2 on Dual{1}; ncu count of the launch / (n x chunks)) x 10^6 x 83334",
+                                              "peak_source": "fdb_measure_fp64_peak (FP64 instruction issue rate; a DFMA issues like a DMUL)"}}
     # the same Rosenbrock written as an ordinary callable on the device Dual array (broadcast + sum), flattened into
     # an op-program: what an arbitrary user f costs on the batched sweep -- through the kernel specialised for it at
     # run time (NVRTC instantiation of the sweep kernel template for the generated functor; the first call compiles,
@@ -421,33 +566,55 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
     ms = t(lambda: run_prog(-1), reps=2)
     st = ctx.jit_stats()
     out["rosenbrock_gradient_generic_callable_specialised"] = {"evals_per_s": 1e3 / ms, "ms": ms, "first_call_s": compile_s,
-                                                               "instructions": int(len(prog.term)), "jit": {k: st[k] for k in ("compiled", "cache_hits", "failures")}}
+                                                               "instructions": int(len(prog.term)), "jit": {k: st[k] for k in ("compiled", "cache_hits", "failures")},
+                                                               "verified": {"ok": bool(np.allclose(g.numpy(), closed, rtol=1e-11, atol=1e-11)),
+                                                                            "against": "closed-form gradient, all entries"}}
     ctx.set_jit(False)
     ms = t(lambda: run_prog(8192), reps=2)
     ctx.set_jit(True)
-    out["rosenbrock_gradient_generic_callable_interpreted"] = {"evals_per_s": 1.0 / (ms * 1e-3 * 83334 / 8192), "timed": "8192 of 83334 chunks, scaled"}
+    out["rosenbrock_gradient_generic_callable_interpreted"] = {"evals_per_s": 1.0 / (ms * 1e-3 * 83334 / 8192), "timed": "8192 of 83334 chunks, scaled",
+                                                               "verified": {"ok": bool(np.allclose(g.numpy()[:8192 * CHUNK], closed[:8192 * CHUNK], rtol=1e-11, atol=1e-11)),
+                                                                            "against": "closed-form gradient over the timed chunk range"}}
     # C1: n = 10 000, Chunk{10} (the reference's published 0.2825 s case, docs/src/user/advanced.md:70-72)
-    x1 = ctx.array(rng.random(10_000)); g1 = ctx.zeros(10_000)
+    x1h = rng.random(10_000)
+    x1 = ctx.array(x1h); g1 = ctx.zeros(10_000)
     ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["rosenbrock"], x1.h, 10, 0, -1, g1.h, v.h)), reps=5)
-    out["rosenbrock_gradient_c1"] = {"evals_per_s": 1e3 / ms, "ms": ms, "reference_published_s": 0.282529}
+    g1_ref, v1_ref = o.gradient("rosenbrock", x1h, 10)
+    out["rosenbrock_gradient_c1"] = {"evals_per_s": 1e3 / ms, "ms": ms, "reference_published_s": 0.282529,
+                                     "verified": {"ok": bool(np.array_equal(g1.numpy(), g1_ref) and abs(float(v.numpy()[0]) - v1_ref) <= 1e-12 * abs(v1_ref)),
+                                                  "against": "oracle, all 1000 chunk sweeps, gradient bit-exact"}}
     # C4: Brusselator Jacobian n = 65 536, Chunk{8}: 34.4 GB dense column-major result
     M = 32768; n = 2 * M
-    xb = ctx.array(np.concatenate([1 + np.sin(2 * np.pi * np.arange(1, M + 1) / (M + 1)), 3 * np.ones(M)]))
+    xbh = np.concatenate([1 + np.sin(2 * np.pi * np.arange(1, M + 1) / (M + 1)), 3 * np.ones(M)])
+    xb = ctx.array(xbh)
     J = fdb200.B200Array.alloc(ctx, n * n); y = ctx.zeros(n)
     al = (M + 1) ** 2 / 50.0
     ms = t(lambda: ctx.check(lib.fdb_jacobian_chunked(ctx.h, fdb200._lib.JFN["brusselator"], xb.h, n, 8, None, n, None, al, 0, -1, J.h, n, y.h)))
-    out["brusselator_jacobian_c4"] = {"evals_per_s": 1e3 / ms, "ms": ms,
+    out["brusselator_jacobian_c4"] = {"evals_per_s": 1e3 / ms, "ms": ms, "verified": checks.brusselator_sample(ctx, o, J, y, xbh, al, 8),
                                       "roofline": {"bound": "hbm", "achieved": 8.0 * n * n / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                                    "frac": 8.0 * n * n / (ms * 1e-3) / 1e9 / hbm_peak,
-                                                   "algorithmic": "8*m*n bytes of J written once (implicit seeds: no dual reads)"}}
+                                                   "algorithmic": "8*m*n bytes of J written once (implicit seeds: no dual reads); the peak is the measured COPY "
+                                                                  "rate (read+write), a write-only stream may exceed it"}}
     del J
-    # C5: Rosenbrock Hessian n = 2048, Chunk{8}
-    xh = ctx.array(rng.random(2048)); H = ctx.zeros(2048 * 2048); gh = ctx.zeros(2048)
-    ms = t(lambda: ctx.check(lib.fdb_hessian_chunked(ctx.h, fid["rosenbrock"], xh.h, 8, 0, -1, H.h, 2048, gh.h, v.h)))
-    out["rosenbrock_hessian_c5"] = {"evals_per_s": 1e3 / ms, "ms": ms}
-    # C3: tanh.(A*x .+ b) Jacobian n = m = 8192, Chunk{12} (CUDA-core kernel)
+    # C5: Rosenbrock Hessian n = 2048, Chunk{8}.  Roofline as for Ackley: ncu FP64 instruction count of the launch
+    # (profiles/r02_hessian_c5_raw.csv) / (terms x chunk pairs)
+    nh = 2048
+    xhh = rng.random(nh)
+    xh = ctx.array(xhh); H = ctx.zeros(nh * nh); ghd = ctx.zeros(nh)
+    ms = t(lambda: ctx.check(lib.fdb_hessian_chunked(ctx.h, fid["rosenbrock"], xh.h, 8, 0, -1, H.h, nh, ghd.h, v.h)))
+    Hh = H.numpy().reshape((nh, nh), order="F")
+    hess_issue = HESSIAN_FP64_ISSUE_PER_TERM * (nh - 1) * 256 * 256 / (ms * 1e-3)
+    out["rosenbrock_hessian_c5"] = {"evals_per_s": 1e3 / ms, "ms": ms,
+                                    "verified": checks.hessian_sample(o, "rosenbrock", xhh, 8, Hh, ghd.numpy(), float(v.numpy()[0])),
+                                    "roofline": {"bound": "fp64", "achieved": hess_issue / 1e12, "peak": dp_peak / 1e12, "unit": "T FP64 instr/s",
+                                                 "frac": hess_issue / dp_peak,
+                                                 "algorithmic": f"{HESSIAN_FP64_ISSUE_PER_TERM} FP64 pipe instructions per term per (inner, outer) chunk pair "
+                                                                "(far terms on Dual{Dual{1},1} = 4 lanes; ncu count of the launch / (2047 x 65536)) x 2047 terms x 256^2 pairs",
+                                                 "peak_source": "fdb_measure_fp64_peak"}}
+    # C3: tanh.(A*x .+ b) Jacobian n = m = 8192, Chunk{12} on the FP64 tensor cores
     m3 = 8192
-    A = ctx.array(rng.uniform(-1, 1, m3 * m3) / np.sqrt(m3)); b = ctx.array(rng.uniform(-1, 1, m3)); x3 = ctx.array(rng.uniform(-1, 1, m3))
+    A_h = (rng.uniform(-1, 1, m3 * m3) / np.sqrt(m3)).reshape((m3, m3), order="F"); b_h = rng.uniform(-1, 1, m3); x3_h = rng.uniform(-1, 1, m3)
+    A = ctx.array(A_h.ravel(order="F")); b = ctx.array(b_h); x3 = ctx.array(x3_h)
     J3 = ctx.zeros(m3 * m3); y3 = ctx.zeros(m3)
     run_c3 = lambda: ctx.check(lib.fdb_jacobian_chunked(ctx.h, fdb200._lib.JFN["tanh_affine"], x3.h, m3, 12, A.h, m3, b.h, 0.0, 0, -1, J3.h, m3, y3.h))
     # FP64 tensor-core denominator: cuBLAS DGEMM 8192^3 on this GPU (MEASURED_PEAKS.json has no FP64 figure)
@@ -456,49 +623,82 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
     dgemm_tf = 2.0 * m3 ** 3 / (dgemm_ms * 1e-3) / 1e12
     del ta, tb
     ms = t(run_c3, reps=3)
-    cols = 2 * 683                                   # lane sharing: value column + representative zero column per chunk
-    out["tanh_affine_jacobian_c3"] = {"evals_per_s": 1e3 / ms, "ms": ms, "kernels": "pack_b + dmma_gemm_kernel + tanh_affine_epilogue",
-                                      "roofline": {"bound": "tensor", "achieved": 2.0 * m3 * m3 * cols / (ms * 1e-3) / 1e12, "peak": dgemm_tf,
-                                                   "unit": "TFLOP/s", "frac": 2.0 * m3 * m3 * cols / (ms * 1e-3) / 1e12 / dgemm_tf,
+    fl_shared = 2.0 * m3 * m3 * 2 * 683             # what the lane-shared sweeps contract: value + representative zero lane per chunk
+    out["tanh_affine_jacobian_c3"] = {"evals_per_s": 1e3 / ms, "ms": ms, "kernels": "pack_b + dmma_gemm_kernel with the fused tanh / extraction epilogue",
+                                      "verified": checks.tanh_affine_sample(ctx, o, J3, y3, A_h, b_h, x3_h, 12),
+                                      "roofline": {"bound": "tensor", "achieved": fl_shared / (ms * 1e-3) / 1e12, "peak": dgemm_tf,
+                                                   "unit": "TFLOP/s", "frac": fl_shared / (ms * 1e-3) / 1e12 / dgemm_tf,
                                                    "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run",
-                                                   "algorithmic": "2*m*n flops per operand column, 2 columns per chunk x 683 chunks (whole call incl. pack and epilogue)"}}
+                                                   "algorithmic": "lane sharing: per chunk sweep only the value lane and ONE representative zero-partial lane go through the "
+                                                                  "contraction (2*m*n flops each), 683 sweeps = 0.183 TFLOP -- a 7.4x algorithmic saving over the reference's "
+                                                                  "13 lanes per sweep; whole call incl. pack and the fused epilogue (reads A once, writes J once)"}}
     ctx.set_lane_sharing(False)
     ms = t(run_c3, reps=2)
+    ver_all = checks.tanh_affine_sample(ctx, o, J3, y3, A_h, b_h, x3_h, 12)
     ctx.set_lane_sharing(True)
-    cols = 13 * 682 + 9
-    out["tanh_affine_jacobian_c3_all_lanes"] = {"evals_per_s": 1e3 / ms, "ms": ms,
-                                                "roofline": {"bound": "tensor", "achieved": 2.0 * m3 * m3 * 13 * 683 / (ms * 1e-3) / 1e12, "peak": dgemm_tf,
-                                                             "unit": "TFLOP/s", "frac": 2.0 * m3 * m3 * 13 * 683 / (ms * 1e-3) / 1e12 / dgemm_tf,
-                                                             "algorithmic": "2*m*n*13*683 = 1.19 TFLOP: A against [value | 12 one-hot partials] of every chunk"}}
+    fl_survey = 2.0 * m3 * m3 * (m3 + 1)            # every one-hot lane once + one value column = 1.0996 TFLOP
+    out["tanh_affine_jacobian_c3_all_lanes"] = {"evals_per_s": 1e3 / ms, "ms": ms, "verified": ver_all,
+                                                "roofline": {"bound": "tensor", "achieved": fl_survey / (ms * 1e-3) / 1e12, "peak": dgemm_tf,
+                                                             "unit": "TFLOP/s", "frac": fl_survey / (ms * 1e-3) / 1e12 / dgemm_tf,
+                                                             "algorithmic": "SURVEY.md 8d count 2*m*n*(n+1) = 1.0996 TFLOP: A against [x | every one-hot seed]; whole call "
+                                                                            "(operand build, pack, contraction, epilogue)"}}
     out["cublas_dgemm_8192_tflops"] = dgemm_tf
     # two layers tanh.(A2*tanh.(A1*x .+ b1) .+ b2), n = h = m = 8192: the second contraction has DENSE partials
-    A2 = ctx.array(rng.uniform(-1, 1, m3 * m3) / np.sqrt(m3)); b2 = ctx.array(rng.uniform(-1, 1, m3))
+    A2_h = (rng.uniform(-1, 1, m3 * m3) / np.sqrt(m3)).reshape((m3, m3), order="F"); b2_h = rng.uniform(-1, 1, m3)
+    A2 = ctx.array(A2_h.ravel(order="F")); b2 = ctx.array(b2_h)
     ms = t(lambda: ctx.check(lib.fdb_jacobian_mlp2_chunked(ctx.h, x3.h, m3, m3, 12, A.h, m3, b.h, A2.h, m3, b2.h, 0, -1, J3.h, m3, y3.h)), reps=2)
     fl = 2.0 * m3 * m3 * (2 * 683 + 13 * 683)
+    # closed form on a sample of rows: J[r, :] = (1 - y_r^2) * A2[r, :] @ (diag(1 - h^2) A1)
+    h1 = np.tanh(A_h @ x3_h + b_h); yy = np.tanh(A2_h @ h1 + b2_h)
+    rows = np.array([0, 1, 4095, 8190, 8191])
+    Jrows = np.stack([checks._dev_block(ctx, J3, c * m3, m3)[rows] for c in (0, 1, 11, 12, 4096, 8184, 8191)], axis=1)
+    refrows = ((1 - yy[rows] ** 2)[:, None] * A2_h[rows, :]) @ ((1 - h1 ** 2)[:, None] * A_h[:, [0, 1, 11, 12, 4096, 8184, 8191]])
+    err = float(np.max(np.abs(Jrows - refrows)) / np.max(np.abs(refrows)))
     out["mlp2_jacobian_8192_dense_partials"] = {"evals_per_s": 1e3 / ms, "ms": ms,
+                                                "verified": {"ok": bool(err <= 1e-11 and np.allclose(y3.numpy(), yy, rtol=1e-11, atol=1e-13)), "max_rel_err": err,
+                                                             "against": "closed form J = diag(1-y^2) A2 diag(1-h^2) A1 on 5 rows x 7 columns (first/last chunk), and y"},
                                                 "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": dgemm_tf, "unit": "TFLOP/s",
                                                              "frac": fl / (ms * 1e-3) / 1e12 / dgemm_tf,
                                                              "algorithmic": "layer 1: 2 shared columns per chunk; layer 2: 13 dense columns per chunk; 683 chunks"}}
     del A, J3, A2
-    # generic HBM-bound kernels on materialised Dual{12} arrays, n = 2^22 (436 MB per array > L2)
-    nn = 1 << 22
-    a = fdb200.B200DualArray.alloc(ctx, nn, 12); bb = fdb200.B200DualArray.alloc(ctx, nn, 12); o = fdb200.B200DualArray.alloc(ctx, nn, 12)
-    o1 = fdb200.B200DualArray.alloc(ctx, 1, 12)
-    xs = ctx.array(rng.uniform(0.5, 1.5, nn))
-    ctx.check(lib.fdb_seed_zero(ctx.h, a.h, xs.h, 0, 0)); ctx.check(lib.fdb_seed_zero(ctx.h, bb.h, xs.h, 0, 0))
-    dual_b = 8.0 * 13 * nn
+    # generic HBM-bound kernels on materialised Dual{N} arrays: n x N sweep, arrays > L2 or L2 flushed between reps
     gk = {}
-    for name, fn, nbytes in (
-            ("map1_exp", lambda: ctx.check(lib.fdb_map1(ctx.h, 2, o.h, a.h)), 2 * dual_b),
-            ("map1_pow2", lambda: ctx.check(lib.fdb_map1(ctx.h, 13, o.h, a.h)), 2 * dual_b),
-            ("map2_mul", lambda: ctx.check(lib.fdb_map2(ctx.h, 3, o.h, a.h, bb.h)), 3 * dual_b),
-            ("map2_scalar_add", lambda: ctx.check(lib.fdb_map2_scalar(ctx.h, 1, o.h, a.h, 1.5, 0)), 2 * dual_b),
-            ("reduce_sum", lambda: ctx.check(lib.fdb_reduce(ctx.h, 1, o1.h, a.h)), dual_b),
-            ("eval_rosenbrock_materialised", lambda: ctx.check(lib.fdb_eval_scalar_fn(ctx.h, 1, o1.h, a.h)), dual_b),
-            ("seed_zero_full", lambda: ctx.check(lib.fdb_seed_zero(ctx.h, a.h, xs.h, 0, 0)), dual_b + 8.0 * nn)):
-        ms = t(fn, reps=5)
-        gk[name] = {"ms": ms, "GBps": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / hbm_peak}
-    out["generic_kernels_dual12_n4M"] = gk
+    for nn, NN in ((1 << 22, 12), (1 << 20, 12), (1 << 24, 12), (1 << 24, 1), (1 << 24, 4), (1 << 24, 8), (1 << 22, 4)):
+        a = fdb200.B200DualArray.alloc(ctx, nn, NN); bb = fdb200.B200DualArray.alloc(ctx, nn, NN); oo = fdb200.B200DualArray.alloc(ctx, nn, NN)
+        o1 = fdb200.B200DualArray.alloc(ctx, 1, NN)
+        xsh = rng.uniform(0.5, 1.5, nn)
+        xs = ctx.array(xsh)
+        ctx.check(lib.fdb_seed_zero(ctx.h, a.h, xs.h, 0, 0)); ctx.check(lib.fdb_seed_zero(ctx.h, bb.h, xs.h, 0, 0))
+        ctx.check(lib.fdb_seed(ctx.h, a.h, xs.h, 1, NN))
+        dual_b = 8.0 * (NN + 1) * nn
+        row = {}
+        for name, fn, nbytes in (
+                ("map1_exp", lambda: ctx.check(lib.fdb_map1(ctx.h, 2, oo.h, a.h)), 2 * dual_b),
+                ("map1_pow2", lambda: ctx.check(lib.fdb_map1(ctx.h, 13, oo.h, a.h)), 2 * dual_b),
+                ("map2_mul", lambda: ctx.check(lib.fdb_map2(ctx.h, 3, oo.h, a.h, bb.h)), 3 * dual_b),
+                ("map2_scalar_add", lambda: ctx.check(lib.fdb_map2_scalar(ctx.h, 1, oo.h, a.h, 1.5, 0)), 2 * dual_b),
+                ("reduce_sum", lambda: ctx.check(lib.fdb_reduce(ctx.h, 1, o1.h, a.h)), dual_b),
+                ("eval_rosenbrock_materialised", lambda: ctx.check(lib.fdb_eval_scalar_fn(ctx.h, 1, o1.h, a.h)), dual_b),
+                ("seed_zero_full", lambda: ctx.check(lib.fdb_seed_zero(ctx.h, bb.h, xs.h, 0, 0)), dual_b + 8.0 * nn)):
+            ms = t(fn, reps=5)
+            row[name] = {"ms": ms, "GBps": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / hbm_peak}
+        # checks (outside the timed loops): sum of the seeded array, and the materialised Rosenbrock value
+        ctx.check(lib.fdb_reduce(ctx.h, 1, o1.h, a.h))
+        s1 = o1.numpy()[0]
+        ok = abs(s1[0] - float(np.sum(xsh))) <= 1e-12 * abs(float(np.sum(xsh))) and np.array_equal(s1[1:], np.ones(NN))
+        ctx.check(lib.fdb_eval_scalar_fn(ctx.h, 1, o1.h, a.h))
+        r1 = o1.numpy()[0]
+        ok = ok and abs(r1[0] - o.value("rosenbrock", xsh)) <= 1e-12 * abs(r1[0]) and \
+            np.allclose(r1[1:], checks.rosenbrock_closed_form(xsh)[:NN], rtol=1e-12, atol=1e-11)
+        ctx.check(lib.fdb_map2(ctx.h, 3, oo.h, a.h, bb.h))
+        head = oo.view(0, 64).numpy()
+        ok = ok and np.array_equal(head[:, 0], xsh[:64] * xsh[:64])
+        row["verified"] = {"ok": bool(ok), "against": "sum and materialised Rosenbrock of the seeded array vs numpy / oracle value / closed-form partials; Dual*Dual values bit-exact"}
+        gk[f"n=2^{int(np.log2(nn))},N={NN}"] = row
+        del a, bb, oo, o1, xs
+    out["generic_kernels"] = gk
+    out["all_verified"] = bool(all(vv.get("verified", {}).get("ok", True) for vv in out.values() if isinstance(vv, dict)) and
+                               all(r["verified"]["ok"] for r in gk.values()))
     return out
 
 

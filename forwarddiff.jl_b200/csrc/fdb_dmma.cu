@@ -4,57 +4,54 @@
 // Dual+Dual per element) is a dense contraction of A against the planes [value | partials]:
 //      Y[m x P] = A[m x k] * X[k x P],   P = N+1 columns per chunk, batched over chunks.
 // This is the only tensor-core kernel in the engine.  FP64 has no tcgen05 kind; the FP64 tensor path
-// on sm_100a is `mma.sync.aligned.m8n8k4.f64` (SASS DMMA).  Operand tiles are staged into shared
-// memory by the TMA engine with bulk asynchronous copies (`cp.async.bulk ... mbarrier::complete_tx`,
-// SASS UBLKCP) issued by one producer thread into a 4-stage mbarrier ring; eight consumer warps each own
-// a 32x32 accumulator tile in registers.  Rows of the shared tiles are padded (A: 132 doubles per
-// k-row, B: 36 doubles per column) so the m8n8k4 fragment loads are bank-conflict free.
+// on sm_100a is `mma.sync.aligned.m8n8k4.f64` (SASS DMMA).
 //
-// Arithmetic note: DMMA accumulates with fused multiply-adds in k order, the reference with separate
-// multiply and add; both are summation-order variants of the same dot product (tolerance 1e-12
-// relative, BASELINE.json north_star).
+// Kernel shape (round 2).  CTA tile 128 x BN x 16 (BN = 64 / 32 / 16 operand columns), eight DMMA warps (4 along m x 2
+// along n; the TMA issue rotates over them), a ring of mbarrier-guarded stages filled by TMA, TWO CTAs resident per SM (<= 111 KB of
+// shared memory and <= 112 registers each): while one CTA sits in its epilogue -- result stores, over NVLink when a peer
+// exchange is enabled -- the other keeps the DMMA pipe busy, so the stores overlap the math without any explicit
+// software pipelining between tiles.
+//   * A tile (128 m x 16 k of the column-major matrix): eight `cp.async.bulk.tensor.2d` boxes of 16 m x 16 k with
+//     CU_TENSOR_MAP_SWIZZLE_128B.  Each box is 16 rows (k) of 128 bytes (16 m); the swizzle XORs the 16-byte chunk index
+//     with k % 8.  An m8n8k4 step lets lane (g, t) pick ANY four k of the slab as long as the B fragment uses the same
+//     ones, so step s4 uses k = 8*(s4/2) + 2t + (s4%2): the XOR term 2t + e then spreads the sixteen lanes of a
+//     half-warp over all sixteen 8-byte banks -- conflict-free (round 1: dense [k][128 m] box, 4-way replays on every A
+//     fragment load, 3.5e9 excess wavefronts per C3 launch).  Out-of-range rows / k are zero-filled by the TMA unit.
+//   * B operand: pre-packed by pack_b_kernel into tiles of BN padded columns (16 + 4 doubles, bank-conflict free) whose
+//     k positions are already in fragment order (position s4*4 + t), staged by ONE bulk copy.
+//   * Thread blocks are rasterised in bands of eight m-tiles (column tile next, m-tile fastest): the blocks in flight share
+//     eight A row-blocks (L2-resident across the band) and a sliding window of B tiles, instead of re-reading all of B
+//     from DRAM for every m-tile row (round 1: 40.7 GB of DRAM reads against 1.7 GB algorithmic).
+//   * Epilogue: plain store of the accumulator fragments, or -- for the lane-shared chunk sweeps of tanh.(A*x .+ b) --
+//     the whole rest of the sweep fused in: z + b, tanh, 1 - val^2, the seeded window column, extraction into the
+//     Jacobian (local and mirrored into every peer's arena).  The product never goes to HBM.
+//
+// Arithmetic note: DMMA accumulates with fused multiply-adds in a permuted k order, the reference with separate
+// multiply and add in ascending k; both are summation-order variants of the same dot product (tolerance 1e-12
+// relative, BASELINE.json north_star).  One-hot operand columns come out exact.
 #include <cuda.h>
 
 #include "fdb_internal.h"
 #include "fdb_mirror.cuh"
 #include "fdb_targets.cuh"
+#include "fdb_tma.cuh"
 
 namespace fdb {
 
-constexpr int DM_BM = 128, DM_BN = 64, DM_KT = 32, DM_STAGES = 4;
-constexpr int DM_BS = DM_KT + 4;          // padded column of the packed B tile (doubles): stride = 8 mod 32 words
-constexpr int DM_A_BYTES = DM_KT * DM_BM * 8;            // dense [KT][BM] box written by one tensor copy
-constexpr int DM_B_ELEMS = DM_BN * DM_BS, DM_B_BYTES = DM_B_ELEMS * 8;
-constexpr int DM_STAGE_BYTES = DM_A_BYTES + DM_B_BYTES;
-constexpr int DM_SMEM = DM_STAGES * DM_STAGE_BYTES + 2 * DM_STAGES * 8 + 128;
+using tma::smem_u32; using tma::mbar_init; using tma::mbar_expect_tx; using tma::mbar_arrive; using tma::mbar_wait; using tma::bulk_g2s;
 
-FDB_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-FDB_DEV void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-FDB_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-FDB_DEV void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-FDB_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> shared (1-D), completion counted in bytes on an mbarrier
-FDB_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
+constexpr int DM_BM = 128, DM_BK = 16, DM_BS = DM_BK + 4;      // BS: padded column of the packed B tile (stride = 8 mod 32 words)
+constexpr int DM_A_BYTES = DM_BK * DM_BM * 8;                  // eight swizzled [16 k][16 m] boxes of 2 KB
+constexpr int DM_THREADS = 256;
+constexpr int DM_BAND = 8;                                     // m-tiles per rasterisation band
+template <int BN> struct DmCfg {
+    static constexpr int B_ELEMS = BN * DM_BS, B_BYTES = B_ELEMS * 8;
+    static constexpr int STAGE_BYTES = (DM_A_BYTES + B_BYTES + 1023) / 1024 * 1024;      // A tiles stay 1024-byte aligned (swizzle atom)
+    static constexpr int STAGES = (108 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;            // + alignment slack
+    static constexpr int WJ = BN / 16;                                                   // 8-column DMMA tiles per warp (warps: 4 m x 2 n)
+};
+
 // TMA tensor copy (2-D box of the column-major A described by a CUtensorMap) global -> shared
 FDB_DEV void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
@@ -65,94 +62,158 @@ FDB_DEV void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// slab position of logical k offset kk (0..15): DMMA step s4 = 2*(kk/8) + kk%2 reads k = 8*(s4/2) + 2t + s4%2 in lane t
+__host__ __device__ inline int dm_kpos(int kk) { return (kk >> 3) * 8 + (kk & 1) * 4 + ((kk & 7) >> 1); }
+
 // Pack B (k x ncols, column-major) into the tile order the kernel consumes: tile (j, s) holds columns
-// [64j, 64j+64) x k-rows [32s, 32s+32) as 64 padded columns of 36 doubles, contiguous, so that one
+// [BN*j, BN*j+BN) x k-rows [16s, 16s+16) as BN padded columns of 20 doubles in fragment order, contiguous, so that one
 // bulk copy stages it.  Out-of-range entries are zero.  Column c of B is read from column c % bmod when
 // bmod > 0 (a batch of chunks sharing identical operand columns).
-__global__ void pack_b_kernel(const double* __restrict__ B, int64_t ldb, int64_t k, int64_t ncols, int bmod, int nslab,
+__global__ void pack_b_kernel(const double* __restrict__ B, int64_t ldb, int64_t k, int64_t ncols, int bmod, int nslab, int BN,
                               double* __restrict__ Bp) {
     const int s = blockIdx.x, j = blockIdx.y;
-    double* tile = Bp + ((int64_t)j * nslab + s) * DM_B_ELEMS;
-    for (int e = threadIdx.x; e < DM_B_ELEMS; e += blockDim.x) {
+    const int belems = BN * DM_BS;
+    double* tile = Bp + ((int64_t)j * nslab + s) * belems;
+    for (int e = threadIdx.x; e < belems; e += blockDim.x) {
         const int c = e / DM_BS, kk = e - c * DM_BS;
-        const int64_t col = (int64_t)j * DM_BN + c, row = (int64_t)s * DM_KT + kk;
+        const int64_t col = (int64_t)j * BN + c, row = (int64_t)s * DM_BK + kk;
         double v = 0.0;
-        if (kk < DM_KT && col < ncols && row < k) v = B[row + (bmod > 0 ? col % bmod : col) * ldb];
-        tile[e] = v;
+        if (kk < DM_BK && col < ncols && row < k) v = B[row + (bmod > 0 ? col % bmod : col) * ldb];
+        tile[c * DM_BS + (kk < DM_BK ? dm_kpos(kk) : kk)] = v;
     }
 }
 
-// C[m x ncols] = A[m x k] * B[k x ncols]; A through a tensor map (box 128 x 32, zero fill out of bounds),
+// Fused epilogue of the lane-shared tanh.(A*x .+ b) chunk sweeps: operand columns come in pairs
+// (2c, 2c+1) = (value lane, representative zero-partial lane) of chunk chunk_lo + c, and the m8n8k4 accumulator
+// fragment gives thread (g, t) exactly such a pair for row g.
+struct TanhEpi {
+    const double* A; int64_t lda; const double* b; int64_t n; int N; int64_t chunk_lo, nchunks_total; int lastchunksize;
+    int64_t nc; double* J; int64_t ldJ; double* yout;
+};
+
+enum { DM_EPI_STORE = 0, DM_EPI_TANH = 1 };
+
+// C[m x ncols] = A[m x k] * B[k x ncols]; A through a tensor map (boxes 16 x 16, swizzle 128B, zero fill out of bounds),
 // B pre-packed (pack_b_kernel); btiles = number of distinct packed column tiles (1 when every tile is identical).
-__global__ void __launch_bounds__(288, 1) dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles,
-                                                          double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + DM_STAGES * DM_STAGE_BYTES);
-    uint64_t* empty = full + DM_STAGES;
+template <int BN, int EPI, bool NS, bool MIR>
+__global__ void __launch_bounds__(DM_THREADS, 2) dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles,
+                                                                 double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
+                                                                 int tiles_m, int tiles_n, const __grid_constant__ TanhEpi E,
+                                                                 const __grid_constant__ fdb_mirrors Mr) {
+    using Cfg = DmCfg<BN>;
+    constexpr int WJ = Cfg::WJ;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + Cfg::STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n0 = (int64_t)blockIdx.x * DM_BN, m0 = (int64_t)blockIdx.y * DM_BM;
-    const int nslab = (int)((k + DM_KT - 1) / DM_KT);
+    // band rasterisation: DM_BAND m-tiles x all column tiles per band, m-tile fastest
+    int tm, tn;
+    {
+        const int bid = blockIdx.x, per_band = DM_BAND * tiles_n, band = bid / per_band, within = bid - band * per_band;
+        const int rows = min(DM_BAND, tiles_m - band * DM_BAND);
+        tn = within / rows; tm = band * DM_BAND + (within - tn * rows);
+    }
+    const int64_t n0 = (int64_t)tn * BN, m0 = (int64_t)tm * DM_BM;
+    const int nslab = (int)((k + DM_BK - 1) / DM_BK);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < DM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        tma::mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == 8) {
-        // ---- producer: one thread, two TMA copies per k-slab -----------------------------------
-        if (lane == 0) {
-            const double* Bt = Bp + (int64_t)(blockIdx.x % btiles) * nslab * DM_B_ELEMS;
-            for (int s = 0; s < nslab; s++) {
-                const int st = s % DM_STAGES;
-                if (s >= DM_STAGES) mbar_wait(&empty[st], ((s / DM_STAGES) - 1) & 1);
-                unsigned char* stage = smem + st * DM_STAGE_BYTES;
-                mbar_expect_tx(&full[st], DM_STAGE_BYTES);
-                tma_load_2d(stage, &tmA, (int)m0, s * DM_KT, &full[st]);                         // A tile: [32 k][128 m]
-                bulk_g2s(stage + DM_A_BYTES, Bt + (int64_t)s * DM_B_ELEMS, DM_B_BYTES, &full[st]);   // packed B tile
-            }
-        }
-    } else {
-        // ---- consumers: 8 warps, 4 (M) x 2 (N), 32x32 accumulators each -----------------------
-        const int wm = warp & 3, wn = warp >> 2;
-        const int g = lane >> 2, t = lane & 3;
-        double acc[4][4][2];
+    // ---- eight DMMA warps, 4 (M) x 2 (N), 32 x (BN/2) accumulators each.  There is no dedicated producer warp (a ninth warp
+    // would cap the kernel at 96 registers with two CTAs per SM and spill accumulators): lane 0 of warp (s mod 8) issues
+    // the TMA copies of slab s + STAGES - 1 before that warp starts on slab s, so the issue cost rotates over the warps.
+    const int wm = warp & 3, wn = warp >> 2;
+    const int g = lane >> 2, t = lane & 3;
+    const double* Bt = Bp + (int64_t)(tn % btiles) * nslab * Cfg::B_ELEMS;
+    auto produce = [&](int sp) {          // called by one thread
+        const int st = sp % Cfg::STAGES;
+        if (sp >= Cfg::STAGES) mbar_wait(&empty[st], ((sp / Cfg::STAGES) - 1) & 1);
+        unsigned char* stage = smem + st * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[st], DM_A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int bx = 0; bx < DM_BM / 16; bx++)
+            tma_load_2d(stage + bx * 2048, &tmA, (int)m0 + 16 * bx, sp * DM_BK, &full[st]);           // [16 k][16 m], 128B-swizzled
+        bulk_g2s(stage + DM_A_BYTES, Bt + (int64_t)sp * Cfg::B_ELEMS, Cfg::B_BYTES, &full[st]);      // packed B tile
+    };
+    if (threadIdx.x == 0)
+        for (int sp = 0; sp < Cfg::STAGES - 1 && sp < nslab; sp++) produce(sp);
+    double acc[4][WJ][2];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-        for (int s = 0; s < nslab; s++) {
-            const int st = s % DM_STAGES;
-            mbar_wait(&full[st], (s / DM_STAGES) & 1);
-            const double* As = reinterpret_cast<const double*>(smem + st * DM_STAGE_BYTES);
-            const double* Bs = As + DM_KT * DM_BM;
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int k4 = 0; k4 < DM_KT / 4; k4++) {
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) a[i] = As[(k4 * 4 + t) * DM_BM + wm * 32 + i * 8 + g];
-#pragma unroll
-                for (int j = 0; j < 4; j++) b[j] = Bs[(wn * 32 + j * 8 + g) * DM_BS + k4 * 4 + t];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
+        for (int j = 0; j < WJ; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    // swizzled A fragment address (in doubles): box (wm*2 + i/2) * 256 + k * 16 + ((chunk ^ k%8) << 1) + (g & 1),
+    // chunk = (i & 1) * 4 + g / 2  ==>  base + krow + (((g/2) ^ x) << 1) ^ ((i & 1) << 3), + 256 for i >= 2
+    const int a_base = wm * 512 + (g & 1), gh = g >> 1;
+    const int b_off = (wn * (BN / 2) + g) * DM_BS + t;
+    for (int s = 0; s < nslab; s++) {
+        if (warp == (s & 7)) {
+            if (lane == 0 && s + Cfg::STAGES - 1 < nslab) produce(s + Cfg::STAGES - 1);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
         }
-        // ---- epilogue: accumulator fragments straight to C (thread holds C[g][2t], C[g][2t+1]) ---
+        const int st = s % Cfg::STAGES;
+        mbar_wait(&full[st], (s / Cfg::STAGES) & 1);
+        const double* As = reinterpret_cast<const double*>(smem + st * Cfg::STAGE_BYTES) + a_base;
+        const double* Bs = reinterpret_cast<const double*>(smem + st * Cfg::STAGE_BYTES + DM_A_BYTES) + b_off;
+#pragma unroll
+        for (int s4 = 0; s4 < DM_BK / 4; s4++) {
+            const int x = 2 * t + (s4 & 1);                            // k % 8 of this lane's k = 8*(s4/2) + x
+            const int o0 = ((s4 >> 1) * 8 + x) * 16 + ((gh ^ x) << 1), o1 = o0 ^ 8;
+            double a[4], b[WJ];
+            a[0] = As[o0]; a[1] = As[o1]; a[2] = As[o0 + 256]; a[3] = As[o1 + 256];
+#pragma unroll
+            for (int j = 0; j < WJ; j++) b[j] = Bs[j * 8 * DM_BS + s4 * 4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < WJ; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    if (EPI == DM_EPI_STORE) {
+        // ---- accumulator fragments straight to C (thread holds C[g][2t], C[g][2t+1]) ----------------------
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int64_t r = m0 + wm * 32 + i * 8 + g;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int64_t c = n0 + wn * 32 + j * 8 + 2 * t;
+            for (int j = 0; j < WJ; j++) {
+                const int64_t c = n0 + wn * (BN / 2) + j * 8 + 2 * t;
                 if (r < m) {
                     if (c < ncols) C[r + c * ldc] = acc[i][j][0];
                     if (c + 1 < ncols) C[r + (c + 1) * ldc] = acc[i][j][1];
                 }
+            }
+        }
+    } else {
+        // ---- z = A*xdual .+ b ; y = tanh.(z) (DiffRules: val = tanh(v), deriv = 1 - val^2) ; J[:, start+kk] = partials(y, kk)
+#pragma unroll
+        for (int j = 0; j < WJ; j++) {
+            const int64_t cl = (n0 + wn * (BN / 2) + j * 8) / 2 + t;            // local chunk of this thread's column pair
+            if (cl >= E.nc) continue;
+            const int64_t c = E.chunk_lo + cl;
+            const bool last = (c == E.nchunks_total - 1);
+            const int cs = last ? E.lastchunksize : E.N;
+            const int64_t start = last ? E.n - E.lastchunksize : c * (int64_t)E.N;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int64_t r = m0 + wm * 32 + i * 8 + g;
+                if (r >= m) continue;
+                const double zv = acc[i][j][0] + E.b[r];                            // Dual + Real: value only
+                const double val = tanh(zv);
+                const double deriv = 1.0 - val * val;
+                const double zero_lane = acc[i][j][1];
+                const double* Ac = E.A + r + start * E.lda;
+                double* Jc = E.J + r + start * E.ldJ;
+                for (int kk = 0; kk < cs; kk++) {
+                    const double p = zero_lane + __ldg(Ac + (int64_t)kk * E.lda) * 1.0;   // shared zero lane + the one seeded column of the window
+                    mstore_cs<MIR>(Mr, Jc + (int64_t)kk * E.ldJ, mulp<NS>(p, deriv));
+                }
+                if (E.yout && last) mstore(Mr, &E.yout[r], val);
             }
         }
     }
@@ -196,47 +257,88 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k) {
-    return (lda % 2 == 0) && ((((uintptr_t)A) & 15) == 0) && m >= DM_BM && k >= DM_KT && encode_tiled_fn() != nullptr;
-}
-size_t gemm_workspace_doubles(int64_t k, int64_t ncols, int bmod) {
-    const int64_t nslab = cdiv(k, DM_KT);
-    const int64_t btiles = (bmod > 0 && DM_BN % bmod == 0) ? 1 : cdiv(ncols, DM_BN);
-    return (size_t)(btiles * nslab * DM_B_ELEMS);
+    return (lda % 2 == 0) && ((((uintptr_t)A) & 15) == 0) && m >= DM_BM && k >= DM_BK && encode_tiled_fn() != nullptr;
 }
 
-// ws: gemm_workspace_doubles() doubles of device scratch for the packed B operand
+// Column-tile width for a contraction with `ncols` operand columns: the CTA tiles are equal-sized units dealt to the SMs
+// (two resident per SM sharing the DMMA pipe), so the run time is ceil(units / SMs) * BN up to the extra L2 -> SM traffic
+// of narrow tiles (the A tile is re-read once per column tile).
+static int pick_bn(fdb_ctx* ctx, int64_t m, int64_t ncols) {
+    if (ctx->dmma_bn == 16 || ctx->dmma_bn == 32 || ctx->dmma_bn == 64) return ctx->dmma_bn;
+    const int64_t tm = cdiv(m, DM_BM);
+    int best = 64; double best_cost = 1e300;
+    const int cand[3] = {64, 32, 16};
+    const double penalty[3] = {1.0, 1.04, 1.12};
+    for (int q = 0; q < 3; q++) {
+        const int64_t units = tm * cdiv(ncols, cand[q]);
+        const double cost = (double)cdiv(units, ctx->sm_count) * cand[q] * penalty[q];
+        if (cost < best_cost) { best_cost = cost; best = cand[q]; }
+    }
+    return best;
+}
+size_t gemm_workspace_doubles(int64_t k, int64_t ncols, int bmod) {
+    // sized for the narrowest tile (most padding): 16-column tiles of 20-double columns
+    const int64_t nslab = cdiv(k, DM_BK);
+    const int64_t cols = (bmod > 0 && 16 % bmod == 0) ? 64 : round_up(ncols, 64);
+    return (size_t)(cols * DM_BS * nslab);
+}
+
+template <int BN, int EPI, bool NS, bool MIR>
+static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws, int btiles, double* C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
+                          const TanhEpi& E, const fdb_mirrors& Mr) {
+    static unsigned long long configured = 0;
+    if (first_use_on_device(configured, ctx->device)) {
+        cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel<BN, EPI, NS, MIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<BN>::SMEM);
+        if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(dmma_gemm_kernel): %s", cudaGetErrorString(e));
+    }
+    const int tiles_m = (int)cdiv(m, DM_BM), tiles_n = (int)cdiv(ncols, BN);
+    dmma_gemm_kernel<BN, EPI, NS, MIR><<<(unsigned)(tiles_m * tiles_n), DM_THREADS, DmCfg<BN>::SMEM, ctx->stream>>>(tm, ws, btiles, C, ldc, m, k, ncols,
+                                                                                                                   tiles_m, tiles_n, E, Mr);
+    return FDB_OK;
+}
+
+// ws: gemm_workspace_doubles() doubles of device scratch for the packed B operand.  epi != null: the fused tanh epilogue
+// (C unused); otherwise the product is stored to C.
 int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m, int64_t k,
-                int64_t ncols, int bmod, double* ws, bool* used_dmma, int* nlaunch) {
+                int64_t ncols, int bmod, double* ws, bool* used_dmma, int* nlaunch, const TanhEpi* epi = nullptr, const fdb_mirrors* mirrors = nullptr) {
     if (m <= 0 || ncols <= 0) { if (nlaunch) *nlaunch = 0; return FDB_OK; }
     EncodeTiledFn enc = encode_tiled_fn();
     const bool ok = enc != nullptr && (lda % 2 == 0) && ((((uintptr_t)A) & 15) == 0) && k > 0 && ws != nullptr;
     if (used_dmma) *used_dmma = ok;
     if (!ok) {
+        if (epi) return fail(ctx, FDB_ERR_UNSUPPORTED, "launch_gemm: the fused epilogue needs the tensor-core path");
         constexpr int PC = 13;
         dim3 grid((unsigned)cdiv(m, 128), (unsigned)cdiv(ncols, PC));
         gemm_fallback_kernel<PC><<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, m, k, ncols, bmod);
         if (nlaunch) *nlaunch = 1;
         return FDB_OK;
     }
-    if (!ctx->dmma_configured) {       // a per-device attribute: every context (GPU) of the process sets it once
-        cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
-        if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(dmma_gemm_kernel): %s", cudaGetErrorString(e));
-        ctx->dmma_configured = true;
-    }
     CUtensorMap tm;
     const cuuint64_t gdim[2] = {(cuuint64_t)m, (cuuint64_t)k};
     const cuuint64_t gstride[1] = {(cuuint64_t)lda * 8};
-    const cuuint32_t box[2] = {DM_BM, DM_KT};
+    const cuuint32_t box[2] = {16, DM_BK};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(ctx, FDB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    const int nslab = (int)cdiv(k, DM_KT);
-    const int btiles = (bmod > 0 && DM_BN % bmod == 0) ? 1 : (int)cdiv(ncols, DM_BN);
+    const int BN = pick_bn(ctx, m, ncols);
+    const int nslab = (int)cdiv(k, DM_BK);
+    const int btiles = (bmod > 0 && BN % bmod == 0) ? 1 : (int)cdiv(ncols, BN);
     dim3 pg((unsigned)nslab, (unsigned)btiles);
-    pack_b_kernel<<<pg, 256, 0, ctx->stream>>>(B, ldb, k, ncols, bmod, nslab, ws);
-    dim3 grid((unsigned)cdiv(ncols, DM_BN), (unsigned)cdiv(m, DM_BM));
-    dmma_gemm_kernel<<<grid, 288, DM_SMEM, ctx->stream>>>(tm, ws, btiles, C, ldc, m, k, ncols);
+    pack_b_kernel<<<pg, 128, 0, ctx->stream>>>(B, ldb, k, ncols, bmod, nslab, BN, ws);
+    TanhEpi E0 = {}; fdb_mirrors M0;
+    const TanhEpi& E = epi ? *epi : E0;
+    const fdb_mirrors& Mr = mirrors ? *mirrors : M0;
+    int rc;
+#define FDB_GEMM_BN(EPI_, NS_, MIR_)                                                                              \
+    (BN == 64 ? launch_gemm_bn<64, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, E, Mr)                \
+     : BN == 32 ? launch_gemm_bn<32, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, E, Mr)              \
+                : launch_gemm_bn<16, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, E, Mr))
+    if (!epi) rc = FDB_GEMM_BN(DM_EPI_STORE, false, false);
+    else if (ctx->nansafe) rc = Mr.count ? FDB_GEMM_BN(DM_EPI_TANH, true, true) : FDB_GEMM_BN(DM_EPI_TANH, true, false);
+    else rc = Mr.count ? FDB_GEMM_BN(DM_EPI_TANH, false, true) : FDB_GEMM_BN(DM_EPI_TANH, false, false);
+#undef FDB_GEMM_BN
+    if (rc) return rc;
     if (nlaunch) *nlaunch = 2;
     return FDB_OK;
 }
@@ -244,13 +346,24 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
 // ---- batched chunk sweeps of f(x) = tanh.(A*x .+ b) on the DMMA contraction ------------------------------
 // Operand columns for the contraction.  SHARE: two columns per chunk, [x | 0] -- the value lane and the
 // representative zero-partial lane (identical for every chunk, so the GEMM reads them with bmod = 2).
-// Dense: N+1 columns per chunk, [x | one-hot seeds of the chunk] (src/apiutils.jl:125-143).
+// All lanes: [x | one-hot seed of every requested structural position] (src/apiutils.jl:125-143): every partial lane of
+// every chunk is a column of the contraction; the value lane, identical in every chunk, is contracted once
+// (2*m*n*(n+1) flops for the whole Jacobian).
 __global__ void build_operand_shared_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ B, int64_t ldb) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     B[j] = x[j];
     B[ldb + j] = 0.0;
 }
+// column 0 = x; column 1 + q = one-hot seed of structural position c0 + q
+__global__ void build_operand_onehot_kernel(const double* __restrict__ x, int64_t n, int64_t c0, int64_t ncolsJ, double* __restrict__ B, int64_t ldb) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t q = blockIdx.y;                       // 0: value column; 1..: blocks of 16 one-hot columns
+    if (j >= n) return;
+    if (q == 0) { B[j] = x[j]; return; }
+    for (int64_t col = (q - 1) * 16; col < min(q * 16, ncolsJ); col++) B[(1 + col) * ldb + j] = (j == c0 + col) ? 1.0 : 0.0;
+}
+// dense, per-chunk operand for consumers that need [value | N partial lanes] of each chunk (the two-layer target)
 __global__ void build_operand_dense_kernel(const double* __restrict__ x, int64_t n, int N, int64_t chunk_lo, int64_t nchunks_total,
                                            int lastchunksize, double* __restrict__ B, int64_t ldb) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,7 +376,7 @@ __global__ void build_operand_dense_kernel(const double* __restrict__ x, int64_t
     col[0] = x[j];
     for (int kk = 0; kk < N; kk++) col[(int64_t)(kk + 1) * ldb] = (j - start == kk && kk < cs) ? 1.0 : 0.0;
 }
-// epilogue: z = A*xdual .+ b ; y = tanh.(z) (DiffRules: val = tanh(v), deriv = 1 - val^2) ; J[:, start+k] = partials(y, k)
+// epilogue on a stored product: z = A*xdual .+ b ; y = tanh.(z) ; J[:, start+k] = partials(y, k)
 template <bool NS, bool SHARE, bool MIR>
 __global__ void __launch_bounds__(256) tanh_affine_epilogue_kernel(const double* __restrict__ Y, int64_t ldy, int P, const double* __restrict__ A,
                                                                   int64_t lda, const double* __restrict__ b, int64_t m, int64_t n, int N,
@@ -288,36 +401,57 @@ __global__ void __launch_bounds__(256) tanh_affine_epilogue_kernel(const double*
     }
     if (yout && last) mstore(Mr, &yout[r], val);
 }
+// the same for the one-hot operand layout: Y[:, 0] = A*x, Y[:, 1 + q] = partial lane of structural position c0 + q;
+// block (row block, strip of 16 columns): one tanh per row and strip
+template <bool NS, bool MIR>
+__global__ void __launch_bounds__(256) tanh_affine_onehot_epilogue_kernel(const double* __restrict__ Y, int64_t ldy, const double* __restrict__ b, int64_t m,
+                                                                         int64_t c0, int64_t ncolsJ, bool has_last, double* __restrict__ J, int64_t ldJ,
+                                                                         double* __restrict__ yout, const __grid_constant__ fdb_mirrors Mr) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const double val = tanh(Y[r] + b[r]);
+    const double deriv = 1.0 - val * val;
+    const int64_t q0 = (int64_t)blockIdx.y * 16, q1 = min(q0 + 16, ncolsJ);
+    for (int64_t q = q0; q < q1; q++) mstore_cs<MIR>(Mr, J + r + (c0 + q) * ldJ, mulp<NS>(Y[r + (1 + q) * ldy], deriv));
+    if (yout && has_last && blockIdx.y == 0) mstore(Mr, &yout[r], val);
+}
 
 int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_array* b, const fdb_array* x, int64_t m, int N, int64_t lo, int64_t hi,
                      int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ, double* yout, bool* used_dmma, const fdb_mirrors& Mr) {
     const int64_t n = x->n, nc = hi - lo;
-    const bool share = ctx->lane_sharing;
-    const int P = share ? 2 : N + 1;
     const int64_t ldb = round_up(n, 32), ldy = round_up(m, 32);
-    // scratch: operand columns + product columns
-    const int64_t bcols = share ? 2 : nc * P;
-    const size_t wsd = gemm_workspace_doubles(n, nc * P, share ? 2 : 0);
-    size_t need = ((size_t)(ldb * bcols + ldy * nc * P) + wsd + 64) * sizeof(double);
-    int rc = ensure_scratch(ctx, need); if (rc) return rc;
-    double* Bop = ctx->scratch; double* Y = ctx->scratch + ldb * bcols;
-    double* ws = Y + ldy * nc * P; ws = (double*)((((uintptr_t)ws) + 127) & ~(uintptr_t)127);
-    if (share) build_operand_shared_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(x->data, n, Bop, ldb);
-    else {
-        dim3 g((unsigned)cdiv(n, 256), (unsigned)nc);
-        build_operand_dense_kernel<<<g, 256, 0, ctx->stream>>>(x->data, n, N, lo, nchunks, lcs, Bop, ldb);
+    if (ctx->lane_sharing) {
+        // value lane + representative zero lane of every chunk through the contraction; everything after it fused into the tile epilogue
+        const size_t wsd = gemm_workspace_doubles(n, nc * 2, 2);
+        int rc = ensure_scratch(ctx, ((size_t)(ldb * 2) + wsd + 64) * sizeof(double)); if (rc) return rc;
+        double* Bop = ctx->scratch;
+        double* ws = Bop + ldb * 2; ws = (double*)((((uintptr_t)ws) + 127) & ~(uintptr_t)127);
+        build_operand_shared_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(x->data, n, Bop, ldb);
+        TanhEpi E = {A->data, lda, b->data, n, N, lo, nchunks, lcs, nc, J->data, ldJ, yout};
+        int ngemm = 0;
+        rc = launch_gemm(ctx, A->data, lda, Bop, ldb, nullptr, 0, m, n, nc * 2, 2, ws, used_dmma, &ngemm, &E, &Mr); if (rc) return rc;
+        return finish(ctx, 1 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma, fused epilogue)");
     }
+    // all lanes: [x | one-hot columns of the requested structural positions]
+    const int64_t c0 = lo * N, c1 = (hi == nchunks) ? n : hi * N, ncolsJ = c1 - c0, P = 1 + ncolsJ;
+    const size_t wsd = gemm_workspace_doubles(n, P, 0);
+    int rc = ensure_scratch(ctx, ((size_t)(ldb * P + ldy * P) + wsd + 64) * sizeof(double)); if (rc) return rc;
+    double* Bop = ctx->scratch; double* Y = Bop + ldb * P;
+    double* ws = Y + ldy * P; ws = (double*)((((uintptr_t)ws) + 127) & ~(uintptr_t)127);
+    dim3 gb((unsigned)cdiv(n, 256), (unsigned)(1 + cdiv(ncolsJ, 16)));
+    build_operand_onehot_kernel<<<gb, 256, 0, ctx->stream>>>(x->data, n, c0, ncolsJ, Bop, ldb);
     int ngemm = 0;
-    rc = launch_gemm(ctx, A->data, lda, Bop, ldb, Y, ldy, m, n, nc * P, share ? 2 : 0, ws, used_dmma, &ngemm); if (rc) return rc;
-    dim3 ge((unsigned)cdiv(m, 256), (unsigned)nc);
+    rc = launch_gemm(ctx, A->data, lda, Bop, ldb, Y, ldy, m, n, P, 0, ws, used_dmma, &ngemm); if (rc) return rc;
+    dim3 ge((unsigned)cdiv(m, 256), (unsigned)cdiv(ncolsJ, 16));
+    const bool has_last = (hi == nchunks);
     if (ctx->nansafe) {
-        if (share) { if (Mr.count) tanh_affine_epilogue_kernel<true, true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<true, true, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
-        else { if (Mr.count) tanh_affine_epilogue_kernel<true, false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<true, false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
+        if (Mr.count) tanh_affine_onehot_epilogue_kernel<true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, b->data, m, c0, ncolsJ, has_last, J->data, ldJ, yout, Mr);
+        else tanh_affine_onehot_epilogue_kernel<true, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, b->data, m, c0, ncolsJ, has_last, J->data, ldJ, yout, Mr);
     } else {
-        if (share) { if (Mr.count) tanh_affine_epilogue_kernel<false, true, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<false, true, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
-        else { if (Mr.count) tanh_affine_epilogue_kernel<false, false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); else tanh_affine_epilogue_kernel<false, false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, P, A->data, lda, b->data, m, n, N, lo, nchunks, lcs, J->data, ldJ, yout, Mr); }
+        if (Mr.count) tanh_affine_onehot_epilogue_kernel<false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, b->data, m, c0, ncolsJ, has_last, J->data, ldJ, yout, Mr);
+        else tanh_affine_onehot_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, b->data, m, c0, ncolsJ, has_last, J->data, ldJ, yout, Mr);
     }
-    return finish(ctx, 2 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma)");
+    return finish(ctx, 2 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma, all lanes)");
 }
 
 // ---- two layers: f(x) = tanh.(A2 * tanh.(A1*x .+ b1) .+ b2) -------------------------------------------------

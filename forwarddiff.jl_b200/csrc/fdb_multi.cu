@@ -116,7 +116,9 @@ static int jac_begin(fdb_ctx* ctx, int fn, const double* x_host, int64_t n, int6
     const int64_t ldn = round_up(n, 32), ld = round_up(m, 32), ncols = j.c1 - j.c0;
     j.ld = ld;
     const bool hasA = A_host != nullptr;
-    const size_t need = (size_t)(ldn + 2 * ld + ld * ncols + (hasA ? ld * n : 0)) * sizeof(double);
+    // with parameters the staging is sized for all n result columns, so that a later call with another chunk range (and
+    // reuse_params = 1) finds A and b where they are
+    const size_t need = (size_t)(ldn + 2 * ld + ld * (hasA ? n : ncols) + (hasA ? ld * n : 0)) * sizeof(double);
     if (reuse_params && ctx->hostws_bytes < need)
         return fail(ctx, FDB_ERR_BADARG, "fdb_jacobian_host: reuse_params = 1 but no previous call of this shape staged A and b on device %d", ctx->device);
     int rc = ensure_hostws(ctx, need); if (rc) return rc;

@@ -294,7 +294,7 @@ def _warn_loop(what, f, n, N, cfg):
     import warnings
     cfg.trace_error = _trace_failure.get(id(f))
     nchunks = -(-n // N)
-    if nchunks >= 64:
+    if nchunks >= 64 and cfg.trace_error is not None:      # fuse=False is the caller's own choice: no warning
         warnings.warn(f"{what}: {getattr(f, '__name__', f)!r} runs on the materialised chunk loop ({nchunks} chunks x one kernel per "
                       f"array statement) because it could not be flattened ({cfg.trace_error or 'fuse=False'}); see cfg.last_path",
                       SlowPathWarning, stacklevel=4)

@@ -100,6 +100,9 @@ int fdb_set_nansafe(fdb_ctx* ctx, int enabled);   /* `nansafe_mode` preference, 
 int fdb_set_lane_sharing(fdb_ctx* ctx, int enabled);
 /* 1 (default): A*xdual contractions run on FP64 tensor cores (DMMA) when shapes allow; 0: CUDA-core kernels */
 int fdb_set_dmma(fdb_ctx* ctx, int enabled);
+/* operand columns per thread-block tile of the DMMA contraction: 0 (default) = chosen per shape so that the equal-sized
+ * tiles fill the SMs evenly, or 16 / 32 / 64 (measurement knob) */
+int fdb_set_dmma_tile(fdb_ctx* ctx, int bn);
 int fdb_kernel_launches(fdb_ctx* ctx, int64_t* count); /* kernels launched on this context so far */
 const char* fdb_version(void);
 

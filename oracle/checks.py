@@ -79,7 +79,7 @@ def tanh_affine_sample(ctx, o, J_dev, y_dev, A, b, x, N, extra=()):
         ok &= bool(np.allclose(J, J_ref, rtol=RED_RTOL, atol=RED_RTOL * float(np.max(np.abs(J_ref)))))
         worst = max(worst, _rel_err(J, J_ref))
         if hi == nchunks and y_dev is not None:
-            ok &= bool(np.allclose(y_dev.numpy(), y_ref, rtol=RED_RTOL, atol=1e-15))
+            ok &= bool(np.allclose(y_dev.numpy(), y_ref, rtol=RED_RTOL, atol=1e-13))
         sampled.append(lo)
     return {"ok": bool(ok), "max_rel_err": worst, "sampled_chunks": sampled, "of_chunks": nchunks, "tolerance": RED_RTOL}
 

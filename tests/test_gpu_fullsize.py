@@ -77,7 +77,7 @@ def test_c3_tanh_affine_jacobian_full_size_on_dmma(ctx, oracle, share):
     J = Jd.numpy().reshape((m, n), order="F")
     ref = (1.0 - y * y)[:, None] * A
     assert np.max(np.abs(J - ref)) <= 1e-12 * np.max(np.abs(ref))
-    assert np.allclose(yd.numpy(), y, rtol=1e-12, atol=1e-15)
+    assert np.allclose(yd.numpy(), y, rtol=1e-12, atol=1e-13)           # |z| error ~1e-15 absolute; y passes through 0
 
 
 def test_c3_chunk_range_at_full_size_matches_the_full_sweep(ctx):
