@@ -98,8 +98,8 @@ enum { DM_EPI_STORE = 0, DM_EPI_TANH = 1 };
 template <int BN, int EPI, bool NS, bool MIR>
 __global__ void __launch_bounds__(DM_THREADS, 2) dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles,
                                                                  double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
-                                                                 int tiles_m, int tiles_n, const __grid_constant__ TanhEpi E,
-                                                                 const __grid_constant__ fdb_mirrors Mr) {
+                                                                 int tiles_m, int tiles_n, const int accumulate,
+                                                                 const __grid_constant__ TanhEpi E, const __grid_constant__ fdb_mirrors Mr) {
     using Cfg = DmCfg<BN>;
     constexpr int WJ = Cfg::WJ;
     extern __shared__ unsigned char smem_raw[];
@@ -184,8 +184,13 @@ __global__ void __launch_bounds__(DM_THREADS, 2) dmma_gemm_kernel(const __grid_c
             for (int j = 0; j < WJ; j++) {
                 const int64_t c = n0 + wn * (BN / 2) + j * 8 + 2 * t;
                 if (r < m) {
-                    if (c < ncols) C[r + c * ldc] = acc[i][j][0];
-                    if (c + 1 < ncols) C[r + (c + 1) * ldc] = acc[i][j][1];
+                    if (accumulate) {        // C += A*B: the second product of a Dual*Dual partial (fdb_dual_matmul)
+                        if (c < ncols) C[r + c * ldc] = C[r + c * ldc] + acc[i][j][0];
+                        if (c + 1 < ncols) C[r + (c + 1) * ldc] = C[r + (c + 1) * ldc] + acc[i][j][1];
+                    } else {
+                        if (c < ncols) C[r + c * ldc] = acc[i][j][0];
+                        if (c + 1 < ncols) C[r + (c + 1) * ldc] = acc[i][j][1];
+                    }
                 }
             }
         }
@@ -222,7 +227,8 @@ __global__ void __launch_bounds__(DM_THREADS, 2) dmma_gemm_kernel(const __grid_c
 // shape-generic fallback (any alignment): one thread per output row, columns in registers
 template <int PC>
 __global__ void __launch_bounds__(128) gemm_fallback_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
-                                                            double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols, int bmod) {
+                                                            double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols, int bmod,
+                                                            bool accumulate) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t c0 = (int64_t)blockIdx.y * PC;
     if (r >= m) return;
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(128) gemm_fallback_kernel(const double* __rest
         }
     }
 #pragma unroll
-    for (int j = 0; j < PC; j++) if (c0 + j < ncols) C[r + (c0 + j) * ldc] = acc[j];
+    for (int j = 0; j < PC; j++) if (c0 + j < ncols) C[r + (c0 + j) * ldc] = accumulate ? C[r + (c0 + j) * ldc] + acc[j] : acc[j];
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
@@ -285,7 +291,7 @@ size_t gemm_workspace_doubles(int64_t k, int64_t ncols, int bmod) {
 
 template <int BN, int EPI, bool NS, bool MIR>
 static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws, int btiles, double* C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
-                          const TanhEpi& E, const fdb_mirrors& Mr) {
+                          int accumulate, const TanhEpi& E, const fdb_mirrors& Mr) {
     static unsigned long long configured = 0;
     if (first_use_on_device(configured, ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel<BN, EPI, NS, MIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<BN>::SMEM);
@@ -293,14 +299,15 @@ static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws,
     }
     const int tiles_m = (int)cdiv(m, DM_BM), tiles_n = (int)cdiv(ncols, BN);
     dmma_gemm_kernel<BN, EPI, NS, MIR><<<(unsigned)(tiles_m * tiles_n), DM_THREADS, DmCfg<BN>::SMEM, ctx->stream>>>(tm, ws, btiles, C, ldc, m, k, ncols,
-                                                                                                                   tiles_m, tiles_n, E, Mr);
+                                                                                                                   tiles_m, tiles_n, accumulate, E, Mr);
     return FDB_OK;
 }
 
 // ws: gemm_workspace_doubles() doubles of device scratch for the packed B operand.  epi != null: the fused tanh epilogue
 // (C unused); otherwise the product is stored to C.
 int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m, int64_t k,
-                int64_t ncols, int bmod, double* ws, bool* used_dmma, int* nlaunch, const TanhEpi* epi = nullptr, const fdb_mirrors* mirrors = nullptr) {
+                int64_t ncols, int bmod, double* ws, bool* used_dmma, int* nlaunch, const TanhEpi* epi = nullptr, const fdb_mirrors* mirrors = nullptr,
+                bool accumulate = false) {
     if (m <= 0 || ncols <= 0) { if (nlaunch) *nlaunch = 0; return FDB_OK; }
     EncodeTiledFn enc = encode_tiled_fn();
     const bool ok = enc != nullptr && (lda % 2 == 0) && ((((uintptr_t)A) & 15) == 0) && k > 0 && ws != nullptr;
@@ -309,7 +316,7 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
         if (epi) return fail(ctx, FDB_ERR_UNSUPPORTED, "launch_gemm: the fused epilogue needs the tensor-core path");
         constexpr int PC = 13;
         dim3 grid((unsigned)cdiv(m, 128), (unsigned)cdiv(ncols, PC));
-        gemm_fallback_kernel<PC><<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, m, k, ncols, bmod);
+        gemm_fallback_kernel<PC><<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, m, k, ncols, bmod, accumulate);
         if (nlaunch) *nlaunch = 1;
         return FDB_OK;
     }
@@ -331,9 +338,9 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
     const fdb_mirrors& Mr = mirrors ? *mirrors : M0;
     int rc;
 #define FDB_GEMM_BN(EPI_, NS_, MIR_)                                                                              \
-    (BN == 64 ? launch_gemm_bn<64, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, E, Mr)                \
-     : BN == 32 ? launch_gemm_bn<32, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, E, Mr)              \
-                : launch_gemm_bn<16, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, E, Mr))
+    (BN == 64 ? launch_gemm_bn<64, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr)                \
+     : BN == 32 ? launch_gemm_bn<32, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr)              \
+                : launch_gemm_bn<16, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr))
     if (!epi) rc = FDB_GEMM_BN(DM_EPI_STORE, false, false);
     else if (ctx->nansafe) rc = Mr.count ? FDB_GEMM_BN(DM_EPI_TANH, true, true) : FDB_GEMM_BN(DM_EPI_TANH, true, false);
     else rc = Mr.count ? FDB_GEMM_BN(DM_EPI_TANH, false, true) : FDB_GEMM_BN(DM_EPI_TANH, false, false);
@@ -454,6 +461,38 @@ int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_ar
     return finish(ctx, 2 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma, all lanes)");
 }
 
+// The product lanes of `A * xdual` for chunks [lo, hi), left in the context's scratch for a consumer kernel that applies
+// an arbitrary elementwise program to z = A*x (fdb_program_matvec_jacobian_chunked).  Lane sharing: 2 columns per chunk
+// [value | zero lane]; all lanes: column 0 = value, column 1 + q = one-hot product of structural position lo*N + q.
+int matvec_product_lanes(fdb_ctx* ctx, const double* A, int64_t lda, int64_t m, const fdb_array* x, int N, int64_t lo, int64_t hi, int64_t nchunks,
+                         double** Y_out, int64_t* ldy_out, int* nlaunch) {
+    const int64_t n = x->n, nc = hi - lo;
+    const int64_t ldb = round_up(n, 32), ldy = round_up(m, 32);
+    int ngemm = 0, rc;
+    if (ctx->lane_sharing) {
+        const size_t wsd = gemm_workspace_doubles(n, nc * 2, 2);
+        rc = ensure_scratch(ctx, ((size_t)(ldb * 2 + ldy * nc * 2) + wsd + 64) * sizeof(double)); if (rc) return rc;
+        double* Bop = ctx->scratch; double* Y = Bop + ldb * 2;
+        double* ws = Y + ldy * nc * 2; ws = (double*)((((uintptr_t)ws) + 127) & ~(uintptr_t)127);
+        build_operand_shared_kernel<<<(unsigned)cdiv(n, 256), 256, 0, ctx->stream>>>(x->data, n, Bop, ldb);
+        rc = launch_gemm(ctx, A, lda, Bop, ldb, Y, ldy, m, n, nc * 2, 2, ws, nullptr, &ngemm); if (rc) return rc;
+        *Y_out = Y;
+    } else {
+        const int64_t c0 = lo * N, c1 = (hi == nchunks) ? n : hi * N, ncolsJ = c1 - c0, P = 1 + ncolsJ;
+        const size_t wsd = gemm_workspace_doubles(n, P, 0);
+        rc = ensure_scratch(ctx, ((size_t)(ldb * P + ldy * P) + wsd + 64) * sizeof(double)); if (rc) return rc;
+        double* Bop = ctx->scratch; double* Y = Bop + ldb * P;
+        double* ws = Y + ldy * P; ws = (double*)((((uintptr_t)ws) + 127) & ~(uintptr_t)127);
+        dim3 gb((unsigned)cdiv(n, 256), (unsigned)(1 + cdiv(ncolsJ, 16)));
+        build_operand_onehot_kernel<<<gb, 256, 0, ctx->stream>>>(x->data, n, c0, ncolsJ, Bop, ldb);
+        rc = launch_gemm(ctx, A, lda, Bop, ldb, Y, ldy, m, n, P, 0, ws, nullptr, &ngemm); if (rc) return rc;
+        *Y_out = Y;
+    }
+    *ldy_out = ldy;
+    if (nlaunch) *nlaunch = 1 + ngemm;
+    return FDB_OK;
+}
+
 // ---- two layers: f(x) = tanh.(A2 * tanh.(A1*x .+ b1) .+ b2) -------------------------------------------------
 // After the first layer the partials are dense, so the second `A * hdual` is a genuine dense contraction of A2
 // against [value | N partials] of every chunk: one DMMA GEMM m x h x (N+1)*nchunks.
@@ -563,6 +602,35 @@ extern "C" int fdb_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t
     int nl = 0;
     rc = launch_gemm(ctx, A->data, lda, B->data, ldb, C->data, ldc, m, k, ncols, 0, ws, nullptr, &nl); if (rc) return rc;
     return finish(ctx, nl, "fdb_matmul");
+}
+
+// C = A * B on matrices of Duals (both operands carry partials): the Dual*Dual body of src/dual.jl:260-300 summed over the inner
+// index, i.e.  value(C) = value(A)*value(B),  partial_j(C) = value(A)*partial_j(B) + partial_j(A)*value(B):  2N+1 real FP64
+// tensor-core contractions, the second product of every partial accumulated onto the first.  A, B, C are level-1 arrays
+// holding column-major m x k, k x n and m x n matrices (leading dimensions lda, ldb, ldc within each plane).
+extern "C" int fdb_dual_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t k, const fdb_array* B, int64_t ldb, int64_t n,
+                               fdb_array* C, int64_t ldc) {
+    FDB_ENTER(ctx);
+    if (!ctx || !A || !B || !C) return fail(ctx, FDB_ERR_BADARG, "fdb_dual_matmul: null argument");
+    if (A->level != 1 || B->level != 1 || C->level != 1 || A->N != B->N || A->N != C->N)
+        return fail(ctx, FDB_ERR_BADARG, "fdb_dual_matmul: A, B, C must be level-1 Dual arrays with the same chunk size (one tag, src/dual.jl:150-210)");
+    if (m <= 0 || k <= 0 || n <= 0 || lda < m || ldb < k || ldc < m || A->n < lda * (k - 1) + m || B->n < ldb * (n - 1) + k || C->n < ldc * (n - 1) + m)
+        return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: A is %lld x %lld, B %lld x %lld, C %lld x %lld", (long long)m, (long long)k, (long long)k,
+                    (long long)n, (long long)m, (long long)n);
+    int rc = ensure_scratch(ctx, (gemm_workspace_doubles(k, n, 0) + 64) * sizeof(double)); if (rc) return rc;
+    double* ws = (double*)((((uintptr_t)ctx->scratch) + 127) & ~(uintptr_t)127);
+    const int N = A->N;
+    int total = 0, nl = 0;
+    for (int q = 0; q <= N; q++) {            // value(A) * plane q of B  ->  plane q of C
+        rc = launch_gemm(ctx, A->data, lda, B->data + (int64_t)q * B->ld, ldb, C->data + (int64_t)q * C->ld, ldc, m, k, n, 0, ws, nullptr, &nl); if (rc) return rc;
+        total += nl;
+    }
+    for (int q = 1; q <= N; q++) {            // partial q of A * value(B), accumulated
+        rc = launch_gemm(ctx, A->data + (int64_t)q * A->ld, lda, B->data, ldb, C->data + (int64_t)q * C->ld, ldc, m, k, n, 0, ws, nullptr, &nl, nullptr, nullptr, true);
+        if (rc) return rc;
+        total += nl;
+    }
+    return finish(ctx, total, "fdb_dual_matmul");
 }
 
 // ydual = A * xdual  (A: m x n plain column-major; xdual: n Duals; ydual: m Duals): the planes are the columns

@@ -341,6 +341,23 @@ template <int N, bool NS> FDB_DEV Dual<double, N, NS> max_v(const Dual<double, N
     for (int i = 0; i < N; i++) r.p[i] = mulp<NS>(x.p[i], dx) + mulp<NS>(y.p[i], dy);
     return r;
 }
+// NaNMath.max / NaNMath.min: a NaN operand is ignored (the other one is returned); derivative 1 for the argument returned
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> nanmax_v(const Dual<double, N, NS>& x, const Dual<double, N, NS>& y) {
+    const bool takex = isnan(y.v) || (!isnan(x.v) && x.v > y.v);
+    Dual<double, N, NS> r; r.v = takex ? x.v : y.v;
+    const double dx = takex ? 1.0 : 0.0, dy = takex ? 0.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.p[i] = mulp<NS>(x.p[i], dx) + mulp<NS>(y.p[i], dy);
+    return r;
+}
+template <int N, bool NS> FDB_DEV Dual<double, N, NS> nanmin_v(const Dual<double, N, NS>& x, const Dual<double, N, NS>& y) {
+    const bool takex = isnan(y.v) || (!isnan(x.v) && !(x.v > y.v));
+    Dual<double, N, NS> r; r.v = takex ? x.v : y.v;
+    const double dx = takex ? 1.0 : 0.0, dy = takex ? 0.0 : 1.0;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.p[i] = mulp<NS>(x.p[i], dx) + mulp<NS>(y.p[i], dy);
+    return r;
+}
 template <int N, bool NS> FDB_DEV Dual<double, N, NS> min_v(const Dual<double, N, NS>& x, const Dual<double, N, NS>& y) {
     Dual<double, N, NS> r; r.v = fmin(x.v, y.v);
     double dx = x.v > y.v ? 0.0 : 1.0, dy = x.v > y.v ? 1.0 : 0.0;

@@ -145,6 +145,8 @@ int mirrors_for(fdb_ctx* ctx, fdb_mirrors* m, const fdb_array* const* outs, int 
 int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_array* b, const fdb_array* x, int64_t m, int N, int64_t lo,
                      int64_t hi, int64_t nchunks, int lcs, fdb_array* J, int64_t ldJ, double* yout, bool* used_dmma, const fdb_mirrors& Mr);
 bool dmma_eligible(const double* A, int64_t lda, int64_t m, int64_t k);
+int matvec_product_lanes(fdb_ctx* ctx, const double* A, int64_t lda, int64_t m, const fdb_array* x, int N, int64_t lo, int64_t hi, int64_t nchunks,
+                         double** Y_out, int64_t* ldy_out, int* nlaunch);
 
 // fdb_jit.cu
 void jit_release(fdb_ctx* ctx);

@@ -41,4 +41,53 @@ FDB_DEV void elementwise_jacobian_body(const bool SHARE, const double* __restric
     }
 }
 
+// ---- elementwise function of a matrix-vector product: y = g.(A * x) -----------------------------------------------------------
+// `A * xdual` with one-hot seeds is a Dual vector z whose value is (A*x)[i] and whose partial k is A[i, start+k]
+// (Real*Dual then Dual+Dual per element, src/dual.jl:476-490).  The contraction runs on the FP64 tensor cores (fdb_dmma.cu) and
+// leaves per chunk either  [value lane | representative zero-partial lane]  (lane sharing: the seeded window column of A is added
+// here, as the reference's last `+=` would)  or  [value lane | one column per seeded position]  (all lanes).  ProductLoader
+// rebuilds z_i from that product; the user's elementwise program g then runs on it exactly like F::apply on a seeded x.
+template <int N, bool NS> struct ProductLoader {
+    const double* Yv;      // value lane of this chunk's product
+    const double* Yl;      // lane sharing: the representative zero lane; all lanes: product column of the chunk's first seeded position
+    const double* Aw;      // lane sharing: A(:, start) (window columns of A, stride lda); all lanes: nullptr
+    int64_t ldy, lda; int chunksize;
+    FDB_DEV Dual<double, N, NS> operator()(int64_t i) const {
+        Dual<double, N, NS> d; d.v = Yv[i];
+        if (Aw) {
+            const double zl = Yl[i];
+#pragma unroll
+            for (int k = 0; k < N; k++) d.p[k] = (k < chunksize) ? zl + Aw[i + (int64_t)k * lda] * 1.0 : zl;
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; k++) d.p[k] = (k < chunksize) ? Yl[i + (int64_t)k * ldy] : 0.0;
+        }
+        return d;
+    }
+};
+
+// value/zero lanes: Y column 2*cl, 2*cl+1 (SHARE) ; value: Y column 0, partial lanes: Y column 1 + (start - c0) + k (all lanes)
+template <class F, int N, bool NS, int THREADS, bool MIR>
+FDB_DEV void matvec_jacobian_body(const bool SHARE, const double* __restrict__ Y, int64_t ldy, const double* __restrict__ A, int64_t lda,
+                                  int64_t m, int64_t n, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize, double* __restrict__ J,
+                                  int64_t ldJ, double* __restrict__ yout, const unsigned nrb, const unsigned nch, const bool rowfast,
+                                  const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> D;
+    const int64_t cl = (rowfast ? blockIdx.x / nrb : blockIdx.x % nch), c = chunk_lo + cl;
+    const bool last = (c == nchunks_total - 1);
+    const int chunksize = last ? lastchunksize : N;
+    const int64_t start = last ? (n - lastchunksize) : c * N;
+    const int64_t i = (int64_t)(rowfast ? blockIdx.x % nrb : blockIdx.x / nch) * THREADS + threadIdx.x;
+    if (i >= m) return;
+    ProductLoader<N, NS> z;
+    z.ldy = ldy; z.lda = lda; z.chunksize = chunksize;
+    if (SHARE) { z.Yv = Y + 2 * cl * ldy; z.Yl = z.Yv + ldy; z.Aw = A + start * lda; }
+    else { z.Yv = Y; z.Yl = Y + (1 + start - chunk_lo * N) * ldy; z.Aw = nullptr; }
+    const D y = F::template apply<D>(z, i);
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        if (k < chunksize) mstore_cs<MIR>(M, J + i + (start + k) * ldJ, y.p[k]);
+    if (yout && last) mstore(M, &yout[i], y.v);
+}
+
 }  // namespace fdb

@@ -113,6 +113,8 @@ static std::string binary_expr(int c, const std::string& a, const std::string& b
         case FDB_MAX: return "max_v(" + a + ", " + b + ")";
         case FDB_MIN: return "min_v(" + a + ", " + b + ")";
         case FDB_ATAN2: return "atan2_v(" + a + ", " + b + ")";
+        case FDB_NANMAX: return "nanmax_v(" + a + ", " + b + ")";
+        case FDB_NANMIN: return "nanmin_v(" + a + ", " + b + ")";
         default: return "hypot_v(" + a + ", " + b + ")";
     }
 }
@@ -137,7 +139,7 @@ static std::string emit_part(const short (*code)[4], int n, int from = 0) {
             case PK_CD: s += R(dst) + " = " + binary_expr(c, C(a), R(b)) + ";"; break;
             case PK_DP: s += R(dst) + " = " + binary_expr(c, R(a), "fdb_prm[" + std::to_string(b) + "][i]") + ";"; break;
             case PK_PD: s += R(dst) + " = " + binary_expr(c, "fdb_prm[" + std::to_string(a) + "][i]", R(b)) + ";"; break;
-            case PK_ACC: s += "acc[" + std::to_string(dst) + "] = acc[" + std::to_string(dst) + "] + " + R(a) + ";"; break;
+            case PK_ACC: s += "acc[" + std::to_string(dst) + "] = acc[" + std::to_string(dst) + (b == 1 ? "] * " : "] + ") + R(a) + ";"; break;
             default: s += R(dst) + " = " + R(a) + ";"; break;
         }
         s += "\n";
@@ -151,7 +153,7 @@ static std::string decl_regs() {
     return s + ";\n";
 }
 
-enum { JIT_GRADIENT = 0, JIT_JACOBIAN = 1, JIT_HESSIAN = 2 };
+enum { JIT_GRADIENT = 0, JIT_JACOBIAN = 1, JIT_HESSIAN = 2, JIT_MATVEC_JACOBIAN = 3 };
 
 static std::string make_source(int kind, const Program& P, int N, bool ns, bool share, bool mir) {
     std::string s = "#include \"fdb_sweep_kernel.cuh\"\n#include \"fdb_hessian_kernel.cuh\"\n#include \"fdb_jac_kernel.cuh\"\n";
@@ -167,11 +169,17 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
     const int K = P.n_acc > 0 ? P.n_acc : 1;
     s += "struct UserFn {\n";
     s += std::string("    static constexpr bool PURE_X = ") + ((P.n_params == 0 && !P.has_guard) ? "true" : "false") + ";\n";
-    s += std::string("    static constexpr bool PLAIN_SUM = ") + ((P.n_epi == 0 && K == 1 && P.result_reg == 0) ? "true" : "false") + ";\n";
+    s += std::string("    static constexpr bool PLAIN_SUM = ") + ((P.n_epi == 0 && K == 1 && P.result_reg == 0 && !P.prod_mask) ? "true" : "false") + ";\n";
     s += "    static constexpr int K = " + std::to_string(K) + ";\n    static constexpr int HALO = " + std::to_string(P.halo) + ";\n";
     s += "    static __device__ int64_t nterms(int64_t n) { return n > " + std::to_string(P.term_halo) + " ? n - " + std::to_string(P.term_halo) + " : 0; }\n";
-    s += "    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }\n";
-    s += "    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }\n";
+    if (P.prod_mask) {          // accumulators of `prod` start at one(Dual) and combine by Dual*Dual (src/dual.jl:260-300)
+        const std::string pm = std::to_string(P.prod_mask);
+        s += "    template <class D> static FDB_DEV D init(int k, const D& like) { return ((" + pm + " >> k) & 1) ? one_of(like) : zero_of(like); }\n";
+        s += "    template <class D> static FDB_DEV D combine(int k, const D& a, const D& b) { return ((" + pm + " >> k) & 1) ? a * b : a + b; }\n";
+    } else {
+        s += "    template <class D> static FDB_DEV D init(int, const D& like) { return zero_of(like); }\n";
+        s += "    template <class D> static FDB_DEV D combine(int, const D& a, const D& b) { return a + b; }\n";
+    }
     int st1 = -1, st2 = -1;                         // positions of the stage markers of a two-pass program
     for (int pc = 0; pc < P.n_term; pc++)
         if ((P.term[pc][0] >> 6) == PK_STAGE) { if (P.term[pc][2] == 1) st1 = pc; else st2 = pc; }
@@ -217,6 +225,13 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
              "        const unsigned nrb, const unsigned nch, const bool rowfast, const __grid_constant__ fdb_mirrors M) {\n"
              "    fdb::elementwise_jacobian_body<" + targs + ", 128, " + (mir ? "true" : "false") +
              ">(share, x, n, chunk_lo, nchunks_total, lastchunksize, J, ldJ, yout, nrb, nch, rowfast, M);\n}\n";
+    } else if (kind == JIT_MATVEC_JACOBIAN) {
+        s += "extern \"C\" __global__ void __launch_bounds__(128) fdb_user_kernel(const bool share, const double* __restrict__ Y, int64_t ldy,\n"
+             "        const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,\n"
+             "        double* __restrict__ J, int64_t ldJ, double* __restrict__ yout, const unsigned nrb, const unsigned nch, const bool rowfast,\n"
+             "        const __grid_constant__ fdb_mirrors M) {\n"
+             "    fdb::matvec_jacobian_body<" + targs + ", 128, " + (mir ? "true" : "false") +
+             ">(share, Y, ldy, A, lda, m, n, chunk_lo, nchunks_total, lastchunksize, J, ldJ, yout, nrb, nch, rowfast, M);\n}\n";
     } else {
         s += "extern \"C\" __global__ void __launch_bounds__(128) fdb_user_kernel(const double* __restrict__ x, int64_t n, int64_t outer_lo,\n"
              "        int64_t nchunks_total, int lastchunksize, double* __restrict__ H, int64_t ldH, double* __restrict__ grad,\n"
@@ -269,7 +284,7 @@ int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share
     if (!ctx->jit) ctx->jit = new fdb_jit_cache();
     fdb_jit_cache& J = *ctx->jit;
     if (kind != JIT_GRADIENT) share = false;          // run-time flag (Jacobian) or not applicable (Hessian)
-    if (kind != JIT_JACOBIAN) mir = false;
+    if (kind != JIT_JACOBIAN && kind != JIT_MATVEC_JACOBIAN) mir = false;
     const std::string key = cache_key(kind, P, N, ns, share, mir);
     auto it = J.map.find(key);
     if (it != J.map.end()) { J.hits++; *fn = it->second.fn ? &it->second : nullptr; return it->second.fn ? FDB_OK : FDB_ERR_UNSUPPORTED; }
@@ -349,9 +364,9 @@ extern "C" const char* fdb_jit_last_log(fdb_ctx* ctx) { return (ctx && ctx->jit)
 extern "C" int fdb_jit_compile_check(int kind, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi, const double* consts,
                                      int n_consts, int n_acc, int halo, int result_reg, int n_params, int N, int nansafe, int lane_sharing,
                                      char* log, int64_t log_capacity, int64_t* cubin_bytes) {
-    if (kind < JIT_GRADIENT || kind > JIT_HESSIAN || N < 1 || N > FDB_MAX_CHUNK) return FDB_ERR_BADARG;
+    if (kind < JIT_GRADIENT || kind > JIT_MATVEC_JACOBIAN || N < 1 || N > FDB_MAX_CHUNK) return FDB_ERR_BADARG;
     Program P;
-    int rc = build_program(nullptr, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, kind == JIT_JACOBIAN, n_params);
+    int rc = build_program(nullptr, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, kind == JIT_JACOBIAN || kind == JIT_MATVEC_JACOBIAN, n_params);
     std::vector<char> cubin;
     std::string lg;
     if (rc == FDB_OK) rc = compile_source(make_source(kind, P, N, nansafe != 0, lane_sharing != 0, false), cubin, lg);

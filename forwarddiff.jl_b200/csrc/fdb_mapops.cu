@@ -54,6 +54,8 @@ template <int N, bool NS> FDB_DEV Dual<double, N, NS> apply2_dd(int op, const Du
         case FDB_MAX: return max_v(x, y);
         case FDB_MIN: return min_v(x, y);
         case FDB_ATAN2: return atan2_v(x, y);
+        case FDB_NANMAX: return nanmax_v(x, y);
+        case FDB_NANMIN: return nanmin_v(x, y);
         default: return hypot_v(x, y);
     }
 }
@@ -165,7 +167,7 @@ extern "C" int fdb_map1(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a
 extern "C" int fdb_map2(fdb_ctx* ctx, int op, fdb_array* out, const fdb_array* a, const fdb_array* b) {
     FDB_ENTER(ctx);
     if (!ctx || !out || !a || !b) return fail(ctx, FDB_ERR_BADARG, "fdb_map2: null argument");
-    if (op < FDB_ADD || op > FDB_HYPOT) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map2: unknown op %d", op);
+    if (op < FDB_ADD || op > FDB_NANMIN) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map2: unknown op %d", op);
     if (out->level != 1 || a->level > 1 || b->level > 1 || (a->level == 0 && b->level == 0))
         return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_map2: need a level-1 output and at least one level-1 operand");
     int N = out->N;

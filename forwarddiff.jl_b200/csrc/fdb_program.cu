@@ -117,7 +117,7 @@ int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, con
     int used_params = 0;
     P.term_halo = halo;
     for (int k = 0; k < FDB_MAX_PARAMS; k++) P.prm_halo[k] = (short)halo;
-    int guard_left = 0, guard_h = halo, min_guard = halo, stage = 0, max_acc = -1;
+    int guard_left = 0, guard_h = halo, min_guard = halo, stage = 0, max_acc = -1, acc_seen = 0;
     bool unguarded_reads = false;
     for (int part = 0; part < 2; part++) {
         const int32_t* src = part ? epi : term; const int cnt = part ? n_epi : n_term;
@@ -146,10 +146,17 @@ int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, con
             if (kind == PK_PD) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < n_params && b >= 0 && b < PG_MAXR; if (a + 1 > used_params) used_params = a + 1; }
             if (kind == PK_LOADX) ok = ok && !part && b >= 0 && b <= halo;
             if (kind == PK_UNARY) ok = ok && code >= FDB_NEG && code <= FDB_CBRT && a >= 0 && a < PG_MAXR;
-            if (kind == PK_DD) ok = ok && code >= FDB_ADD && code <= FDB_HYPOT && a >= 0 && a < PG_MAXR && b >= 0 && b < PG_MAXR;
+            if (kind == PK_DD) ok = ok && code >= FDB_ADD && code <= FDB_NANMIN && a >= 0 && a < PG_MAXR && b >= 0 && b < PG_MAXR;
             if (kind == PK_DC) ok = ok && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < PG_MAXR && b >= 0 && b < n_consts;
             if (kind == PK_CD) ok = ok && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < n_consts && b >= 0 && b < PG_MAXR;
-            if (kind == PK_ACC) ok = ok && !part && !array_form && dst < n_acc && a >= 0 && a < PG_MAXR;
+            if (kind == PK_ACC) {          // b = 1: product accumulator (prod); an accumulator is either a sum or a product throughout
+                ok = ok && !part && !array_form && dst < n_acc && a >= 0 && a < PG_MAXR && (b == 0 || (b == 1 && stage == 0));
+                if (ok) {
+                    const int bit = 1 << dst;
+                    if ((acc_seen & bit) && (((P.prod_mask & bit) != 0) != (b == 1))) ok = false;
+                    acc_seen |= bit; if (b == 1) P.prod_mask |= bit;
+                }
+            }
             if (kind == PK_MOV) ok = ok && a >= 0 && a < PG_MAXR;
             if (!ok) return fail(ctx, FDB_ERR_BADARG, "op-program: malformed instruction %d of the %s part", i, part ? "epilogue" : "term");
             short* d = part ? P.epi[i] : P.term[i];
@@ -215,7 +222,7 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
             return finish(ctx, 1, "fdb_program_gradient_chunked(specialised)");
         }
     }
-    if (P.n_params || P.has_guard || P.two_pass) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters, reductions of different lengths or two passes needs the run-time specialised kernel (%s)",
+    if (P.n_params || P.has_guard || P.two_pass || P.prod_mask) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters, reductions of different lengths, products or two passes needs the run-time specialised kernel (%s)",
                                 ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     int nregs = 1;
     for (int i = 0; i < n_term; i++) { const int d = term_prog[4 * i + 1]; if ((term_prog[4 * i] >> 6) != PK_ACC && d + 1 > nregs) nregs = d + 1; }

@@ -18,6 +18,7 @@ constexpr int PG_VEC = 4;        // terms per thread per decoded instruction on 
 struct Program {
     int n_term, n_epi, n_acc, halo, result_reg, n_params;
     int term_halo, has_guard;    // terms run for i in [0, n - term_halo); guards restrict groups whose views are shorter
+    int prod_mask;               // bit k: accumulator k is a product (`prod`), PK_ACC with b = 1; specialised kernels only
     int two_pass, k1;            // PK_STAGE markers split the term part into term1 | epilogue1 | term2; accumulators [0, k1) belong to pass 1
     short prm_halo[FDB_MAX_PARAMS];   // parameter k is read for i < n - prm_halo[k]
     short term[PG_MAXI][4];      // {op, dst, a, b}
@@ -72,6 +73,8 @@ template <int N, bool NS> FDB_DEV Dual<double, N, NS> pg_dd(int code, const Dual
         case FDB_MAX: return max_v(x, y);
         case FDB_MIN: return min_v(x, y);
         case FDB_ATAN2: return atan2_v(x, y);
+        case FDB_NANMAX: return nanmax_v(x, y);
+        case FDB_NANMIN: return nanmin_v(x, y);
         default: return hypot_v(x, y);
     }
 }
@@ -203,6 +206,8 @@ __device__ __noinline__ void pg_run_shared_vec(const short (*code)[4], int ninst
             case (PK_DD << 6) | FDB_MIN: PGV(min_v(xa[v], xb[v]))
             case (PK_DD << 6) | FDB_ATAN2: PGV(atan2_v(xa[v], xb[v]))
             case (PK_DD << 6) | FDB_HYPOT: PGV(hypot_v(xa[v], xb[v]))
+            case (PK_DD << 6) | FDB_NANMAX: PGV(nanmax_v(xa[v], xb[v]))
+            case (PK_DD << 6) | FDB_NANMIN: PGV(nanmin_v(xa[v], xb[v]))
             case (PK_DC << 6) | FDB_ADD: PGV(xa[v] + s)
             case (PK_DC << 6) | FDB_SUB: PGV(xa[v] - s)
             case (PK_DC << 6) | FDB_MUL: PGV(xa[v] * s)

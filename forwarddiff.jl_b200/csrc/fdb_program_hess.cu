@@ -209,6 +209,7 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
         }
     // f = one plain sum of terms: both executors.  K sums + arithmetic after the reductions: the specialised kernel only
     if (P.two_pass) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: two-pass programs are not supported");
+    if (P.prod_mask) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: product accumulators have no nested-dual batched kernel");
     const bool plain = (n_epi == 0 && n_acc == 1 && result_reg == 0 && P.n_params == 0 && !P.has_guard);
     Plan p = make_plan(n, N);
     const int64_t nchunks = (n == N) ? 1 : p.nchunks;

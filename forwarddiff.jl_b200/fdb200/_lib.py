@@ -106,6 +106,7 @@ SIGNATURES = {
     "fdb_map2_scalar": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr, C.c_double, C.c_int]),
     "fdb_fma": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr, c_arr, c_arr, C.c_double]),
     "fdb_dual_matvec": (C.c_int, [c_ctx, c_arr, i64, i64, i64, c_arr, c_arr]),
+    "fdb_dual_matmul": (C.c_int, [c_ctx, c_arr, i64, i64, i64, c_arr, i64, i64, c_arr, i64]),
     "fdb_matmul": (C.c_int, [c_ctx, c_arr, i64, i64, i64, c_arr, i64, i64, c_arr, i64]),
     "fdb_reduce": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr]),
     "fdb_eval_scalar_fn": (C.c_int, [c_ctx, C.c_int, c_arr, c_arr]),
@@ -119,6 +120,8 @@ SIGNATURES = {
                                                C.c_int, C.c_int, C.c_int, c_arr, C.c_int, i64, i64, c_arr, c_arr]),
     "fdb_program_jacobian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, C.c_int, c_arr,
                                                C.c_int, i64, i64, c_arr, i64, c_arr]),
+    "fdb_program_matvec_jacobian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, c_arr, i64, i64, c_arr,
+                                                      C.c_int, i64, i64, c_arr, i64, c_arr]),
     "fdb_program_hessian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int,
                                               C.c_int, C.c_int, C.c_int, c_arr, C.c_int, i64, i64, c_arr, i64, c_arr, c_arr]),
     "fdb_set_jit": (C.c_int, [c_ctx, C.c_int]),
@@ -169,7 +172,7 @@ IPC_HANDLE_BYTES = 64
 # enums of fdb200.h
 OP1 = dict(neg=1, exp=2, log=3, sin=4, cos=5, tanh=6, sqrt=7, abs=8, abs2=9, inv=10, pow0=11, pow1=12, pow2=13, pow3=14,
            tan=15, exp2=16, log2=17, log10=18, log1p=19, expm1=20, sinh=21, cosh=22, asin=23, acos=24, atan=25, cbrt=26)
-OP2 = dict(add=1, sub=2, mul=3, div=4, pow=5, max=6, min=7, atan2=8, hypot=9)
+OP2 = dict(add=1, sub=2, mul=3, div=4, pow=5, max=6, min=7, atan2=8, hypot=9, nanmax=10, nanmin=11)
 REDOP = dict(sum=1, prod=2)
 FN = dict(rosenbrock=1, ackley=2, sumsq=3, prod=4)
 JFN = dict(tanh_affine=1, brusselator=2, jactest=3)

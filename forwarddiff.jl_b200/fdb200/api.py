@@ -458,6 +458,8 @@ def _program_hessian(ctx, result, H, f, x, N, lo, hi):
         raise _lib.UnsupportedOp("hessian: f must be a catalogue target or flatten to sums of elementwise terms (no prod, no strided views)")
     if prog.needs_jit and not ctx.jit_enabled():
         raise _lib.UnsupportedOp("hessian: a function with data arrays or reductions of different lengths needs the run-time specialised kernel")
+    if getattr(prog, "has_prod", False):
+        raise _lib.UnsupportedOp("hessian: prod has no nested-dual batched kernel")
     xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
     Hd = B200Array.alloc(ctx, n * n); gd = B200Array.alloc(ctx, n); vd = B200Array.alloc(ctx, 1)
     with _bound_params(ctx, prog):
@@ -707,7 +709,8 @@ def _mlp2_jacobian(ctx, result, out, f, x, N, lo, hi):
 
 
 def _program_jacobian(ctx, prog, result, out, x, N, lo, hi):
-    """A flattened elementwise / stencil f through the batched sweep (fdb_program_jacobian_chunked)."""
+    """A flattened elementwise / stencil f through the batched sweep (fdb_program_jacobian_chunked); with `A @ x` inside f,
+    the contraction on the FP64 tensor cores followed by the elementwise program (fdb_program_matvec_jacobian_chunked)."""
     lib = ctx.lib
     xd = x if isinstance(x, _DeviceArray) else ctx.array(x)
     n, m = xd.n, prog.out_len
@@ -721,9 +724,15 @@ def _program_jacobian(ctx, prog, result, out, x, N, lo, hi):
         Jd = B200Array.alloc(ctx, m * n)
     yd = B200Array.alloc(ctx, m)
     with _bound_params(ctx, prog):
-        ctx.check(lib.fdb_program_jacobian_chunked(ctx.h, _i32p(prog.term), len(prog.term),
-                                                   prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
-                                                   prog.halo, prog.result_reg, xd.h, N, lo, hi, Jd.h, m, yd.h))
+        if prog.matvec is not None:
+            Ad = ctx.matrix_array(prog.matvec)               # column-major device copy, cached per matrix object
+            ctx.check(lib.fdb_program_matvec_jacobian_chunked(ctx.h, _i32p(prog.term), len(prog.term),
+                                                              prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
+                                                              prog.result_reg, Ad.h, m, m, xd.h, N, lo, hi, Jd.h, m, yd.h))
+        else:
+            ctx.check(lib.fdb_program_jacobian_chunked(ctx.h, _i32p(prog.term), len(prog.term),
+                                                       prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size,
+                                                       prog.halo, prog.result_reg, xd.h, N, lo, hi, Jd.h, m, yd.h))
     nchunks = 1 if n == N else chunk_plan(n, N)["nchunks"]
     last = hi < 0 or hi == nchunks
     if Jd is not out:

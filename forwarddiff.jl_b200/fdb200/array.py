@@ -87,6 +87,27 @@ class Context:
             hit = cache[key] = self.array(flat)
         return hit
 
+    def matrix_array(self, A):
+        """Column-major device copy of a closed-over Float64 matrix (the `A` of `A @ x`).  Cached per matrix OBJECT together
+        with a cheap fingerprint (shape, data pointer, a strided sample of 4096 entries), so that repeated jacobian calls do
+        not upload A again; a matrix modified in place beyond what the sample sees needs `forget_matrices()`."""
+        cache = self.__dict__.setdefault("_matrix_cache", {})
+        A = np.asarray(A, dtype=np.float64)
+        flat = A.reshape(-1)[:: max(1, A.size // 4096)]
+        key = id(A)
+        fp = (A.shape, A.__array_interface__["data"][0], float(np.sum(flat)), float(flat[-1]) if flat.size else 0.0)
+        hit = cache.get(key)
+        if hit is None or hit[0] != fp:
+            if self._capturing:
+                raise FdbError("a matrix was first seen while the chunk loop was being captured")
+            if len(cache) > 8:
+                cache.clear()
+            hit = cache[key] = (fp, self.array(np.asfortranarray(A).ravel(order="F")), A)      # keep A alive: id() stays unique
+        return hit[1]
+
+    def forget_matrices(self):
+        self.__dict__.pop("_matrix_cache", None)
+
     def jit_stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self.check(self.lib.fdb_jit_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
@@ -348,6 +369,20 @@ class B200DualArray(_DeviceArray):
 
     def __rpow__(self, o): return self._map2("pow", o, True)
 
+    def __rmatmul__(self, A):
+        """A @ xdual for a Float64 matrix A (m x n): Julia's generic matvec over Dual (Real*Dual, Dual+Dual; src/dual.jl:476-490)
+        as ONE contraction of A against the planes [value | partials] on the FP64 tensor cores (fdb_dual_matvec)."""
+        A = np.asarray(A, dtype=np.float64)
+        if A.ndim != 2 or A.shape[1] != self.n:
+            raise DimensionMismatch(f"A has dimensions {A.shape}, vector has length {self.n}")
+        if self.level != 1:
+            raise FdbError("A @ x is implemented for Vector{Dual{T,Float64,N}}")
+        m = A.shape[0]
+        Ad = self.ctx.matrix_array(A)
+        out = B200DualArray.alloc(self.ctx, m, self.N, 1)
+        self.ctx.check(self.ctx.lib.fdb_dual_matvec(self.ctx.h, Ad.h, m, m, self.n, self.h, out.h))
+        return out
+
     def sum(self):
         return self._reduce("sum")
 
@@ -393,6 +428,16 @@ def minimum(a, b):
     return a._map2("min", b)
 
 
+class nanmath:
+    """NaNMath.jl variants (src/dual.jl:477,549).  NaNMath.f returns NaN where Base.f throws a DomainError; device math never
+    throws and already returns NaN there, so pow / log / sqrt / sin / cos / tan / asin / acos / log2 / log10 / log1p are the
+    plain device ops.  max / min differ in value: a NaN operand is ignored."""
+    pow = staticmethod(lambda x, y: x ** y if not isinstance(x, (int, float)) else y.__rpow__(x))
+    log, sqrt, sin, cos, tan, asin, acos, log2, log10, log1p = log, sqrt, sin, cos, tan, asin, acos, log2, log10, log1p
+    max = staticmethod(lambda a, b: a._map2("nanmax", b))
+    min = staticmethod(lambda a, b: a._map2("nanmin", b))
+
+
 def atan2(y, x):
     """atan(y, x) on two Dual arrays (DiffRules binary rule)."""
     return y._map2("atan2", x)
@@ -405,6 +450,17 @@ def hypot(x, y):
 def dot(a, b):
     """dot(a, b) where at least one operand is a Dual array (or a symbolic array while f is being flattened)."""
     return a.dot(b) if hasattr(a, "dot") and not isinstance(a, np.ndarray) else b.dot(a)
+
+
+def dual_matmul(A, shape_a, B, shape_b):
+    """C = A * B for column-major matrices of Duals stored as flat B200DualArrays: shape_a = (m, k), shape_b = (k, n).
+    Julia: the generic matrix product over Dual*Dual (src/dual.jl:260-300); here 2N+1 FP64 tensor-core contractions."""
+    (m, k), (k2, n) = shape_a, shape_b
+    if k != k2 or A.n != m * k or B.n != k * n:
+        raise DimensionMismatch(f"A has dimensions {shape_a}, B has dimensions {shape_b}")
+    out = B200DualArray.alloc(A.ctx, m * n, A.N, 1)
+    A.ctx.check(A.ctx.lib.fdb_dual_matmul(A.ctx.h, A.h, m, m, k, B.h, k, n, out.h, m))
+    return out
 
 
 def fma(x, y, z):

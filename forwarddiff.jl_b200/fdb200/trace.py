@@ -25,10 +25,11 @@ _NUM = (int, float, np.floating, np.integer)
 
 
 class _Node:
-    __slots__ = ("kind", "op", "args", "const", "stage", "id")
+    __slots__ = ("kind", "op", "args", "const", "stage", "id", "is_z")
 
     def __init__(self, tr, kind, op=0, args=(), const=None, stage="term"):
         self.kind, self.op, self.args, self.const, self.stage = kind, op, args, const, stage
+        self.is_z = False
         self.id = len(tr.nodes)
         tr.nodes.append(self)
 
@@ -143,6 +144,7 @@ class TArray(_Sym):
         if len(tr.accs) >= MAX_ACC:
             raise TraceError("too many reductions")
         tr.accs.append(self.node)
+        tr.acc_prod.append(False)
         tr.acc_lengths.append(self.n)
         tr.term_lengths.add(self.n)
         node = _Node(tr, K_ACC, len(tr.accs) - 1, (), stage="scalar" if _LEVEL[self.node.stage] == 0 else "scalar2")
@@ -158,13 +160,44 @@ class TArray(_Sym):
         return (self * other).sum()
 
     def prod(self):
-        raise TraceError("prod is not an additive reduction")
+        """prod(x): an accumulator that starts at one(Dual) and combines by Dual*Dual (specialised kernels only)."""
+        if _LEVEL[self.node.stage] != 0:
+            raise TraceError("prod over a second-pass broadcast")
+        s = self.sum()
+        self.tr.acc_prod[-1] = True
+        return s
+
+    def __rmatmul__(self, A):
+        """A @ x for a closed-over Float64 matrix: `A * xdual` of the reference (LinearAlgebra.generic_matvecmul! over Dual,
+        src/dual.jl:476-490 for the Real*Dual / Dual+Dual it is made of).  Only the input array itself may be contracted,
+        once; what follows is an elementwise program over z = A*x, whose Dual z_i the device builds from the FP64
+        tensor-core contraction (fdb_program_matvec_jacobian_chunked)."""
+        tr = self.tr
+        if self.node.kind != K_LOADX or self.node.args or self.node.const != 0 or self.n != tr.n or self.node.stage != "term" \
+                or getattr(self.node, "is_z", False):
+            raise TraceError("A @ v is only supported for v = the whole input array")
+        if tr.matvec is not None:
+            raise TraceError("only one matrix-vector product per function")
+        A = np.asarray(A)
+        if A.ndim != 2 or A.dtype != np.float64:
+            raise TraceError("A @ x needs a 2-d float64 matrix")
+        if A.shape[1] != self.n:
+            from ._lib import DimensionMismatch
+            raise DimensionMismatch(f"A has dimensions {A.shape}, vector has length {self.n}")
+        tr.matvec = A
+        tr.x_node = self.node
+        node = _Node(tr, K_LOADX, 0, (), const=0)
+        node.is_z = True
+        tr.z_node = node
+        return TArray(tr, node, A.shape[0])
 
 
 class _Trace:
     def __init__(self, n):
         self.n = n
         self.nodes, self.accs, self.acc_lengths, self.term_lengths, self.params, self.acc_nodes = [], [], [], set(), [], []
+        self.matvec, self.x_node, self.z_node = None, None, None
+        self.acc_prod = []
 
 
 def _emit(tr, roots, stage, preloaded, sreg=None):
@@ -245,16 +278,18 @@ def _emit(tr, roots, stage, preloaded, sreg=None):
 class Program:
     """term/epilogue instruction arrays + constants, ready for fdb_program_*_chunked."""
 
-    def __init__(self, term, epi, consts, n_acc, halo, result_reg, out_len, params=()):
+    def __init__(self, term, epi, consts, n_acc, halo, result_reg, out_len, params=(), matvec=None):
         self.term = np.asarray(term, dtype=np.int32).reshape(-1, 4)
         self.epi = np.asarray(epi, dtype=np.int32).reshape(-1, 4)
         self.consts = np.asarray(consts, dtype=np.float64)
         self.n_acc, self.halo, self.result_reg, self.out_len = n_acc, halo, result_reg, out_len
+        self.matvec = matvec                     # A of `A @ x`: the program is elementwise over z = A*x (LOADX 0 = z_i)
         self.params = [np.ascontiguousarray(a, dtype=np.float64) for a in params]     # data arrays, one entry per term
         # data arrays and guarded groups exist only in the run-time specialised kernels, not in the interpreter
         kinds = (self.term[:, 0] >> 6) if self.term.size else np.zeros(0, dtype=np.int32)
         self.two_pass = bool(np.any(kinds == K_STAGE))
-        self.needs_jit = bool(self.params) or bool(np.any(kinds == K_GUARD)) or self.two_pass
+        self.has_prod = bool(np.any((kinds == K_ACC) & (self.term[:, 3] == 1))) if self.term.size else False
+        self.needs_jit = bool(self.params) or bool(np.any(kinds == K_GUARD)) or self.two_pass or self.has_prod
 
 
 def _common_halo(tr, lengths):
@@ -276,14 +311,18 @@ def trace_scalar(f, n):
     y = f(x)
     if not isinstance(y, TScalar):
         raise TraceError("f did not return a reduced scalar")
+    if tr.matvec is not None:
+        raise TraceError("a reduction over A @ x has no batched kernel (the reference loop contracts on the tensor cores)")
     if any(_LEVEL[nd.stage] >= 2 for nd in tr.accs):
+        if any(tr.acc_prod):
+            raise TraceError("prod in a two-pass function")
         return _two_pass_program(tr, y)
     if len(tr.term_lengths) == 1:
         L, halo = _common_halo(tr, set(tr.term_lengths))
         # term part: evaluate every accumulated expression, then ACC
         term, reg = _emit(tr, tr.accs, "term", {})
         for k, nd in enumerate(tr.accs):
-            term.append((K_ACC << 6, k, reg[nd.id], 0))
+            term.append((K_ACC << 6, k, reg[nd.id], int(tr.acc_prod[k])))
     else:
         # reductions over views of different lengths (sum(g.(x[2:end], x[1:end-1])) + sum(h.(x))): one guarded group per
         # reduction, term i of group k runs while i + halo_k < n (specialised kernels only)
@@ -294,7 +333,7 @@ def trace_scalar(f, n):
             group, reg = _emit(tr, [nd], "term", {})
             if any((ins[0] >> 6) == K_LOADX and ins[3] > tr.n - L for ins in group):
                 raise TraceError("view outside the input")
-            group.append((K_ACC << 6, k, reg[nd.id], 0))
+            group.append((K_ACC << 6, k, reg[nd.id], int(tr.acc_prod[k])))
             term.append((K_GUARD << 6, 0, tr.n - L, len(group)))
             term += group
     if len(term) > MAX_INSTR:
@@ -353,6 +392,28 @@ def trace_array(f, n):
         raise TraceError("f did not return an array")
     if tr.accs:
         raise TraceError("reductions inside an array-valued f need two passes")
+    if tr.matvec is not None:
+        # elementwise over z = A @ x: every leaf must be z itself (x may not appear again, nor views of z)
+        m = tr.matvec.shape[0]
+        if y.n != m:
+            raise TraceError("result length differs from the rows of A")
+        term, reg = _emit(tr, [y.node], "term", {})
+        used = {ins[3] for ins in term if (ins[0] >> 6) == K_LOADX}
+        reach = _reachable(y.node)
+        if tr.x_node.id in reach or any(nd.kind == K_LOADX and not nd.is_z for nd in tr.nodes if nd.id in reach) or used - {0}:
+            raise TraceError("x may only enter through A @ x")
+        return Program(term, [], tr.consts, 0, 0, reg[y.node.id], m, tr.params, matvec=tr.matvec)
     L, halo = _common_halo(tr, {y.n})
     term, reg = _emit(tr, [y.node], "term", {})
     return Program(term, [], tr.consts, 0, halo, reg[y.node.id], L, tr.params)
+
+
+def _reachable(root):
+    seen, stack = set(), [root]
+    while stack:
+        nd = stack.pop()
+        if nd.id in seen:
+            continue
+        seen.add(nd.id)
+        stack.extend(nd.args)
+    return seen

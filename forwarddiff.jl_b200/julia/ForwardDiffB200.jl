@@ -4,7 +4,9 @@
 # NOT RUNNABLE IN THIS IMAGE (no `julia` binary): this file is the declarative statement of the
 # bindings a ForwardDiff maintainer would add; the same C ABI is exercised by the Python/ctypes host
 # in forwarddiff.jl_b200/fdb200/, which is what the tests and the benchmark run.  All logic that needs
-# verification lives below the C ABI.
+# verification lives below the C ABI, and every C-ABI call SEQUENCE this file makes (argument order and
+# types included) is executed by examples/julia_call_sequences.c on the GPU (tests/test_gpu_sharded.py),
+# section by section under the same headings.
 #
 # Seam: ForwardDiff's config constructors call `similar(x, Dual{T,V,N})` (src/config.jl:122,159,
 # 185-186,225-226).  For `x::B200Array` that returns a `B200DualArray{T,Float64,N}`; from then on
@@ -14,8 +16,7 @@ module ForwardDiffB200
 using ForwardDiff
 using ForwardDiff: Dual, Partials, Chunk, GradientConfig, JacobianConfig, HessianConfig, DiffResults
 import ForwardDiff: seed!, seed_zero_partials!, extract_gradient_chunk!, extract_jacobian_chunk!,
-                    extract_jacobian!, extract_value!, chunk_mode_gradient, chunk_mode_gradient!,
-                    chunk_mode_jacobian, chunk_mode_jacobian!, hessian!, structural_length
+                    extract_jacobian!, extract_value!, chunk_mode_gradient!, chunk_mode_jacobian!, hessian!
 
 const libfdb200 = joinpath(@__DIR__, "..", "lib", "libfdb200.so")
 
@@ -95,8 +96,10 @@ end
 
 # ---- array arithmetic: Base.broadcast / sum / prod on B200Array{<:Dual} ------------------------------
 # op codes = fdb_op1 / fdb_op2 of include/fdb200.h (src/dual.jl:476-597,709-717)
-const OP1 = Dict(:- => 1, :exp => 2, :log => 3, :sin => 4, :cos => 5, :tanh => 6, :sqrt => 7, :abs => 8, :abs2 => 9, :inv => 10)
-const OP2 = Dict(:+ => 1, :- => 2, :* => 3, :/ => 4, :^ => 5, :max => 6, :min => 7)
+const OP1 = Dict(:- => 1, :exp => 2, :log => 3, :sin => 4, :cos => 5, :tanh => 6, :sqrt => 7, :abs => 8, :abs2 => 9, :inv => 10,
+                 :pow0 => 11, :pow1 => 12, :pow2 => 13, :pow3 => 14, :tan => 15, :exp2 => 16, :log2 => 17, :log10 => 18, :log1p => 19,
+                 :expm1 => 20, :sinh => 21, :cosh => 22, :asin => 23, :acos => 24, :atan => 25, :cbrt => 26)
+const OP2 = Dict(:+ => 1, :- => 2, :* => 3, :/ => 4, :^ => 5, :max => 6, :min => 7, :atan => 8, :hypot => 9)
 function map1(op::Symbol, a::B200Array{D}) where {D<:Dual}
     out = similar(a, D)
     check(a.ctx.h, ccall((:fdb_map1, libfdb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), a.ctx.h, OP1[op], out.h, a.h)); out
@@ -137,6 +140,103 @@ function chunk_mode_gradient!(result::B200Array{Float64}, f::F, x::B200Array{Flo
                          x.ctx.h, id, x.h, N, plan[][8], plan[][9], result.h, value.h))
     return result                          # multi-rank: see sharded_gradient! below (peer-memory exchange) or all-gather the slices
 end
+# value.(ydual) -> y (src/apiutils.jl:9-12); the DiffResult form (apiutils.jl:5-7) calls this through DiffResults.value!
+function extract_value!(::Type{T}, out::B200Array, ydual::B200Array{<:Dual}) where {T}
+    check(out.ctx.h, ccall((:fdb_extract_value, libfdb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), out.ctx.h, out.h, ydual.h)); out
+end
+
+# array-valued catalogue targets carry their Float64 parameters: A (m x n column-major), b (m), alpha
+struct JacobianTarget
+    id::Int; m::Int
+    A::Union{Nothing,B200Array{Float64}}; b::Union{Nothing,B200Array{Float64}}; alpha::Float64
+end
+jacobian_target(f) = nothing              # users opt in:  ForwardDiffB200.jacobian_target(f::MyLayer) = JacobianTarget(1, m, A, b, 0.0)
+handle(a::Nothing) = C_NULL
+handle(a::B200Array) = a.h
+# chunk_mode_jacobian!(result, f, x, cfg) (src/jacobian.jl:218-223) and the f!(y, x) form (:225-244): `result` is the column-major
+# m x n matrix stored flat; every chunk of this rank's range in one launch (DMMA contraction for tanh.(A*x .+ b))
+function chunk_mode_jacobian!(result::B200Array{Float64}, f::F, x::B200Array{Float64}, cfg::JacobianConfig{T,V,N};
+                              y::Union{Nothing,B200Array{Float64}} = nothing, lo = 0, hi = -1) where {F,T,V,N}
+    t = jacobian_target(f)
+    t === nothing && return invoke(chunk_mode_jacobian!, Tuple{Any,F,Any,JacobianConfig{T,V,N}}, result, f, x, cfg)   # reference loop on device arrays
+    check(x.ctx.h, ccall((:fdb_jacobian_chunked, libfdb200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cdouble, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+        x.ctx.h, t.id, x.h, t.m, N, handle(t.A), t.m, handle(t.b), t.alpha, lo, hi, result.h, t.m, handle(y)))
+    return result
+end
+chunk_mode_jacobian!(result::B200Array{Float64}, f!::F, y::B200Array{Float64}, x::B200Array{Float64}, cfg::JacobianConfig{T,V,N}) where {F,T,V,N} =
+    chunk_mode_jacobian!(result, f!, x, cfg; y = y)
+# jacobian!(J::Matrix, f, x::Vector, cfg) on host arrays -> fdb_jacobian_host (A, b: host arrays or nothing)
+function jacobian_host!(J::Matrix{Float64}, y::Vector{Float64}, id::Integer, x::Vector{Float64}, ::Chunk{N}; A = nothing, b = nothing,
+                        alpha = 0.0, reuse_params = false, ctx = context()) where {N}
+    m = size(J, 1)
+    GC.@preserve J y x A b check(ctx.h, ccall((:fdb_jacobian_host, libfdb200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Int64, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Cdouble, Cint, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
+        ctx.h, id, x, length(x), m, N, A === nothing ? C_NULL : pointer(A), m, b === nothing ? C_NULL : pointer(b), alpha, reuse_params, 0, -1, J, m, y))
+    return J
+end
+
+# hessian!(result, f, x, cfg) (src/hessian.jl:31-37; the DiffResult form :66-71 reads value and gradient from the same sweep):
+# nested Dual{T,Dual{T,V,N},N} sweeps of every (inner, outer) chunk pair in one launch
+function hessian!(result::B200Array{Float64}, f::F, x::B200Array{Float64}, cfg::HessianConfig{T,V,N};
+                  grad::Union{Nothing,B200Array{Float64}} = nothing, value::Union{Nothing,B200Array{Float64}} = nothing, lo = 0, hi = -1) where {F,T,V,N}
+    id = catalogue_id(f)
+    if id === nothing                                # a flattened f: fdb_program_hessian_chunked
+        g = grad === nothing ? B200Array{Float64}(undef, length(x); ctx = x.ctx) : grad
+        program_hessian!(result, g, trace_scalar(f, length(x)), x, Chunk{N}(); lo = lo, hi = hi)
+        return result
+    end
+    check(x.ctx.h, ccall((:fdb_hessian_chunked, libfdb200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+        x.ctx.h, id, x.h, N, lo, hi, result.h, length(x), handle(grad), handle(value)))
+    return result
+end
+function hessian_host!(H::Matrix{Float64}, grad::Vector{Float64}, id::Integer, x::Vector{Float64}, ::Chunk{N}; ctx = context()) where {N}
+    value = Ref{Float64}(0.0)
+    GC.@preserve H grad x check(ctx.h, ccall((:fdb_hessian_host, libfdb200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Cint, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ref{Float64}),
+        ctx.h, id, x, length(x), N, 0, -1, H, size(H, 1), grad, value))
+    return H, grad, value[]
+end
+
+# ---- ONE Julia session, all GPUs (fdb_multi_*): what gradient!/jacobian!/hessian! on host Vectors bind to when several devices
+# are visible.  Device i of n sweeps the chunk range fdb_plan_chunks(xlen, N, i, n) and copies its slice into the host result. ----
+mutable struct DeviceGroup
+    h::Ptr{Cvoid}
+    function DeviceGroup(devices::Union{Nothing,Vector{Cint}} = nothing)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = devices === nothing ? ccall((:fdb_multi_init, libfdb200), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), 0, C_NULL, r) :
+                                   ccall((:fdb_multi_init, libfdb200), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), length(devices), devices, r)
+        rc == 0 || error(unsafe_string(ccall((:fdb_multi_last_error, libfdb200), Cstring, (Ptr{Cvoid},), C_NULL)))
+        g = new(r[]); finalizer(g -> ccall((:fdb_multi_shutdown, libfdb200), Cint, (Ptr{Cvoid},), g.h), g); g
+    end
+end
+function mcheck(g::DeviceGroup, rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:fdb_multi_last_error, libfdb200), Cstring, (Ptr{Cvoid},), g.h))
+    rc == 2 && throw(DimensionMismatch(msg)); rc == 6 && throw(ArgumentError(msg)); throw(FdbError(rc, msg))
+end
+function gradient_host!(g::DeviceGroup, out::Vector{Float64}, id::Integer, x::Vector{Float64}, ::Chunk{N}) where {N}
+    value = Ref{Float64}(0.0)
+    GC.@preserve out x mcheck(g, ccall((:fdb_multi_gradient_host, libfdb200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ref{Float64}), g.h, id, x, length(x), N, out, value))
+    return out, value[]
+end
+function jacobian_host!(g::DeviceGroup, J::Matrix{Float64}, y::Vector{Float64}, id::Integer, x::Vector{Float64}, ::Chunk{N}; A = nothing,
+                        b = nothing, alpha = 0.0, reuse_params = false) where {N}
+    m = size(J, 1)
+    GC.@preserve J y x A b mcheck(g, ccall((:fdb_multi_jacobian_host, libfdb200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Int64, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Cdouble, Cint, Ptr{Float64}, Int64, Ptr{Float64}),
+        g.h, id, x, length(x), m, N, A === nothing ? C_NULL : pointer(A), m, b === nothing ? C_NULL : pointer(b), alpha, reuse_params, J, m, y))
+    return J
+end
+function hessian_host!(g::DeviceGroup, H::Matrix{Float64}, grad::Vector{Float64}, id::Integer, x::Vector{Float64}, ::Chunk{N}) where {N}
+    value = Ref{Float64}(0.0)
+    GC.@preserve H grad x mcheck(g, ccall((:fdb_multi_hessian_host, libfdb200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Ref{Float64}), g.h, id, x, length(x), N, H, size(H, 1), grad, value))
+    return H, grad, value[]
+end
+
 # Host Vectors: ForwardDiff.gradient!(out::Vector, f, x::Vector, cfg) for a catalogue f -> fdb_gradient_host
 function gradient_host!(out::Vector{Float64}, f, x::Vector{Float64}, ::Chunk{N}; ctx = context()) where {N}
     value = Ref{Float64}(NaN)
@@ -176,9 +276,7 @@ end
 # f is called once on a TraceArray; broadcasting over TraceArrays records nodes instead of computing (BroadcastStyle below),
 # `sum` closes a reduction.  The recorded DAG is linearised into {op,dst,a,b} words exactly as trace.py:_emit does
 # (post-order, registers released at last use).  Guards, data arrays and the two-pass form follow trace.py the same way.
-const K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC = 0, 1, 2, 3, 4, 5
-const OP1 = Dict(:- => 1, :exp => 2, :log => 3, :sin => 4, :cos => 5, :tanh => 6, :sqrt => 7, :abs => 8, :abs2 => 9, :inv => 10)
-const OP2 = Dict(:+ => 1, :- => 2, :* => 3, :/ => 4, :^ => 5, :max => 6, :min => 7)
+const K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC = 0, 1, 2, 3, 4, 5      # op codes: OP1 / OP2 above
 mutable struct TNode; kind::Int; op::Int; args::Vector{TNode}; c::Float64; scalar::Bool; end
 struct TraceArray <: AbstractVector{Float64}; node::TNode; n::Int; accs::Vector{TNode}; end      # a view x[a:b] or a broadcast result
 struct TraceScalar; node::TNode; accs::Vector{TNode}; end                                       # sum(...) and scalar math on it
@@ -191,6 +289,11 @@ B200TraceStyle(::Val{1}) = B200TraceStyle()
 function Base.copy(bc::Broadcast.Broadcasted{B200TraceStyle})                                    # x .op y -> a node, nothing computed
     args = map(a -> a isa Broadcast.Broadcasted ? copy(a) : a, bc.args)
     arr = args[findfirst(a -> a isa TraceArray, args)]
+    if bc.f === Base.literal_pow                    # x .^ 2 lowers to literal_pow.(^, x, Val(2)): FDB_POW0..3, src/dual.jl:587-597
+        x, k = args[2], typeof(args[3]).parameters[1]
+        (x isa TraceArray && k isa Integer && 0 <= k <= 3) || error("literal power outside 0..3 cannot be flattened")
+        return TraceArray(TNode(K_UNARY, OP1[Symbol(:pow, k)], [x.node], 0.0, false), arr.n, arr.accs)
+    end
     f = nameof(bc.f)
     if length(args) == 1
         return TraceArray(TNode(K_UNARY, OP1[f], [args[1].node], 0.0, false), arr.n, arr.accs)

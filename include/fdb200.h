@@ -62,7 +62,11 @@ typedef enum {
     FDB_TAN, FDB_EXP2, FDB_LOG2, FDB_LOG10, FDB_LOG1P, FDB_EXPM1, FDB_SINH, FDB_COSH, FDB_ASIN, FDB_ACOS, FDB_ATAN, FDB_CBRT
 } fdb_op1;
 /* binary ops: src/dual.jl:499-519 (+ -), DiffRules * max min, :532-544 (/), :549-585 (^) */
-typedef enum { FDB_ADD = 1, FDB_SUB, FDB_MUL, FDB_DIV, FDB_POW, FDB_MAX, FDB_MIN, FDB_ATAN2, FDB_HYPOT } fdb_op2;
+/* NaNMath (src/dual.jl:477,549): NaNMath.pow / log / sin / sqrt ... return NaN outside their domain where Base throws a DomainError.
+ * Device math never throws -- out-of-domain arguments already give NaN -- so FDB_POW, FDB_LOG, FDB_SIN ... ARE the NaNMath variants
+ * (pinned by test/DualTest.jl:514, test/DerivativeTest.jl:98-102).  NaNMath.max / NaNMath.min differ in value: they ignore a NaN
+ * operand (FDB_NANMAX / FDB_NANMIN; derivative 1 for the argument returned). */
+typedef enum { FDB_ADD = 1, FDB_SUB, FDB_MUL, FDB_DIV, FDB_POW, FDB_MAX, FDB_MIN, FDB_ATAN2, FDB_HYPOT, FDB_NANMAX, FDB_NANMIN } fdb_op2;
 typedef enum { FDB_SUM = 1, FDB_PROD = 2 } fdb_redop;
 
 /* scalar-valued catalogue targets for fdb_gradient_chunked / fdb_hessian_chunked */
@@ -210,6 +214,11 @@ int fdb_fma(fdb_ctx* ctx, int kind, fdb_array* out, const fdb_array* a, const fd
 int fdb_dual_matvec(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t n, const fdb_array* xdual, fdb_array* ydual);
 int fdb_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t k, const fdb_array* B, int64_t ldb, int64_t ncols,
                fdb_array* C, int64_t ldc);
+/* C = A * B where BOTH matrices hold Duals (Julia: generic matrix product over the Dual*Dual body, src/dual.jl:260-300):
+ * value(C) = value(A) value(B), partial_j(C) = value(A) partial_j(B) + partial_j(A) value(B): 2N+1 real FP64 tensor-core
+ * contractions.  A (m x k), B (k x n), C (m x n): level-1 Dual arrays of column-major matrices, same chunk size. */
+int fdb_dual_matmul(fdb_ctx* ctx, const fdb_array* A, int64_t lda, int64_t m, int64_t k, const fdb_array* B, int64_t ldb, int64_t n,
+                    fdb_array* C, int64_t ldc);
 /* sum / prod of a Dual array -> Dual array of length 1 (two-pass, deterministic) */
 int fdb_reduce(fdb_ctx* ctx, int redop, fdb_array* out1, const fdb_array* a);
 /* evaluate a catalogue target on a materialised dual array: out1 = f(xdual) */
@@ -275,6 +284,15 @@ int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, int n_instr,
                                  int result_reg, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* J,
                                  int64_t ldJ, fdb_array* y);
 
+/* jacobian(x -> g.(A * x), x, cfg) for a user function that contracts the input with a Float64 matrix A (m x xlen, plain,
+ * column-major, lda) and applies an elementwise program g to the product: `A * xdual` through Julia's generic matvec over Dual
+ * (src/dual.jl:476-490 bodies; caller src/jacobian.jl:220 `ydual = f(xdual)`).  The contraction of A against the chunk's lanes
+ * runs on the FP64 tensor cores (DMMA), the program -- same instruction format, LOADX with offset 0 yields z_i = (A*x)_i, array
+ * parameters are indexed by the row i -- runs on the product.  Same chunk-range semantics as fdb_jacobian_chunked. */
+int fdb_program_matvec_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, int n_instr, const double* consts, int n_consts, int result_reg,
+                                        const fdb_array* A, int64_t lda, int64_t m, const fdb_array* x, int N, int64_t chunk_lo,
+                                        int64_t chunk_hi, fdb_array* J, int64_t ldJ, fdb_array* y);
+
 /* hessian(f, x, cfg) of a flattened f (same program form as fdb_program_gradient_chunked; ops with a nested-dual rule:
  * + - * / neg, literal powers, exp log sin cos tanh sqrt abs abs2 inv).  Outer chunks [lo, hi).  f = one plain sum of terms
  * (n_acc = 1, no epilogue) runs on either executor; several sums and arithmetic after the reductions (e.g. Ackley) need the
@@ -299,7 +317,7 @@ int fdb_set_jit(fdb_ctx* ctx, int enabled);
 int fdb_jit_stats(fdb_ctx* ctx, int64_t* compiled, int64_t* cache_hits, int64_t* failures);
 const char* fdb_jit_last_log(fdb_ctx* ctx);   /* NVRTC log of the last failed specialisation ("" if none) */
 /* host-only (no GPU, no context): generate and compile the specialised kernel of a program; kind 0 gradient,
- * 1 Jacobian, 2 Hessian.  Returns 0 and the cubin size, or the NVRTC log in `log`. */
+ * 1 Jacobian, 2 Hessian, 3 Jacobian of g.(A * x).  Returns 0 and the cubin size, or the NVRTC log in `log`. */
 int fdb_jit_compile_check(int kind, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi, const double* consts,
                           int n_consts, int n_acc, int halo, int result_reg, int n_params, int N, int nansafe, int lane_sharing,
                           char* log, int64_t log_capacity, int64_t* cubin_bytes);

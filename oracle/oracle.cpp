@@ -292,6 +292,23 @@ template <int N> inline Dual<double, N> min_v(const Dual<double, N>& x, const Du
     return r;
 }
 
+// NaNMath.max / NaNMath.min (NaNMath.jl: a NaN operand is ignored); derivative 1 for the argument returned.  The DiffRules rule for
+// these (src/dual.jl:476-490 generates the Dual methods from it) is not pinned by any test in the reference tree: parity unpinned.
+template <int N> inline Dual<double, N> nanmax_v(const Dual<double, N>& x, const Dual<double, N>& y) {
+    const bool takex = std::isnan(y.v) || (!std::isnan(x.v) && x.v > y.v);
+    Dual<double, N> r; r.v = takex ? x.v : y.v;
+    const double dx = takex ? 1.0 : 0.0, dy = takex ? 0.0 : 1.0;
+    for (int i = 0; i < N; i++) r.p[i] = mul_partial(x.p[i], dx) + mul_partial(y.p[i], dy);
+    return r;
+}
+template <int N> inline Dual<double, N> nanmin_v(const Dual<double, N>& x, const Dual<double, N>& y) {
+    const bool takex = std::isnan(y.v) || (!std::isnan(x.v) && !(x.v > y.v));
+    Dual<double, N> r; r.v = takex ? x.v : y.v;
+    const double dx = takex ? 1.0 : 0.0, dy = takex ? 0.0 : 1.0;
+    for (int i = 0; i < N; i++) r.p[i] = mul_partial(x.p[i], dx) + mul_partial(y.p[i], dy);
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // seeds and windows  (src/apiutils.jl:39-41, 76-143; src/partials.jl:9-12)
 // ---------------------------------------------------------------------------
@@ -642,7 +659,7 @@ void third_order_vector_mode(int fn, const double* x, double* T3) {
 enum Op1 { OP_NEG = 1, OP_EXP, OP_LOG, OP_SIN, OP_COS, OP_TANH, OP_SQRT, OP_ABS, OP_ABS2, OP_INV,
            OP_POW0, OP_POW1, OP_POW2, OP_POW3, OP_TAN, OP_EXP2, OP_LOG2, OP_LOG10, OP_LOG1P, OP_EXPM1, OP_SINH, OP_COSH,
            OP_ASIN, OP_ACOS, OP_ATAN, OP_CBRT };
-enum Op2 { OP_ADD = 1, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_MAX, OP_MIN, OP_ATAN2, OP_HYPOT };
+enum Op2 { OP_ADD = 1, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_MAX, OP_MIN, OP_ATAN2, OP_HYPOT, OP_NANMAX, OP_NANMIN };
 
 template <int N> int map1(int op, Dual<double, N>* out, const Dual<double, N>* a, long n) {
     for (long i = 0; i < n; i++) {
@@ -677,7 +694,8 @@ template <int N> int map2(int op, int kind, Dual<double, N>* out, const Dual<dou
             switch (op) { case OP_ADD: r = x + y; break; case OP_SUB: r = x - y; break; case OP_MUL: r = x * y; break;
                           case OP_DIV: r = x / y; break; case OP_POW: r = pow_v(x, y); break;
                           case OP_MAX: r = max_v(x, y); break; case OP_MIN: r = min_v(x, y); break;
-                          case OP_ATAN2: r = atan2_v(x, y); break; case OP_HYPOT: r = hypot_v(x, y); break; default: return -2; }
+                          case OP_ATAN2: r = atan2_v(x, y); break; case OP_HYPOT: r = hypot_v(x, y); break;
+                          case OP_NANMAX: r = nanmax_v(x, y); break; case OP_NANMIN: r = nanmin_v(x, y); break; default: return -2; }
         } else if (kind == 1) {
             const D& x = a[i];
             switch (op) { case OP_ADD: r = x + s; break; case OP_SUB: r = x - s; break; case OP_MUL: r = x * s; break;
@@ -803,6 +821,20 @@ int orc_reduce(int op, double* out, const double* a, long n, int N) {
         r = x[0];
         for (long i = 1; i < n; i++) r = (op == 1) ? (r + x[i]) : (r * x[i]);
         std::memcpy(out, &r, sizeof(D));
+    }));
+    return 0;
+}
+// C = A * B on column-major matrices of Duals (AoS): Julia's generic matrix product, C[i,j] = sum over l of A[i,l]*B[l,j]
+// with the Dual*Dual body of src/dual.jl:260-300 (val = va*vb; p = pa*vb + pb*va) and Dual+Dual, accumulated in ascending l.
+int orc_dual_matmul(double* c, const double* a, const double* b, long m, long k, long n, int N) {
+    ORC_DISPATCH_N(N, ({
+        typedef Dual<double, NN> D; const D* A = (const D*)a; const D* B = (const D*)b; D* C = (D*)c;
+        for (long j = 0; j < n; j++)
+            for (long i = 0; i < m; i++) {
+                D r = A[i] * B[j * k];
+                for (long l = 1; l < k; l++) r = r + A[i + l * m] * B[l + j * k];
+                C[i + j * m] = r;
+            }
     }));
     return 0;
 }

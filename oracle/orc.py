@@ -22,7 +22,7 @@ _lp = C.POINTER(C.c_long)
 OP1 = dict(neg=1, exp=2, log=3, sin=4, cos=5, tanh=6, sqrt=7, abs=8, abs2=9, inv=10,
            pow0=11, pow1=12, pow2=13, pow3=14, tan=15, exp2=16, log2=17, log10=18, log1p=19, expm1=20, sinh=21, cosh=22,
            asin=23, acos=24, atan=25, cbrt=26)
-OP2 = dict(add=1, sub=2, mul=3, div=4, pow=5, max=6, min=7, atan2=8, hypot=9)
+OP2 = dict(add=1, sub=2, mul=3, div=4, pow=5, max=6, min=7, atan2=8, hypot=9, nanmax=10, nanmin=11)
 FN = dict(rosenbrock=1, ackley=2, sumsq=3, prod=4)
 JFN = dict(tanh_affine=1, brusselator=2, jactest=3)
 
@@ -65,6 +65,7 @@ class Oracle:
         L.orc_map2.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_long, C.c_int]
         L.orc_fma3.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_long, C.c_int]
         L.orc_reduce.argtypes = [C.c_int, _dp, _dp, C.c_long, C.c_int]
+        L.orc_dual_matmul.argtypes = [_dp, _dp, _dp, C.c_long, C.c_long, C.c_long, C.c_int]
         L.orc_eval_scalar_fn.argtypes = [C.c_int, _dp, _dp, C.c_long, C.c_int]
         L.orc_eval_scalar_fn_value.restype = C.c_double
         L.orc_eval_scalar_fn_value.argtypes = [C.c_int, _dp, C.c_long]
@@ -146,6 +147,12 @@ class Oracle:
     def reduce(self, op, a):
         a = _f64(a); out = np.empty(a.shape[1])
         assert self.lib.orc_reduce(dict(sum=1, prod=2)[op], _p(out), _p(a), a.shape[0], a.shape[1] - 1) == 0
+        return out
+
+    def dual_matmul(self, A, B, m, k, n):
+        """A: (m*k, N+1) AoS duals of a column-major m x k matrix, B: (k*n, N+1) -> (m*n, N+1)"""
+        A = _f64(A); B = _f64(B); out = np.empty((m * n, A.shape[1]))
+        assert self.lib.orc_dual_matmul(_p(out), _p(A), _p(B), m, k, n, A.shape[1] - 1) == 0
         return out
 
     def eval_scalar_fn(self, fn, xdual):

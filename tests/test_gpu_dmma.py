@@ -102,3 +102,20 @@ def test_two_layer_dense_partials_on_dmma(ctx, oracle, N, share):
         assert np.allclose(res.derivs[0], J_ref, rtol=1e-11, atol=1e-14), (n, h, m, N, share)
         h1 = np.tanh(A1 @ x + b1); yy = np.tanh(A2 @ h1 + b2)
         assert np.allclose(res.derivs[0], (1 - yy ** 2)[:, None] * A2 @ ((1 - h1 ** 2)[:, None] * A1), rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.parametrize("N", [1, 5, 12])
+def test_dual_times_dual_matrix_product(ctx, oracle, N):
+    """C = A * B with Duals on both sides (the Dual*Dual body of src/dual.jl:260-300 summed over the inner index)."""
+    rng = np.random.default_rng(N)
+    for m, k, n in ((128, 64, 40), (256, 96, 130), (37, 19, 11), (130, 33, 7)):      # the last two take the CUDA-core contraction
+        A = rng.uniform(-1, 1, (m * k, N + 1)); B = rng.uniform(-1, 1, (k * n, N + 1))
+        Cd = fdb200.dual_matmul(ctx.duals(A), (m, k), ctx.duals(B), (k, n))
+        got = Cd.numpy()
+        ref = oracle.dual_matmul(A, B, m, k, n)
+        assert np.allclose(got, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max()), (m, k, n, N)
+        # the value plane alone is the plain product
+        Av = A[:, 0].reshape((m, k), order="F"); Bv = B[:, 0].reshape((k, n), order="F")
+        assert np.allclose(got[:, 0].reshape((m, n), order="F"), Av @ Bv, rtol=1e-12, atol=1e-13)
+    with pytest.raises(fdb200.DimensionMismatch):
+        fdb200.dual_matmul(ctx.duals(np.zeros((6, N + 1))), (2, 3), ctx.duals(np.zeros((8, N + 1))), (4, 2))

@@ -538,7 +538,7 @@ def test_gradients_match_vectors_generated_by_the_reference_cpp_program(ctx):
 @pytest.mark.parametrize("N", [1, 2, 3, 4])
 def test_readme_example_gradient(ctx, N):
     """README.md:26-45: f(x) = sin(x[1]) + prod(x[2:end]) at x = [pi/4, 2, 3, 4] -> [0.7071067811865476, 12, 8, 6].
-    Written with views instead of scalar indexing; prod keeps it on the reference chunk loop over device Dual arrays."""
+    Written with views instead of scalar indexing; flattened into an op-program with a product accumulator (specialised kernel)."""
     x = np.array([np.pi / 4, 2.0, 3.0, 4.0])
 
     def f(xd):

@@ -38,3 +38,14 @@ def test_c_abi_demo_runs_from_plain_c(tmp_path):
                     "-lfdb200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "c_abi_demo ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_julia_shim_call_sequences_run_from_plain_c(tmp_path):
+    """examples/julia_call_sequences.c: every C-ABI call sequence of julia/ForwardDiffB200.jl (which cannot run here: no Julia),
+    with the ccall argument order and types, checked against closed forms."""
+    libdir = os.path.join(ROOT, "forwarddiff.jl_b200", "lib")
+    exe = str(tmp_path / "julia_call_sequences")
+    subprocess.run(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "julia_call_sequences.c"), "-L" + libdir,
+                    "-lfdb200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "julia_call_sequences ok" in r.stdout, r.stdout + r.stderr

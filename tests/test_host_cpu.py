@@ -233,3 +233,34 @@ def test_c_abi_links_from_plain_c_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode == 0 and "c_abi_demo ok" in r.stdout, r.stdout + r.stderr
     else:
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_julia_shim_is_consistent_with_the_c_abi():
+    """Julia is not installed, so ForwardDiffB200.jl cannot be loaded; what CAN be checked statically is: no constant defined
+    twice, every function imported from ForwardDiff for extension gets at least one method, and every `ccall` names a symbol of
+    include/fdb200.h with the right number of argument types (C types mapped onto the ctypes signatures)."""
+    import re
+    import fdb200
+    src = open(os.path.join(ROOT, "forwarddiff.jl_b200", "julia", "ForwardDiffB200.jl")).read()
+    consts = re.findall(r"^const\s+([A-Za-z_0-9, ]+?)\s*=", src, flags=re.M)
+    names = [n.strip() for c in consts for n in c.split(",")]
+    assert len(names) == len(set(names)), [n for n in names if names.count(n) > 1]
+    imported = re.search(r"import ForwardDiff:(.*?)\n\n", src, flags=re.S).group(1).replace("\n", " ")
+    for fn in [t.strip() for t in imported.split(",") if t.strip()]:
+        pat = r"^(function\s+)?" + re.escape(fn) + r"\("
+        assert re.search(pat, src, flags=re.M), f"{fn} is imported for extension but has no method"
+    ctype_ok = {"Ptr{Cvoid}": (fdb200._lib.C.c_void_p,), "Ref{Ptr{Cvoid}}": (fdb200._lib.C.POINTER(fdb200._lib.C.c_void_p),),
+                "Cint": (fdb200._lib.C.c_int,), "Int64": (fdb200._lib.C.c_int64,), "Cdouble": (fdb200._lib.C.c_double,)}
+    calls = re.findall(r"ccall\(\(:(fdb_\w+), libfdb200\),\s*(\w+),\s*\((.*?)\),", src, flags=re.S)
+    assert len(calls) > 40
+    for name, ret, argtypes in calls:
+        assert name in fdb200._lib.SIGNATURES, f"{name} is not declared in include/fdb200.h"
+        res, args = fdb200._lib.SIGNATURES[name]
+        jl = [t.strip() for t in re.sub(r"\s+", " ", argtypes).split(",") if t.strip()]
+        assert len(jl) == len(args), (name, jl, args)
+        for t, a in zip(jl, args):
+            if t == "Ptr{Cvoid}":           # an opaque handle or a pointer to a plain struct (fdb_chunk_plan)
+                import ctypes
+                assert a in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(a, ctypes._Pointer), (name, t, a)
+            elif t in ctype_ok:
+                assert a in ctype_ok[t], (name, t, a)

@@ -84,3 +84,61 @@ def test_device_binary_rules(ctx, oracle):
         got = fn(ad, bd).numpy(); ref = oracle.map2(name, a, b)
         assert _ulp(got[:, 0], ref[:, 0]) <= 4
         assert np.allclose(got[:, 1:], ref[:, 1:], rtol=1e-14, atol=1e-15)
+
+
+# ---- NaNMath variants (src/dual.jl:477,549) --------------------------------------------------------------------------
+def _nanmath_pow_cases():
+    """test/DualTest.jl:514 and test/DerivativeTest.jl:98-102 as (base dual, exponent dual | float, kind, expected partial / predicate)"""
+    nan = float("nan")
+    return [
+        # partials(NaNMath.pow(Dual(-2.0, 1.0), Dual(2.0, 0.0)), 1) == -4.0: a constant exponent never takes log of the negative base
+        (np.array([[-2.0, 1.0]]), np.array([[2.0, 0.0]]), "dd", lambda p: p == -4.0),
+        # derivative(x -> NaNMath.pow(NaN, x), 1.0) is NaN
+        (nan, np.array([[1.0, 1.0]]), "rd", np.isnan),
+        # derivative(x -> NaNMath.pow(x, NaN), 1.0) is NaN
+        (np.array([[1.0, 1.0]]), nan, "dr", np.isnan),
+        # derivative(x -> NaNMath.pow(1.0, x), 1.0) is not NaN
+        (1.0, np.array([[1.0, 1.0]]), "rd", lambda p: not np.isnan(p)),
+        # derivative(x -> NaNMath.pow(x, 0.5), -1.0) is NaN (Base.^ throws a DomainError here; the device cannot throw)
+        (np.array([[-1.0, 1.0]]), 0.5, "dr", np.isnan),
+    ]
+
+
+def test_oracle_nanmath_pow_and_max_min(oracle):
+    for a, b, kind, pred in _nanmath_pow_cases():
+        r = oracle.map2("pow", a, b)
+        assert pred(r[0, 1]), (a, b, kind, r)
+    nan = float("nan")
+    x = np.array([[1.0, 1.0, 0.0], [nan, 1.0, 0.0], [3.0, 1.0, 0.0], [nan, 1.0, 0.0]])
+    y = np.array([[2.0, 0.0, 1.0], [2.0, 0.0, 1.0], [nan, 0.0, 1.0], [nan, 0.0, 1.0]])
+    mx = oracle.map2("nanmax", x, y); mn = oracle.map2("nanmin", x, y)
+    assert np.array_equal(mx[:3], [[2.0, 0.0, 1.0], [2.0, 0.0, 1.0], [3.0, 1.0, 0.0]]) and np.isnan(mx[3, 0])
+    assert np.array_equal(mn[:3], [[1.0, 1.0, 0.0], [2.0, 0.0, 1.0], [3.0, 1.0, 0.0]]) and np.isnan(mn[3, 0])
+    # Base.max propagates the NaN instead (value), which is what distinguishes the two
+    assert oracle.map2("max", x, y)[0, 0] == 2.0
+
+
+@pytest.mark.gpu
+def test_device_nanmath_pow_and_max_min(ctx, oracle):
+    import fdb200
+    for a, b, kind, pred in _nanmath_pow_cases():
+        if kind == "dd":
+            r = fdb200.nanmath.pow(ctx.duals(a), ctx.duals(b)).numpy()
+        elif kind == "dr":
+            r = fdb200.nanmath.pow(ctx.duals(a), b).numpy()
+        else:
+            r = fdb200.nanmath.pow(a, ctx.duals(b)).numpy()
+        assert pred(r[0, 1]), (a, b, kind, r)
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (200, 4)); y = rng.uniform(-1, 1, (200, 4))
+    x[::7, 0] = np.nan; y[::5, 0] = np.nan
+    for op, fn in (("nanmax", fdb200.nanmath.max), ("nanmin", fdb200.nanmath.min)):
+        got = fn(ctx.duals(x), ctx.duals(y)).numpy(); ref = oracle.map2(op, x, y)
+        assert np.array_equal(got, ref, equal_nan=True), op
+    # in a traced user function (op-program, both executors share the device functions)
+    xs = rng.uniform(0.5, 1.5, 300)
+    f = lambda xd: fdb200.nanmath.max(xd[1:], xd[:-1] ** 2).sum()
+    g = fdb200.gradient(f, xs, fdb200.GradientConfig(f, xs, fdb200.Chunk(7)), ctx=ctx)
+    take = xs[1:] > xs[:-1] ** 2
+    ref = np.zeros(300); ref[1:] += take; ref[:-1] += (~take) * 2.0 * xs[:-1]
+    assert np.allclose(g, ref, rtol=1e-14)

@@ -604,3 +604,135 @@ def test_program_hessian_vs_oracle_and_finite_differences(ctx, oracle, N, mode):
     else:
         with pytest.raises(fdb200.UnsupportedOp):
             fdb200.hessian(F.ackley_generic, x, fdb200.HessianConfig(F.ackley_generic, x, fdb200.Chunk(N)), ctx=ctx)
+
+
+# ---- A @ x inside a user function: contraction on the FP64 tensor cores + elementwise program -----------------------------
+def test_tracer_matvec_node_and_host_compile():
+    """`lambda x: tanh(A @ x + b)` flattens to an elementwise program over z = A*x (LOADX 0 = z_i, b an array parameter read at
+    the row index); anything that uses x besides A @ x is rejected.  The specialised kernel (kind 3) compiles on the host."""
+    import ctypes as C
+    from fdb200.api import _i32p
+    rng = np.random.default_rng(0)
+    A = rng.random((40, 24)); b = rng.random(40)
+    prog = trace.trace_array(lambda x: fdb200.tanh(A @ x + b), 24)
+    assert prog.matvec is A and prog.out_len == 40 and prog.halo == 0 and len(prog.params) == 1 and prog.needs_jit
+    kinds = [int(k) >> 6 for k in prog.term[:, 0]]
+    assert kinds == [trace.K_LOADX, trace.K_DP, trace.K_UNARY]
+    plain = trace.trace_array(lambda x: fdb200.exp(0.5 * (A @ x)) * 2.0, 24)
+    assert plain.matvec is A and not plain.needs_jit
+    sq = rng.random((24, 24))
+    for bad in (lambda x: fdb200.tanh(sq @ x) + x, lambda x: A @ (2.0 * x), lambda x: (A @ x)[1:], lambda x: A @ x[:24] + (A @ x)):
+        with pytest.raises((trace.TraceError, fdb200.DimensionMismatch)):
+            trace.trace_array(bad, 24)
+    with pytest.raises(trace.TraceError, match="reduction over A @ x"):
+        trace.trace_scalar(lambda x: fdb200.tanh(A @ x).sum(), 24)
+    with pytest.raises(fdb200.DimensionMismatch):
+        trace.trace_array(lambda x: A @ x, 23)
+    lib = fdb200._lib.load()
+    for p, N in ((prog, 12), (plain, 5)):
+        log = C.create_string_buffer(1 << 16); nbytes = C.c_int64()
+        rc = lib.fdb_jit_compile_check(3, _i32p(p.term), len(p.term), None, 0, p.consts.ctypes.data_as(C.POINTER(C.c_double)) if p.consts.size else None,
+                                       p.consts.size, 0, 0, p.result_reg, len(p.params), N, 0, 1, log, len(log), C.byref(nbytes))
+        assert rc == 0 and nbytes.value > 1000, log.value.decode()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 8, 12])
+@pytest.mark.parametrize("share", [True, False])
+def test_user_function_through_a_linear_map_runs_on_the_tensor_cores(ctx, oracle, N, share, mode):
+    """jacobian(x -> tanh.(A*x .+ b), x, cfg) written by the USER (src/jacobian.jl:220 `ydual = f(xdual)` with Julia's generic
+    matvec over Dual): same numbers as the catalogue target and the oracle, contraction on the DMMA kernel."""
+    rng = np.random.default_rng(5)
+    for m, n in ((256, 128), (384, 160), (50, 33)):          # last shape: not TMA-eligible -> CUDA-core contraction
+        A = rng.uniform(-1, 1, (m, n)) / np.sqrt(n); b = rng.uniform(-1, 1, m); x = rng.uniform(-1, 1, n)
+        f = lambda xd: fdb200.tanh(A @ xd + b)
+        if mode == "interpreted":                             # array parameters exist in the specialised kernels only
+            f = lambda xd: fdb200.tanh(A @ xd + 0.25)
+        res = fdb200.JacobianResult(np.zeros(m), x)
+        cfg = fdb200.JacobianConfig(f, x, fdb200.Chunk(N))
+        ctx.set_lane_sharing(share)
+        try:
+            l0 = ctx.launches()
+            fdb200.jacobian_b(res, f, x, cfg, ctx=ctx)
+            nl = ctx.launches() - l0
+        finally:
+            ctx.set_lane_sharing(True)
+        assert cfg.last_path == ("program:specialised" if mode == "specialised" else "program:interpreted")
+        assert nl == 4                                        # operand build, pack, contraction, elementwise program
+        bb = b if mode == "specialised" else np.full(m, 0.25)
+        J_ref, y_ref = oracle.jacobian("tanh_affine", x, m, N, A=A, b=bb)
+        assert np.allclose(res.value, y_ref, rtol=1e-12, atol=1e-13)
+        assert np.allclose(res.derivs[0], J_ref, rtol=1e-12, atol=1e-15), (m, n, N, share)
+        if mode == "specialised":
+            cat = F.tanh_affine.with_params(A=A, b=b)
+            Jc = fdb200.jacobian(cat, x, fdb200.JacobianConfig(cat, x, fdb200.Chunk(N)), ctx=ctx, m=m)
+            assert np.allclose(res.derivs[0], Jc, rtol=1e-13, atol=1e-15)
+    # chunk ranges tile
+    m, n = 256, 128
+    A = rng.uniform(-1, 1, (m, n)) / np.sqrt(n); x = rng.uniform(-1, 1, n)
+    f = lambda xd: fdb200.sin(A @ xd) * 3.0
+    cfg = fdb200.JacobianConfig(f, x, fdb200.Chunk(N))
+    full = fdb200.jacobian(f, x, cfg, ctx=ctx)
+    assert np.allclose(full, 3.0 * np.cos(A @ x)[:, None] * A, rtol=1e-12, atol=1e-14)
+    out = np.zeros((m, n), order="F")
+    for r in range(3):
+        p = fdb200.chunk_plan(n, N, r, 3)
+        part = np.zeros((m, n), order="F")
+        fdb200.jacobian_b(part, f, x, cfg, ctx=ctx, chunks=(p["chunk_lo"], p["chunk_hi"]))
+        out[:, p["elem_lo"]:p["elem_hi"]] = part[:, p["elem_lo"]:p["elem_hi"]]
+    assert np.array_equal(out, full)
+
+
+@pytest.mark.gpu
+def test_matvec_on_materialised_duals_in_the_reference_loop(ctx):
+    """gradient(x -> sum(tanh.(A*x)), x, cfg): no batched kernel, so the reference loop runs -- with `A @ xdual` as one DMMA
+    contraction per chunk (B200DualArray.__rmatmul__ -> fdb_dual_matvec)."""
+    rng = np.random.default_rng(6)
+    m, n, N = 160, 96, 12
+    A = rng.uniform(-1, 1, (m, n)) / np.sqrt(n); x = rng.uniform(-1, 1, n)
+    f = lambda xd: fdb200.tanh(A @ xd).sum()
+    cfg = fdb200.GradientConfig(f, x, fdb200.Chunk(N))
+    res = fdb200.GradientResult(x)
+    fdb200.gradient_b(res, f, x, cfg, ctx=ctx)
+    assert cfg.last_path.startswith("loop") and "A @ x" in cfg.trace_error
+    y = np.tanh(A @ x)
+    assert np.allclose(res.derivs[0], A.T @ (1.0 - y * y), rtol=1e-11, atol=1e-13)
+    assert res.value == pytest.approx(float(y.sum()), rel=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 5, 12])
+def test_prod_reductions_run_on_the_batched_sweep(ctx, oracle, N):
+    """prod(x): an accumulator that starts at one(Dual) and combines by Dual*Dual; lane sharing still applies (far factors have
+    identical partial lanes).  Specialised kernels only; without them f takes the reference loop."""
+    rng = np.random.default_rng(N)
+    for n in (13, 300, 2000):
+        x = rng.uniform(0.9, 1.1, n)
+        f = lambda xd: xd.prod()
+        cfg = fdb200.GradientConfig(f, x, fdb200.Chunk(N))
+        res = fdb200.GradientResult(x)
+        fdb200.gradient_b(res, f, x, cfg, ctx=ctx)
+        assert cfg.last_path == "program:specialised"
+        g_ref, v_ref = oracle.gradient("prod", x, N)
+        assert np.allclose(res.derivs[0], g_ref, rtol=1e-11) and res.value == pytest.approx(v_ref, rel=1e-12)
+        ctx.set_lane_sharing(False)
+        try:
+            g2 = fdb200.gradient(f, x, cfg, ctx=ctx)
+        finally:
+            ctx.set_lane_sharing(True)
+        assert np.allclose(g2, res.derivs[0], rtol=1e-12)
+    # README.md:26-45 shape: a sum over one view plus a product over another, and arithmetic after the reductions
+    x = np.array([np.pi / 4, 2.0, 3.0, 4.0, 0.5, 1.5, 2.5])
+    f = lambda xd: fdb200.sin(xd[:1]).sum() + xd[1:].prod() * 2.0
+    cfg = fdb200.GradientConfig(f, x, fdb200.Chunk(min(N, 7)))
+    g = fdb200.gradient(f, x, cfg, ctx=ctx)
+    assert cfg.last_path == "program:specialised"
+    p = np.prod(x[1:])
+    assert np.allclose(g, np.concatenate([[np.cos(x[0])], 2.0 * p / x[1:]]), rtol=1e-13)
+    # interpreter: products are not available -> the reference loop, same numbers
+    ctx.set_jit(False)
+    try:
+        g3 = fdb200.gradient(f, x, cfg, ctx=ctx)
+        assert cfg.last_path.startswith("loop") and np.allclose(g3, g, rtol=1e-13)
+    finally:
+        ctx.set_jit(True)

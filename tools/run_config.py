@@ -21,11 +21,13 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-share", action="store_true")
     ap.add_argument("--no-dmma", action="store_true")
+    ap.add_argument("--bn", type=int, default=0, help="DMMA column-tile width (0 = auto, 16, 32, 64)")
     a = ap.parse_args()
     ctx = fdb200.Context(0)
     lib = ctx.lib
     ctx.set_lane_sharing(not a.no_share)
     ctx.check(lib.fdb_set_dmma(ctx.h, 0 if a.no_dmma else 1))
+    ctx.check(lib.fdb_set_dmma_tile(ctx.h, a.bn))
     rng = np.random.default_rng(1)
     FN, JFN = fdb200._lib.FN, fdb200._lib.JFN
     v = ctx.zeros(1)
