@@ -149,11 +149,11 @@ static std::string emit_part(const short (*code)[4], int n, int from = 0) {
 }
 static std::string decl_regs() {
     std::string s = "        D";
-    for (int r = 0; r < PG_MAXR; r++) s += std::string(r ? ", " : " ") + R(r) + "{}";
+    for (int r = 0; r < PJ_MAXR; r++) s += std::string(r ? ", " : " ") + R(r) + "{}";
     return s + ";\n";
 }
 
-enum { JIT_GRADIENT = 0, JIT_JACOBIAN = 1, JIT_HESSIAN = 2, JIT_MATVEC_JACOBIAN = 3 };
+enum { JIT_GRADIENT = 0, JIT_JACOBIAN = 1, JIT_HESSIAN = 2, JIT_MATVEC_JACOBIAN = 3, JIT_JACOBIAN2 = 4 };
 
 static std::string make_source(int kind, const Program& P, int N, bool ns, bool share, bool mir) {
     std::string s = "#include \"fdb_sweep_kernel.cuh\"\n#include \"fdb_hessian_kernel.cuh\"\n#include \"fdb_jac_kernel.cuh\"\n";
@@ -161,7 +161,7 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
     s += "extern \"C\" { __constant__ const double* fdb_prm[" + std::to_string(FDB_MAX_PARAMS) + "]; }\n";
     s += "namespace fdb {\n";
     char buf[96];
-    for (int i = 0; i < PG_MAXC; i++) {            // constants by bit pattern: exact for every double including Inf/NaN
+    for (int i = 0; i < PJ_MAXC; i++) {            // constants by bit pattern: exact for every double including Inf/NaN
         long long bits; memcpy(&bits, &P.consts[i], 8);
         snprintf(buf, sizeof buf, "#define c%d __longlong_as_double(0x%016llxLL)\n", i, (unsigned long long)bits);
         s += buf;
@@ -184,28 +184,31 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
     for (int pc = 0; pc < P.n_term; pc++)
         if ((P.term[pc][0] >> 6) == PK_STAGE) { if (P.term[pc][2] == 1) st1 = pc; else st2 = pc; }
     s += std::string("    static constexpr bool TWO_PASS = ") + (P.two_pass ? "true" : "false") + ";\n";
-    s += "    static constexpr int NSCAL = " + std::to_string(PG_MAXR) + ";\n";
+    s += "    static constexpr int NSCAL = " + std::to_string(PJ_MAXR) + ";\n";
     // term: the user's broadcast body for one i, adding into the sum accumulators (pass 1 of a two-pass program)
     s += "    template <class D, class L> static FDB_DEV void term(const L& x, int64_t i, int64_t n, D (&acc)[K]) {\n" + decl_regs() +
          emit_part(P.term, P.two_pass ? st1 : P.n_term) + "    }\n";
     if (P.two_pass) {
         // finalize1: scalar Dual code on the pass-1 sums; the whole register file is published as S
         s += "    template <class D> static FDB_DEV void finalize1(const D (&acc)[K], D* S) {\n" + decl_regs();
-        for (int k = 0; k < P.k1 && k < PG_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
+        for (int k = 0; k < P.k1 && k < PJ_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
         s += emit_part(P.term, st2, st1 + 1);
-        for (int r = 0; r < PG_MAXR; r++) s += "        S[" + std::to_string(r) + "] = " + R(r) + ";\n";
+        for (int r = 0; r < PJ_MAXR; r++) s += "        S[" + std::to_string(r) + "] = " + R(r) + ";\n";
         s += "    }\n";
         // term2: the second broadcast, reading x and the scalars S
         s += "    template <class D, class L> static FDB_DEV void term2(const L& x, int64_t i, int64_t n, const D* S, D (&acc)[K]) {\n" + decl_regs() +
              emit_part(P.term, P.n_term, st2 + 1) + "    }\n";
+        // apply2: the array-valued second broadcast, y[i] = result register (jacobian_sweep2_body)
+        s += "    template <class D, class L> static FDB_DEV D apply2(const L& x, int64_t i, int64_t n, const D* S) {\n        D acc[K]; (void)acc;\n" + decl_regs() +
+             emit_part(P.term, P.n_term, st2 + 1) + "        return " + R(P.result_reg) + ";\n    }\n";
         // finalize2: registers k1..K-1 start as the pass-2 sums
         s += "    template <class D> static FDB_DEV D finalize2(const D (&acc)[K], const D* S, int64_t) {\n" + decl_regs();
-        for (int k = P.k1; k < K && k < PG_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
+        for (int k = P.k1; k < K && k < PJ_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
         s += emit_part(P.epi, P.n_epi) + "        return " + R(P.result_reg) + ";\n    }\n";
     }
     // finalize: scalar Dual arithmetic after the reductions; registers 0..K-1 start as the reduced accumulators
     s += "    template <class D> static FDB_DEV D finalize(const D (&acc)[K], int64_t) {\n" + decl_regs();
-    for (int k = 0; k < K && k < PG_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
+    for (int k = 0; k < K && k < PJ_MAXK; k++) s += "        " + R(k) + " = acc[" + std::to_string(k) + "];\n";
     s += (P.two_pass ? std::string() : emit_part(P.epi, P.n_epi)) + "        return " + R(P.result_reg) + ";\n    }\n";
     // apply: array-valued form, y[i] = result register after the term part
     if (!P.two_pass)
@@ -225,6 +228,12 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
              "        const unsigned nrb, const unsigned nch, const bool rowfast, const __grid_constant__ fdb_mirrors M) {\n"
              "    fdb::elementwise_jacobian_body<" + targs + ", 128, " + (mir ? "true" : "false") +
              ">(share, x, n, chunk_lo, nchunks_total, lastchunksize, J, ldJ, yout, nrb, nch, rowfast, M);\n}\n";
+    } else if (kind == JIT_JACOBIAN2) {
+        s += "extern \"C\" __global__ void __launch_bounds__(256) fdb_user_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo,\n"
+             "        int64_t nchunks_total, int lastchunksize, double* __restrict__ J, int64_t ldJ, double* __restrict__ yout,\n"
+             "        const __grid_constant__ fdb_mirrors M) {\n"
+             "    fdb::jacobian_sweep2_body<" + targs + ", 256, " + (share ? "true" : "false") + ", " + (mir ? "true" : "false") +
+             ">(x, n, chunk_lo, nchunks_total, lastchunksize, J, ldJ, yout, M);\n}\n";
     } else if (kind == JIT_MATVEC_JACOBIAN) {
         s += "extern \"C\" __global__ void __launch_bounds__(128) fdb_user_kernel(const bool share, const double* __restrict__ Y, int64_t ldy,\n"
              "        const double* __restrict__ A, int64_t lda, int64_t m, int64_t n, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,\n"
@@ -283,8 +292,8 @@ int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share
     if (!ctx->use_jit) return FDB_ERR_UNSUPPORTED;
     if (!ctx->jit) ctx->jit = new fdb_jit_cache();
     fdb_jit_cache& J = *ctx->jit;
-    if (kind != JIT_GRADIENT) share = false;          // run-time flag (Jacobian) or not applicable (Hessian)
-    if (kind != JIT_JACOBIAN && kind != JIT_MATVEC_JACOBIAN) mir = false;
+    if (kind != JIT_GRADIENT && kind != JIT_JACOBIAN2) share = false;          // run-time flag (Jacobian) or not applicable (Hessian)
+    if (kind != JIT_JACOBIAN && kind != JIT_MATVEC_JACOBIAN && kind != JIT_JACOBIAN2) mir = false;
     const std::string key = cache_key(kind, P, N, ns, share, mir);
     auto it = J.map.find(key);
     if (it != J.map.end()) { J.hits++; *fn = it->second.fn ? &it->second : nullptr; return it->second.fn ? FDB_OK : FDB_ERR_UNSUPPORTED; }
@@ -364,9 +373,9 @@ extern "C" const char* fdb_jit_last_log(fdb_ctx* ctx) { return (ctx && ctx->jit)
 extern "C" int fdb_jit_compile_check(int kind, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi, const double* consts,
                                      int n_consts, int n_acc, int halo, int result_reg, int n_params, int N, int nansafe, int lane_sharing,
                                      char* log, int64_t log_capacity, int64_t* cubin_bytes) {
-    if (kind < JIT_GRADIENT || kind > JIT_MATVEC_JACOBIAN || N < 1 || N > FDB_MAX_CHUNK) return FDB_ERR_BADARG;
+    if (kind < JIT_GRADIENT || kind > JIT_JACOBIAN2 || N < 1 || N > FDB_MAX_CHUNK) return FDB_ERR_BADARG;
     Program P;
-    int rc = build_program(nullptr, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, kind == JIT_JACOBIAN || kind == JIT_MATVEC_JACOBIAN, n_params);
+    int rc = build_program(nullptr, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, kind == JIT_JACOBIAN || kind == JIT_MATVEC_JACOBIAN || kind == JIT_JACOBIAN2, n_params);
     std::vector<char> cubin;
     std::string lg;
     if (rc == FDB_OK) rc = compile_source(make_source(kind, P, N, nansafe != 0, lane_sharing != 0, false), cubin, lg);

@@ -108,28 +108,29 @@ static int launch_program_gradient(fdb_ctx* ctx, unsigned grid, size_t smem, con
 
 int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, const int32_t* epi, int n_epi, const double* consts,
                          int n_consts, int n_acc, int halo, int result_reg, bool array_form, int n_params) {
-    if (n_term < 0 || n_term > PG_MAXI || n_epi < 0 || n_epi > PG_MAXI || n_consts < 0 || n_consts > PG_MAXC || n_acc < 0 || n_acc > PG_MAXK ||
-        halo < 0 || result_reg < 0 || result_reg >= PG_MAXR || (n_term && !term) || (n_epi && !epi) || (n_consts && !consts))
-        return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program exceeds interpreter limits (%d instr, %d consts, %d registers, %d accumulators)",
-                    PG_MAXI, PG_MAXC, PG_MAXR, PG_MAXK);
+    if (n_term < 0 || n_term > PJ_MAXI || n_epi < 0 || n_epi > PJ_MAXI || n_consts < 0 || n_consts > PJ_MAXC || n_acc < 0 || n_acc > PJ_MAXK ||
+        halo < 0 || result_reg < 0 || result_reg >= PJ_MAXR || (n_term && !term) || (n_epi && !epi) || (n_consts && !consts))
+        return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program exceeds the program limits (%d instr, %d consts, %d registers, %d accumulators)",
+                    PJ_MAXI, PJ_MAXC, PJ_MAXR, PJ_MAXK);
     memset(&P, 0, sizeof P);
     P.n_term = n_term; P.n_epi = n_epi; P.n_acc = n_acc; P.halo = halo; P.result_reg = result_reg;
     int used_params = 0;
     P.term_halo = halo;
     for (int k = 0; k < FDB_MAX_PARAMS; k++) P.prm_halo[k] = (short)halo;
-    int guard_left = 0, guard_h = halo, min_guard = halo, stage = 0, max_acc = -1, acc_seen = 0;
+    int guard_left = 0, guard_h = halo, min_guard = halo, stage = 0, max_acc = -1, acc_seen = 0, max_reg = result_reg;
     bool unguarded_reads = false;
     for (int part = 0; part < 2; part++) {
         const int32_t* src = part ? epi : term; const int cnt = part ? n_epi : n_term;
         for (int i = 0; i < cnt; i++) {
             const int op = src[4 * i], dst = src[4 * i + 1], a = src[4 * i + 2], b = src[4 * i + 3];
             const int kind = op >> 6, code = op & 63;
-            bool ok = dst >= 0 && dst < PG_MAXR && kind >= PK_LOADX && kind <= PK_LOADS;
+            bool ok = dst >= 0 && dst < PJ_MAXR && kind >= PK_LOADX && kind <= PK_LOADS;
+            if (kind != PK_ACC && kind != PK_GUARD && kind != PK_STAGE && dst > max_reg) max_reg = dst;
             if (kind == PK_STAGE) {
-                ok = !part && !array_form && guard_left == 0 && a == stage + 1 && a <= 2;
+                ok = !part && guard_left == 0 && a == stage + 1 && a <= 2;
                 if (ok) { stage = a; P.two_pass = 1; if (a == 1) P.k1 = max_acc + 1; }
             }
-            if (kind == PK_LOADS) ok = ok && a >= 0 && a < PG_MAXR && P.two_pass && (part || stage == 2);
+            if (kind == PK_LOADS) ok = ok && a >= 0 && a < PJ_MAXR && P.two_pass && (part || stage == 2);
             if (!part && stage == 1 && (kind == PK_LOADX || kind == PK_ACC || kind == PK_DP || kind == PK_PD || kind == PK_GUARD)) ok = false;   // scalar code only
             if (kind == PK_ACC && dst > max_acc) max_acc = dst;
             if (kind == PK_GUARD) {
@@ -142,29 +143,33 @@ int build_program(fdb_ctx* ctx, Program& P, const int32_t* term, int n_term, con
             if (kind == PK_DP && b >= 0 && b < FDB_MAX_PARAMS && h_here < P.prm_halo[b]) P.prm_halo[b] = (short)h_here;
             if (kind == PK_PD && a >= 0 && a < FDB_MAX_PARAMS && h_here < P.prm_halo[a]) P.prm_halo[a] = (short)h_here;
             if (guard_left > 0) guard_left--;
-            if (kind == PK_DP) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < PG_MAXR && b >= 0 && b < n_params; if (b + 1 > used_params) used_params = b + 1; }
-            if (kind == PK_PD) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < n_params && b >= 0 && b < PG_MAXR; if (a + 1 > used_params) used_params = a + 1; }
+            if (kind == PK_DP) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < PJ_MAXR && b >= 0 && b < n_params; if (b + 1 > used_params) used_params = b + 1; }
+            if (kind == PK_PD) { ok = ok && !part && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < n_params && b >= 0 && b < PJ_MAXR; if (a + 1 > used_params) used_params = a + 1; }
             if (kind == PK_LOADX) ok = ok && !part && b >= 0 && b <= halo;
-            if (kind == PK_UNARY) ok = ok && code >= FDB_NEG && code <= FDB_CBRT && a >= 0 && a < PG_MAXR;
-            if (kind == PK_DD) ok = ok && code >= FDB_ADD && code <= FDB_NANMIN && a >= 0 && a < PG_MAXR && b >= 0 && b < PG_MAXR;
-            if (kind == PK_DC) ok = ok && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < PG_MAXR && b >= 0 && b < n_consts;
-            if (kind == PK_CD) ok = ok && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < n_consts && b >= 0 && b < PG_MAXR;
+            if (kind == PK_UNARY) ok = ok && code >= FDB_NEG && code <= FDB_CBRT && a >= 0 && a < PJ_MAXR;
+            if (kind == PK_DD) ok = ok && code >= FDB_ADD && code <= FDB_NANMIN && a >= 0 && a < PJ_MAXR && b >= 0 && b < PJ_MAXR;
+            if (kind == PK_DC) ok = ok && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < PJ_MAXR && b >= 0 && b < n_consts;
+            if (kind == PK_CD) ok = ok && code >= FDB_ADD && code <= FDB_POW && a >= 0 && a < n_consts && b >= 0 && b < PJ_MAXR;
             if (kind == PK_ACC) {          // b = 1: product accumulator (prod); an accumulator is either a sum or a product throughout
-                ok = ok && !part && !array_form && dst < n_acc && a >= 0 && a < PG_MAXR && (b == 0 || (b == 1 && stage == 0));
+                // array-valued form: sums exist only in pass 1 of a two-pass program (softmax: exp.(x) ./ sum(exp.(x))), pass 2 yields y[i]
+                ok = ok && !part && !(array_form && stage != 0) && dst < n_acc && a >= 0 && a < PJ_MAXR && (b == 0 || (b == 1 && stage == 0));
                 if (ok) {
                     const int bit = 1 << dst;
                     if ((acc_seen & bit) && (((P.prod_mask & bit) != 0) != (b == 1))) ok = false;
                     acc_seen |= bit; if (b == 1) P.prod_mask |= bit;
                 }
             }
-            if (kind == PK_MOV) ok = ok && a >= 0 && a < PG_MAXR;
+            if (kind == PK_MOV) ok = ok && a >= 0 && a < PJ_MAXR;
             if (!ok) return fail(ctx, FDB_ERR_BADARG, "op-program: malformed instruction %d of the %s part", i, part ? "epilogue" : "term");
             short* d = part ? P.epi[i] : P.term[i];
             d[0] = (short)op; d[1] = (short)dst; d[2] = (short)a; d[3] = (short)b;
         }
     }
     for (int i = 0; i < n_consts; i++) P.consts[i] = consts[i];
+    P.max_reg = max_reg;
+    P.fits_interpreter = n_term <= PG_MAXI && n_epi <= PG_MAXI && n_consts <= PG_MAXC && n_acc <= PG_MAXK && max_reg < PG_MAXR && result_reg < PG_MAXR;
     P.n_params = used_params;
+    if (array_form && max_acc >= 0 && !P.two_pass) return fail(ctx, FDB_ERR_BADARG, "op-program: an array-valued program with reductions needs the two-pass form");
     if (P.two_pass && (stage != 2 || P.has_guard))
         return fail(ctx, FDB_ERR_BADARG, "op-program: a two-pass program needs both stage markers and no guarded groups");
     if (P.has_guard) {
@@ -222,6 +227,8 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
             return finish(ctx, 1, "fdb_program_gradient_chunked(specialised)");
         }
     }
+    if (!P.fits_interpreter) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program beyond the interpreter's limits (%d instr, %d consts, %d registers, %d accumulators) needs the run-time specialised kernel (%s)",
+                                         PG_MAXI, PG_MAXC, PG_MAXR, PG_MAXK, ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     if (P.n_params || P.has_guard || P.two_pass || P.prod_mask) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters, reductions of different lengths, products or two passes needs the run-time specialised kernel (%s)",
                                 ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     int nregs = 1;

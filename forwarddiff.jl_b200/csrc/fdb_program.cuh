@@ -9,10 +9,14 @@
 
 namespace fdb {
 
+// limits of the per-thread INTERPRETER (register file in local / shared memory, instruction words in the constant bank)
 constexpr int PG_MAXI = 96;      // instructions per program part
 constexpr int PG_MAXC = 24;      // Float64 constants
 constexpr int PG_MAXR = 12;      // virtual Dual registers
 constexpr int PG_MAXK = 4;       // sum accumulators
+// limits of the program representation itself = what the run-time specialised kernels accept (there a "register" is a C++
+// variable and spilling is the compiler's business)
+constexpr int PJ_MAXI = 256, PJ_MAXC = 64, PJ_MAXR = 32, PJ_MAXK = 8;
 constexpr int PG_VEC = 4;        // terms per thread per decoded instruction on the lane-shared path
 
 struct Program {
@@ -21,9 +25,10 @@ struct Program {
     int prod_mask;               // bit k: accumulator k is a product (`prod`), PK_ACC with b = 1; specialised kernels only
     int two_pass, k1;            // PK_STAGE markers split the term part into term1 | epilogue1 | term2; accumulators [0, k1) belong to pass 1
     short prm_halo[FDB_MAX_PARAMS];   // parameter k is read for i < n - prm_halo[k]
-    short term[PG_MAXI][4];      // {op, dst, a, b}
-    short epi[PG_MAXI][4];
-    double consts[PG_MAXC];
+    int fits_interpreter, max_reg;   // within the PG_* limits; highest register number used
+    short term[PJ_MAXI][4];      // {op, dst, a, b}
+    short epi[PJ_MAXI][4];
+    double consts[PJ_MAXC];
 };
 
 enum { PK_LOADX = 0, PK_UNARY = 1, PK_DD = 2, PK_DC = 3, PK_CD = 4, PK_ACC = 5, PK_MOV = 6,

@@ -232,8 +232,8 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
             return finish(ctx, 1, "fdb_program_hessian_chunked(specialised)");
         }
     }
-    if (!plain)
-        return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: arithmetic after the reduction or array parameters need the run-time specialised kernel (%s)",
+    if (!plain || !P.fits_interpreter)
+        return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program Hessian: arithmetic after the reduction, array parameters or programs beyond the interpreter's limits need the run-time specialised kernel (%s)",
                     ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
         (program_hessian_kernel<NN, NS, T><<<grid, T, 0, ctx->stream>>>(P, x->data, n, chunk_lo, nchunks, (int)p.lastchunksize, Hp, ldH, gp, vp, M))));

@@ -118,7 +118,7 @@ extern "C" int fdb_program_matvec_jacobian_chunked(fdb_ctx* ctx, const int32_t* 
             return finish(ctx, nl + 1, "fdb_program_matvec_jacobian_chunked(specialised)");
         }
     }
-    if (P.n_params) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters needs the run-time specialised kernel (%s)",
+    if (P.n_params || !P.fits_interpreter) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters or beyond the interpreter's limits needs the run-time specialised kernel (%s)",
                                 ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     if (M.count) {
         FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
@@ -143,7 +143,9 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
     if (ldJ < m || J->n < ldJ * (n - 1) + m) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: Jacobian result must hold %lld x %lld", (long long)m, (long long)n);
     if (y && y->n != m) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: y has %lld entries, f(x) has %lld", (long long)y->n, (long long)m);
     Program P;
-    int rc = build_program(ctx, P, prog, n_instr, nullptr, 0, consts, n_consts, 0, halo, result_reg, true, ctx->n_prm); if (rc) return rc;
+    int n_acc = 0;                                   // pass-1 sums of a two-pass program (softmax ...): accumulators are numbered densely
+    for (int i = 0; i < n_instr && prog; i++) if ((prog[4 * i] >> 6) == PK_ACC && prog[4 * i + 1] + 1 > n_acc) n_acc = prog[4 * i + 1] + 1;
+    int rc = build_program(ctx, P, prog, n_instr, nullptr, 0, consts, n_consts, n_acc, halo, result_reg, true, ctx->n_prm); if (rc) return rc;
     rc = check_params(ctx, P, n, "fdb_program_jacobian_chunked"); if (rc) return rc;
     Plan p = make_plan(n, N);
     const int64_t nchunks = (n == N) ? 1 : p.nchunks;
@@ -159,6 +161,17 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
     fdb_mirrors M;
     const fdb_array* outs[2] = {J, y};
     rc = mirrors_for(ctx, &M, outs, 2, "fdb_program_jacobian_chunked"); if (rc) return rc;
+    if (P.two_pass) {
+        // reductions inside an array-valued f: one block per chunk, pass 1 reduces, pass 2 writes the dense Jacobian rows
+        void* fn = nullptr;
+        if (jit_get(ctx, 4, P, N, ctx->nansafe, ctx->lane_sharing, M.count > 0, &fn) != FDB_OK)
+            return fail(ctx, FDB_ERR_UNSUPPORTED, "a two-pass array-valued op-program needs the run-time specialised kernel (%s)",
+                        ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
+        const double* xp = x->data; int64_t nn = n, lo = chunk_lo, nc = nchunks, ld = ldJ; int lcs = (int)p.lastchunksize; double* Jp = J->data;
+        void* args[] = {&xp, &nn, &lo, &nc, &lcs, &Jp, &ld, &yp, &M};
+        rc = jit_launch(ctx, fn, nch, 1, 256, args, "fdb_program_jacobian_chunked(two-pass, specialised)"); if (rc) return rc;
+        return finish(ctx, 1, "fdb_program_jacobian_chunked(two-pass, specialised)");
+    }
     {   // specialised kernel for this program (fdb_jit.cu)
         void* fn = nullptr;
         if (jit_get(ctx, 1, P, N, ctx->nansafe, false, M.count > 0, &fn) == FDB_OK) {
@@ -170,7 +183,7 @@ extern "C" int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, i
             return finish(ctx, 1, "fdb_program_jacobian_chunked(specialised)");
         }
     }
-    if (P.n_params) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters needs the run-time specialised kernel (%s)",
+    if (P.n_params || !P.fits_interpreter) return fail(ctx, FDB_ERR_UNSUPPORTED, "op-program with array parameters or beyond the interpreter's limits needs the run-time specialised kernel (%s)",
                                 ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
     if (M.count) {
         FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,

@@ -174,6 +174,35 @@ FDB_DEV void gradient_sweep2_body(const double* __restrict__ x, int64_t n, int64
     }
 }
 
+// Array-valued two-pass form: y = g.(x, reduced values), e.g. softmax exp.(x) ./ sum(exp.(x)) or (x .- mean(x)) ./ std.  The
+// Jacobian is dense (every output depends on every input through the reduced Duals), so one block sweeps one chunk: pass 1
+// reduces (lane sharing included), finalize1 publishes the scalar Duals S, pass 2 evaluates y[i] on all N lanes for every row
+// and stores J[i, start+k] = partials(y[i], k) straight from registers (extract_jacobian_chunk!, src/jacobian.jl:109-118).
+template <class F, int N, bool NS, int THREADS, bool SHARE, bool MIR>
+FDB_DEV void jacobian_sweep2_body(const double* __restrict__ x, int64_t n, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize,
+                                  double* __restrict__ J, int64_t ldJ, double* __restrict__ yout, const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> D;
+    const int64_t c = chunk_lo + blockIdx.x;
+    const bool last = (c == nchunks_total - 1);
+    const int chunksize = last ? lastchunksize : N;
+    const int64_t start = last ? (n - lastchunksize) : c * N;
+    __shared__ D s_S[F::NSCAL];
+    D acc[F::K];
+    sweep_terms<F, N, NS, THREADS, SHARE>(x, n, start, chunksize, acc);
+    block_combine<F, D, THREADS>(acc);
+    if (threadIdx.x == 0) F::finalize1(acc, s_S);
+    __syncthreads();
+    SeedLoader<N, NS> xs{x, start, chunksize};
+    const int64_t m = n - F::HALO;
+    for (int64_t i = threadIdx.x; i < m; i += THREADS) {
+        const D y = F::template apply2<D>(xs, i, n, s_S);
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (k < chunksize) mstore_cs<MIR>(M, J + i + (start + k) * ldJ, y.p[k]);
+        if (yout && last) mstore(M, &yout[i], y.v);
+    }
+}
+
 template <class F, int N, bool NS, int THREADS, bool SHARE>
 __global__ void __launch_bounds__(THREADS) gradient_sweep_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo,
                                                                  int64_t nchunks_total, int lastchunksize,

@@ -14,7 +14,9 @@ import numpy as np
 from ._lib import OP1, OP2
 
 K_LOADX, K_UNARY, K_DD, K_DC, K_CD, K_ACC, K_MOV, K_DP, K_PD, K_GUARD, K_STAGE, K_LOADS = range(12)
-MAX_INSTR, MAX_CONST, MAX_REG, MAX_ACC, MAX_PARAMS = 96, 24, 12, 4, 4
+# limits of the program representation (what the run-time specialised kernels accept) and of the per-thread interpreter
+MAX_INSTR, MAX_CONST, MAX_REG, MAX_ACC, MAX_PARAMS = 256, 64, 32, 8, 4
+I_MAX_INSTR, I_MAX_CONST, I_MAX_REG, I_MAX_ACC = 96, 24, 12, 4
 
 
 class TraceError(Exception):
@@ -289,7 +291,10 @@ class Program:
         kinds = (self.term[:, 0] >> 6) if self.term.size else np.zeros(0, dtype=np.int32)
         self.two_pass = bool(np.any(kinds == K_STAGE))
         self.has_prod = bool(np.any((kinds == K_ACC) & (self.term[:, 3] == 1))) if self.term.size else False
-        self.needs_jit = bool(self.params) or bool(np.any(kinds == K_GUARD)) or self.two_pass or self.has_prod
+        regs = [int(r) for part in (self.term, self.epi) for ins in part for r in ((ins[1],) if (ins[0] >> 6) not in (K_ACC, K_GUARD, K_STAGE) else ())]
+        self.beyond_interpreter = (len(self.term) > I_MAX_INSTR or len(self.epi) > I_MAX_INSTR or self.consts.size > I_MAX_CONST or
+                                   n_acc > I_MAX_ACC or max(regs + [result_reg]) >= I_MAX_REG)
+        self.needs_jit = bool(self.params) or bool(np.any(kinds == K_GUARD)) or self.two_pass or self.has_prod or self.beyond_interpreter
 
 
 def _common_halo(tr, lengths):
@@ -391,7 +396,9 @@ def trace_array(f, n):
     if not isinstance(y, TArray):
         raise TraceError("f did not return an array")
     if tr.accs:
-        raise TraceError("reductions inside an array-valued f need two passes")
+        if tr.matvec is not None:
+            raise TraceError("reductions over A @ x inside an array-valued f")
+        return _two_pass_array_program(tr, y)
     if tr.matvec is not None:
         # elementwise over z = A @ x: every leaf must be z itself (x may not appear again, nor views of z)
         m = tr.matvec.shape[0]
@@ -406,6 +413,37 @@ def trace_array(f, n):
     L, halo = _common_halo(tr, {y.n})
     term, reg = _emit(tr, [y.node], "term", {})
     return Program(term, [], tr.consts, 0, halo, reg[y.node.id], L, tr.params)
+
+
+def _two_pass_array_program(tr, y):
+    """y = g.(x, reduced values): term1 | STAGE 1 | epilogue1 | STAGE 2 | term2, the result register of term2 is y[i]
+    (softmax: exp.(x) ./ sum(exp.(x))).  Specialised kernels only (jacobian_sweep2_body)."""
+    if any(tr.acc_prod) or any(_LEVEL[nd.stage] != 0 for nd in tr.accs):
+        raise TraceError("only plain first-pass sums may feed an array-valued second broadcast")
+    if _LEVEL[y.node.stage] != 2:
+        raise TraceError("the reductions do not contribute to the result")
+    L, halo = _common_halo(tr, set(tr.term_lengths) | {y.n})
+    term, reg = _emit(tr, tr.accs, "term", {})
+    for k, nd in enumerate(tr.accs):
+        term.append((K_ACC << 6, k, reg[nd.id], 0))
+    needed, seen = [], set()
+    for nd in tr.nodes:
+        if _LEVEL[nd.stage] >= 2:
+            for a in nd.args:
+                if _LEVEL[a.stage] == 1 and a.id not in seen:
+                    seen.add(a.id)
+                    needed.append(a)
+    pre1 = {nd.id: nd.op for nd in tr.acc_nodes}
+    epi1, sreg = _emit(tr, needed, "scalar", pre1)
+    sreg = {nd.id: sreg[nd.id] for nd in needed}
+    term.append((K_STAGE << 6, 0, 1, 0))
+    term += epi1
+    term.append((K_STAGE << 6, 0, 2, 0))
+    term2, reg2 = _emit(tr, [y.node], {"term", "term2"}, {}, sreg)
+    term += term2
+    if len(term) > MAX_INSTR:
+        raise TraceError("program too long")
+    return Program(term, [], tr.consts, len(tr.accs), halo, reg2[y.node.id], L, tr.params)
 
 
 def _reachable(root):

@@ -273,10 +273,14 @@ int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t
  *   kind 11 LOADS dst <- S[a], S = the register file as the first-stage epilogue left it (term2 and final epilogue;
  *                 there registers K1..n_acc-1 are preloaded with the second-stage accumulators)
  * The term part runs for every i in [0, n - halo); the epilogue part runs once per chunk with registers
- * 0..n_acc-1 preloaded with the reduced accumulators; `result_reg` holds f(xdual).  Limits: 96 instructions
- * per part, 24 constants, 12 registers, 4 accumulators (FDB_ERR_UNSUPPORTED beyond).  Same chunk-range
+ * 0..n_acc-1 preloaded with the reduced accumulators; `result_reg` holds f(xdual).  PK_ACC with b = 1 is a PRODUCT
+ * accumulator (`prod`: starts at one(Dual), combines by Dual*Dual; single-pass gradient programs, specialised kernels only).
+ * Limits: 256 instructions per part, 64 constants, 32 registers, 8 accumulators for the run-time specialised kernels; the
+ * interpreter takes 96 / 24 / 12 / 4 (FDB_ERR_UNSUPPORTED beyond).  Same chunk-range
  * semantics as fdb_gradient_chunked / fdb_jacobian_chunked.  The Jacobian form evaluates
- * y[i] = program(x[i .. i+halo]), i in [0, n - halo) (elementwise / stencil array functions). */
+ * y[i] = program(x[i .. i+halo]), i in [0, n - halo) (elementwise / stencil array functions); with the two-pass markers
+ * (pass-1 sums, scalar epilogue, second broadcast whose result register is y[i]) it evaluates array functions that use reduced
+ * values -- softmax exp.(x) ./ sum(exp.(x)) -- whose Jacobian is dense: one thread block per chunk, specialised kernels only. */
 int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi,
                                  const double* consts, int n_consts, int n_acc, int halo, int result_reg, const fdb_array* x, int N,
                                  int64_t chunk_lo, int64_t chunk_hi, fdb_array* grad, fdb_array* value_dev);

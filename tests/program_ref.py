@@ -94,7 +94,7 @@ def _run(instrs, R, consts, m, n, xload=None, params=None, acc=None, S=None, idx
         elif kind == K_CD: R[dst] = binary(_B[code], D.const(consts[a], m, n), R[b])
         elif kind == K_DP: R[dst] = binary(_B[code], R[a], D(params[b][idx], np.zeros((m, n))))
         elif kind == K_PD: R[dst] = binary(_B[code], D(params[a][idx], np.zeros((m, n))), R[b])
-        elif kind == K_ACC: _acc_add(acc, dst, R[a])
+        elif kind == K_ACC: (_acc_mul if b == 1 else _acc_add)(acc, dst, R[a])
         elif kind == K_MOV: R[dst] = R[a]
         elif kind == K_LOADS: R[dst] = D(np.repeat(S[a].v, m), np.repeat(S[a].g, m, axis=0))
         else: raise ValueError(f"kind {kind} not executable here")
@@ -107,6 +107,18 @@ def _acc_add(acc, k, d):
         acc[k] = D(acc[k].v + v, acc[k].g + g)
     else:
         acc[k] = D(v, g)
+    return acc[k]
+
+
+def _acc_mul(acc, k, d):
+    """product accumulator (`prod`, PK_ACC with b = 1): starts at one(Dual), combines by Dual*Dual term by term"""
+    n = d.g.shape[1]
+    cur = acc.get(k, D(np.ones(1), np.zeros((1, n))))
+    v, g = cur.v.copy(), cur.g.copy()
+    for i in range(d.v.size):
+        g = g * d.v[i] + d.g[i:i + 1] * v
+        v = v * d.v[i]
+    acc[k] = D(v, g)
     return acc[k]
 
 
@@ -147,7 +159,8 @@ def evaluate(prog, x):
         for instrs, m in _term_groups(term, n, prog.halo):
             idx = np.arange(max(m, 0)); R = {}
             _run(instrs, R, consts, idx.size, n, loader(idx), params, acc, None, idx)
-        R = {k: acc.get(k, D.const(0.0, 1, n)) for k in range(prog.n_acc)}
+        prod = {int(ins[1]) for ins in term if (ins[0] >> 6) == K_ACC and ins[3] == 1}
+        R = {k: acc.get(k, D.const(1.0 if k in prod else 0.0, 1, n)) for k in range(prog.n_acc)}
         _run(epi, R, consts, 1, n)
         y = R[prog.result_reg]
         return float(y.v[0]), y.g[0]
@@ -159,6 +172,8 @@ def evaluate(prog, x):
     _run(term[st1 + 1: st2], S, consts, 1, n)                    # first-stage epilogue; its register file is S
     R = {}
     _run(term[st2 + 1:], R, consts, m, n, loader(idx), params, acc, S, idx)
+    if prog.out_len > 1 and not epi:                             # array-valued two-pass form: y[i] = result register of the second broadcast
+        return R[prog.result_reg].v, R[prog.result_reg].g
     R = {k: acc.get(k, D.const(0.0, 1, n)) for k in range(k1, prog.n_acc)}
     _run(epi, R, consts, 1, n, S=S)
     y = R[prog.result_reg]

@@ -21,8 +21,10 @@ def test_tracer_flattens_rosenbrock_and_ackley():
 
 
 def test_tracer_rejects_what_the_interpreter_cannot_run():
+    pr = trace.trace_scalar(F.prod_generic, 10)                      # prod: a product accumulator, specialised kernels only
+    assert pr.has_prod and pr.needs_jit and pr.term[-1, 3] == 1
     with pytest.raises(trace.TraceError):
-        trace.trace_scalar(F.prod_generic, 10)                       # not an additive reduction
+        trace.trace_scalar(lambda x: (x * x.prod()).sum(), 10)        # a product re-entering a broadcast
     assert trace.trace_scalar(lambda x: (x * x.sum()).sum(), 10).two_pass    # reduced value inside a broadcast: two passes
     with pytest.raises(trace.TraceError):
         trace.trace_scalar(lambda x: x * 2.0, 10)                    # not a scalar
@@ -736,3 +738,132 @@ def test_prod_reductions_run_on_the_batched_sweep(ctx, oracle, N):
         assert cfg.last_path.startswith("loop") and np.allclose(g3, g, rtol=1e-13)
     finally:
         ctx.set_jit(True)
+
+
+def test_two_pass_array_programs_trace_and_compile_on_the_host():
+    """reductions inside an array-valued f (softmax, centring): term1 | STAGE 1 | epilogue1 | STAGE 2 | term2 with the result register of
+    term2 as y[i]; specialised kernel kind 4 (jacobian_sweep2_body) compiles for sm_100a without a GPU."""
+    import ctypes as C
+    from fdb200.api import _i32p
+    lib = fdb200._lib.load()
+    softmax = lambda x: fdb200.exp(x) / fdb200.exp(x).sum()
+    centre = lambda x: (x - x.mean()) * 2.0
+    for f in (softmax, centre):
+        p = trace.trace_array(f, 60)
+        assert p.two_pass and p.needs_jit and p.out_len == 60 and p.n_acc == 1
+        log = C.create_string_buffer(1 << 16); nbytes = C.c_int64()
+        rc = lib.fdb_jit_compile_check(4, _i32p(p.term), len(p.term), None, 0, p.consts.ctypes.data_as(C.POINTER(C.c_double)) if p.consts.size else None,
+                                       p.consts.size, p.n_acc, p.halo, p.result_reg, len(p.params), 12, 0, 1, log, len(log), C.byref(nbytes))
+        assert rc == 0 and nbytes.value > 1000, log.value.decode()
+    with pytest.raises(trace.TraceError):                        # three stages
+        trace.trace_array(lambda x: (x - x.mean()) / fdb200.sqrt(((x - x.mean()) ** 2).sum()), 60)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 7, 12])
+def test_softmax_like_jacobians_run_as_two_pass_programs(ctx, N):
+    """jacobian(x -> exp.(x) ./ sum(exp.(x)), x): dense, every output depends on every input through the reduced Dual."""
+    rng = np.random.default_rng(N)
+    for n in (13, 200, 1031):
+        x = rng.uniform(-1, 1, n)
+        softmax = lambda xd: fdb200.exp(xd) / fdb200.exp(xd).sum()
+        cfg = fdb200.JacobianConfig(softmax, x, fdb200.Chunk(N))
+        res = fdb200.JacobianResult(np.zeros(n), x)
+        fdb200.jacobian_b(res, softmax, x, cfg, ctx=ctx)
+        assert cfg.last_path == "program:specialised"
+        s = np.exp(x) / np.exp(x).sum()
+        assert np.allclose(res.value, s, rtol=1e-13)
+        assert np.allclose(res.derivs[0], np.diag(s) - np.outer(s, s), rtol=1e-11, atol=1e-15)
+        centre = lambda xd: (xd - xd.mean()) * 2.0
+        J = fdb200.jacobian(centre, x, fdb200.JacobianConfig(centre, x, fdb200.Chunk(N)), ctx=ctx)
+        assert np.allclose(J, 2.0 * (np.eye(n) - 1.0 / n), rtol=1e-12, atol=1e-15)
+        # lane sharing off and chunk ranges give the same matrix
+        ctx.set_lane_sharing(False)
+        try:
+            J2 = fdb200.jacobian(softmax, x, cfg, ctx=ctx)
+        finally:
+            ctx.set_lane_sharing(True)
+        assert np.allclose(J2, res.derivs[0], rtol=1e-12, atol=1e-16)
+        out = np.zeros((n, n), order="F")
+        for r in range(2):
+            p = fdb200.chunk_plan(n, N, r, 2)
+            part = np.zeros((n, n), order="F")
+            fdb200.jacobian_b(part, softmax, x, cfg, ctx=ctx, chunks=(p["chunk_lo"], p["chunk_hi"]))
+            out[:, p["elem_lo"]:p["elem_hi"]] = part[:, p["elem_lo"]:p["elem_hi"]]
+        assert np.array_equal(out, res.derivs[0])
+
+
+def _many_live_values(xd):
+    """fifteen broadcast results alive at once and > 96 instructions: beyond the interpreter (12 registers), fine for the specialised kernel"""
+    terms = [fdb200.sin(float(k) * xd[1:]) * fdb200.cos(0.5 * k * xd[:-1]) for k in range(1, 16)]
+    acc = terms[0]
+    for t in terms[1:]:
+        acc = acc * 0.5 + t
+    for t in terms:
+        acc = acc + t * t
+    return acc.sum()
+
+
+def test_programs_beyond_the_interpreter_limits_and_new_forms_mean_what_the_evaluator_says():
+    """programs that only the specialised kernels accept (more registers / instructions, product accumulators, array-valued two-pass
+    form) against the NumPy reference evaluator and closed forms, plus host compilation"""
+    import ctypes as C
+    from fdb200.api import _i32p
+    import program_ref
+    lib = fdb200._lib.load()
+    rng = np.random.default_rng(3)
+    x = rng.uniform(0.5, 1.5, 40)
+    big = trace.trace_scalar(_many_live_values, 40)
+    assert big.beyond_interpreter and big.needs_jit and len(big.term) > 96
+    v, g = program_ref.evaluate(big, x)
+    h = 1e-6
+    fd = np.array([(_np_many(x + h * e) - _np_many(x - h * e)) / (2 * h) for e in np.eye(40)])
+    assert v == pytest.approx(_np_many(x), rel=1e-13) and np.allclose(g, fd, rtol=1e-6, atol=1e-6)
+    pr = trace.trace_scalar(lambda xd: xd[1:].prod() * 2.0 + (xd * xd).sum(), 40)
+    v, g = program_ref.evaluate(pr, x)
+    p = np.prod(x[1:])
+    gref = 2.0 * x; gref[1:] += 2.0 * p / x[1:]
+    assert v == pytest.approx(2.0 * p + np.sum(x * x), rel=1e-13) and np.allclose(g, gref, rtol=1e-12)
+    sm = trace.trace_array(lambda xd: fdb200.exp(xd) / fdb200.exp(xd).sum(), 40)
+    y, J = program_ref.evaluate(sm, x)
+    s = np.exp(x) / np.exp(x).sum()
+    assert np.allclose(y, s, rtol=1e-14) and np.allclose(J, np.diag(s) - np.outer(s, s), rtol=1e-12, atol=1e-16)
+    for kind, prog in ((0, big), (0, pr), (4, sm)):
+        log = C.create_string_buffer(1 << 16); nbytes = C.c_int64()
+        rc = lib.fdb_jit_compile_check(kind, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
+                                       prog.consts.ctypes.data_as(C.POINTER(C.c_double)) if prog.consts.size else None, prog.consts.size, prog.n_acc,
+                                       prog.halo, prog.result_reg, len(prog.params), 12, 0, 1, log, len(log), C.byref(nbytes))
+        assert rc == 0 and nbytes.value > 1000, log.value.decode()
+
+
+def _np_many(x):
+    a, b = x[1:], x[:-1]
+    terms = [np.sin(k * a) * np.cos(0.5 * k * b) for k in range(1, 16)]
+    acc = terms[0]
+    for t in terms[1:]:
+        acc = acc * 0.5 + t
+    for t in terms:
+        acc = acc + t * t
+    return float(acc.sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [3, 12])
+def test_programs_beyond_the_interpreter_limits_run_specialised(ctx, N):
+    rng = np.random.default_rng(N)
+    x = rng.uniform(0.5, 1.5, 500)
+    cfg = fdb200.GradientConfig(_many_live_values, x, fdb200.Chunk(N))
+    res = fdb200.GradientResult(x)
+    fdb200.gradient_b(res, _many_live_values, x, cfg, ctx=ctx)
+    assert cfg.last_path == "program:specialised"
+    import program_ref
+    v, g = program_ref.evaluate(trace.trace_scalar(_many_live_values, 500), x)
+    assert res.value == pytest.approx(v, rel=1e-12) and np.allclose(res.derivs[0], g, rtol=1e-10, atol=1e-12)
+    # without the specialiser such a program takes the reference loop, not the interpreter
+    ctx.set_jit(False)
+    try:
+        g2 = fdb200.gradient(_many_live_values, x[:60], fdb200.GradientConfig(_many_live_values, x[:60], fdb200.Chunk(N)), ctx=ctx)
+    finally:
+        ctx.set_jit(True)
+    v60, g60 = program_ref.evaluate(trace.trace_scalar(_many_live_values, 60), x[:60])
+    assert np.allclose(g2, g60, rtol=1e-10, atol=1e-12)
