@@ -39,8 +39,8 @@ DP_OPS_PER_TERM_SHARED = 20
 DP_OPS_PER_TERM_FULL = 133          # all 12 lanes: 120 in the term + 13 accumulate (lane sharing off)
 # FP64-pipe instructions (thread level) per element per chunk sweep / per term per chunk pair, measured with ncu on the C2 Ackley launch
 # and the C5 Hessian launch (profiles/r02_fp64_counts.md): sum of smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on / units
-ACKLEY_FP64_ISSUE_PER_TERM = 0.0    # filled in from the ncu capture (0 = not yet measured: roofline frac reads 0)
-HESSIAN_FP64_ISSUE_PER_TERM = 0.0
+ACKLEY_FP64_ISSUE_PER_TERM = 28.06   # (938.6 DADD + 1117.4 DMUL + 3161.3 DFMA) inst/cycle x 448.13e6 cycles / (1e6 x 83334)   [profiles/r02_ackley_sweep_raw.csv]
+HESSIAN_FP64_ISSUE_PER_TERM = 52.88  # (4286.1 DADD + 2470.6 DMUL) inst/cycle x 1.04999e6 cycles / (2047 x 65536)                [profiles/r02_hessian_c5_raw.csv]
 
 
 def load_peaks():
