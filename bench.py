@@ -411,6 +411,7 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
         ms = []
         for _ in range(reps):
             flush.zero_(); sync_all()
+            torch.cuda._sleep(400_000)                      # the host enqueues the whole step while the GPU is parked (see extras.t)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record(); e1.synchronize()
             ms.append(e0.elapsed_time(e1))
@@ -511,10 +512,14 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
     out = {}
 
     def t(fn, reps=3):
+        """median device time of fn() in ms.  L2 is flushed first; then the GPU is parked in a short spin kernel while the host
+        enqueues [event, fn's launches, event], so the interval between the events is device work only -- without it the
+        15-20 us the host needs to get a launch through Python / ctypes sit inside the interval (visible on the sub-100 us kernels)."""
         fn(); torch.cuda.synchronize()
         best = []
         for _ in range(reps):
             flush.zero_()
+            torch.cuda._sleep(400_000)                      # ~0.2 ms at 1.965 GHz
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record(); e1.synchronize()
             best.append(e0.elapsed_time(e1))

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "fdb_internal.h"
+#include "fdb_dual.cuh"
 
 namespace fdb {
 thread_local std::string g_init_error;
@@ -38,32 +39,8 @@ int ensure_pinned(fdb_ctx* ctx, size_t bytes) {
     return FDB_OK;
 }
 
-// 0-based storage index of structural position `pos` (src/apiutils.jl:44-71)
-__host__ __device__ inline int64_t structural_index(int structure, int64_t rows, int64_t pos) {
-    switch (structure) {
-        case FDB_DENSE: return pos;
-        case FDB_DIAGONAL: return pos * (rows + 1);                 // diagind
-        case FDB_UPPER: {                                           // (i,j) for j in 1:n for i in 1:j
-            int64_t j = (int64_t)((sqrt(8.0 * (double)pos + 1.0) - 1.0) * 0.5);
-            while (j * (j + 1) / 2 > pos) j--;
-            while ((j + 1) * (j + 2) / 2 <= pos) j++;
-            int64_t i = pos - j * (j + 1) / 2;
-            return i + j * rows;
-        }
-        case FDB_LOWER: {                                           // (i,j) for j in 1:n for i in j:n
-            // entries before column j: c(j) = j*rows - j*(j-1)/2
-            double r = (double)rows + 0.5;
-            int64_t j = (int64_t)(r - sqrt(r * r - 2.0 * (double)pos));
-            if (j < 0) j = 0;
-            if (j > rows - 1) j = rows - 1;
-            while (j > 0 && j * rows - j * (j - 1) / 2 > pos) j--;
-            while (j + 1 < rows && (j + 1) * rows - (j + 1) * j / 2 <= pos) j++;
-            int64_t i = j + (pos - (j * rows - j * (j - 1) / 2));
-            return i + j * rows;
-        }
-    }
-    return pos;
-}
+// 0-based storage index of structural position `pos` (src/apiutils.jl:44-71): fdb_dual.cuh, shared with the sweep kernels
+__host__ __device__ inline int64_t structural_index(int structure, int64_t rows, int64_t pos) { return (int64_t)struct_index_of(structure, (long)rows, (long)pos); }
 
 // ---------------------------------------------------------------------------
 // kernels

@@ -366,6 +366,39 @@ template <int N, bool NS> FDB_DEV Dual<double, N, NS> min_v(const Dual<double, N
     return r;
 }
 
+// ----- structural index sets (src/apiutils.jl:44-71): UpperTriangular, LowerTriangular, Diagonal over rows x rows column-major storage
+// kind 0 dense, 1 upper ((i,j) for j in 1:n for i in 1:j), 2 lower ((i,j) for j in 1:n for i in j:n), 3 diagonal
+// 0-based storage index of structural position pos
+__host__ __device__ inline long struct_index_of(int kind, long rows, long pos) {
+    switch (kind) {
+        case 3: return pos * (rows + 1);
+        case 1: {
+            long j = (long)((sqrt(8.0 * (double)pos + 1.0) - 1.0) * 0.5);
+            while (j * (j + 1) / 2 > pos) j--;
+            while ((j + 1) * (j + 2) / 2 <= pos) j++;
+            return (pos - j * (j + 1) / 2) + j * rows;
+        }
+        case 2: {
+            const double r = (double)rows + 0.5;
+            long j = (long)(r - sqrt(r * r - 2.0 * (double)pos));
+            if (j < 0) j = 0;
+            if (j > rows - 1) j = rows - 1;
+            while (j > 0 && j * rows - j * (j - 1) / 2 > pos) j--;
+            while (j + 1 < rows && (j + 1) * rows - (j + 1) * j / 2 <= pos) j++;
+            return (j + (pos - (j * rows - j * (j - 1) / 2))) + j * rows;
+        }
+    }
+    return pos;
+}
+// structural position of storage index idx, or -1 when the entry is structurally zero
+__host__ __device__ inline long struct_pos_of(int kind, long rows, long idx) {
+    if (kind == 0) return idx;
+    const long c = idx / rows, r = idx - c * rows;
+    if (kind == 3) return r == c ? r : -1;
+    if (kind == 1) return r <= c ? c * (c + 1) / 2 + r : -1;
+    return r >= c ? c * rows - c * (c - 1) / 2 + (r - c) : -1;
+}
+
 // ----- implicit seeds --------------------------------------------------------
 // The Dual that seed!/seed_zero_partials! would have stored at structural
 // position `pos` (0-based) while the chunk [start, start+chunksize) is seeded:

@@ -153,7 +153,7 @@ static std::string decl_regs() {
     return s + ";\n";
 }
 
-enum { JIT_GRADIENT = 0, JIT_JACOBIAN = 1, JIT_HESSIAN = 2, JIT_MATVEC_JACOBIAN = 3, JIT_JACOBIAN2 = 4 };
+enum { JIT_GRADIENT = 0, JIT_JACOBIAN = 1, JIT_HESSIAN = 2, JIT_MATVEC_JACOBIAN = 3, JIT_JACOBIAN2 = 4, JIT_GRADIENT_STRUCT = 5 };
 
 static std::string make_source(int kind, const Program& P, int N, bool ns, bool share, bool mir) {
     std::string s = "#include \"fdb_sweep_kernel.cuh\"\n#include \"fdb_hessian_kernel.cuh\"\n#include \"fdb_jac_kernel.cuh\"\n";
@@ -228,6 +228,12 @@ static std::string make_source(int kind, const Program& P, int N, bool ns, bool 
              "        const unsigned nrb, const unsigned nch, const bool rowfast, const __grid_constant__ fdb_mirrors M) {\n"
              "    fdb::elementwise_jacobian_body<" + targs + ", 128, " + (mir ? "true" : "false") +
              ">(share, x, n, chunk_lo, nchunks_total, lastchunksize, J, ldJ, yout, nrb, nch, rowfast, M);\n}\n";
+    } else if (kind == JIT_GRADIENT_STRUCT) {
+        s += "extern \"C\" __global__ void __launch_bounds__(256) fdb_user_kernel(const double* __restrict__ x, int64_t nx, int kind, int64_t rows,\n"
+             "        int64_t nstruct, int64_t chunk_lo, int64_t nchunks_total, int lastchunksize, double* __restrict__ grad,\n"
+             "        double* __restrict__ value_out, const __grid_constant__ fdb_mirrors M) {\n"
+             "    fdb::gradient_sweep_struct_body<" + targs + ", 256, " + (share ? "true" : "false") +
+             ">(x, nx, kind, rows, nstruct, chunk_lo, nchunks_total, lastchunksize, grad, value_out, M);\n}\n";
     } else if (kind == JIT_JACOBIAN2) {
         s += "extern \"C\" __global__ void __launch_bounds__(256) fdb_user_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo,\n"
              "        int64_t nchunks_total, int lastchunksize, double* __restrict__ J, int64_t ldJ, double* __restrict__ yout,\n"
@@ -292,7 +298,7 @@ int jit_get(fdb_ctx* ctx, int kind, const Program& P, int N, bool ns, bool share
     if (!ctx->use_jit) return FDB_ERR_UNSUPPORTED;
     if (!ctx->jit) ctx->jit = new fdb_jit_cache();
     fdb_jit_cache& J = *ctx->jit;
-    if (kind != JIT_GRADIENT && kind != JIT_JACOBIAN2) share = false;          // run-time flag (Jacobian) or not applicable (Hessian)
+    if (kind != JIT_GRADIENT && kind != JIT_JACOBIAN2 && kind != JIT_GRADIENT_STRUCT) share = false;          // run-time flag (Jacobian) or not applicable (Hessian)
     if (kind != JIT_JACOBIAN && kind != JIT_MATVEC_JACOBIAN && kind != JIT_JACOBIAN2) mir = false;
     const std::string key = cache_key(kind, P, N, ns, share, mir);
     auto it = J.map.find(key);
@@ -373,7 +379,7 @@ extern "C" const char* fdb_jit_last_log(fdb_ctx* ctx) { return (ctx && ctx->jit)
 extern "C" int fdb_jit_compile_check(int kind, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi, const double* consts,
                                      int n_consts, int n_acc, int halo, int result_reg, int n_params, int N, int nansafe, int lane_sharing,
                                      char* log, int64_t log_capacity, int64_t* cubin_bytes) {
-    if (kind < JIT_GRADIENT || kind > JIT_JACOBIAN2 || N < 1 || N > FDB_MAX_CHUNK) return FDB_ERR_BADARG;
+    if (kind < JIT_GRADIENT || kind > JIT_GRADIENT_STRUCT || N < 1 || N > FDB_MAX_CHUNK) return FDB_ERR_BADARG;
     Program P;
     int rc = build_program(nullptr, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, kind == JIT_JACOBIAN || kind == JIT_MATVEC_JACOBIAN || kind == JIT_JACOBIAN2, n_params);
     std::vector<char> cubin;

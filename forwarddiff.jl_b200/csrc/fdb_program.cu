@@ -240,6 +240,44 @@ extern "C" int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_pr
     return finish(ctx, 1, "fdb_program_gradient_chunked");
 }
 
+// gradient(f, x::UpperTriangular / LowerTriangular / Diagonal, cfg) of a flattened f (src/apiutils.jl:44-71): x and grad hold the
+// rows x rows column-major storage, chunks run over the structural positions, only those entries of grad are written.
+// Single-pass programs, specialised kernels only.
+extern "C" int fdb_program_gradient_chunked_structured(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi,
+                                                       const double* consts, int n_consts, int n_acc, int halo, int result_reg, int structure,
+                                                       int64_t rows, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* grad,
+                                                       fdb_array* value_dev) {
+    FDB_ENTER(ctx);
+    if (!ctx || !x || !grad) return fail(ctx, FDB_ERR_BADARG, "fdb_program_gradient_chunked_structured: null argument");
+    if (x->level != 0 || grad->level != 0 || (value_dev && value_dev->level != 0)) return fail(ctx, FDB_ERR_BADARG, "x, grad, value must be plain arrays");
+    if (structure < FDB_UPPER || structure > FDB_DIAGONAL) return fail(ctx, FDB_ERR_BADARG, "unknown structure %d (dense inputs: fdb_program_gradient_chunked)", structure);
+    if (rows < 1 || x->n != rows * rows || grad->n != rows * rows) return fail(ctx, FDB_ERR_SHAPE, "DimensionMismatch: structured arrays need rows*rows storage");
+    const int64_t ns = fdb_structural_length(structure, rows);
+    if (N < 1 || N > FDB_MAX_CHUNK) return fail(ctx, FDB_ERR_BADARG, "chunk size N=%d outside 1..12", N);
+    if (ns < N) return fail(ctx, FDB_ERR_CHUNK, "chunk size cannot be greater than ForwardDiff.structural_length(x) (%d > %lld)", N, (long long)ns);
+    Program P;
+    int rc = build_program(ctx, P, term_prog, n_term, epi_prog, n_epi, consts, n_consts, n_acc, halo, result_reg, false, ctx->n_prm); if (rc) return rc;
+    rc = check_params(ctx, P, x->n, "fdb_program_gradient_chunked_structured"); if (rc) return rc;
+    if (P.two_pass) return fail(ctx, FDB_ERR_UNSUPPORTED, "structured inputs: two-pass programs are not supported");
+    Plan p = make_plan(ns, N);
+    const int64_t nchunks = (ns == N) ? 1 : p.nchunks;
+    if (chunk_hi < 0) chunk_hi = nchunks;
+    if (chunk_lo < 0 || chunk_lo > chunk_hi || chunk_hi > nchunks) return fail(ctx, FDB_ERR_BADARG, "bad chunk range");
+    if (chunk_lo == chunk_hi) return FDB_OK;
+    fdb_mirrors M;
+    const fdb_array* outs[2] = {grad, value_dev};
+    rc = mirrors_for(ctx, &M, outs, 2, "fdb_program_gradient_chunked_structured"); if (rc) return rc;
+    void* fn = nullptr;
+    if (jit_get(ctx, 5, P, N, ctx->nansafe, ctx->lane_sharing, false, &fn) != FDB_OK)
+        return fail(ctx, FDB_ERR_UNSUPPORTED, "structured inputs on the batched sweep need the run-time specialised kernel (%s)",
+                    ctx->use_jit ? fdb_jit_last_log(ctx) : "disabled by fdb_set_jit");
+    const double* xp = x->data; int64_t nx = x->n, rw = rows, nst = ns, lo = chunk_lo, nc = nchunks; int kind = structure, lcs = (int)p.lastchunksize;
+    double* gp = grad->data; double* vout = value_dev ? value_dev->data : nullptr;
+    void* args[] = {&xp, &nx, &kind, &rw, &nst, &lo, &nc, &lcs, &gp, &vout, &M};
+    rc = jit_launch(ctx, fn, (unsigned)(chunk_hi - chunk_lo), 1, 256, args, "fdb_program_gradient_chunked_structured"); if (rc) return rc;
+    return finish(ctx, 1, "fdb_program_gradient_chunked_structured");
+}
+
 extern "C" int fdb_program_bind_params(fdb_ctx* ctx, int count, const fdb_array* const* arrays) {
     FDB_ENTER(ctx);
     if (!ctx || count < 0 || count > FDB_MAX_PARAMS || (count && !arrays))

@@ -174,6 +174,67 @@ FDB_DEV void gradient_sweep2_body(const double* __restrict__ x, int64_t n, int64
     }
 }
 
+// ---- structured inputs: gradient(f, x::UpperTriangular / LowerTriangular / Diagonal) on the batched sweep --------------------------
+// Only structurally non-zero positions are seeded and extracted (src/apiutils.jl:44-71, test/GradientTest.jl:250-276); f sees the
+// rows x rows column-major storage whose off-structure entries are zero(Dual).  Chunks run over STRUCTURAL positions; the seeded
+// window of a chunk is the storage span [idx(start), idx(start+chunksize-1)], which is what the far / near split works on.
+template <int N, bool NS> struct StructSeedLoader {
+    const double* x; long start; int chunksize; int kind; long rows;
+    FDB_DEV Dual<double, N, NS> operator()(int64_t i) const {
+        const long pos = struct_pos_of(kind, rows, (long)i);
+        return seeded<N, NS>(x[i], pos < 0 ? -1000000 : pos, start, chunksize);       // off-structure: Dual(x[i] = 0, zero partials)
+    }
+};
+template <class F, int N, bool NS, int THREADS, bool SHARE>
+FDB_DEV void gradient_sweep_struct_body(const double* __restrict__ x, int64_t nx, int kind, int64_t rows, int64_t nstruct, int64_t chunk_lo,
+                                        int64_t nchunks_total, int lastchunksize, double* __restrict__ grad, double* __restrict__ value_out,
+                                        const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> D;
+    typedef Dual<double, 1, NS> D1;
+    const int64_t c = chunk_lo + blockIdx.x;
+    const bool last = (c == nchunks_total - 1);
+    const int chunksize = last ? lastchunksize : N;
+    const int64_t start = last ? (nstruct - lastchunksize) : c * N;               // structural position of the window
+    const int64_t w0 = struct_index_of(kind, rows, start), w1 = struct_index_of(kind, rows, start + chunksize - 1) + 1;   // storage span
+    StructSeedLoader<N, NS> xs{x, (long)start, chunksize, kind, (long)rows};
+    ZeroLoader<1, NS> xz{x};
+    D acc[F::K]; D1 acc1[F::K];
+    D like; like.v = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) like.p[k] = 0.0;
+    D1 like1; like1.v = 0.0; like1.p[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < F::K; k++) { acc[k] = F::init(k, like); acc1[k] = F::init(k, like1); }
+    const int64_t nt = F::nterms(nx);
+    if (SHARE) {
+        const int64_t nit = (nt + THREADS - 1) / THREADS;
+        int64_t itA = (w0 - F::HALO) / THREADS; if (itA < 0) itA = 0; if (itA > nit) itA = nit;
+        int64_t itB = (w1 + THREADS - 1) / THREADS; if (itB > nit) itB = nit; if (itB < itA) itB = itA;
+        for (int64_t it = 0; it < nit; it++) {
+            const int64_t i = it * THREADS + threadIdx.x;
+            if (i >= nt) continue;
+            if (it >= itA && it < itB) F::term(xs, i, nx, acc); else F::term(xz, i, nx, acc1);
+        }
+#pragma unroll
+        for (int k = 0; k < F::K; k++) {
+            D e; e.v = acc1[k].v;
+#pragma unroll
+            for (int j = 0; j < N; j++) e.p[j] = acc1[k].p[0];
+            acc[k] = F::combine(k, acc[k], e);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < nt; i += THREADS) F::term(xs, i, nx, acc);
+    }
+    block_combine<F, D, THREADS>(acc);
+    if (threadIdx.x == 0) {
+        D y = F::finalize(acc, nx);
+#pragma unroll
+        for (int k = 0; k < N; k++)
+            if (k < chunksize) mstore(M, &grad[struct_index_of(kind, rows, start + k)], y.p[k]);    // structural_eachindex(result), gradient.jl:76
+        if (last && value_out) mstore(M, value_out, y.v);
+    }
+}
+
 // Array-valued two-pass form: y = g.(x, reduced values), e.g. softmax exp.(x) ./ sum(exp.(x)) or (x .- mean(x)) ./ std.  The
 // Jacobian is dense (every output depends on every input through the reduced Duals), so one block sweeps one chunk: pass 1
 // reduces (lane sharing included), finalize1 publishes the scalar Duals S, pass 2 evaluates y[i] on all N lanes for every row

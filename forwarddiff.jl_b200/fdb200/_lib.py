@@ -118,6 +118,8 @@ SIGNATURES = {
     "fdb_hessian_chunked": (C.c_int, [c_ctx, C.c_int, c_arr, C.c_int, i64, i64, c_arr, i64, c_arr, c_arr]),
     "fdb_program_gradient_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int,
                                                C.c_int, C.c_int, C.c_int, c_arr, C.c_int, i64, i64, c_arr, c_arr]),
+    "fdb_program_gradient_chunked_structured": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int,
+                                                          C.c_int, C.c_int, C.c_int, C.c_int, i64, c_arr, C.c_int, i64, i64, c_arr, c_arr]),
     "fdb_program_jacobian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, C.c_int, c_arr,
                                                C.c_int, i64, i64, c_arr, i64, c_arr]),
     "fdb_program_matvec_jacobian_chunked": (C.c_int, [c_ctx, C.POINTER(C.c_int32), C.c_int, _dp, C.c_int, C.c_int, c_arr, i64, i64, c_arr,

@@ -331,7 +331,7 @@ def _usable(ctx, prog):
 def gradient(f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=True, graph=True):
     """ForwardDiff.gradient(f, x, cfg, Val{check}()) (src/gradient.jl:16-24)."""
     if isinstance(x, _Structured):
-        return gradient_b(None, f, x, cfg, check, ctx)
+        return gradient_b(None, f, x, cfg, check, ctx, None, fuse)
     if isinstance(x, np.ndarray) and x.ndim > 1:
         result = np.zeros(x.shape, order="F")
     else:
@@ -349,7 +349,7 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
     if check:
         checktag(cfg.tag, f, x)
     if isinstance(x, _Structured):
-        return _structured_gradient(_ctx_of(x, ctx), result, f, x, cfg)
+        return _structured_gradient(_ctx_of(x, ctx), result, f, x, cfg, fuse)
     if isinstance(x, np.ndarray) and x.ndim > 1:
         # an N-d input is seeded in linear-index (column-major) order (structural_eachindex, src/apiutils.jl:44-47);
         # f sees vec(x) and the gradient comes back in the shape of x
@@ -409,7 +409,7 @@ def gradient_b(result, f, x, cfg=None, check=True, ctx=None, chunks=None, fuse=T
     return result
 
 
-def _structured_gradient(ctx, result, f, X, cfg):
+def _structured_gradient(ctx, result, f, X, cfg, fuse=True):
     """gradient(f, x::Union{UpperTriangular,LowerTriangular,Diagonal}): the reference loop with structural seeding.
     `f` receives the rows*rows Dual storage (column-major) whose off-structure entries are zero(Dual), exactly what
     the Julia wrapper types return for them.  Sets cfg.fevals = number of evaluations of f (GradientTest.jl:257-274)."""
@@ -418,9 +418,30 @@ def _structured_gradient(ctx, result, f, X, cfg):
     if N > n:
         raise ChunkSizeError(f"chunk size cannot be greater than ForwardDiff.structural_length(x) ({N} > {n})")
     xd = ctx.array(X.storage())
+    res = ctx.zeros(rows * rows)
+    # batched sweep: f flattened into an op-program, chunks over the structural positions, only those are seeded and extracted
+    # (fdb_program_gradient_chunked_structured; specialised kernels)
+    prog = _try_trace("scalar", f, rows * rows) if (fuse and ctx.jit_enabled()) else None
+    if prog is not None and not prog.two_pass:
+        val = B200Array.alloc(ctx, 1)
+        try:
+            with _bound_params(ctx, prog):
+                ctx.check(lib.fdb_program_gradient_chunked_structured(
+                    ctx.h, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
+                    prog.consts.ctypes.data_as(_dp) if prog.consts.size else None, prog.consts.size, prog.n_acc, prog.halo, prog.result_reg,
+                    S, rows, xd.h, N, 0, -1, res.h, val.h))
+            cfg.last_path = "program:specialised"
+            cfg.fevals = 1 if n == N else chunk_plan(n, N)["nchunks"]          # one evaluation of f per chunk sweep
+            G = type(X)(res.numpy().reshape((rows, rows), order="F"))
+            if isinstance(result, DiffResult):
+                result.value = float(val.numpy()[0]); result.derivs[0] = G
+                return result
+            return G
+        except _lib.UnsupportedOp:
+            pass
+    cfg.last_path = "loop:eager"
     xdual = B200DualArray.alloc(ctx, rows * rows, N, 1)
     ctx.check(lib.fdb_fill(ctx.h, xdual.h, 0.0))
-    res = ctx.zeros(rows * rows)
     cfg.fevals = 0
 
     def call_f():

@@ -284,6 +284,12 @@ int fdb_hessian_chunked(fdb_ctx* ctx, int fn, const fdb_array* x, int N, int64_t
 int fdb_program_gradient_chunked(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi,
                                  const double* consts, int n_consts, int n_acc, int halo, int result_reg, const fdb_array* x, int N,
                                  int64_t chunk_lo, int64_t chunk_hi, fdb_array* grad, fdb_array* value_dev);
+/* the gradient form for UpperTriangular / LowerTriangular / Diagonal inputs (src/apiutils.jl:44-71, test/GradientTest.jl:250-276):
+ * x and grad are the rows x rows column-major storage (off-structure entries of x must be zero; only structural entries of grad are
+ * written), chunks run over the structural positions.  Single-pass programs; specialised kernels only. */
+int fdb_program_gradient_chunked_structured(fdb_ctx* ctx, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi,
+                                            const double* consts, int n_consts, int n_acc, int halo, int result_reg, int structure, int64_t rows,
+                                            const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* grad, fdb_array* value_dev);
 int fdb_program_jacobian_chunked(fdb_ctx* ctx, const int32_t* prog, int n_instr, const double* consts, int n_consts, int halo,
                                  int result_reg, const fdb_array* x, int N, int64_t chunk_lo, int64_t chunk_hi, fdb_array* J,
                                  int64_t ldJ, fdb_array* y);
@@ -321,7 +327,7 @@ int fdb_set_jit(fdb_ctx* ctx, int enabled);
 int fdb_jit_stats(fdb_ctx* ctx, int64_t* compiled, int64_t* cache_hits, int64_t* failures);
 const char* fdb_jit_last_log(fdb_ctx* ctx);   /* NVRTC log of the last failed specialisation ("" if none) */
 /* host-only (no GPU, no context): generate and compile the specialised kernel of a program; kind 0 gradient,
- * 1 Jacobian, 2 Hessian, 3 Jacobian of g.(A * x).  Returns 0 and the cubin size, or the NVRTC log in `log`. */
+ * 1 Jacobian, 2 Hessian, 3 Jacobian of g.(A * x), 4 two-pass array-valued Jacobian, 5 gradient of a structured input.  Returns 0 and the cubin size, or the NVRTC log in `log`. */
 int fdb_jit_compile_check(int kind, const int32_t* term_prog, int n_term, const int32_t* epi_prog, int n_epi, const double* consts,
                           int n_consts, int n_acc, int halo, int result_reg, int n_params, int N, int nansafe, int lane_sharing,
                           char* log, int64_t log_capacity, int64_t* cubin_bytes);
