@@ -495,6 +495,36 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
         if "gathered_p2p_ms" in res:
             entry["gathered_p2p_ingress_GBps_per_gpu"] = 8.0 * m * n * (world - 1) / world / (res["gathered_p2p_ms"] * 1e-3) / 1e9
         out[name] = entry
+
+    # ONE host process driving all GPUs (fdb_multi_*: what a single Julia session binds to).  Rank 0 alone builds a DeviceGroup
+    # over the `world` devices while the other ranks wait; C2 through the host-buffer call: x (pinned host) -> every device,
+    # every device's chunk range, every slice -> the host gradient.  Host wall clock of the blocking call (it returns when the
+    # last slice has landed), median of 5.
+    sync_all()
+    if rank == 0:
+        try:
+            import ctypes as C
+            grp = fdb200.DeviceGroup(list(range(world)))
+            xs = np.random.default_rng(1).random(N_ELEMS); gout = np.zeros(N_ELEMS)
+            for a in (xs, gout):
+                ctx.lib.fdb_host_register(C.c_void_p(a.ctypes.data), a.nbytes)
+            grp.gradient(F.rosenbrock, xs, CHUNK, gout)
+            wall = []
+            for _ in range(5):
+                t0 = time.perf_counter(); _, val = grp.gradient(F.rosenbrock, xs, CHUNK, gout); wall.append(time.perf_counter() - t0)
+            a = np.zeros(N_ELEMS)
+            a[:-1] += -2.0 * (1.0 - xs[:-1]) - 400.0 * xs[:-1] * (xs[1:] - xs[:-1] ** 2)
+            a[1:] += 200.0 * (xs[1:] - xs[:-1] ** 2)
+            out["single_process_device_group_c2"] = {"devices": world, "ms_per_eval_host_wall": float(np.median(wall)) * 1e3,
+                                                     "evals_per_s": 1.0 / float(np.median(wall)),
+                                                     "verified": {"ok": bool(np.allclose(gout, a, rtol=1e-12, atol=1e-11)), "against": "closed-form gradient, all entries"},
+                                                     "api": "fdb_multi_gradient_host: one process, one context per device, no inter-GPU traffic"}
+            for a_ in (xs, gout):
+                ctx.lib.fdb_host_unregister(C.c_void_p(a_.ctypes.data))
+            grp.close()
+        except Exception as e:
+            out["single_process_device_group_c2"] = {"error": repr(e)}
+    sync_all()
     return out
 
 

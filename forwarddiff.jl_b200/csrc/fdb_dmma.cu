@@ -69,8 +69,10 @@ __host__ __device__ inline int dm_kpos(int kk) { return (kk >> 3) * 8 + (kk & 1)
 // [BN*j, BN*j+BN) x k-rows [16s, 16s+16) as BN padded columns of 20 doubles in fragment order, contiguous, so that one
 // bulk copy stages it.  Out-of-range entries are zero.  Column c of B is read from column c % bmod when
 // bmod > 0 (a batch of chunks sharing identical operand columns).
+// onehot_c0 >= 0: the operand is not read from memory but generated: column 0 = x (= B), column 1 + q = the one-hot seed of
+// structural position onehot_c0 + q (src/apiutils.jl:125-143) -- the all-lanes operand of the tanh.(A*x .+ b) sweeps.
 __global__ void pack_b_kernel(const double* __restrict__ B, int64_t ldb, int64_t k, int64_t ncols, int bmod, int nslab, int BN,
-                              double* __restrict__ Bp) {
+                              int64_t onehot_c0, double* __restrict__ Bp) {
     const int s = blockIdx.x, j = blockIdx.y;
     const int belems = BN * DM_BS;
     double* tile = Bp + ((int64_t)j * nslab + s) * belems;
@@ -78,7 +80,10 @@ __global__ void pack_b_kernel(const double* __restrict__ B, int64_t ldb, int64_t
         const int c = e / DM_BS, kk = e - c * DM_BS;
         const int64_t col = (int64_t)j * BN + c, row = (int64_t)s * DM_BK + kk;
         double v = 0.0;
-        if (kk < DM_BK && col < ncols && row < k) v = B[row + (bmod > 0 ? col % bmod : col) * ldb];
+        if (kk < DM_BK && col < ncols && row < k) {
+            if (onehot_c0 >= 0) v = col == 0 ? B[row] : (row == onehot_c0 + col - 1 ? 1.0 : 0.0);
+            else v = B[row + (bmod > 0 ? col % bmod : col) * ldb];
+        }
         tile[c * DM_BS + (kk < DM_BK ? dm_kpos(kk) : kk)] = v;
     }
 }
@@ -93,13 +98,23 @@ struct TanhEpi {
 
 enum { DM_EPI_STORE = 0, DM_EPI_TANH = 1 };
 
+// Tensor maps of the Jacobian for the tile epilogue's TMA stores: [0] = the local result, [1 .. count-1] = the same matrix in
+// every peer's arena (fdb_mirror.cuh deltas).  Box = 128 rows x 4N columns = the four chunks one DMMA column group carries.
+struct StoreMaps { CUtensorMap map[FDB_MAX_RANKS]; int count; };
+
+FDB_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src))
+                 : "memory");
+}
+
 // C[m x ncols] = A[m x k] * B[k x ncols]; A through a tensor map (boxes 16 x 16, swizzle 128B, zero fill out of bounds),
 // B pre-packed (pack_b_kernel); btiles = number of distinct packed column tiles (1 when every tile is identical).
 template <int BN, int EPI, bool NS, bool MIR>
 __global__ void __launch_bounds__(DM_THREADS, 2) dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles,
                                                                  double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
                                                                  int tiles_m, int tiles_n, const int accumulate,
-                                                                 const __grid_constant__ TanhEpi E, const __grid_constant__ fdb_mirrors Mr) {
+                                                                 const __grid_constant__ TanhEpi E, const __grid_constant__ fdb_mirrors Mr,
+                                                                 const __grid_constant__ StoreMaps SM) {
     using Cfg = DmCfg<BN>;
     constexpr int WJ = Cfg::WJ;
     extern __shared__ unsigned char smem_raw[];
@@ -195,32 +210,72 @@ __global__ void __launch_bounds__(DM_THREADS, 2) dmma_gemm_kernel(const __grid_c
             }
         }
     } else {
-        // ---- z = A*xdual .+ b ; y = tanh.(z) (DiffRules: val = tanh(v), deriv = 1 - val^2) ; J[:, start+kk] = partials(y, kk)
+        // ---- z = A*xdual .+ b ; y = tanh.(z) (DiffRules: val = tanh(v), deriv = 1 - val^2) ; J[:, start+kk] = partials(y, kk) ----
+        // A DMMA column group (8 operand columns) carries four chunks: lane t of the owning warps holds (value lane, zero lane) of
+        // chunk 4*gi + t for its rows.  Full groups are staged in shared memory as the dense 128 x 4N block of J they are and
+        // written by the TMA engine -- one tensor store for the local result and one per peer arena (1 KB contiguous per column:
+        // round 1 measured 661 vs 235 GB/s over NVLink between long and short store runs); the DMMA warps wait only for the engine
+        // to have READ the staging buffer, and the co-resident CTA computes meanwhile.  Groups cut by the end of the chunk range
+        // (or a result the TMA cannot address) are stored by the threads themselves.
+        __syncthreads();                                          // every warp is done with the ring: it becomes the staging buffer
+        double* stg = reinterpret_cast<double*>(smem);            // [4N columns][128 rows]
+        const int N = E.N;
 #pragma unroll
-        for (int j = 0; j < WJ; j++) {
-            const int64_t cl = (n0 + wn * (BN / 2) + j * 8) / 2 + t;            // local chunk of this thread's column pair
-            if (cl >= E.nc) continue;
-            const int64_t c = E.chunk_lo + cl;
-            const bool last = (c == E.nchunks_total - 1);
-            const int cs = last ? E.lastchunksize : E.N;
-            const int64_t start = last ? E.n - E.lastchunksize : c * (int64_t)E.N;
+        for (int gi = 0; gi < BN / 8; gi++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int gw = gi / WJ, j = gi % WJ;                  // owning warp column and its accumulator index (compile time)
+            const int64_t cl0 = n0 / 2 + gi * 4;                  // first local chunk of the group
+            if (cl0 >= E.nc) break;
+            const bool staged = SM.count > 0 && cl0 + 4 <= E.nc;  // block-uniform
+            if (wn == gw) {
+                const int64_t cl = cl0 + t;
+                if (cl < E.nc) {
+                    const int64_t c = E.chunk_lo + cl;
+                    const bool last = (c == E.nchunks_total - 1);
+                    const int cs = last ? E.lastchunksize : N;
+                    const int64_t start = last ? E.n - E.lastchunksize : c * (int64_t)N;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int64_t r = m0 + wm * 32 + i * 8 + g;
-                if (r >= m) continue;
-                const double zv = acc[i][j][0] + E.b[r];                            // Dual + Real: value only
-                const double val = tanh(zv);
-                const double deriv = 1.0 - val * val;
-                const double zero_lane = acc[i][j][1];
-                const double* Ac = E.A + r + start * E.lda;
-                double* Jc = E.J + r + start * E.ldJ;
-                for (int kk = 0; kk < cs; kk++) {
-                    const double p = zero_lane + __ldg(Ac + (int64_t)kk * E.lda) * 1.0;   // shared zero lane + the one seeded column of the window
-                    mstore_cs<MIR>(Mr, Jc + (int64_t)kk * E.ldJ, mulp<NS>(p, deriv));
+                    for (int i = 0; i < 4; i++) {
+                        const int rl = wm * 32 + i * 8 + g;
+                        const int64_t r = m0 + rl;
+                        if (r >= m) continue;
+                        const double zv = acc[i][j][0] + E.b[r];                            // Dual + Real: value only
+                        const double val = tanh(zv);
+                        const double deriv = 1.0 - val * val;
+                        const double zero_lane = acc[i][j][1];
+                        const double* Ac = E.A + r + start * E.lda;
+                        if (staged) {
+                            double* sc = stg + (t * N) * DM_BM + rl;
+                            for (int kk = 0; kk < cs; kk++) {
+                                const double p = zero_lane + __ldg(Ac + (int64_t)kk * E.lda) * 1.0;   // shared zero lane + the one seeded column of the window
+                                sc[kk * DM_BM] = mulp<NS>(p, deriv);
+                            }
+                        } else {
+                            double* Jc = E.J + r + start * E.ldJ;
+                            for (int kk = 0; kk < cs; kk++) {
+                                const double p = zero_lane + __ldg(Ac + (int64_t)kk * E.lda) * 1.0;
+                                mstore_cs<MIR>(Mr, Jc + (int64_t)kk * E.ldJ, mulp<NS>(p, deriv));
+                            }
+                        }
+                        if (E.yout && last) mstore(Mr, &E.yout[r], val);
+                    }
                 }
-                if (E.yout && last) mstore(Mr, &E.yout[r], val);
+            }
+            if (staged) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (TMA) reads
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const int col0 = (int)((E.chunk_lo + cl0) * N);               // columns past n (short last chunk) and rows past m are clipped
+                    for (int d = 0; d < SM.count; d++) tma_store_2d(&SM.map[d], stg, (int)m0, col0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncthreads();                                                  // staging buffer free again
             }
         }
+        // the block retires only when its tensor stores have been performed (not just read from shared memory): whatever follows
+        // this kernel on the stream -- the exchange's flag barrier -- is ordered behind them
+        if (threadIdx.x == 0 && SM.count > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
@@ -291,7 +346,7 @@ size_t gemm_workspace_doubles(int64_t k, int64_t ncols, int bmod) {
 
 template <int BN, int EPI, bool NS, bool MIR>
 static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws, int btiles, double* C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
-                          int accumulate, const TanhEpi& E, const fdb_mirrors& Mr) {
+                          int accumulate, const TanhEpi& E, const fdb_mirrors& Mr, const StoreMaps& SM) {
     static unsigned long long configured = 0;
     if (first_use_on_device(configured, ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel<BN, EPI, NS, MIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<BN>::SMEM);
@@ -299,7 +354,7 @@ static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws,
     }
     const int tiles_m = (int)cdiv(m, DM_BM), tiles_n = (int)cdiv(ncols, BN);
     dmma_gemm_kernel<BN, EPI, NS, MIR><<<(unsigned)(tiles_m * tiles_n), DM_THREADS, DmCfg<BN>::SMEM, ctx->stream>>>(tm, ws, btiles, C, ldc, m, k, ncols,
-                                                                                                                   tiles_m, tiles_n, accumulate, E, Mr);
+                                                                                                                   tiles_m, tiles_n, accumulate, E, Mr, SM);
     return FDB_OK;
 }
 
@@ -307,13 +362,13 @@ static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws,
 // (C unused); otherwise the product is stored to C.
 int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t m, int64_t k,
                 int64_t ncols, int bmod, double* ws, bool* used_dmma, int* nlaunch, const TanhEpi* epi = nullptr, const fdb_mirrors* mirrors = nullptr,
-                bool accumulate = false) {
+                bool accumulate = false, int64_t onehot_c0 = -1) {
     if (m <= 0 || ncols <= 0) { if (nlaunch) *nlaunch = 0; return FDB_OK; }
     EncodeTiledFn enc = encode_tiled_fn();
     const bool ok = enc != nullptr && (lda % 2 == 0) && ((((uintptr_t)A) & 15) == 0) && k > 0 && ws != nullptr;
     if (used_dmma) *used_dmma = ok;
     if (!ok) {
-        if (epi) return fail(ctx, FDB_ERR_UNSUPPORTED, "launch_gemm: the fused epilogue needs the tensor-core path");
+        if (epi || onehot_c0 >= 0) return fail(ctx, FDB_ERR_UNSUPPORTED, "launch_gemm: the fused epilogue / generated operand need the tensor-core path");
         constexpr int PC = 13;
         dim3 grid((unsigned)cdiv(m, 128), (unsigned)cdiv(ncols, PC));
         gemm_fallback_kernel<PC><<<grid, 128, 0, ctx->stream>>>(A, lda, B, ldb, C, ldc, m, k, ncols, bmod, accumulate);
@@ -332,15 +387,30 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
     const int nslab = (int)cdiv(k, DM_BK);
     const int btiles = (bmod > 0 && BN % bmod == 0) ? 1 : (int)cdiv(ncols, BN);
     dim3 pg((unsigned)nslab, (unsigned)btiles);
-    pack_b_kernel<<<pg, 128, 0, ctx->stream>>>(B, ldb, k, ncols, bmod, nslab, BN, ws);
+    pack_b_kernel<<<pg, 128, 0, ctx->stream>>>(B, ldb, k, ncols, bmod, nslab, BN, onehot_c0, ws);
     TanhEpi E0 = {}; fdb_mirrors M0;
     const TanhEpi& E = epi ? *epi : E0;
     const fdb_mirrors& Mr = mirrors ? *mirrors : M0;
+    thread_local static StoreMaps SM;    // 1 KB: kept out of the stack frame; filled per launch (copied into the launch's parameters)
+    SM.count = 0;
+    if (epi && ctx->dmma_tma_store && (E.ldJ % 2 == 0) && ((((uintptr_t)E.J) & 15) == 0) && E.N * 4 <= 256) {
+        // the Jacobian as a tensor: 128-row x 4N-column boxes for the epilogue's TMA stores, one map per destination arena
+        const cuuint64_t jdim[2] = {(cuuint64_t)m, (cuuint64_t)E.n};
+        const cuuint64_t jstride[1] = {(cuuint64_t)E.ldJ * 8};
+        const cuuint32_t jbox[2] = {DM_BM, (cuuint32_t)(4 * E.N)};
+        bool good = true;
+        for (int d = 0; d <= Mr.count && good; d++) {
+            char* base = reinterpret_cast<char*>(E.J) + (d == 0 ? 0 : Mr.delta[d - 1]);
+            good = enc(&SM.map[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, jdim, jstride, jbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        SM.count = good ? Mr.count + 1 : 0;
+    }
     int rc;
 #define FDB_GEMM_BN(EPI_, NS_, MIR_)                                                                              \
-    (BN == 64 ? launch_gemm_bn<64, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr)                \
-     : BN == 32 ? launch_gemm_bn<32, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr)              \
-                : launch_gemm_bn<16, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr))
+    (BN == 64 ? launch_gemm_bn<64, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr, SM)                \
+     : BN == 32 ? launch_gemm_bn<32, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr, SM)              \
+                : launch_gemm_bn<16, EPI_, NS_, MIR_>(ctx, tm, ws, btiles, C, ldc, m, k, ncols, accumulate ? 1 : 0, E, Mr, SM))
     if (!epi) rc = FDB_GEMM_BN(DM_EPI_STORE, false, false);
     else if (ctx->nansafe) rc = Mr.count ? FDB_GEMM_BN(DM_EPI_TANH, true, true) : FDB_GEMM_BN(DM_EPI_TANH, true, false);
     else rc = Mr.count ? FDB_GEMM_BN(DM_EPI_TANH, false, true) : FDB_GEMM_BN(DM_EPI_TANH, false, false);
@@ -441,14 +511,14 @@ int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_ar
     }
     // all lanes: [x | one-hot columns of the requested structural positions]
     const int64_t c0 = lo * N, c1 = (hi == nchunks) ? n : hi * N, ncolsJ = c1 - c0, P = 1 + ncolsJ;
+    // the operand [x | one-hot seeds] is generated straight into the packed tiles (no materialised operand matrix)
     const size_t wsd = gemm_workspace_doubles(n, P, 0);
-    int rc = ensure_scratch(ctx, ((size_t)(ldb * P + ldy * P) + wsd + 64) * sizeof(double)); if (rc) return rc;
-    double* Bop = ctx->scratch; double* Y = Bop + ldb * P;
+    int rc = ensure_scratch(ctx, ((size_t)(ldy * P) + wsd + 64) * sizeof(double)); if (rc) return rc;
+    double* Y = ctx->scratch;
     double* ws = Y + ldy * P; ws = (double*)((((uintptr_t)ws) + 127) & ~(uintptr_t)127);
-    dim3 gb((unsigned)cdiv(n, 256), (unsigned)(1 + cdiv(ncolsJ, 16)));
-    build_operand_onehot_kernel<<<gb, 256, 0, ctx->stream>>>(x->data, n, c0, ncolsJ, Bop, ldb);
+    (void)ldb;
     int ngemm = 0;
-    rc = launch_gemm(ctx, A->data, lda, Bop, ldb, Y, ldy, m, n, P, 0, ws, used_dmma, &ngemm); if (rc) return rc;
+    rc = launch_gemm(ctx, A->data, lda, x->data, n, Y, ldy, m, n, P, 0, ws, used_dmma, &ngemm, nullptr, nullptr, false, c0); if (rc) return rc;
     dim3 ge((unsigned)cdiv(m, 256), (unsigned)cdiv(ncolsJ, 16));
     const bool has_last = (hi == nchunks);
     if (ctx->nansafe) {
@@ -458,7 +528,7 @@ int tanh_affine_dmma(fdb_ctx* ctx, const fdb_array* A, int64_t lda, const fdb_ar
         if (Mr.count) tanh_affine_onehot_epilogue_kernel<false, true><<<ge, 256, 0, ctx->stream>>>(Y, ldy, b->data, m, c0, ncolsJ, has_last, J->data, ldJ, yout, Mr);
         else tanh_affine_onehot_epilogue_kernel<false, false><<<ge, 256, 0, ctx->stream>>>(Y, ldy, b->data, m, c0, ncolsJ, has_last, J->data, ldJ, yout, Mr);
     }
-    return finish(ctx, 2 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma, all lanes)");
+    return finish(ctx, 1 + ngemm, "fdb_jacobian_chunked(tanh_affine, dmma, all lanes)");
 }
 
 // The product lanes of `A * xdual` for chunks [lo, hi), left in the context's scratch for a consumer kernel that applies

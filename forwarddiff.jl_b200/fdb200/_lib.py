@@ -63,6 +63,7 @@ SIGNATURES = {
     "fdb_set_lane_sharing": (C.c_int, [c_ctx, C.c_int]),
     "fdb_set_dmma": (C.c_int, [c_ctx, C.c_int]),
     "fdb_set_dmma_tile": (C.c_int, [c_ctx, C.c_int]),
+    "fdb_set_dmma_tma_store": (C.c_int, [c_ctx, C.c_int]),
     "fdb_kernel_launches": (C.c_int, [c_ctx, C.POINTER(i64)]),
     "fdb_version": (C.c_char_p, []),
     "fdb_array_alloc": (C.c_int, [c_ctx, i64, C.c_int, C.c_int, C.POINTER(c_arr)]),

@@ -107,6 +107,9 @@ int fdb_set_dmma(fdb_ctx* ctx, int enabled);
 /* operand columns per thread-block tile of the DMMA contraction: 0 (default) = chosen per shape so that the equal-sized
  * tiles fill the SMs evenly, or 16 / 32 / 64 (measurement knob) */
 int fdb_set_dmma_tile(fdb_ctx* ctx, int bn);
+/* 1 (default): the fused DMMA epilogue stages 128 x 4N result blocks in shared memory and writes them with TMA tensor stores
+ * (local result + every peer arena); 0: the threads store their own entries (measurement knob / fallback) */
+int fdb_set_dmma_tma_store(fdb_ctx* ctx, int enabled);
 int fdb_kernel_launches(fdb_ctx* ctx, int64_t* count); /* kernels launched on this context so far */
 const char* fdb_version(void);
 

@@ -22,12 +22,14 @@ def main():
     ap.add_argument("--no-share", action="store_true")
     ap.add_argument("--no-dmma", action="store_true")
     ap.add_argument("--bn", type=int, default=0, help="DMMA column-tile width (0 = auto, 16, 32, 64)")
+    ap.add_argument("--no-tma-store", action="store_true", help="fused DMMA epilogue: per-thread stores instead of TMA tensor stores")
     a = ap.parse_args()
     ctx = fdb200.Context(0)
     lib = ctx.lib
     ctx.set_lane_sharing(not a.no_share)
     ctx.check(lib.fdb_set_dmma(ctx.h, 0 if a.no_dmma else 1))
     ctx.check(lib.fdb_set_dmma_tile(ctx.h, a.bn))
+    ctx.check(lib.fdb_set_dmma_tma_store(ctx.h, 0 if a.no_tma_store else 1))
     rng = np.random.default_rng(1)
     FN, JFN = fdb200._lib.FN, fdb200._lib.JFN
     v = ctx.zeros(1)
@@ -81,7 +83,7 @@ def main():
         raise SystemExit("unknown config")
     for i in range(a.reps):
         t0 = time.perf_counter(); fn(); ctx.sync(); dt = time.perf_counter() - t0
-        print(f"{a.config} rep {i}: {dt * 1e3:.3f} ms (host wall, synchronous call)")
+        print(f"{a.config} rep {i}: {dt * 1e3:.3f} ms (host wall, synchronous call)", flush=True)
     ctx.close()
 
 
