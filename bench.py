@@ -323,6 +323,7 @@ def main():
         return
 
     hbm_peak, peak_src = load_peaks()
+    ctx_sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     dp_peak, dfma_peak = ctx.fp64_peak()                           # FP64 instruction issue rate (non-fused / fused), ops/s
     my_chunks = sg.plan["chunk_hi"] - sg.plan["chunk_lo"]
     kernel_s = (tot_kms / K) * 1e-3
@@ -336,6 +337,8 @@ def main():
                 "traffic": 8.165e6 if my_chunks == 83334 else None,
                 "peak_source": "fdb_measure_fp64_peak: non-fused DMUL/DADD issue rate measured live on this GPU "
                                "(MEASURED_PEAKS.json has no FP64 figure); FMA peak %.1f TFLOP/s" % (2 * dfma_peak / 1e12),
+                # independent of the probe: SMs x 64 FP64 lanes x the SM clock sampled by nvidia-smi during the timed region
+                "peak_spec_crosscheck": (ctx_sm_count * 64 * (clocks or {}).get("sm_mhz", 0) * 1e6 / 1e12) if clocks and clocks.get("sm_mhz") else None,
                 "algorithmic": f"{DP_OPS_PER_TERM_SHARED} FP64 ops per term per chunk sweep x {N_ELEMS - 1} terms x {my_chunks} chunks "
                                "(SURVEY.md 8d: implicit seeds => bound is FP64 issue, not HBM)",
                 "hbm_equivalent": {"achieved": 8.0 * (CHUNK + 1) * N_ELEMS * my_chunks / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

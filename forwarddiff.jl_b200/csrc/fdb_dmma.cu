@@ -393,7 +393,9 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
     const fdb_mirrors& Mr = mirrors ? *mirrors : M0;
     thread_local static StoreMaps SM;    // 1 KB: kept out of the stack frame; filled per launch (copied into the launch's parameters)
     SM.count = 0;
-    if (epi && ctx->dmma_tma_store && (E.ldJ % 2 == 0) && ((((uintptr_t)E.J) & 15) == 0) && E.N * 4 <= 256) {
+    // staged TMA stores pay off when the blocks also go to peers over NVLink (long contiguous runs); locally the threads' own
+    // streaming stores are 1 % faster (5.49 vs 5.56 ms at C3), so mode 1 = peers only, 2 = always
+    if (epi && (ctx->dmma_tma_store == 2 || (ctx->dmma_tma_store == 1 && Mr.count > 0)) && (E.ldJ % 2 == 0) && ((((uintptr_t)E.J) & 15) == 0) && E.N * 4 <= 256) {
         // the Jacobian as a tensor: 128-row x 4N-column boxes for the epilogue's TMA stores, one map per destination arena
         const cuuint64_t jdim[2] = {(cuuint64_t)m, (cuuint64_t)E.n};
         const cuuint64_t jstride[1] = {(cuuint64_t)E.ldJ * 8};

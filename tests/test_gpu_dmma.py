@@ -119,3 +119,25 @@ def test_dual_times_dual_matrix_product(ctx, oracle, N):
         assert np.allclose(got[:, 0].reshape((m, n), order="F"), Av @ Bv, rtol=1e-12, atol=1e-13)
     with pytest.raises(fdb200.DimensionMismatch):
         fdb200.dual_matmul(ctx.duals(np.zeros((6, N + 1))), (2, 3), ctx.duals(np.zeros((8, N + 1))), (4, 2))
+
+
+@pytest.mark.parametrize("N", [1, 5, 12])
+def test_fused_epilogue_tma_stores_match_thread_stores(ctx, oracle, N):
+    """the fused tile epilogue writes J either with the threads' own stores or as staged 128 x 4N blocks through TMA tensor stores
+    (the default when peers are mirrored): same bits, including the short last chunk, ragged m and partial column groups"""
+    rng = np.random.default_rng(N)
+    for m, n in ((256, 160), (384, 203), (130, 64)):
+        if n < N:
+            continue
+        A = rng.uniform(-1, 1, (m, n + (n % 2))) [:, :n] / np.sqrt(n); b = rng.uniform(-1, 1, m); x = rng.uniform(-1, 1, n)
+        f = F.tanh_affine.with_params(A=A, b=b)
+        out = {}
+        for mode in (0, 2):
+            ctx.check(ctx.lib.fdb_set_dmma_tma_store(ctx.h, mode))
+            try:
+                out[mode] = fdb200.jacobian(f, x, fdb200.JacobianConfig(f, x, fdb200.Chunk(N)), ctx=ctx, m=m)
+            finally:
+                ctx.check(ctx.lib.fdb_set_dmma_tma_store(ctx.h, 1))
+        assert np.array_equal(out[0], out[2]), (m, n, N)
+        J_ref, _ = oracle.jacobian("tanh_affine", x, m, N, A=A, b=b)
+        assert np.allclose(out[2], J_ref, rtol=1e-12, atol=1e-15)

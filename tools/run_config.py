@@ -29,7 +29,7 @@ def main():
     ctx.set_lane_sharing(not a.no_share)
     ctx.check(lib.fdb_set_dmma(ctx.h, 0 if a.no_dmma else 1))
     ctx.check(lib.fdb_set_dmma_tile(ctx.h, a.bn))
-    ctx.check(lib.fdb_set_dmma_tma_store(ctx.h, 0 if a.no_tma_store else 1))
+    ctx.check(lib.fdb_set_dmma_tma_store(ctx.h, 0 if a.no_tma_store else 2))
     rng = np.random.default_rng(1)
     FN, JFN = fdb200._lib.FN, fdb200._lib.JFN
     v = ctx.zeros(1)
