@@ -488,6 +488,13 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
             else:
                 rec = lambda c, arr: ctx.check(lib.fdb_hessian_chunked(ctx.h, sh.fid, sh.x_a.h, N, c, c + 1, arr.h, n, None, None))
             res[f"gathered_{mode}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
+            if kind == "hess" and mode == "p2p":
+                # the two ways of getting the column block to the peers (fdb200.dist.ShardedHessian.peer_stores); the default picks by rank count
+                for ps in ("mirror", "push"):
+                    sh.peer_stores = ps
+                    res[f"gathered_p2p_{ps}_ms"] = timed(step, reps)
+                    res[f"gathered_p2p_{ps}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
+                sh.peer_stores = "auto"
             if sh.xch is not None:
                 res["barrier_timeouts"] = int(sh.xch.timeouts())
             sh.close()
@@ -504,6 +511,11 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
     # every device's chunk range, every slice -> the host gradient.  Host wall clock of the blocking call (it returns when the
     # last slice has landed), median of 5.
     sync_all()
+    # the other ranks must wait on the HOST: an NCCL barrier is a kernel spinning on their GPUs, which would time-slice with the
+    # group's contexts on the same devices
+    store = dist.distributed_c10d._get_default_store()
+    if rank != 0:
+        store.wait(["fdb_group_done"])
     if rank == 0:
         try:
             import ctypes as C
@@ -527,6 +539,7 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
             grp.close()
         except Exception as e:
             out["single_process_device_group_c2"] = {"error": repr(e)}
+        store.set("fdb_group_done", "1")
     sync_all()
     return out
 

@@ -289,8 +289,12 @@ class ShardedHessian(_ShardedColumns):
     """ForwardDiff.hessian!(result, f, x, cfg): outer chunks (column blocks of H) sharded over the ranks;
     every rank runs all inner chunks for its columns (src/hessian.jl:14-19)."""
 
-    def __init__(self, ctx, f, xlen, cfg=None, group=None, exchange="auto"):
+    def __init__(self, ctx, f, xlen, cfg=None, group=None, exchange="auto", peer_stores="auto"):
+        """peer_stores: "mirror" = the sweep kernel stores every entry into all peers (one launch), "push" = local stores, then one
+        streaming copy of the column block to the peers; "auto" = mirror for two ranks, push beyond (measured: 0.300 vs 0.336 ms at
+        2 ranks, 0.169 vs the push at 8 -- see DESIGN.md section 6)."""
         self.f = f
+        self.peer_stores = peer_stores
         self.cfg = cfg if cfg is not None else HessianConfig(f, np.empty(int(xlen)))
         self.fid = _catalogue_id(f, _lib.FN)
         if self.fid is None:
@@ -307,6 +311,15 @@ class ShardedHessian(_ShardedColumns):
         which cross NVLink at a fraction of the link rate (measured at 8 ranks: 0.169 ms with the stores mirrored from the sweep
         kernel, the 29 MB push runs at the link rate); same bits either way."""
         c = self.ctx
+        mode = self.peer_stores if self.peer_stores != "auto" else ("mirror" if self.world <= 2 else "push")
+        if mode == "mirror":
+            self._sweep_begin()
+            try:
+                c.check(c.lib.fdb_hessian_chunked(c.h, self.fid, self.x_a.h, self.N, self.plan["chunk_lo"], self.plan["chunk_hi"],
+                                                  self.J_a.h, self.n, self.g_a.h, self.v_a.h))
+            finally:
+                self._sweep_end()
+            return
         if self.xch is not None:
             self.xch.barrier()          # all peers have consumed the previous result before it is overwritten
         c.check(c.lib.fdb_hessian_chunked(c.h, self.fid, self.x_a.h, self.N, self.plan["chunk_lo"], self.plan["chunk_hi"],
