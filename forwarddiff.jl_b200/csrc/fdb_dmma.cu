@@ -44,11 +44,16 @@ constexpr int DM_BM = 128, DM_BK = 16, DM_BS = DM_BK + 4;      // BS: padded col
 constexpr int DM_A_BYTES = DM_BK * DM_BM * 8;                  // eight swizzled [16 k][16 m] boxes of 2 KB
 constexpr int DM_THREADS = 256;
 constexpr int DM_BAND = 8;                                     // m-tiles per rasterisation band
+constexpr int DM_STG_BYTES = 4 * FDB_MAX_CHUNK * DM_BM * 8;    // staging buffer of the fused epilogue: 128 rows x 4N columns
 template <int BN> struct DmCfg {
     static constexpr int B_ELEMS = BN * DM_BS, B_BYTES = B_ELEMS * 8;
     static constexpr int STAGE_BYTES = (DM_A_BYTES + B_BYTES + 1023) / 1024 * 1024;      // A tiles stay 1024-byte aligned (swizzle atom)
     static constexpr int STAGES = (108 * 1024) / STAGE_BYTES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;            // + alignment slack
+    // persistent variant (one block per SM): ring + two staging buffers of one 128 x 4N result block each
+    static constexpr int STAGES_P0 = (227 * 1024 - 1024 - 256 - 2 * DM_STG_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES_P = STAGES_P0 > 8 ? 8 : STAGES_P0;
+    static constexpr int SMEM_P = STAGES_P * STAGE_BYTES + 2 * DM_STG_BYTES + 2 * STAGES_P * 8 + 1024;
     static constexpr int WJ = BN / 16;                                                   // 8-column DMMA tiles per warp (warps: 4 m x 2 n)
 };
 
@@ -109,174 +114,193 @@ FDB_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c
 
 // C[m x ncols] = A[m x k] * B[k x ncols]; A through a tensor map (boxes 16 x 16, swizzle 128B, zero fill out of bounds),
 // B pre-packed (pack_b_kernel); btiles = number of distinct packed column tiles (1 when every tile is identical).
+// A thread block walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... (one tile per block unless PERSIST); the slab ring and
+// its mbarrier phases run on across tiles, so the first slabs of the next tile are in flight during the epilogue of this one.
+// PERSIST (fused epilogue + peer mirroring): one block per SM, and the epilogue's TMA stores leave from two dedicated staging
+// buffers, so the DMMA warps go straight on to the next tile while the TMA engine pushes the finished block to the peers over
+// NVLink; they wait for a staging buffer only when it is needed again, two column groups later.
 template <int BN, int EPI, bool NS, bool MIR>
-__global__ void __launch_bounds__(DM_THREADS, 2) dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles,
-                                                                 double* __restrict__ C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
-                                                                 int tiles_m, int tiles_n, const int accumulate,
-                                                                 const __grid_constant__ TanhEpi E, const __grid_constant__ fdb_mirrors Mr,
-                                                                 const __grid_constant__ StoreMaps SM) {
+__global__ void __launch_bounds__(DM_THREADS, (EPI == DM_EPI_TANH && MIR) ? 1 : 2)
+dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles, double* __restrict__ C, int64_t ldc,
+                 int64_t m, int64_t k, int64_t ncols, int tiles_m, int tiles_n, const int accumulate, const __grid_constant__ TanhEpi E,
+                 const __grid_constant__ fdb_mirrors Mr, const __grid_constant__ StoreMaps SM) {
     using Cfg = DmCfg<BN>;
     constexpr int WJ = Cfg::WJ;
+    constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR);
+    constexpr int STAGES = PERSIST ? Cfg::STAGES_P : Cfg::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty = full + Cfg::STAGES;
+    unsigned char* stg_base = smem + STAGES * Cfg::STAGE_BYTES;                       // PERSIST: two staging buffers behind the ring
+    uint64_t* full = reinterpret_cast<uint64_t*>(stg_base + (PERSIST ? 2 * DM_STG_BYTES : 0));
+    uint64_t* empty = full + STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nslab = (int)((k + DM_BK - 1) / DM_BK);
+    const int ntiles = tiles_m * tiles_n;
+    const int my_tiles = PERSIST ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+    const int total = my_tiles * nslab;                                               // slabs this block consumes (< 2^31: tiles per block x k/16)
     // band rasterisation: DM_BAND m-tiles x all column tiles per band, m-tile fastest
-    int tm, tn;
-    {
-        const int bid = blockIdx.x, per_band = DM_BAND * tiles_n, band = bid / per_band, within = bid - band * per_band;
+    auto tile_coords = [&](int tile, int& tm, int& tn) {
+        const int per_band = DM_BAND * tiles_n, band = tile / per_band, within = tile - band * per_band;
         const int rows = min(DM_BAND, tiles_m - band * DM_BAND);
         tn = within / rows; tm = band * DM_BAND + (within - tn * rows);
-    }
-    const int64_t n0 = (int64_t)tn * BN, m0 = (int64_t)tm * DM_BM;
-    const int nslab = (int)((k + DM_BK - 1) / DM_BK);
+    };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
         tma::mbar_fence_init();
     }
     __syncthreads();
 
     // ---- eight DMMA warps, 4 (M) x 2 (N), 32 x (BN/2) accumulators each.  There is no dedicated producer warp (a ninth warp
-    // would cap the kernel at 96 registers with two CTAs per SM and spill accumulators): lane 0 of warp (s mod 8) issues
-    // the TMA copies of slab s + STAGES - 1 before that warp starts on slab s, so the issue cost rotates over the warps.
+    // would cap the kernel at 96 registers with two CTAs per SM and spill accumulators): lane 0 of warp (slab mod 8) issues
+    // the TMA copies of the slab STAGES - 1 ahead before that warp starts on its own slab, so the issue cost rotates over the warps.
     const int wm = warp & 3, wn = warp >> 2;
     const int g = lane >> 2, t = lane & 3;
-    const double* Bt = Bp + (int64_t)(tn % btiles) * nslab * Cfg::B_ELEMS;
-    auto produce = [&](int sp) {          // called by one thread
-        const int st = sp % Cfg::STAGES;
-        if (sp >= Cfg::STAGES) mbar_wait(&empty[st], ((sp / Cfg::STAGES) - 1) & 1);
+    auto produce = [&](int gp) {              // called by one thread; gp = slab number within this block's tile sequence
+        const int ti = PERSIST ? gp / nslab : 0, sp = gp - ti * nslab;
+        int ptm, ptn; tile_coords((int)blockIdx.x + ti * (int)gridDim.x, ptm, ptn);
+        const int st = gp % STAGES;
+        if (gp >= STAGES) mbar_wait(&empty[st], (uint32_t)(((gp / STAGES) - 1) & 1));
         unsigned char* stage = smem + st * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[st], DM_A_BYTES + Cfg::B_BYTES);
 #pragma unroll
         for (int bx = 0; bx < DM_BM / 16; bx++)
-            tma_load_2d(stage + bx * 2048, &tmA, (int)m0 + 16 * bx, sp * DM_BK, &full[st]);           // [16 k][16 m], 128B-swizzled
-        bulk_g2s(stage + DM_A_BYTES, Bt + (int64_t)sp * Cfg::B_ELEMS, Cfg::B_BYTES, &full[st]);      // packed B tile
+            tma_load_2d(stage + bx * 2048, &tmA, ptm * DM_BM + 16 * bx, sp * DM_BK, &full[st]);      // [16 k][16 m], 128B-swizzled
+        bulk_g2s(stage + DM_A_BYTES, Bp + ((int64_t)(ptn % btiles) * nslab + sp) * Cfg::B_ELEMS, Cfg::B_BYTES, &full[st]);   // packed B tile
     };
     if (threadIdx.x == 0)
-        for (int sp = 0; sp < Cfg::STAGES - 1 && sp < nslab; sp++) produce(sp);
-    double acc[4][WJ][2];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < WJ; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int gp = 0; gp < STAGES - 1 && gp < total; gp++) produce(gp);
     // swizzled A fragment address (in doubles): box (wm*2 + i/2) * 256 + k * 16 + ((chunk ^ k%8) << 1) + (g & 1),
     // chunk = (i & 1) * 4 + g / 2  ==>  base + krow + (((g/2) ^ x) << 1) ^ ((i & 1) << 3), + 256 for i >= 2
     const int a_base = wm * 512 + (g & 1), gh = g >> 1;
     const int b_off = (wn * (BN / 2) + g) * DM_BS + t;
-    for (int s = 0; s < nslab; s++) {
-        if (warp == (s & 7)) {
-            if (lane == 0 && s + Cfg::STAGES - 1 < nslab) produce(s + Cfg::STAGES - 1);
+    int stg_sel = 0;                                                              // PERSIST: staging buffer of the next column group
+    int gc = 0;                                                                   // slabs consumed so far
+    for (int ti = 0; ti < my_tiles; ti++) {
+        int tm, tn; tile_coords((int)blockIdx.x + ti * (int)gridDim.x, tm, tn);
+        const int64_t n0 = (int64_t)tn * BN, m0 = (int64_t)tm * DM_BM;
+        double acc[4][WJ][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < WJ; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int s = 0; s < nslab; s++, gc++) {
+            if (warp == (gc & 7)) {
+                if (lane == 0 && gc + STAGES - 1 < total) produce(gc + STAGES - 1);
+                __syncwarp();
+            }
+            const int st = gc % STAGES;
+            mbar_wait(&full[st], (uint32_t)((gc / STAGES) & 1));
+            const double* As = reinterpret_cast<const double*>(smem + st * Cfg::STAGE_BYTES) + a_base;
+            const double* Bs = reinterpret_cast<const double*>(smem + st * Cfg::STAGE_BYTES + DM_A_BYTES) + b_off;
+#pragma unroll
+            for (int s4 = 0; s4 < DM_BK / 4; s4++) {
+                const int x = 2 * t + (s4 & 1);                            // k % 8 of this lane's k = 8*(s4/2) + x
+                const int o0 = ((s4 >> 1) * 8 + x) * 16 + ((gh ^ x) << 1), o1 = o0 ^ 8;
+                double a[4], b[WJ];
+                a[0] = As[o0]; a[1] = As[o1]; a[2] = As[o0 + 256]; a[3] = As[o1 + 256];
+#pragma unroll
+                for (int j = 0; j < WJ; j++) b[j] = Bs[j * 8 * DM_BS + s4 * 4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < WJ; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
             __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
         }
-        const int st = s % Cfg::STAGES;
-        mbar_wait(&full[st], (s / Cfg::STAGES) & 1);
-        const double* As = reinterpret_cast<const double*>(smem + st * Cfg::STAGE_BYTES) + a_base;
-        const double* Bs = reinterpret_cast<const double*>(smem + st * Cfg::STAGE_BYTES + DM_A_BYTES) + b_off;
+        if (EPI == DM_EPI_STORE) {
+            // ---- accumulator fragments straight to C (thread holds C[g][2t], C[g][2t+1]) ----------------------
 #pragma unroll
-        for (int s4 = 0; s4 < DM_BK / 4; s4++) {
-            const int x = 2 * t + (s4 & 1);                            // k % 8 of this lane's k = 8*(s4/2) + x
-            const int o0 = ((s4 >> 1) * 8 + x) * 16 + ((gh ^ x) << 1), o1 = o0 ^ 8;
-            double a[4], b[WJ];
-            a[0] = As[o0]; a[1] = As[o1]; a[2] = As[o0 + 256]; a[3] = As[o1 + 256];
+            for (int i = 0; i < 4; i++) {
+                const int64_t r = m0 + wm * 32 + i * 8 + g;
 #pragma unroll
-            for (int j = 0; j < WJ; j++) b[j] = Bs[j * 8 * DM_BS + s4 * 4];
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < WJ; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
-    }
-    if (EPI == DM_EPI_STORE) {
-        // ---- accumulator fragments straight to C (thread holds C[g][2t], C[g][2t+1]) ----------------------
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int64_t r = m0 + wm * 32 + i * 8 + g;
-#pragma unroll
-            for (int j = 0; j < WJ; j++) {
-                const int64_t c = n0 + wn * (BN / 2) + j * 8 + 2 * t;
-                if (r < m) {
-                    if (accumulate) {        // C += A*B: the second product of a Dual*Dual partial (fdb_dual_matmul)
-                        if (c < ncols) C[r + c * ldc] = C[r + c * ldc] + acc[i][j][0];
-                        if (c + 1 < ncols) C[r + (c + 1) * ldc] = C[r + (c + 1) * ldc] + acc[i][j][1];
-                    } else {
-                        if (c < ncols) C[r + c * ldc] = acc[i][j][0];
-                        if (c + 1 < ncols) C[r + (c + 1) * ldc] = acc[i][j][1];
-                    }
-                }
-            }
-        }
-    } else {
-        // ---- z = A*xdual .+ b ; y = tanh.(z) (DiffRules: val = tanh(v), deriv = 1 - val^2) ; J[:, start+kk] = partials(y, kk) ----
-        // A DMMA column group (8 operand columns) carries four chunks: lane t of the owning warps holds (value lane, zero lane) of
-        // chunk 4*gi + t for its rows.  Full groups are staged in shared memory as the dense 128 x 4N block of J they are and
-        // written by the TMA engine -- one tensor store for the local result and one per peer arena (1 KB contiguous per column:
-        // round 1 measured 661 vs 235 GB/s over NVLink between long and short store runs); the DMMA warps wait only for the engine
-        // to have READ the staging buffer, and the co-resident CTA computes meanwhile.  Groups cut by the end of the chunk range
-        // (or a result the TMA cannot address) are stored by the threads themselves.
-        __syncthreads();                                          // every warp is done with the ring: it becomes the staging buffer
-        double* stg = reinterpret_cast<double*>(smem);            // [4N columns][128 rows]
-        const int N = E.N;
-#pragma unroll
-        for (int gi = 0; gi < BN / 8; gi++) {
-            constexpr int dummy = 0; (void)dummy;
-            const int gw = gi / WJ, j = gi % WJ;                  // owning warp column and its accumulator index (compile time)
-            const int64_t cl0 = n0 / 2 + gi * 4;                  // first local chunk of the group
-            if (cl0 >= E.nc) break;
-            const bool staged = SM.count > 0 && cl0 + 4 <= E.nc;  // block-uniform
-            if (wn == gw) {
-                const int64_t cl = cl0 + t;
-                if (cl < E.nc) {
-                    const int64_t c = E.chunk_lo + cl;
-                    const bool last = (c == E.nchunks_total - 1);
-                    const int cs = last ? E.lastchunksize : N;
-                    const int64_t start = last ? E.n - E.lastchunksize : c * (int64_t)N;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int rl = wm * 32 + i * 8 + g;
-                        const int64_t r = m0 + rl;
-                        if (r >= m) continue;
-                        const double zv = acc[i][j][0] + E.b[r];                            // Dual + Real: value only
-                        const double val = tanh(zv);
-                        const double deriv = 1.0 - val * val;
-                        const double zero_lane = acc[i][j][1];
-                        const double* Ac = E.A + r + start * E.lda;
-                        if (staged) {
-                            double* sc = stg + (t * N) * DM_BM + rl;
-                            for (int kk = 0; kk < cs; kk++) {
-                                const double p = zero_lane + __ldg(Ac + (int64_t)kk * E.lda) * 1.0;   // shared zero lane + the one seeded column of the window
-                                sc[kk * DM_BM] = mulp<NS>(p, deriv);
-                            }
+                for (int j = 0; j < WJ; j++) {
+                    const int64_t c = n0 + wn * (BN / 2) + j * 8 + 2 * t;
+                    if (r < m) {
+                        if (accumulate) {        // C += A*B: the second product of a Dual*Dual partial (fdb_dual_matmul)
+                            if (c < ncols) C[r + c * ldc] = C[r + c * ldc] + acc[i][j][0];
+                            if (c + 1 < ncols) C[r + (c + 1) * ldc] = C[r + (c + 1) * ldc] + acc[i][j][1];
                         } else {
-                            double* Jc = E.J + r + start * E.ldJ;
-                            for (int kk = 0; kk < cs; kk++) {
-                                const double p = zero_lane + __ldg(Ac + (int64_t)kk * E.lda) * 1.0;
-                                mstore_cs<MIR>(Mr, Jc + (int64_t)kk * E.ldJ, mulp<NS>(p, deriv));
-                            }
+                            if (c < ncols) C[r + c * ldc] = acc[i][j][0];
+                            if (c + 1 < ncols) C[r + (c + 1) * ldc] = acc[i][j][1];
                         }
-                        if (E.yout && last) mstore(Mr, &E.yout[r], val);
                     }
                 }
             }
-            if (staged) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (TMA) reads
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    const int col0 = (int)((E.chunk_lo + cl0) * N);               // columns past n (short last chunk) and rows past m are clipped
-                    for (int d = 0; d < SM.count; d++) tma_store_2d(&SM.map[d], stg, (int)m0, col0);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        } else {
+            // ---- z = A*xdual .+ b ; y = tanh.(z) (DiffRules: val = tanh(v), deriv = 1 - val^2) ; J[:, start+kk] = partials(y, kk) ----
+            // A DMMA column group (8 operand columns) carries four chunks: lane t of the owning warps holds (value lane, zero lane)
+            // of chunk 4*gi + t for its rows.  Full groups are staged in shared memory as the dense 128 x 4N block of J they are
+            // and written by the TMA engine -- one tensor store for the local result and one per peer arena (1 KB contiguous per
+            // column: round 1 measured 661 vs 235 GB/s over NVLink between long and short store runs).  Groups cut by the end of
+            // the chunk range (or a result the TMA cannot address) are stored by the threads themselves.
+            if (!PERSIST) __syncthreads();                            // every warp is done with the ring: it doubles as the staging buffer
+            const int N = E.N;
+#pragma unroll
+            for (int gi = 0; gi < BN / 8; gi++) {
+                const int gw = gi / WJ, j = gi % WJ;                  // owning warp column and its accumulator index (compile time)
+                const int64_t cl0 = n0 / 2 + gi * 4;                  // first local chunk of the group
+                if (cl0 >= E.nc) break;
+                const bool staged = SM.count > 0 && cl0 + 4 <= E.nc;  // block-uniform
+                double* stg = reinterpret_cast<double*>(PERSIST ? stg_base + stg_sel * DM_STG_BYTES : smem);     // [4N columns][128 rows]
+                if (PERSIST && staged) {
+                    // the buffer was handed to the TMA engine two groups ago: wait until that store has read it
+                    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncthreads();
                 }
-                __syncthreads();                                                  // staging buffer free again
+                if (wn == gw) {
+                    const int64_t cl = cl0 + t;
+                    if (cl < E.nc) {
+                        const int64_t c = E.chunk_lo + cl;
+                        const bool last = (c == E.nchunks_total - 1);
+                        const int cs = last ? E.lastchunksize : N;
+                        const int64_t start = last ? E.n - E.lastchunksize : c * (int64_t)N;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int rl = wm * 32 + i * 8 + g;
+                            const int64_t r = m0 + rl;
+                            if (r >= m) continue;
+                            const double zv = acc[i][j][0] + E.b[r];                            // Dual + Real: value only
+                            const double val = tanh(zv);
+                            const double deriv = 1.0 - val * val;
+                            const double zero_lane = acc[i][j][1];
+                            const double* Ac = E.A + r + start * E.lda;
+                            if (staged) {
+                                double* sc = stg + (t * N) * DM_BM + rl;
+                                for (int kk = 0; kk < cs; kk++) {
+                                    const double p = zero_lane + __ldg(Ac + (int64_t)kk * E.lda) * 1.0;   // shared zero lane + the one seeded column of the window
+                                    sc[kk * DM_BM] = mulp<NS>(p, deriv);
+                                }
+                            } else {
+                                double* Jc = E.J + r + start * E.ldJ;
+                                for (int kk = 0; kk < cs; kk++) {
+                                    const double p = zero_lane + __ldg(Ac + (int64_t)kk * E.lda) * 1.0;
+                                    mstore_cs<MIR>(Mr, Jc + (int64_t)kk * E.ldJ, mulp<NS>(p, deriv));
+                                }
+                            }
+                            if (E.yout && last) mstore(Mr, &E.yout[r], val);
+                        }
+                    }
+                }
+                if (staged) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (TMA) reads
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        const int col0 = (int)((E.chunk_lo + cl0) * N);               // columns past n (short last chunk) and rows past m are clipped
+                        for (int d = 0; d < SM.count; d++) tma_store_2d(&SM.map[d], stg, (int)m0, col0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (!PERSIST) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    if (PERSIST) stg_sel ^= 1;
+                    else __syncthreads();                                             // the ring (= staging buffer) is free again
+                }
             }
         }
-        // the block retires only when its tensor stores have been performed (not just read from shared memory): whatever follows
-        // this kernel on the stream -- the exchange's flag barrier -- is ordered behind them
-        if (threadIdx.x == 0 && SM.count > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+    // the block retires only when its tensor stores have been performed (not just read from shared memory): whatever follows
+    // this kernel on the stream -- the exchange's flag barrier -- is ordered behind them
+    if (EPI == DM_EPI_TANH && threadIdx.x == 0 && SM.count > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // shape-generic fallback (any alignment): one thread per output row, columns in registers
@@ -347,14 +371,18 @@ size_t gemm_workspace_doubles(int64_t k, int64_t ncols, int bmod) {
 template <int BN, int EPI, bool NS, bool MIR>
 static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws, int btiles, double* C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
                           int accumulate, const TanhEpi& E, const fdb_mirrors& Mr, const StoreMaps& SM) {
+    constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR);
+    constexpr int SMEM = PERSIST ? DmCfg<BN>::SMEM_P : DmCfg<BN>::SMEM;
     static unsigned long long configured = 0;
     if (first_use_on_device(configured, ctx->device)) {
-        cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel<BN, EPI, NS, MIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<BN>::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel<BN, EPI, NS, MIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return fail(ctx, FDB_ERR_CUDA, "cudaFuncSetAttribute(dmma_gemm_kernel): %s", cudaGetErrorString(e));
     }
     const int tiles_m = (int)cdiv(m, DM_BM), tiles_n = (int)cdiv(ncols, BN);
-    dmma_gemm_kernel<BN, EPI, NS, MIR><<<(unsigned)(tiles_m * tiles_n), DM_THREADS, DmCfg<BN>::SMEM, ctx->stream>>>(tm, ws, btiles, C, ldc, m, k, ncols,
-                                                                                                                   tiles_m, tiles_n, accumulate, E, Mr, SM);
+    const int ntiles = tiles_m * tiles_n;
+    const int grid = PERSIST ? (ntiles < ctx->sm_count ? ntiles : ctx->sm_count) : ntiles;
+    dmma_gemm_kernel<BN, EPI, NS, MIR><<<(unsigned)grid, DM_THREADS, SMEM, ctx->stream>>>(tm, ws, btiles, C, ldc, m, k, ncols, tiles_m, tiles_n, accumulate, E,
+                                                                                          Mr, SM);
     return FDB_OK;
 }
 

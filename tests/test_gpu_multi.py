@@ -279,3 +279,36 @@ def test_paths_are_reported(ctx):
         g = fdb200.gradient(f, x2, cfg, ctx=ctx)
     assert cfg.last_path in ("loop:graph", "loop:eager") and cfg.trace_error
     assert np.allclose(g, 2.0 * x2 + 1.0, rtol=1e-14)
+
+
+def test_persistent_dmma_kernel_with_tma_peer_stores_at_a_sharded_c3_shape(oracle):
+    """the mirrored form of the fused DMMA kernel (one persistent block per SM, result blocks pushed to every peer arena by TMA
+    tensor stores from two staging buffers while the next tile is contracted): several tiles per block, ragged last column group,
+    short last chunk -- complete and equal on every device, and equal to the closed form"""
+    g = fdb200.DeviceGroup([0, 0, 0])
+    try:
+        rng = np.random.default_rng(11)
+        m, n, N = 2048 + 128, 4100, 12                          # 342 chunks over 3 contexts; last chunk has 8 columns
+        A = rng.uniform(-1, 1, (m, n)) / np.sqrt(n); b = rng.uniform(-1, 1, m); x = rng.uniform(-1, 1, n)
+        Ad = [c.array(np.asfortranarray(A).ravel(order="F")) for c in g.contexts]
+        bd = [c.array(b) for c in g.contexts]
+        xoff, joff = 0, 4128
+        ar = g.arena(joff + m * n + m + 64)
+        try:
+            ar.upload(xoff, x)
+            ar.jacobian(F.tanh_affine, xoff, n, m, N, joff, joff + m * n, A=Ad, b=bd)
+            y = np.tanh(A @ x + b)
+            ref = (1.0 - y * y)[:, None] * A
+            for d in range(g.size):
+                J = ar.download(d, joff, m * n).reshape((m, n), order="F")
+                assert np.max(np.abs(J - ref)) <= 1e-12 * np.max(np.abs(ref)), d
+                assert np.allclose(ar.download(d, joff + m * n, m), y, rtol=1e-12, atol=1e-13)
+            J0 = ar.download(0, joff, m * n)
+            assert np.array_equal(J0, ar.download(1, joff, m * n)) and np.array_equal(J0, ar.download(2, joff, m * n))
+            J_ref, _ = oracle.jacobian("tanh_affine", x, m, N, A=A, b=b, chunks=(341, 342), cols=(4092, 4100))
+            assert np.allclose(J0.reshape((m, n), order="F")[:, 4092:], J_ref, rtol=1e-12, atol=1e-15)
+        finally:
+            ar.close()
+            del Ad, bd
+    finally:
+        g.close()
