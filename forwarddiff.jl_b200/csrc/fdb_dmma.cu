@@ -156,9 +156,8 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
     // the TMA copies of the slab STAGES - 1 ahead before that warp starts on its own slab, so the issue cost rotates over the warps.
     const int wm = warp & 3, wn = warp >> 2;
     const int g = lane >> 2, t = lane & 3;
-    auto produce = [&](int gp) {              // called by one thread; gp = slab number within this block's tile sequence
-        const int ti = PERSIST ? gp / nslab : 0, sp = gp - ti * nslab;
-        int ptm, ptn; tile_coords((int)blockIdx.x + ti * (int)gridDim.x, ptm, ptn);
+    // slab gp of this block's tile sequence = slab sp of the tile with coordinates (ptm, ptn)
+    auto produce = [&](int gp, int sp, int ptm, int ptn) {              // called by one thread
         const int st = gp % STAGES;
         if (gp >= STAGES) mbar_wait(&empty[st], (uint32_t)(((gp / STAGES) - 1) & 1));
         unsigned char* stage = smem + st * Cfg::STAGE_BYTES;
@@ -169,7 +168,14 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
         bulk_g2s(stage + DM_A_BYTES, Bp + ((int64_t)(ptn % btiles) * nslab + sp) * Cfg::B_ELEMS, Cfg::B_BYTES, &full[st]);   // packed B tile
     };
     if (threadIdx.x == 0)
-        for (int gp = 0; gp < STAGES - 1 && gp < total; gp++) produce(gp);
+        for (int gp = 0; gp < STAGES - 1 && gp < total; gp++) {
+            int ptm, ptn; tile_coords((int)blockIdx.x + (gp / nslab) * (int)gridDim.x, ptm, ptn);
+            produce(gp, gp % nslab, ptm, ptn);
+        }
+    // warp w issues the slabs w + STAGES - 1, w + STAGES - 1 + 8, ...: it tracks (tile, slab in tile) of its next one incrementally,
+    // so the tile coordinates (integer divisions) are recomputed only when that slab enters a new tile
+    int p_gp = warp + STAGES - 1, p_ti = p_gp / nslab, p_sp = p_gp - p_ti * nslab, p_tm = 0, p_tn = 0;
+    if (p_gp < total) tile_coords((int)blockIdx.x + p_ti * (int)gridDim.x, p_tm, p_tn);
     // swizzled A fragment address (in doubles): box (wm*2 + i/2) * 256 + k * 16 + ((chunk ^ k%8) << 1) + (g & 1),
     // chunk = (i & 1) * 4 + g / 2  ==>  base + krow + (((g/2) ^ x) << 1) ^ ((i & 1) << 3), + 256 for i >= 2
     const int a_base = wm * 512 + (g & 1), gh = g >> 1;
@@ -186,7 +192,14 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
             for (int j = 0; j < WJ; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
         for (int s = 0; s < nslab; s++, gc++) {
             if (warp == (gc & 7)) {
-                if (lane == 0 && gc + STAGES - 1 < total) produce(gc + STAGES - 1);
+                if (p_gp < total) {
+                    if (lane == 0) produce(p_gp, p_sp, p_tm, p_tn);
+                    p_gp += 8; p_sp += 8;
+                    if (PERSIST && p_sp >= nslab && p_gp < total) {
+                        do { p_sp -= nslab; p_ti++; } while (p_sp >= nslab);
+                        tile_coords((int)blockIdx.x + p_ti * (int)gridDim.x, p_tm, p_tn);
+                    }
+                }
                 __syncwarp();
             }
             const int st = gc % STAGES;
