@@ -488,6 +488,14 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
             else:
                 rec = lambda c, arr: ctx.check(lib.fdb_hessian_chunked(ctx.h, sh.fid, sh.x_a.h, N, c, c + 1, arr.h, n, None, None))
             res[f"gathered_{mode}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
+            if name == "tanh_affine_jacobian_c3" and mode == "p2p":
+                # how the fused DMMA epilogue gets its result blocks to the peers (fdb_set_dmma_tma_store): every thread its own
+                # accumulator entries / staged + TMA tensor stores / staged + 256-byte runs stored by the block's threads
+                for label, sm in (("own_entries", 0), ("staged_tma", 2), ("staged_thread_runs", 3)):
+                    ctx.check(lib.fdb_set_dmma_tma_store(ctx.h, sm))
+                    res[f"gathered_p2p_{label}_ms"] = timed(step, reps)
+                    res[f"gathered_p2p_{label}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
+                ctx.check(lib.fdb_set_dmma_tma_store(ctx.h, 1))
             if kind == "hess" and mode == "p2p":
                 # the two ways of getting the column block to the peers (fdb200.dist.ShardedHessian.peer_stores); the default picks by rank count
                 for ps in ("mirror", "push"):

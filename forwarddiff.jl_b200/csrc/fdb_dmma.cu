@@ -105,7 +105,18 @@ enum { DM_EPI_STORE = 0, DM_EPI_TANH = 1 };
 
 // Tensor maps of the Jacobian for the tile epilogue's TMA stores: [0] = the local result, [1 .. count-1] = the same matrix in
 // every peer's arena (fdb_mirror.cuh deltas).  Box = 128 rows x 4N columns = the four chunks one DMMA column group carries.
-struct StoreMaps { CUtensorMap map[FDB_MAX_RANKS]; int count; };
+// mode 1: TMA tensor stores from the staging buffer; mode 2: the block's threads copy the staged block out themselves, a warp
+// per 32 consecutive rows of a column (256-byte runs: the pattern that reaches the link rate in fdb_exchange_measure_store_bw)
+struct StoreMaps { CUtensorMap map[FDB_MAX_RANKS]; int count; int mode; };
+
+// Measured at 8 ranks (C3, 172 operand columns per rank; profiles/r02_bench_8gpu_*.json), sweep + exchange:
+//   threads store their own accumulator entries (64-byte runs)                         1.79 ms
+//   staged, TMA tensor stores, two blocks per SM (wait for the engine to read)          1.45 ms
+//   persistent, one block per SM, two staging buffers, stores overlap the next tile    2.16 ms  (BN = 16 leaves two warps per
+//       scheduler with four independent DMMA chains each: the tensor pipe starves; BN = 64 tiles quantise to two waves)
+// so the persistent variant is compiled out.
+constexpr bool DM_PERSIST_MIRROR = false;
+constexpr int DM_MIRROR_STORE_MODE = 2;      // default when mirroring: 1 = TMA tensor stores, 2 = staged thread stores
 
 FDB_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src))
@@ -120,13 +131,13 @@ FDB_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c
 // buffers, so the DMMA warps go straight on to the next tile while the TMA engine pushes the finished block to the peers over
 // NVLink; they wait for a staging buffer only when it is needed again, two column groups later.
 template <int BN, int EPI, bool NS, bool MIR>
-__global__ void __launch_bounds__(DM_THREADS, (EPI == DM_EPI_TANH && MIR) ? 1 : 2)
+__global__ void __launch_bounds__(DM_THREADS, (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR) ? 1 : 2)
 dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles, double* __restrict__ C, int64_t ldc,
                  int64_t m, int64_t k, int64_t ncols, int tiles_m, int tiles_n, const int accumulate, const __grid_constant__ TanhEpi E,
                  const __grid_constant__ fdb_mirrors Mr, const __grid_constant__ StoreMaps SM) {
     using Cfg = DmCfg<BN>;
     constexpr int WJ = Cfg::WJ;
-    constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR);
+    constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR);
     constexpr int STAGES = PERSIST ? Cfg::STAGES_P : Cfg::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -296,7 +307,18 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
                         }
                     }
                 }
-                if (staged) {
+                if (staged && SM.mode == 2) {
+                    // the block copies the staged 128 x 4N block out itself: consecutive lanes take consecutive rows of a column, so
+                    // every warp store is one 256-byte run -- locally and at the same offset of every peer arena.  The stores are
+                    // posted: nobody waits for them, the block goes on (or retires) while they drain over NVLink.
+                    __syncthreads();
+                    const int64_t col0 = (E.chunk_lo + cl0) * N;
+                    for (int idx = threadIdx.x; idx < 4 * N * DM_BM; idx += DM_THREADS) {
+                        const int col = idx >> 7, row = idx & (DM_BM - 1);
+                        if (m0 + row < m && col0 + col < E.n) mstore_cs<MIR>(Mr, E.J + (m0 + row) + (col0 + col) * E.ldJ, stg[idx]);
+                    }
+                    __syncthreads();                                                  // the staging buffer is free again
+                } else if (staged) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (TMA) reads
                     __syncthreads();
                     if (threadIdx.x == 0) {
@@ -313,7 +335,7 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
     }
     // the block retires only when its tensor stores have been performed (not just read from shared memory): whatever follows
     // this kernel on the stream -- the exchange's flag barrier -- is ordered behind them
-    if (EPI == DM_EPI_TANH && threadIdx.x == 0 && SM.count > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (EPI == DM_EPI_TANH && threadIdx.x == 0 && SM.count > 0 && SM.mode == 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // shape-generic fallback (any alignment): one thread per output row, columns in registers
@@ -384,7 +406,7 @@ size_t gemm_workspace_doubles(int64_t k, int64_t ncols, int bmod) {
 template <int BN, int EPI, bool NS, bool MIR>
 static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws, int btiles, double* C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
                           int accumulate, const TanhEpi& E, const fdb_mirrors& Mr, const StoreMaps& SM) {
-    constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR);
+    constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR);
     constexpr int SMEM = PERSIST ? DmCfg<BN>::SMEM_P : DmCfg<BN>::SMEM;
     static unsigned long long configured = 0;
     if (first_use_on_device(configured, ctx->device)) {
@@ -433,10 +455,13 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
     const TanhEpi& E = epi ? *epi : E0;
     const fdb_mirrors& Mr = mirrors ? *mirrors : M0;
     thread_local static StoreMaps SM;    // 1 KB: kept out of the stack frame; filled per launch (copied into the launch's parameters)
-    SM.count = 0;
-    // staged TMA stores pay off when the blocks also go to peers over NVLink (long contiguous runs); locally the threads' own
-    // streaming stores are 1 % faster (5.49 vs 5.56 ms at C3), so mode 1 = peers only, 2 = always
-    if (epi && (ctx->dmma_tma_store == 2 || (ctx->dmma_tma_store == 1 && Mr.count > 0)) && (E.ldJ % 2 == 0) && ((((uintptr_t)E.J) & 15) == 0) && E.N * 4 <= 256) {
+    SM.count = 0; SM.mode = 0;
+    // Staging pays off when the blocks also go to peers over NVLink (long contiguous runs); locally the threads' own streaming
+    // stores are 1 % faster (5.49 vs 5.56 ms at C3).  ctx->dmma_tma_store: 0 = never stage, 1 = default (stage when mirroring),
+    // 2 = always TMA tensor stores, 3 = always staged thread stores.
+    const int want = ctx->dmma_tma_store == 1 ? (Mr.count > 0 ? DM_MIRROR_STORE_MODE : 0) : (ctx->dmma_tma_store == 2 ? 1 : (ctx->dmma_tma_store == 3 ? 2 : 0));
+    if (epi && want == 2) { SM.count = 1; SM.mode = 2; }
+    if (epi && want == 1 && (E.ldJ % 2 == 0) && ((((uintptr_t)E.J) & 15) == 0) && E.N * 4 <= 256) {
         // the Jacobian as a tensor: 128-row x 4N-column boxes for the epilogue's TMA stores, one map per destination arena
         const cuuint64_t jdim[2] = {(cuuint64_t)m, (cuuint64_t)E.n};
         const cuuint64_t jstride[1] = {(cuuint64_t)E.ldJ * 8};
@@ -448,6 +473,7 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
         SM.count = good ? Mr.count + 1 : 0;
+        SM.mode = 1;
     }
     int rc;
 #define FDB_GEMM_BN(EPI_, NS_, MIR_)                                                                              \

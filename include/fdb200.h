@@ -107,9 +107,9 @@ int fdb_set_dmma(fdb_ctx* ctx, int enabled);
 /* operand columns per thread-block tile of the DMMA contraction: 0 (default) = chosen per shape so that the equal-sized
  * tiles fill the SMs evenly, or 16 / 32 / 64 (measurement knob) */
 int fdb_set_dmma_tile(fdb_ctx* ctx, int bn);
-/* how the fused DMMA epilogue writes its 128 x 4N result blocks: 2 = staged in shared memory and written by TMA tensor stores
- * (local result + one store per peer arena); 0 = the threads store their own entries; 1 (default) = TMA stores when the result is
- * mirrored to peers over NVLink, thread stores otherwise */
+/* how the fused DMMA epilogue writes its 128 x 4N result blocks: 0 = every thread stores its own accumulator entries;
+ * 2 = staged in shared memory and written by TMA tensor stores (local result + one store per peer arena); 3 = staged and copied
+ * out by the block's threads in 256-byte runs; 1 (default) = staged when the result is mirrored to peers over NVLink, 0 otherwise */
 int fdb_set_dmma_tma_store(fdb_ctx* ctx, int mode);
 int fdb_kernel_launches(fdb_ctx* ctx, int64_t* count); /* kernels launched on this context so far */
 const char* fdb_version(void);

@@ -132,12 +132,12 @@ def test_fused_epilogue_tma_stores_match_thread_stores(ctx, oracle, N):
         A = rng.uniform(-1, 1, (m, n + (n % 2))) [:, :n] / np.sqrt(n); b = rng.uniform(-1, 1, m); x = rng.uniform(-1, 1, n)
         f = F.tanh_affine.with_params(A=A, b=b)
         out = {}
-        for mode in (0, 2):
+        for mode in (0, 2, 3):
             ctx.check(ctx.lib.fdb_set_dmma_tma_store(ctx.h, mode))
             try:
                 out[mode] = fdb200.jacobian(f, x, fdb200.JacobianConfig(f, x, fdb200.Chunk(N)), ctx=ctx, m=m)
             finally:
                 ctx.check(ctx.lib.fdb_set_dmma_tma_store(ctx.h, 1))
-        assert np.array_equal(out[0], out[2]), (m, n, N)
+        assert np.array_equal(out[0], out[2]) and np.array_equal(out[0], out[3]), (m, n, N)
         J_ref, _ = oracle.jacobian("tanh_affine", x, m, N, A=A, b=b)
         assert np.allclose(out[2], J_ref, rtol=1e-12, atol=1e-15)
