@@ -131,14 +131,15 @@ FDB_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c
 // buffers, so the DMMA warps go straight on to the next tile while the TMA engine pushes the finished block to the peers over
 // NVLink; they wait for a staging buffer only when it is needed again, two column groups later.
 template <int BN, int EPI, bool NS, bool MIR>
-__global__ void __launch_bounds__(DM_THREADS, (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR) ? 1 : 2)
+__global__ void __launch_bounds__(DM_THREADS, (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR) ? 1 : ((EPI == DM_EPI_TANH && MIR && BN == 16) ? 3 : 2))
 dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles, double* __restrict__ C, int64_t ldc,
                  int64_t m, int64_t k, int64_t ncols, int tiles_m, int tiles_n, const int accumulate, const __grid_constant__ TanhEpi E,
                  const __grid_constant__ fdb_mirrors Mr, const __grid_constant__ StoreMaps SM) {
     using Cfg = DmCfg<BN>;
     constexpr int WJ = Cfg::WJ;
     constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR);
-    constexpr int STAGES = PERSIST ? Cfg::STAGES_P : Cfg::STAGES;
+    // mirrored 16-column tiles: THREE blocks per SM (3-stage ring, <= 80 registers), so that a block computes while others sit in their NVLink stores
+    constexpr int STAGES = PERSIST ? Cfg::STAGES_P : ((EPI == DM_EPI_TANH && MIR && BN == 16) ? 3 : Cfg::STAGES);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* stg_base = smem + STAGES * Cfg::STAGE_BYTES;                       // PERSIST: two staging buffers behind the ring
@@ -407,7 +408,7 @@ template <int BN, int EPI, bool NS, bool MIR>
 static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws, int btiles, double* C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
                           int accumulate, const TanhEpi& E, const fdb_mirrors& Mr, const StoreMaps& SM) {
     constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR);
-    constexpr int SMEM = PERSIST ? DmCfg<BN>::SMEM_P : DmCfg<BN>::SMEM;
+    constexpr int SMEM = PERSIST ? DmCfg<BN>::SMEM_P : ((EPI == DM_EPI_TANH && MIR && BN == 16) ? 3 * DmCfg<BN>::STAGE_BYTES + 2 * 3 * 8 + 1024 : DmCfg<BN>::SMEM);
     static unsigned long long configured = 0;
     if (first_use_on_device(configured, ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel<BN, EPI, NS, MIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
