@@ -169,25 +169,29 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
     const int wm = warp & 3, wn = warp >> 2;
     const int g = lane >> 2, t = lane & 3;
     // slab gp of this block's tile sequence = slab sp of the tile with coordinates (ptm, ptn)
-    auto produce = [&](int gp, int sp, int ptm, int ptn) {              // called by one thread
+    auto produce = [&](int gp, int sp, int pm0, const double* pbt) {    // called by one thread; pm0 = first row of the tile, pbt = its packed B tiles
         const int st = gp % STAGES;
         if (gp >= STAGES) mbar_wait(&empty[st], (uint32_t)(((gp / STAGES) - 1) & 1));
         unsigned char* stage = smem + st * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[st], DM_A_BYTES + Cfg::B_BYTES);
 #pragma unroll
         for (int bx = 0; bx < DM_BM / 16; bx++)
-            tma_load_2d(stage + bx * 2048, &tmA, ptm * DM_BM + 16 * bx, sp * DM_BK, &full[st]);      // [16 k][16 m], 128B-swizzled
-        bulk_g2s(stage + DM_A_BYTES, Bp + ((int64_t)(ptn % btiles) * nslab + sp) * Cfg::B_ELEMS, Cfg::B_BYTES, &full[st]);   // packed B tile
+            tma_load_2d(stage + bx * 2048, &tmA, pm0 + 16 * bx, sp * DM_BK, &full[st]);             // [16 k][16 m], 128B-swizzled
+        bulk_g2s(stage + DM_A_BYTES, pbt + (int64_t)sp * Cfg::B_ELEMS, Cfg::B_BYTES, &full[st]);       // packed B tile
     };
     if (threadIdx.x == 0)
         for (int gp = 0; gp < STAGES - 1 && gp < total; gp++) {
             int ptm, ptn; tile_coords((int)blockIdx.x + (gp / nslab) * (int)gridDim.x, ptm, ptn);
-            produce(gp, gp % nslab, ptm, ptn);
+            produce(gp, gp % nslab, ptm * DM_BM, Bp + (int64_t)(ptn % btiles) * nslab * Cfg::B_ELEMS);
         }
     // warp w issues the slabs w + STAGES - 1, w + STAGES - 1 + 8, ...: it tracks (tile, slab in tile) of its next one incrementally,
     // so the tile coordinates (integer divisions) are recomputed only when that slab enters a new tile
-    int p_gp = warp + STAGES - 1, p_ti = p_gp / nslab, p_sp = p_gp - p_ti * nslab, p_tm = 0, p_tn = 0;
-    if (p_gp < total) tile_coords((int)blockIdx.x + p_ti * (int)gridDim.x, p_tm, p_tn);
+    int p_gp = warp + STAGES - 1, p_ti = p_gp / nslab, p_sp = p_gp - p_ti * nslab, p_m0 = 0;
+    const double* p_bt = Bp;
+    if (p_gp < total) {
+        int ptm, ptn; tile_coords((int)blockIdx.x + p_ti * (int)gridDim.x, ptm, ptn);
+        p_m0 = ptm * DM_BM; p_bt = Bp + (int64_t)(ptn % btiles) * nslab * Cfg::B_ELEMS;
+    }
     // swizzled A fragment address (in doubles): box (wm*2 + i/2) * 256 + k * 16 + ((chunk ^ k%8) << 1) + (g & 1),
     // chunk = (i & 1) * 4 + g / 2  ==>  base + krow + (((g/2) ^ x) << 1) ^ ((i & 1) << 3), + 256 for i >= 2
     const int a_base = wm * 512 + (g & 1), gh = g >> 1;
@@ -205,11 +209,12 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
         for (int s = 0; s < nslab; s++, gc++) {
             if (warp == (gc & 7)) {
                 if (p_gp < total) {
-                    if (lane == 0) produce(p_gp, p_sp, p_tm, p_tn);
+                    if (lane == 0) produce(p_gp, p_sp, p_m0, p_bt);
                     p_gp += 8; p_sp += 8;
                     if (PERSIST && p_sp >= nslab && p_gp < total) {
                         do { p_sp -= nslab; p_ti++; } while (p_sp >= nslab);
-                        tile_coords((int)blockIdx.x + p_ti * (int)gridDim.x, p_tm, p_tn);
+                        int ptm, ptn; tile_coords((int)blockIdx.x + p_ti * (int)gridDim.x, ptm, ptn);
+                        p_m0 = ptm * DM_BM; p_bt = Bp + (int64_t)(ptn % btiles) * nslab * Cfg::B_ELEMS;
                     }
                 }
                 __syncwarp();
