@@ -116,6 +116,10 @@ struct StoreMaps { CUtensorMap map[FDB_MAX_RANKS]; int count; int mode; };
 //       scheduler with four independent DMMA chains each: the tensor pipe starves; BN = 64 tiles quantise to two waves)
 // so the persistent variant is compiled out.
 constexpr bool DM_PERSIST_MIRROR = false;
+// 16-column tiles with the fused epilogue: THREE blocks per SM (3-stage ring, <= 80 registers).  One block's 8 warps issue 20
+// shared loads per 16 DMMAs and cannot keep the pipe busy through a neighbour's epilogue (A reads + J stores, ~10 us of a
+// ~350 us block life) or its NVLink stores; measured at C3 with BN = 16 on one B200: 5.98 ms against 6.52 ms with two blocks.
+__host__ __device__ constexpr bool DM_BN16_THREE(int EPI, int BN) { return EPI == DM_EPI_TANH && BN == 16; }
 constexpr int DM_MIRROR_STORE_MODE = 2;      // default when mirroring: 1 = TMA tensor stores, 2 = staged thread stores
 
 FDB_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -131,15 +135,14 @@ FDB_DEV void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c
 // buffers, so the DMMA warps go straight on to the next tile while the TMA engine pushes the finished block to the peers over
 // NVLink; they wait for a staging buffer only when it is needed again, two column groups later.
 template <int BN, int EPI, bool NS, bool MIR>
-__global__ void __launch_bounds__(DM_THREADS, (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR) ? 1 : ((EPI == DM_EPI_TANH && MIR && BN == 16) ? 3 : 2))
+__global__ void __launch_bounds__(DM_THREADS, (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR) ? 1 : (DM_BN16_THREE(EPI, BN) ? 3 : 2))
 dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restrict__ Bp, int btiles, double* __restrict__ C, int64_t ldc,
                  int64_t m, int64_t k, int64_t ncols, int tiles_m, int tiles_n, const int accumulate, const __grid_constant__ TanhEpi E,
                  const __grid_constant__ fdb_mirrors Mr, const __grid_constant__ StoreMaps SM) {
     using Cfg = DmCfg<BN>;
     constexpr int WJ = Cfg::WJ;
     constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR);
-    // mirrored 16-column tiles: THREE blocks per SM (3-stage ring, <= 80 registers), so that a block computes while others sit in their NVLink stores
-    constexpr int STAGES = PERSIST ? Cfg::STAGES_P : ((EPI == DM_EPI_TANH && MIR && BN == 16) ? 3 : Cfg::STAGES);
+    constexpr int STAGES = PERSIST ? Cfg::STAGES_P : (DM_BN16_THREE(EPI, BN) ? 3 : Cfg::STAGES);
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* stg_base = smem + STAGES * Cfg::STAGE_BYTES;                       // PERSIST: two staging buffers behind the ring
@@ -201,6 +204,7 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
     for (int ti = 0; ti < my_tiles; ti++) {
         int tm, tn; tile_coords((int)blockIdx.x + ti * (int)gridDim.x, tm, tn);
         const int64_t n0 = (int64_t)tn * BN, m0 = (int64_t)tm * DM_BM;
+        const double* bt0 = Bp + (int64_t)(tn % btiles) * nslab * Cfg::B_ELEMS;
         double acc[4][WJ][2];
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -208,10 +212,12 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
             for (int j = 0; j < WJ; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
         for (int s = 0; s < nslab; s++, gc++) {
             if (warp == (gc & 7)) {
-                if (p_gp < total) {
+                if constexpr (!PERSIST) {                             // one tile per block: the slab ahead belongs to this tile (block-uniform operands)
+                    if (lane == 0 && s + STAGES - 1 < nslab) produce(s + STAGES - 1, s + STAGES - 1, (int)m0, bt0);
+                } else if (p_gp < total) {
                     if (lane == 0) produce(p_gp, p_sp, p_m0, p_bt);
                     p_gp += 8; p_sp += 8;
-                    if (PERSIST && p_sp >= nslab && p_gp < total) {
+                    if (p_sp >= nslab && p_gp < total) {
                         do { p_sp -= nslab; p_ti++; } while (p_sp >= nslab);
                         int ptm, ptn; tile_coords((int)blockIdx.x + p_ti * (int)gridDim.x, ptm, ptn);
                         p_m0 = ptm * DM_BM; p_bt = Bp + (int64_t)(ptn % btiles) * nslab * Cfg::B_ELEMS;
@@ -265,7 +271,7 @@ dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const double* __restri
             // and written by the TMA engine -- one tensor store for the local result and one per peer arena (1 KB contiguous per
             // column: round 1 measured 661 vs 235 GB/s over NVLink between long and short store runs).  Groups cut by the end of
             // the chunk range (or a result the TMA cannot address) are stored by the threads themselves.
-            if (!PERSIST) __syncthreads();                            // every warp is done with the ring: it doubles as the staging buffer
+            if (!PERSIST && SM.count > 0) __syncthreads();            // every warp is done with the ring: it doubles as the staging buffer
             const int N = E.N;
 #pragma unroll
             for (int gi = 0; gi < BN / 8; gi++) {
@@ -413,7 +419,7 @@ template <int BN, int EPI, bool NS, bool MIR>
 static int launch_gemm_bn(fdb_ctx* ctx, const CUtensorMap& tm, const double* ws, int btiles, double* C, int64_t ldc, int64_t m, int64_t k, int64_t ncols,
                           int accumulate, const TanhEpi& E, const fdb_mirrors& Mr, const StoreMaps& SM) {
     constexpr bool PERSIST = (EPI == DM_EPI_TANH && MIR && DM_PERSIST_MIRROR);
-    constexpr int SMEM = PERSIST ? DmCfg<BN>::SMEM_P : ((EPI == DM_EPI_TANH && MIR && BN == 16) ? 3 * DmCfg<BN>::STAGE_BYTES + 2 * 3 * 8 + 1024 : DmCfg<BN>::SMEM);
+    constexpr int SMEM = PERSIST ? DmCfg<BN>::SMEM_P : (DM_BN16_THREE(EPI, BN) ? 3 * DmCfg<BN>::STAGE_BYTES + 2 * 3 * 8 + 1024 : DmCfg<BN>::SMEM);
     static unsigned long long configured = 0;
     if (first_use_on_device(configured, ctx->device)) {
         cudaError_t e = cudaFuncSetAttribute(dmma_gemm_kernel<BN, EPI, NS, MIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
