@@ -398,6 +398,7 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
       sharded_resident : every rank sweeps its chunk range into its own column block, no exchange (the result stays sharded);
       gathered_p2p     : the sweep kernels also store every entry into all peers' arenas over NVLink + device-side flag barrier
                          (the complete matrix is resident on every rank);
+      gathered_multicast: the same with ONE store per entry through the NVSwitch multicast mapping of all arenas (when supported);
       gathered_nccl    : the sharded-resident sweep followed by one NCCL all-gather of the column blocks;
     and a bit-for-bit check of sampled chunk column blocks (first / middle / last chunk, wherever they were computed) of both
     gathered matrices against the same chunks recomputed on THIS rank alone."""
@@ -460,12 +461,17 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
     configs.append(("rosenbrock_hessian_c5", "hess", F.rosenbrock, xh, 2048, 8, 10,
                     "latency: 256/W outer chunks x 256 inner chunks of 2047 short terms per rank, then a 33.5 MB exchange"))
 
+    modes = ["nccl", "p2p"]
+    sup = [None] * world
+    dist.all_gather_object(sup, bool(fdb200.dist.multicast_supported(ctx)))
+    if all(sup):
+        modes.append("multicast")      # NVSwitch multicast: each entry stored once, replicated by the switch (csrc/fdb_multicast.cu)
     for name, kind, f, xhost, m, N, reps, limiting in configs:
         n = xhost.size
         nchunks = fdb200.chunk_plan(n, N)["nchunks"]
         entry = {"ranks": world, "n": int(n), "chunk": N, "limiting_element": limiting}
         res = {}
-        for mode in ("nccl", "p2p"):
+        for mode in modes:
             try:
                 if kind == "jac":
                     sh = fdb200.dist.ShardedJacobian(ctx, f, n, m, fdb200.JacobianConfig(f, xhost, fdb200.Chunk(N)), exchange=mode)
@@ -488,23 +494,23 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
             else:
                 rec = lambda c, arr: ctx.check(lib.fdb_hessian_chunked(ctx.h, sh.fid, sh.x_a.h, N, c, c + 1, arr.h, n, None, None))
             res[f"gathered_{mode}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
-            if name == "tanh_affine_jacobian_c3" and mode == "p2p":
+            if name == "tanh_affine_jacobian_c3" and mode in ("p2p", "multicast"):
                 # how the fused DMMA epilogue gets its result blocks to the peers (fdb_set_dmma_tma_store): every thread its own
                 # accumulator entries / staged + TMA tensor stores / staged + 256-byte runs stored by the block's threads
                 for label, sm in (("own_entries", 0), ("staged_tma", 2), ("staged_thread_runs", 3)):
                     ctx.check(lib.fdb_set_dmma_tma_store(ctx.h, sm))
-                    res[f"gathered_p2p_{label}_ms"] = timed(step, reps)
-                    res[f"gathered_p2p_{label}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
+                    res[f"gathered_{mode}_{label}_ms"] = timed(step, reps)
+                    res[f"gathered_{mode}_{label}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
                 ctx.check(lib.fdb_set_dmma_tma_store(ctx.h, 1))
-            if kind == "hess" and mode == "p2p":
+            if kind == "hess" and mode in ("p2p", "multicast"):
                 # the two ways of getting the column block to the peers (fdb200.dist.ShardedHessian.peer_stores); the default picks by rank count
                 for ps in ("mirror", "push"):
                     sh.peer_stores = ps
-                    res[f"gathered_p2p_{ps}_ms"] = timed(step, reps)
-                    res[f"gathered_p2p_{ps}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
+                    res[f"gathered_{mode}_{ps}_ms"] = timed(step, reps)
+                    res[f"gathered_{mode}_{ps}_bitwise_vs_single_rank"] = check_columns(sh, rec, nchunks, N, n, m)
                 sh.peer_stores = "auto"
             if sh.xch is not None:
-                res["barrier_timeouts"] = int(sh.xch.timeouts())
+                res["barrier_timeouts"] = res.get("barrier_timeouts", 0) + int(sh.xch.timeouts())
             sh.close()
             del sh
             torch.cuda.empty_cache()

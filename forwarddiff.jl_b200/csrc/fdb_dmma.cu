@@ -479,12 +479,13 @@ int launch_gemm(fdb_ctx* ctx, const double* A, int64_t lda, const double* B, int
         const cuuint64_t jstride[1] = {(cuuint64_t)E.ldJ * 8};
         const cuuint32_t jbox[2] = {DM_BM, (cuuint32_t)(4 * E.N)};
         bool good = true;
-        for (int d = 0; d <= Mr.count && good; d++) {
+        int nmaps = 0;
+        for (int d = Mr.mc ? 1 : 0; d <= Mr.count && good; d++) {      // multicast: the one mapping at delta[0] reaches every arena, this rank's included
             char* base = reinterpret_cast<char*>(E.J) + (d == 0 ? 0 : Mr.delta[d - 1]);
-            good = enc(&SM.map[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, jdim, jstride, jbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            good = enc(&SM.map[nmaps++], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, jdim, jstride, jbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
-        SM.count = good ? Mr.count + 1 : 0;
+        SM.count = good ? nmaps : 0;
         SM.mode = 1;
     }
     int rc;

@@ -80,6 +80,10 @@ int mirrors_for(fdb_ctx* ctx, fdb_mirrors* m, const fdb_array* const* outs, int 
             return fail(ctx, FDB_ERR_BADARG, "%s: with a peer exchange enabled every result array must be a view of the exchange arena "
                                              "(fdb_exchange_view); output %d is not", what, i);
     }
+    if (x->mc_base && x->mc_on && x->world > 1) {      // NVSwitch multicast: one store, replicated into every arena (fdb_multicast.cu)
+        m->mc = 1; m->count = 1; m->delta[0] = (long long)(x->mc_base - x->base);
+        return FDB_OK;
+    }
     // rank r visits its peers as r+1, r+2, ...: at any instant the ranks address different destinations
     for (int k = 1; k < x->world; k++) {
         const int r = (x->rank + k) % x->world;
@@ -121,6 +125,7 @@ extern "C" int fdb_exchange_handle(fdb_exchange* x, unsigned char handle[FDB_IPC
     FDB_ENTER(x ? x->ctx : nullptr);
     if (!x || !handle) return FDB_ERR_BADARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == FDB_IPC_HANDLE_BYTES, "IPC handle size");
+    if (x->vmm) return fail(x->ctx, FDB_ERR_BADARG, "fdb_exchange_handle: a multicast arena is shared with fdb_exchange_share_handle, not through CUDA IPC");
     cudaIpcMemHandle_t h;
     FDB_CUDA(x->ctx, cudaIpcGetMemHandle(&h, x->base));
     memcpy(handle, &h, sizeof h);
@@ -131,6 +136,7 @@ extern "C" int fdb_exchange_connect(fdb_exchange* x, const unsigned char* handle
     FDB_ENTER(x ? x->ctx : nullptr);
     if (!x || !handles) return FDB_ERR_BADARG;
     fdb_ctx* ctx = x->ctx;
+    if (x->vmm) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_connect: a multicast arena connects with fdb_exchange_connect_multicast");
     if (x->connected) return FDB_OK;
     cudaSetDevice(ctx->device);
     for (int r = 0; r < x->world; r++) {
@@ -159,7 +165,7 @@ extern "C" int fdb_exchange_connect_local(fdb_exchange* const* xs, int world) {
         if (!xs[r] || xs[r]->world != world || xs[r]->rank != r) return fail(xs[0] ? xs[0]->ctx : nullptr, FDB_ERR_BADARG,
             "fdb_exchange_connect_local: xs[%d] must be rank %d of %d", r, r, world);
     for (int r = 0; r < world; r++)
-        if (xs[r]->data_bytes != xs[0]->data_bytes) return fail(xs[0]->ctx, FDB_ERR_BADARG, "fdb_exchange_connect_local: arenas must be symmetric");
+        if (xs[r]->data_bytes != xs[0]->data_bytes || xs[r]->vmm) return fail(xs[0]->ctx, FDB_ERR_BADARG, "fdb_exchange_connect_local: arenas must be symmetric fdb_exchange_create arenas");
     int prev = 0; cudaGetDevice(&prev);
     for (int r = 0; r < world; r++) {
         fdb_ctx* ctx = xs[r]->ctx;
@@ -272,7 +278,8 @@ extern "C" int fdb_exchange_push(fdb_exchange* x, int64_t offset, int64_t count)
         return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_push: [%lld, %lld) outside the arena", (long long)offset, (long long)(offset + count));
     if (x->world == 1 || count == 0) return FDB_OK;
     fdb_mirrors M;
-    for (int k = 1; k < x->world; k++) M.delta[M.count++] = (long long)(x->peer[(x->rank + k) % x->world] - x->base);
+    if (x->mc_base && x->mc_on) { M.count = 1; M.delta[0] = (long long)(x->mc_base - x->base); }      // one copy, replicated by the switch
+    else for (int k = 1; k < x->world; k++) M.delta[M.count++] = (long long)(x->peer[(x->rank + k) % x->world] - x->base);
     const double* src = reinterpret_cast<const double*>(x->base) + offset;
     int64_t blocks = cdiv(count, 256 * 4); if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8; if (blocks < 1) blocks = 1;
     exchange_probe_kernel<0><<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, count, M);
@@ -295,6 +302,7 @@ extern "C" int fdb_exchange_destroy(fdb_exchange* x) {
     fdb_ctx* ctx = x->ctx;
     if (ctx->xch == x) ctx->xch = nullptr;
     cudaStreamSynchronize(ctx->stream);
+    if (x->vmm) { multicast_destroy(x); delete x; return FDB_OK; }
     if (!x->in_process)
         for (int r = 0; r < x->world; r++)
             if (r != x->rank && x->peer[r]) cudaIpcCloseMemHandle(x->peer[r]);

@@ -72,9 +72,20 @@ struct fdb_exchange {
     unsigned long long epoch = 0;
     unsigned long long timeout_ns = 20ull * 1000000000ull;   // a barrier gives up after this long (fdb_exchange_set_timeout)
     bool in_process = false;       // peers linked with cudaDeviceEnablePeerAccess inside one process (fdb_exchange_connect_local)
+    // NVSwitch multicast (fdb_multicast.cu): the arena is a cuMemCreate allocation shared as a POSIX file descriptor, bound
+    // into a multicast object together with every peer's arena; a store to mc_base + off lands at off in EVERY rank's arena
+    bool vmm = false;                       // arena (and the peer mappings) are virtual-memory-management mappings, not cudaMalloc / IPC
+    unsigned long long mem_handle = 0;      // CUmemGenericAllocationHandle of the local arena
+    size_t map_bytes = 0;                   // mapped size (data | flag page, rounded up to the multicast granularity)
+    unsigned long long mc_handle = 0;       // CUmemGenericAllocationHandle of the multicast object (0 = none)
+    char* mc_base = nullptr;                // multicast mapping of all arenas (null until fdb_exchange_multicast_bind)
+    bool mc_on = true;                      // result stores go through mc_base when it is mapped (fdb_exchange_set_multicast)
+    int exported_fd[2] = {-1, -1};          // descriptors handed out by fdb_exchange_share_handle / fdb_exchange_multicast_create
 };
 
 namespace fdb {
+
+int multicast_destroy(fdb_exchange* x);     // fdb_multicast.cu: unmap / release a virtual-memory arena and its multicast object
 
 extern thread_local std::string g_init_error;
 

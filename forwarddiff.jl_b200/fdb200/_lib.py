@@ -168,9 +168,17 @@ SIGNATURES = {
     "fdb_exchange_timeouts": (C.c_int, [C.c_void_p, C.POINTER(i64)]),
     "fdb_exchange_destroy": (C.c_int, [C.c_void_p]),
     "fdb_exchange_measure_store_bw": (C.c_int, [C.c_void_p, i64, C.c_int, C.c_int, _dp]),
+    "fdb_multicast_supported": (C.c_int, [c_ctx, C.POINTER(C.c_int)]),
+    "fdb_exchange_create_multicast": (C.c_int, [c_ctx, i64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fdb_exchange_share_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "fdb_exchange_multicast_create": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "fdb_exchange_connect_multicast": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "fdb_exchange_multicast_bind": (C.c_int, [C.c_void_p]),
+    "fdb_exchange_set_multicast": (C.c_int, [C.c_void_p, C.c_int]),
     "fdb_measure_fp64_peak": (C.c_int, [c_ctx, _dp, _dp]),
 }
 IPC_HANDLE_BYTES = 64
+SHARE_HANDLE_BYTES = 16
 
 # enums of fdb200.h
 OP1 = dict(neg=1, exp=2, log=3, sin=4, cos=5, tanh=6, sqrt=7, abs=8, abs2=9, inv=10, pow0=11, pow1=12, pow2=13, pow3=14,

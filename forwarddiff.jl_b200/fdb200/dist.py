@@ -138,10 +138,94 @@ class PeerExchange:
         self.h = None
 
 
+# "auto" picks the multicast exchange from this many ranks up (None: never); set from the measurements in DESIGN.md section 6
+MULTICAST_AUTO_MIN_RANKS = None
+
+
+class MulticastExchange(PeerExchange):
+    """The same arena bound into an NVSwitch multicast object (fdb_exchange_create_multicast, csrc/fdb_multicast.cu): the
+    drivers store each result entry ONCE through the multicast mapping and the switch replicates it into every rank's arena
+    (egress per rank = its own slice instead of (W-1) x it).  The {pid, fd} handles travel through the process group; every
+    rank must agree on each step before the next one (a device that was not added, or an arena that is not bound yet, would
+    make the first multicast store fault)."""
+
+    def __init__(self, ctx, n_doubles, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = _rank_world(group)
+        self.n = int(n_doubles)
+        self.h = None
+        lib = ctx.lib
+
+        def agree(rc, what):
+            """all ranks learn whether the step worked everywhere; the local error (if any) is raised, else a summary"""
+            flags = [None] * self.world
+            dist.all_gather_object(flags, int(rc), group=group)
+            if any(flags):
+                if self.h is not None:
+                    lib.fdb_exchange_destroy(self.h)
+                    self.h = None
+                ctx.check(rc)
+                raise _lib.UnsupportedOp(f"multicast exchange: {what} failed on rank(s) {[r for r, f in enumerate(flags) if f]}")
+
+        h = C.c_void_p()
+        rc = lib.fdb_exchange_create_multicast(ctx.h, self.n, self.rank, self.world, C.byref(h))
+        if rc == 0:
+            self.h = h
+        agree(rc, "arena allocation")
+        buf = C.create_string_buffer(_lib.SHARE_HANDLE_BYTES)
+        rc = lib.fdb_exchange_share_handle(self.h, buf)
+        mcb = C.create_string_buffer(_lib.SHARE_HANDLE_BYTES)
+        if rc == 0 and self.rank == 0:
+            rc = lib.fdb_exchange_multicast_create(self.h, mcb)
+        agree(rc, "handle export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (bytes(buf.raw), bytes(mcb.raw)), group=group)
+        rc = lib.fdb_exchange_connect_multicast(self.h, b"".join(a for a, _ in handles), handles[0][1])
+        agree(rc, "peer mapping / cuMulticastAddDevice")          # doubles as the host barrier before binding
+        rc = lib.fdb_exchange_multicast_bind(self.h)
+        agree(rc, "cuMulticastBindMem")                            # ... and as the barrier before the first multicast store
+        v = self.view(0, 0)
+        self.base_ptr = v.ptr
+        self._views = []
+
+    def set_multicast(self, on):
+        """on=False: keep the mapping but store once per peer again (comparison runs)."""
+        self.ctx.check(self.ctx.lib.fdb_exchange_set_multicast(self.h, 1 if on else 0))
+
+
+def multicast_supported(ctx):
+    import ctypes as C
+    v = C.c_int(0)
+    ctx.check(ctx.lib.fdb_multicast_supported(ctx.h, C.byref(v)))
+    return bool(v.value)
+
+
 def _make_exchange(ctx, n_doubles, group, mode):
-    """mode: "p2p" (raise if the peers cannot be mapped), "nccl" (no arena), "auto" (p2p, else nccl)."""
+    """mode: "p2p" (per-peer stores; raise if the peers cannot be mapped), "multicast" (NVSwitch multicast stores; raise if
+    unsupported), "nccl" (no arena), "auto" (multicast from four ranks up where the box supports it, else p2p, else nccl)."""
     if mode == "nccl":
         return None
+    _, world = _rank_world(group)
+    if mode == "multicast" or (mode == "auto" and MULTICAST_AUTO_MIN_RANKS is not None and world >= MULTICAST_AUTO_MIN_RANKS):
+        import torch.distributed as dist
+        # all ranks must take the same branch: decide on the AND of the per-rank capability
+        sup = [None] * world
+        if world > 1:
+            dist.all_gather_object(sup, bool(multicast_supported(ctx)), group=group)
+        else:
+            sup = [multicast_supported(ctx)]
+        if all(sup):
+            try:
+                return MulticastExchange(ctx, n_doubles, group)
+            except _lib.FdbError as e:
+                if mode == "multicast":
+                    raise
+                import sys
+                print(f"fdb200.dist: multicast exchange unavailable ({e}); using per-peer stores", file=sys.stderr)
+        elif mode == "multicast":
+            raise _lib.UnsupportedOp("multicast exchange: not supported on every rank's device")
     try:
         return PeerExchange(ctx, n_doubles, group)
     except _lib.FdbError as e:
@@ -185,7 +269,7 @@ class _ShardedColumns:
         self.full = None
         self._mat = self.m * per * self.world                     # padded full matrix (whole chunks per rank)
         self.xch = _make_exchange(ctx, self._mat + extra, group, exchange) if self.world > 1 or exchange == "p2p" else None
-        self.exchange = "p2p" if self.xch is not None else "nccl"
+        self.exchange = "nccl" if self.xch is None else ("multicast" if isinstance(self.xch, MulticastExchange) else "p2p")
         if self.xch is not None:
             # every rank holds the full matrix in its arena; the kernels fill the peers' copies of this rank's columns
             self.full = self.xch.torch_view(0, self._mat)
@@ -364,7 +448,7 @@ class ShardedGradient:
         glen = -(-max(self.lay["padded"], self.n) // 32) * 32
         slot = glen + 32                                               # one result: gradient | value
         self.xch = _make_exchange(ctx, 2 * slot, group, exchange) if self.world > 1 or exchange == "p2p" else None
-        self.exchange = "p2p" if self.xch is not None else "nccl"
+        self.exchange = "nccl" if self.xch is None else ("multicast" if isinstance(self.xch, MulticastExchange) else "p2p")
         if self.xch is not None:
             # Gradient and value live in the arena every peer maps: the sweep kernel stores each entry everywhere.
             # Two result slots used alternately: a peer overwrites slot s again only two sweeps later, after the

@@ -437,6 +437,27 @@ int fdb_exchange_destroy(fdb_exchange* x);
  * 1: 16-byte stores, 2: one peer per thread block.  rotate != 0: rank r visits peers r+1, r+2, ... */
 int fdb_exchange_measure_store_bw(fdb_exchange* x, int64_t n_doubles, int variant, int rotate, double* gb_per_s);
 
+/* ---- NVSwitch multicast form of the exchange (csrc/fdb_multicast.cu) --------------------------------------------------
+ * With fdb_exchange_create the drivers repeat each result store once per peer (egress = (W-1) x the rank's slice).  NVSwitch
+ * can replicate a write itself (NVLS): the ranks bind their arenas into one multicast object, and a store through its mapping
+ * lands at the same offset of EVERY rank's arena -- each entry leaves the GPU once.  Such arenas are cuMemCreate allocations
+ * shared as POSIX file descriptors; the handle that travels through the host transport is {pid, fd} (16 bytes) and the
+ * importer duplicates the descriptor with pidfd_getfd(2).  Collective sequence:
+ *   fdb_exchange_create_multicast;  fdb_exchange_share_handle -> all-gather;  rank 0: fdb_exchange_multicast_create -> broadcast;
+ *   fdb_exchange_connect_multicast;  HOST BARRIER;  fdb_exchange_multicast_bind;  HOST BARRIER;  then as any exchange
+ * (fdb_exchange_view / enable / barrier / push / destroy).  FDB_ERR_UNSUPPORTED when the device, driver or kernel (pidfd_getfd)
+ * cannot do it: fall back to fdb_exchange_create. */
+#define FDB_SHARE_HANDLE_BYTES 16
+int fdb_multicast_supported(fdb_ctx* ctx, int* supported);
+int fdb_exchange_create_multicast(fdb_ctx* ctx, int64_t n_doubles, int rank, int world, fdb_exchange** out);
+int fdb_exchange_share_handle(fdb_exchange* x, unsigned char handle[FDB_SHARE_HANDLE_BYTES]);
+int fdb_exchange_multicast_create(fdb_exchange* x_rank0, unsigned char handle[FDB_SHARE_HANDLE_BYTES]);
+/* arena_handles: world * FDB_SHARE_HANDLE_BYTES bytes in rank order; mc_handle: rank 0's fdb_exchange_multicast_create output */
+int fdb_exchange_connect_multicast(fdb_exchange* x, const unsigned char* arena_handles, const unsigned char* mc_handle);
+int fdb_exchange_multicast_bind(fdb_exchange* x);
+/* on = 0: keep the multicast mapping but store per peer again (comparison runs); on = 1: back to multicast */
+int fdb_exchange_set_multicast(fdb_exchange* x, int on);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------- */
 /* FP64 instruction-issue peak: a register-only chain of independent DMUL/DADD pairs;
  * returns achieved non-fused FP64 operations per second on this device. */

@@ -26,17 +26,24 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.cuda.set_stream(torch.cuda.Stream(dev))
     ctx = fdb200.Context(local)
-    for exchange in ("nccl", "p2p"):
+    modes = ["nccl", "p2p"]
+    if world > 1:
+        sup = [None] * world
+        dist.all_gather_object(sup, fdb200.dist.multicast_supported(ctx))
+        if all(sup):
+            modes.append("multicast")          # NVSwitch multicast stores (csrc/fdb_multicast.cu)
+    for exchange in modes:
         check(ctx, rank, world, exchange)
     if world > 1:
         dist.barrier()
-    print(f"rank {rank}/{world}: sharded gradient / Jacobian / Hessian match the single-rank results (nccl and p2p exchange)", flush=True)
+    print(f"rank {rank}/{world}: sharded gradient / Jacobian / Hessian match the single-rank results ({', '.join(modes)} exchange)", flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def check(ctx, rank, world, exchange):
-    """exchange="nccl": all-gather after the sweeps; "p2p": the sweep kernels store into every peer's arena."""
+    """exchange="nccl": all-gather after the sweeps; "p2p": the sweep kernels store into every peer's arena; "multicast": they
+    store once through the NVSwitch multicast mapping of all arenas."""
     rng = np.random.default_rng(3)
 
     # gradient: Ackley n = 100 003 (remainder chunk), Chunk{12}
@@ -85,7 +92,7 @@ def check(ctx, rank, world, exchange):
     # a second sweep reuses the arenas (pre-sweep barrier protects the previous result) and must reproduce the first
     sg.x_t.copy_(torch.from_numpy(x)); sg.sweep(); sg.gather()
     assert np.array_equal(sg.g_t[:n].cpu().numpy(), ref.derivs[0])
-    if exchange == "p2p":
+    if exchange in ("p2p", "multicast"):
         # with an exchange enabled a result outside the arena is refused, not silently left un-mirrored
         sg.xch.enable()
         try:
@@ -95,10 +102,10 @@ def check(ctx, rank, world, exchange):
         finally:
             sg.xch.disable()
         assert sg.xch.timeouts() == 0 and sj.xch.timeouts() == 0
-    if exchange == "p2p":
+    if exchange in ("p2p", "multicast"):
         # all-gather of data no driver mirrored: every rank fills its slice of a fresh arena, pushes it, barrier
         per = 1000
-        xa = fdb200.dist.PeerExchange(ctx, per * world)
+        xa = (fdb200.dist.PeerExchange if exchange == "p2p" else fdb200.dist.MulticastExchange)(ctx, per * world)
         mine = xa.torch_view(rank * per, per)
         mine.copy_(torch.arange(per, dtype=torch.float64, device=mine.device) + 1000.0 * rank)
         xa.push(rank * per, per); xa.barrier()

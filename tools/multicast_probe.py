@@ -71,6 +71,40 @@ def main():
         ck(cu.cuMemSetAccess(va, size, descs, ndev), "cuMemSetAccess(mc)")
         out["map"] = "ok"
         out["result"] = "multicast arena set-up works"
+        # the same with FABRIC handles (64-byte opaque handles that travel through any host transport, like CUDA IPC handles)
+        try:
+            ck(cu.cuCtxSetCurrent(ctxs[0]), "setctx")
+            ap = cu.CUmemAllocationProp()
+            ap.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+            ap.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+            ap.location.id = 0
+            ap.requestedHandleTypes = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_FABRIC
+            g2 = ck(cu.cuMemGetAllocationGranularity(ap, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_MINIMUM), "gran")
+            out["alloc_granularity_min"] = int(g2)
+            hf = ck(cu.cuMemCreate(size, ap, 0), "cuMemCreate(fabric)")
+            fh = ck(cu.cuMemExportToShareableHandle(hf, cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_FABRIC, 0), "export(fabric)")
+            out["fabric_alloc_export"] = "ok"
+            prop2 = cu.CUmulticastObjectProp()
+            prop2.numDevices = ndev; prop2.size = size; prop2.flags = 0
+            prop2.handleTypes = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_FABRIC
+            mc2 = ck(cu.cuMulticastCreate(prop2), "cuMulticastCreate(fabric)")
+            fh2 = ck(cu.cuMemExportToShareableHandle(mc2, cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_FABRIC, 0), "export mc(fabric)")
+            out["fabric_multicast_export"] = "ok"
+        except Exception as e:       # noqa: BLE001
+            out["fabric"] = f"failed: {e}"
+        try:
+            gmin = ck(cu.cuMulticastGetGranularity(prop, cu.CUmulticastGranularity_flags.CU_MULTICAST_GRANULARITY_MINIMUM), "mc granularity min")
+            out["granularity_min"] = int(gmin)
+            fd = ck(cu.cuMemExportToShareableHandle(mc, cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0), "export mc(fd)")
+            out["posix_fd_multicast_export"] = "ok"
+            import os
+            pidfd = os.pidfd_open(os.getpid())
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            r = libc.syscall(438, pidfd, int(fd), 0)
+            out["pidfd_getfd"] = "ok" if r >= 0 else f"errno {ctypes.get_errno()}"
+        except Exception as e:       # noqa: BLE001
+            out["fd_export"] = f"failed: {e}"
     except Exception as e:       # noqa: BLE001 -- a probe: report whatever stopped it
         out["result"] = f"failed: {e}"
     print(json.dumps(out))
