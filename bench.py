@@ -449,7 +449,10 @@ def extras_sharded(ctx, torch, dist, dev, rank, world, flush):
     A_h = (rng.uniform(-1, 1, m3 * m3) / np.sqrt(m3)).reshape((m3, m3), order="F"); b_h = rng.uniform(-1, 1, m3); x3 = rng.uniform(-1, 1, m3)
     f3 = F.tanh_affine.with_params(A=A_h, b=b_h)
     configs.append(("tanh_affine_jacobian_c3", "jac", f3, x3, m3, 12, 5,
-                    "per rank: DMMA contraction of its 683/W chunk sweeps (tile-count quantisation on 148 SMs) with the peer stores issued from the tile epilogue"))
+                    "sharded-resident: DMMA contraction of 683/W chunk sweeps per rank (128 x 16 tiles, three blocks per SM: 704 tiles on 444 slots at W = 8); "
+                    "gathered: every GPU must RECEIVE (W-1)/W of the 512 MB result over its NVLink ingress (W/W with multicast stores, which also "
+                    "come back to the sender) -- 0.65-0.73 ms at ~700 GB/s against ~0.85 ms of contraction at W = 8, overlapped only in part because "
+                    "all ranks produce at the same time; per-peer stores additionally send (W-1) x the slice through each GPU's egress"))
     # C4: Brusselator n = 65 536, Chunk{8}: 34.4 GB, every rank ends up holding all of it when gathered
     M = 32768
     xb = np.concatenate([1 + np.sin(2 * np.pi * np.arange(1, M + 1) / (M + 1)), 3 * np.ones(M)])
