@@ -247,6 +247,7 @@ extern "C" int fdb_exchange_multicast_create(fdb_exchange* x, unsigned char hand
     fdb_ctx* ctx = x->ctx;
     if (!x->vmm) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_multicast_create: the arena was not created by fdb_exchange_create_multicast");
     if (x->rank != 0) return fail(ctx, FDB_ERR_BADARG, "fdb_exchange_multicast_create: rank 0 creates the multicast object, the others import it");
+    if (x->world < 2) return fail(ctx, FDB_ERR_UNSUPPORTED, "fdb_exchange_multicast_create: a multicast object spans at least two devices");
     const Drv& d = drv();
     if (!x->mc_handle) {
         CUmulticastObjectProp mp = mc_prop(x->world, x->map_bytes);

@@ -312,3 +312,113 @@ def test_persistent_dmma_kernel_with_tma_peer_stores_at_a_sharded_c3_shape(oracl
             del Ad, bd
     finally:
         g.close()
+
+
+def _multicast_ok(c):
+    v = C.c_int(0)
+    c.check(c.lib.fdb_multicast_supported(c.h, C.byref(v)))
+    return bool(v.value)
+
+
+def test_multicast_arena_single_rank(ctx):
+    """csrc/fdb_multicast.cu on one GPU: a virtual-memory arena and its {pid, fd} handle; CUDA IPC calls refuse it, a multicast
+    object over fewer than two devices is refused cleanly, and the arena behaves like any exchange arena for the drivers."""
+    if not _multicast_ok(ctx):
+        pytest.skip("no NVSwitch multicast support on this box")
+    lib = ctx.lib
+    x = C.c_void_p()
+    ctx.check(lib.fdb_exchange_create_multicast(ctx.h, 4096, 0, 1, C.byref(x)))
+    try:
+        h = C.create_string_buffer(fdb200._lib.SHARE_HANDLE_BYTES); mc = C.create_string_buffer(fdb200._lib.SHARE_HANDLE_BYTES)
+        ctx.check(lib.fdb_exchange_share_handle(x, h))
+        pid, fd = np.frombuffer(h.raw, dtype=np.int32)[:2]
+        import os
+        assert pid == os.getpid() and fd > 2
+        ipc = C.create_string_buffer(fdb200._lib.IPC_HANDLE_BYTES)
+        assert lib.fdb_exchange_handle(x, ipc) != 0 and b"fdb_exchange_share_handle" in lib.fdb_last_error(ctx.h)
+        assert lib.fdb_exchange_multicast_create(x, mc) != 0 and b"at least two" in lib.fdb_last_error(ctx.h)
+        assert lib.fdb_exchange_set_multicast(x, 1) != 0                      # no mapping
+        # the arena is ordinary device memory for the drivers
+        xs = np.random.default_rng(5).uniform(0.5, 1.5, 1000)
+        xd = ctx.array(xs)
+        gv = C.c_void_p(); vv = C.c_void_p()
+        ctx.check(lib.fdb_exchange_view(x, 0, 1000, 1000, C.byref(gv))); ctx.check(lib.fdb_exchange_view(x, 1024, 1, 1, C.byref(vv)))
+        ctx.check(lib.fdb_exchange_enable(ctx.h, x))
+        ctx.check(lib.fdb_gradient_chunked(ctx.h, fdb200._lib.FN["rosenbrock"], xd.h, 12, 0, -1, gv, vv))
+        ctx.check(lib.fdb_exchange_enable(ctx.h, None))
+        ctx.check(lib.fdb_exchange_barrier(x))
+        out = np.zeros(1000)
+        ctx.check(lib.fdb_download_values(gv, out.ctypes.data_as(C.POINTER(C.c_double))))
+        ref = fdb200.gradient(F.rosenbrock, xs, fdb200.GradientConfig(F.rosenbrock, xs, fdb200.Chunk(12)), ctx=ctx)
+        assert np.array_equal(out, ref)
+        lib.fdb_array_free(gv); lib.fdb_array_free(vv)
+    finally:
+        ctx.check(lib.fdb_exchange_destroy(x))
+
+
+def test_multicast_exchange_between_two_devices_of_one_process(oracle):
+    """Two contexts on two GPUs of this process, arenas bound into one multicast object (the descriptors are dup()ed inside one
+    process): each context sweeps half of the chunks with the exchange enabled, every entry is stored ONCE through the multicast
+    mapping, and both arenas end up holding the complete gradient and the value -- bit-identical to a single-context gradient."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cs = [fdb200.Context(0), fdb200.Context(1)]
+    try:
+        if not all(_multicast_ok(c) for c in cs):
+            pytest.skip("no NVSwitch multicast support on this box")
+        lib = cs[0].lib
+        n, N = 10_007, 12
+        xs = np.random.default_rng(6).uniform(0.5, 1.5, n)
+        xch = []
+        for r, c in enumerate(cs):
+            x = C.c_void_p()
+            c.check(lib.fdb_exchange_create_multicast(c.h, n + 64, r, 2, C.byref(x)))
+            xch.append(x)
+        hs = []
+        for r, c in enumerate(cs):
+            h = C.create_string_buffer(fdb200._lib.SHARE_HANDLE_BYTES)
+            c.check(lib.fdb_exchange_share_handle(xch[r], h)); hs.append(h.raw)
+        mc = C.create_string_buffer(fdb200._lib.SHARE_HANDLE_BYTES)
+        cs[0].check(lib.fdb_exchange_multicast_create(xch[0], mc))
+        for r, c in enumerate(cs):
+            c.check(lib.fdb_exchange_connect_multicast(xch[r], b"".join(hs), mc.raw))
+        for r, c in enumerate(cs):                                   # every device added before anyone binds
+            c.check(lib.fdb_exchange_multicast_bind(xch[r]))
+        nchunks = fdb200.chunk_plan(n, N)["nchunks"]
+        half = nchunks // 2
+        views = []
+        for r, c in enumerate(cs):
+            c.set_async(True)
+            xd = c.array(xs)
+            gv = C.c_void_p(); vv = C.c_void_p()
+            c.check(lib.fdb_exchange_view(xch[r], 0, n, n, C.byref(gv))); c.check(lib.fdb_exchange_view(xch[r], n + 32, 1, 1, C.byref(vv)))
+            views.append((xd, gv, vv))
+        for rep in range(2):                                          # the second sweep overwrites the first behind the pre-sweep barrier
+            for r, c in enumerate(cs):
+                c.check(lib.fdb_exchange_barrier(xch[r]))
+            for r, c in enumerate(cs):
+                xd, gv, vv = views[r]
+                c.check(lib.fdb_exchange_enable(c.h, xch[r]))
+                lo, hi = (0, half) if r == 0 else (half, -1)
+                c.check(lib.fdb_gradient_chunked(c.h, fdb200._lib.FN["ackley"], xd.h, N, lo, hi, gv, vv))
+                c.check(lib.fdb_exchange_enable(c.h, None))
+                c.check(lib.fdb_exchange_barrier(xch[r]))
+            for c in cs:
+                c.sync()
+        ref = fdb200.GradientResult(xs)
+        fdb200.gradient_b(ref, F.ackley, xs, fdb200.GradientConfig(F.ackley, xs, fdb200.Chunk(N)), ctx=cs[0])
+        for r, c in enumerate(cs):
+            xd, gv, vv = views[r]
+            out = np.zeros(n); val = np.zeros(1)
+            c.check(lib.fdb_download_values(gv, out.ctypes.data_as(C.POINTER(C.c_double))))
+            c.check(lib.fdb_download_values(vv, val.ctypes.data_as(C.POINTER(C.c_double))))
+            assert np.array_equal(out, ref.derivs[0]), f"arena of device {r} is not the complete gradient"
+            assert val[0] == ref.value
+            t = C.c_int64(); c.check(lib.fdb_exchange_timeouts(xch[r], C.byref(t))); assert t.value == 0
+            lib.fdb_array_free(gv); lib.fdb_array_free(vv)
+        for r, c in enumerate(cs):
+            c.check(lib.fdb_exchange_destroy(xch[r]))
+    finally:
+        for c in cs:
+            c.close()
