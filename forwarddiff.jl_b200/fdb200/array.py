@@ -93,7 +93,7 @@ class Context:
         not upload A again; a matrix modified in place beyond what the sample sees needs `forget_matrices()`."""
         cache = self.__dict__.setdefault("_matrix_cache", {})
         A = np.asarray(A, dtype=np.float64)
-        flat = A.reshape(-1)[:: max(1, A.size // 4096)]
+        flat = A.ravel(order="K")[:: max(1, A.size // 4096)]          # memory order: a view for C- and F-contiguous matrices (no 512 MB copy per call)
         key = id(A)
         fp = (A.shape, A.__array_interface__["data"][0], float(np.sum(flat)), float(flat[-1]) if flat.size else 0.0)
         hit = cache.get(key)
