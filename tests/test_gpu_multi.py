@@ -422,3 +422,43 @@ def test_multicast_exchange_between_two_devices_of_one_process(oracle):
     finally:
         for c in cs:
             c.close()
+
+
+def test_readme_examples_run_and_agree_with_finite_differences(ctx):
+    """The `What f may be` block of README.md, at small sizes: every example runs on the path the README names and its derivative
+    agrees with central differences of the same function evaluated in NumPy."""
+    rng = np.random.default_rng(11)
+    n = 600
+    x = rng.uniform(0.2, 1.0, n); w = rng.uniform(0.5, 1.5, n - 1); d = rng.uniform(0.0, 1.0, n)
+    A = rng.uniform(-1, 1, (128, n)) / 30; b = rng.uniform(-1, 1, 128)
+    cases = [
+        (lambda xd: ((1.0 - xd[:-1]) ** 2 + 100.0 * (xd[1:] - xd[:-1] ** 2) ** 2).sum(),
+         lambda v: ((1.0 - v[:-1]) ** 2 + 100.0 * (v[1:] - v[:-1] ** 2) ** 2).sum(), "program"),
+        (lambda xd: (w * (xd[1:] - xd[:-1]) ** 2).sum() + 0.5 * ((xd - d) ** 2).sum(),
+         lambda v: (w * (v[1:] - v[:-1]) ** 2).sum() + 0.5 * ((v - d) ** 2).sum(), "program"),
+        (lambda xd: ((xd - xd.mean()) ** 2).sum() / (len(xd) - 1), lambda v: ((v - v.mean()) ** 2).sum() / (len(v) - 1), "program"),
+        (lambda xd: fdb200.exp(xd * 1e-3).prod(), lambda v: np.exp(v * 1e-3).prod(), "program"),
+        (lambda xd: fdb200.fma(xd[1:], xd[:-1], xd[:-1]).sum(), lambda v: (v[1:] * v[:-1] + v[:-1]).sum(), "loop"),
+    ]
+    for f, fnp, path in cases:
+        cfg = fdb200.GradientConfig(f, x, fdb200.Chunk(12))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", fdb200.SlowPathWarning)
+            g = fdb200.gradient(f, x, cfg, ctx=ctx)
+        assert cfg.last_path.startswith(path), (cfg.last_path, cfg.trace_error)
+        for i in (0, 1, n // 2, n - 1):
+            e = np.zeros(n); e[i] = 1e-6
+            fd = (fnp(x + e) - fnp(x - e)) / 2e-6
+            assert abs(g[i] - fd) <= 1e-6 * max(1.0, abs(fd)), (path, i, g[i], fd)
+    f5 = lambda xd: fdb200.tanh(A @ xd + b)
+    c5 = fdb200.JacobianConfig(f5, x, fdb200.Chunk(12))
+    J = fdb200.jacobian(f5, x, c5, ctx=ctx)
+    assert c5.last_path.startswith("program")
+    assert np.allclose(J, (1.0 - np.tanh(A @ x + b) ** 2)[:, None] * A, rtol=1e-12, atol=1e-15)
+    xs, ws = x[:96], w[:95]
+    f2s = lambda xd: (ws * (xd[1:] - xd[:-1]) ** 2).sum() + fdb200.exp(xd * 0.1).sum()
+    H = fdb200.hessian(f2s, xs, fdb200.HessianConfig(f2s, xs, fdb200.Chunk(8)), ctx=ctx)
+    Href = np.diag(0.01 * np.exp(0.1 * xs))
+    for i in range(95):
+        Href[i, i] += 2 * ws[i]; Href[i + 1, i + 1] += 2 * ws[i]; Href[i, i + 1] -= 2 * ws[i]; Href[i + 1, i] -= 2 * ws[i]
+    assert np.allclose(H, Href, rtol=1e-12, atol=1e-13)
