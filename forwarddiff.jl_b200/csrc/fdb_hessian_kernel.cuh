@@ -31,6 +31,16 @@ template <int N, bool NS> struct NearLoader {
     }
 };
 
+// A block handles HESS_GROUP consecutive inner chunks against one outer chunk.  A term that reads no seeded position has the
+// same four shared lanes whatever the pair, so the terms far from ALL the group's inner windows and from the outer window are
+// evaluated once per block (phase 1) instead of once per pair -- at C5 that is 2047 four-lane evaluations per eight pairs, where
+// the first version spent three quarters of its FP64 instructions on them.  Terms inside the group's inner range are far for
+// some pairs and near for others: their four-lane contribution is computed once (phase 1b) and added per pair when the term is
+// not near that pair's window.  Every term of every pair is still evaluated exactly as the reference's nested duals would see it
+// (seeded lanes per inner lane k when near, the representative zero lanes when far: 0 * Inf still poisons), only the order of the
+// additions differs (a tree either way).
+constexpr int HESS_GROUP = 8;     // measured at C5: 16 gains another 2 %, 8 keeps more blocks in flight for small n
+
 template <class F, int N, bool NS, int THREADS>
 FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t outer_lo,
                                                                 int64_t nchunks_total, int lastchunksize, double* __restrict__ H,
@@ -40,30 +50,35 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
     typedef Dual<DI, 1, NS> DG;
     typedef Dual<Dual<double, 1, NS>, 1, NS> DF;
     constexpr int MAXNEAR = 2 * (N + F::HALO);
+    constexpr int MAXU = HESS_GROUP * N + F::HALO;
     __shared__ double s_p[MAXNEAR][N][N + 1];   // per near term, per inner lane k: partials(y,k) as Dual{N}
     __shared__ double s_v[MAXNEAR][N + 1];      // per near term: value(y) as Dual{N}
-    __shared__ double s_ff[4];
+    __shared__ double s_c4[MAXU][4];            // four shared lanes of every term of the group's inner range (zero for terms near the outer window)
+    __shared__ double s_common[4];              // far from every window of the block
+    __shared__ double s_ff[4];                  // far sum of the current pair
     __shared__ double s_red[THREADS / 32][4];
 
-    const int64_t ci = blockIdx.x, co = outer_lo + blockIdx.y;
-    const bool ilast = (ci == nchunks_total - 1), olast = (co == nchunks_total - 1);
-    const int ics = ilast ? lastchunksize : N, ocs = olast ? lastchunksize : N;
-    const int64_t istart = ilast ? n - lastchunksize : ci * N;
+    const int64_t cg0 = (int64_t)blockIdx.x * HESS_GROUP, co = outer_lo + blockIdx.y;
+    const int gcount = (int)((nchunks_total - cg0) < HESS_GROUP ? (nchunks_total - cg0) : HESS_GROUP);
+    const bool olast = (co == nchunks_total - 1);
+    const int ocs = olast ? lastchunksize : N;
     const int64_t ostart = olast ? n - lastchunksize : co * N;
     const int64_t nt = F::nterms(n);
+    auto inner_start = [&](int64_t ci) { return ci == nchunks_total - 1 ? n - lastchunksize : ci * N; };
+    auto inner_size = [&](int64_t ci) { return ci == nchunks_total - 1 ? lastchunksize : N; };
 
-    // near-term ranges (terms reading a seeded position): A for the inner window, B for the outer
-    int64_t a0 = istart - F::HALO, a1 = istart + ics, b0 = ostart - F::HALO, b1 = ostart + ocs;
-    if (a0 < 0) a0 = 0; if (b0 < 0) b0 = 0; if (a1 > nt) a1 = nt; if (b1 > nt) b1 = nt;
-    if (a1 < a0) a1 = a0; if (b1 < b0) b1 = b0;
-    if (b0 <= a1 && a0 <= b1) { a0 = a0 < b0 ? a0 : b0; a1 = a1 > b1 ? a1 : b1; b0 = b1 = a1; }   // merge overlapping ranges
-    const int na = (int)(a1 - a0), nb = (int)(b1 - b0), nnear = na + nb;
+    // raw near ranges: B for the outer window, U for the union of the group's inner windows
+    int64_t br0 = ostart - F::HALO, br1 = ostart + ocs;
+    if (br0 < 0) br0 = 0; if (br1 > nt) br1 = nt; if (br1 < br0) br1 = br0;
+    int64_t u0 = inner_start(cg0) - F::HALO, u1 = inner_start(cg0 + gcount - 1) + inner_size(cg0 + gcount - 1);
+    if (u0 < 0) u0 = 0; if (u1 > nt) u1 = nt; if (u1 < u0) u1 = u0;
+    const int nu = (int)(u1 - u0);
 
-    // ---- phase 1: terms far from both windows, four shared lanes --------------------------------
+    // ---- phase 1: terms far from every window of the block, four shared lanes ------------------------
     DF accff[1]; accff[0].v.v = 0.0; accff[0].v.p[0] = 0.0; accff[0].p[0].v = 0.0; accff[0].p[0].p[0] = 0.0;
     FFLoader<NS> xf{x};
     for (int64_t i = threadIdx.x; i < nt; i += THREADS) {
-        const bool near = (i >= a0 && i < a1) || (i >= b0 && i < b1);
+        const bool near = (i >= u0 && i < u1) || (i >= br0 && i < br1);
         if (!near) F::term(xf, i, n, accff);
     }
     {
@@ -75,47 +90,91 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
             if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][q] = r[q];
         }
     }
-    // ---- phase 2: near terms, one work item per (term, inner lane k) ------------------------------
-    for (int w = threadIdx.x; w < nnear * N; w += THREADS) {
-        const int t = w / N, k = w - t * N;
-        const int64_t i = t < na ? a0 + t : b0 + (t - na);
-        NearLoader<N, NS> xn{x, ostart, ocs, istart, ics, k};
-        DG acc[1];
-        acc[0].v.v = 0.0; acc[0].p[0].v = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; j++) { acc[0].v.p[j] = 0.0; acc[0].p[0].p[j] = 0.0; }
-        F::term(xn, i, n, acc);
-        s_p[t][k][0] = acc[0].p[0].v;
-#pragma unroll
-        for (int j = 0; j < N; j++) s_p[t][k][j + 1] = acc[0].p[0].p[j];
-        if (k == 0) {
-            s_v[t][0] = acc[0].v.v;
-#pragma unroll
-            for (int j = 0; j < N; j++) s_v[t][j + 1] = acc[0].v.p[j];
-        }
+    // ---- phase 1b: the terms of the inner range, each on its own (far for the pairs whose window it does not touch) ----
+    for (int w = threadIdx.x; w < nu; w += THREADS) {
+        const int64_t i = u0 + w;
+        DF a[1]; a[0].v.v = 0.0; a[0].v.p[0] = 0.0; a[0].p[0].v = 0.0; a[0].p[0].p[0] = 0.0;
+        if (!(i >= br0 && i < br1)) F::term(xf, i, n, a);            // near the outer window: never far, contributes nothing here
+        s_c4[w][0] = a[0].v.v; s_c4[w][1] = a[0].v.p[0]; s_c4[w][2] = a[0].p[0].v; s_c4[w][3] = a[0].p[0].p[0];
     }
     __syncthreads();
     if (threadIdx.x < 4) {
         double s = 0.0;
         for (int wq = 0; wq < THREADS / 32; wq++) s = s + s_red[wq][threadIdx.x];
-        s_ff[threadIdx.x] = s;
+        s_common[threadIdx.x] = s;
     }
     __syncthreads();
-    // ---- phase 3: fold and store (fused extract_gradient_chunk! + extract_jacobian_chunk!) --------
-    // lanes: s_ff[0] = value.value, [1] = value.outer-partial, [2] = inner-partial.value, [3] = inner-partial.outer-partial
-    for (int e = threadIdx.x; e < N * (N + 1); e += THREADS) {
-        const int k = e / (N + 1), j = e - k * (N + 1);     // j = 0: value of partials(y,k); j >= 1: outer partial j
-        if (k >= ics) continue;
-        double s = 0.0;
-        for (int t = 0; t < nnear; t++) s = s + s_p[t][k][j];
-        s = s + (j == 0 ? s_ff[2] : s_ff[3]);
-        if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
-        else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
-    }
-    if (threadIdx.x == 0 && olast && ilast && value_out) {
-        double s = 0.0;
-        for (int t = 0; t < nnear; t++) s = s + s_v[t][0];
-        mstore(M, value_out, s + s_ff[0]);
+
+    for (int g = 0; g < gcount; g++) {
+        const int64_t ci = cg0 + g;
+        const bool ilast = (ci == nchunks_total - 1);
+        const int ics = ilast ? lastchunksize : N;
+        const int64_t istart = ilast ? n - lastchunksize : ci * N;
+        // near-term ranges (terms reading a seeded position): A for the inner window, B for the outer
+        int64_t ar0 = istart - F::HALO, ar1 = istart + ics;
+        if (ar0 < 0) ar0 = 0; if (ar1 > nt) ar1 = nt; if (ar1 < ar0) ar1 = ar0;
+        int64_t a0 = ar0, a1 = ar1, b0 = br0, b1 = br1;
+        if (b0 <= a1 && a0 <= b1) { a0 = a0 < b0 ? a0 : b0; a1 = a1 > b1 ? a1 : b1; b0 = b1 = a1; }   // merge overlapping ranges
+        const int na = (int)(a1 - a0), nb = (int)(b1 - b0), nnear = na + nb;
+
+        // ---- phase 2: near terms, one work item per (term, inner lane k) ------------------------------
+        for (int w = threadIdx.x; w < nnear * N; w += THREADS) {
+            const int t = w / N, k = w - t * N;
+            const int64_t i = t < na ? a0 + t : b0 + (t - na);
+            NearLoader<N, NS> xn{x, ostart, ocs, istart, ics, k};
+            DG acc[1];
+            acc[0].v.v = 0.0; acc[0].p[0].v = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; j++) { acc[0].v.p[j] = 0.0; acc[0].p[0].p[j] = 0.0; }
+            F::term(xn, i, n, acc);
+            s_p[t][k][0] = acc[0].p[0].v;
+#pragma unroll
+            for (int j = 0; j < N; j++) s_p[t][k][j + 1] = acc[0].p[0].p[j];
+            if (k == 0) {
+                s_v[t][0] = acc[0].v.v;
+#pragma unroll
+                for (int j = 0; j < N; j++) s_v[t][j + 1] = acc[0].v.p[j];
+            }
+        }
+        // far sum of this pair: the block's common part + the inner-range terms outside this pair's window (by the last warp: it
+        // has the fewest near items)
+        if (threadIdx.x >= THREADS - 32) {
+            const int l = threadIdx.x - (THREADS - 32);
+            double r[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int w = l; w < nu; w += 32) {
+                const int64_t i = u0 + w;
+                if (i >= ar0 && i < ar1) continue;
+#pragma unroll
+                for (int q = 0; q < 4; q++) r[q] = r[q] + s_c4[w][q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) r[q] = r[q] + shfl_down_d(r[q], off);
+            }
+            if (l == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) s_ff[q] = r[q] + s_common[q];
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: fold and store (fused extract_gradient_chunk! + extract_jacobian_chunk!) --------
+        // lanes: s_ff[0] = value.value, [1] = value.outer-partial, [2] = inner-partial.value, [3] = inner-partial.outer-partial
+        for (int e = threadIdx.x; e < N * (N + 1); e += THREADS) {
+            const int k = e / (N + 1), j = e - k * (N + 1);     // j = 0: value of partials(y,k); j >= 1: outer partial j
+            if (k >= ics) continue;
+            double s = 0.0;
+            for (int t = 0; t < nnear; t++) s = s + s_p[t][k][j];
+            s = s + (j == 0 ? s_ff[2] : s_ff[3]);
+            if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
+            else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
+        }
+        if (threadIdx.x == 0 && olast && ilast && value_out) {
+            double s = 0.0;
+            for (int t = 0; t < nnear; t++) s = s + s_v[t][0];
+            mstore(M, value_out, s + s_ff[0]);
+        }
+        __syncthreads();                                         // s_p / s_v / s_ff are rewritten by the next pair
     }
 }
 

@@ -7,6 +7,7 @@
 // Restrictions (checked on the host): one sum accumulator, no epilogue, and the op subset whose rules exist one
 // dual level up (+ - * / neg, literal powers, exp log sin cos tanh sqrt abs abs2 inv).
 #include "fdb_program.cuh"
+#include "fdb_hessian_kernel.cuh"   // HESS_GROUP: grid of the specialised plain-sum kernel
 
 namespace fdb {
 
@@ -228,7 +229,10 @@ extern "C" int fdb_program_hessian_chunked(fdb_ctx* ctx, const int32_t* term_pro
         if (jit_get(ctx, 2, P, N, ctx->nansafe, false, false, &fn) == FDB_OK) {
             const double* xp = x->data; int64_t nn = n, lo = chunk_lo, nc = nchunks, ld = ldH; int lcs = (int)p.lastchunksize;
             void* args[] = {&xp, &nn, &lo, &nc, &lcs, &Hp, &ld, &gp, &vp, &M};
-            rc = jit_launch(ctx, fn, grid.x, grid.y, T, args, "fdb_program_hessian_chunked(specialised)"); if (rc) return rc;
+            // UserFn::PLAIN_SUM (fdb_jit.cu) selects hessian_sweep_body, whose blocks take HESS_GROUP inner chunks each
+            const bool jit_plain = (n_epi == 0 && n_acc == 1 && result_reg == 0 && !P.prod_mask);
+            const unsigned gx = jit_plain ? (unsigned)cdiv(nchunks, (int64_t)HESS_GROUP) : grid.x;
+            rc = jit_launch(ctx, fn, gx, grid.y, T, args, "fdb_program_hessian_chunked(specialised)"); if (rc) return rc;
             return finish(ctx, 1, "fdb_program_hessian_chunked(specialised)");
         }
     }
