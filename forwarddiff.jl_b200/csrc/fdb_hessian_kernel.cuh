@@ -14,6 +14,17 @@ template <bool NS> struct FFLoader {
         DO d; d.v.v = x[i]; d.v.p[0] = 0.0; d.p[0].v = 0.0; d.p[0].p[0] = 0.0; return d;
     }
 };
+// a term that reads the inner window but no position of the outer window: every outer partial lane of every intermediate is the
+// same "zero lane", so one representative outer lane is enough -- Dual{Dual{1},1} with the inner one-hot seed of lane k
+template <bool NS> struct NearInnerLoader {
+    typedef Dual<Dual<double, 1, NS>, 1, NS> DO;
+    const double* x; int64_t istart; int ics; int k;
+    FDB_DEV DO operator()(int64_t pos) const {
+        DO d; d.v.v = x[pos]; d.v.p[0] = 0.0;
+        d.p[0].v = ((pos - istart == k) && (k < ics)) ? 1.0 : 0.0; d.p[0].p[0] = 0.0;
+        return d;
+    }
+};
 // general loader for inner lane k: value = outer-seeded Dual{N}; the single inner partial lane
 // carries one(Dual{N}) iff pos is slot k of the inner window (src/apiutils.jl:125-143 with
 // Partials{N,Dual{T,V,N}} seeds, src/config.jl:225-226)
@@ -51,8 +62,11 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
     typedef Dual<Dual<double, 1, NS>, 1, NS> DF;
     constexpr int MAXNEAR = 2 * (N + F::HALO);
     constexpr int MAXU = HESS_GROUP * N + F::HALO;
-    __shared__ double s_p[MAXNEAR][N][N + 1];   // per near term, per inner lane k: partials(y,k) as Dual{N}
-    __shared__ double s_v[MAXNEAR][N + 1];      // per near term: value(y) as Dual{N}
+    // per near term t: a term reading both windows fills s_p[t][k][0..N] = partials(y,k) as Dual{N} for every inner lane k; one reading
+    // only the inner window fills s_p[t][k][0..1] = (value, representative outer lane) of partials(y,k); one reading only the outer
+    // window fills s_p[t][0][0..N] = the (k-independent) partials(y,.) as Dual{N}
+    __shared__ double s_p[MAXNEAR][N][N + 1];
+    __shared__ double s_v[MAXNEAR];             // per near term: value(value(y))
     __shared__ double s_c4[MAXU][4];            // four shared lanes of every term of the group's inner range (zero for terms near the outer window)
     __shared__ double s_common[4];              // far from every window of the block
     __shared__ double s_ff[4];                  // far sum of the current pair
@@ -117,23 +131,33 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
         if (b0 <= a1 && a0 <= b1) { a0 = a0 < b0 ? a0 : b0; a1 = a1 > b1 ? a1 : b1; b0 = b1 = a1; }   // merge overlapping ranges
         const int na = (int)(a1 - a0), nb = (int)(b1 - b0), nnear = na + nb;
 
-        // ---- phase 2: near terms, one work item per (term, inner lane k) ------------------------------
-        for (int w = threadIdx.x; w < nnear * N; w += THREADS) {
-            const int t = w / N, k = w - t * N;
+        // ---- phase 2: near terms.  Work items: (term, inner lane k) for the terms of the A range, one per term of the B range (after
+        // the merge above the B range holds terms that read the outer window only).  Three kinds of term:
+        //   both windows : Dual{Dual{N},1} per inner lane k (the full nested evaluation)
+        //   inner only   : Dual{Dual{1},1} per inner lane k (all outer lanes are the same zero lane)
+        //   outer only   : Dual{Dual{N},1} once (the inner partial is zero(Dual{N}) for every k)
+        for (int w = threadIdx.x; w < na * N + nb; w += THREADS) {
+            const bool arange = w < na * N;
+            const int t = arange ? w / N : na + (w - na * N), k = arange ? w - t * N : 0;
             const int64_t i = t < na ? a0 + t : b0 + (t - na);
-            NearLoader<N, NS> xn{x, ostart, ocs, istart, ics, k};
-            DG acc[1];
-            acc[0].v.v = 0.0; acc[0].p[0].v = 0.0;
+            const bool inA = (i >= ar0 && i < ar1), inB = (i >= br0 && i < br1);
+            if (inA && !inB) {
+                NearInnerLoader<NS> xa{x, istart, ics, k};
+                DF a[1]; a[0].v.v = 0.0; a[0].v.p[0] = 0.0; a[0].p[0].v = 0.0; a[0].p[0].p[0] = 0.0;
+                F::term(xa, i, n, a);
+                s_p[t][k][0] = a[0].p[0].v; s_p[t][k][1] = a[0].p[0].p[0];
+                if (k == 0) s_v[t] = a[0].v.v;
+            } else if (inA || k == 0) {
+                NearLoader<N, NS> xn{x, ostart, ocs, istart, ics, k};
+                DG acc[1];
+                acc[0].v.v = 0.0; acc[0].p[0].v = 0.0;
 #pragma unroll
-            for (int j = 0; j < N; j++) { acc[0].v.p[j] = 0.0; acc[0].p[0].p[j] = 0.0; }
-            F::term(xn, i, n, acc);
-            s_p[t][k][0] = acc[0].p[0].v;
+                for (int j = 0; j < N; j++) { acc[0].v.p[j] = 0.0; acc[0].p[0].p[j] = 0.0; }
+                F::term(xn, i, n, acc);
+                s_p[t][k][0] = acc[0].p[0].v;
 #pragma unroll
-            for (int j = 0; j < N; j++) s_p[t][k][j + 1] = acc[0].p[0].p[j];
-            if (k == 0) {
-                s_v[t][0] = acc[0].v.v;
-#pragma unroll
-                for (int j = 0; j < N; j++) s_v[t][j + 1] = acc[0].v.p[j];
+                for (int j = 0; j < N; j++) s_p[t][k][j + 1] = acc[0].p[0].p[j];
+                if (k == 0) s_v[t] = acc[0].v.v;
             }
         }
         // far sum of this pair: the block's common part + the inner-range terms outside this pair's window (by the last warp: it
@@ -164,14 +188,18 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
             const int k = e / (N + 1), j = e - k * (N + 1);     // j = 0: value of partials(y,k); j >= 1: outer partial j
             if (k >= ics) continue;
             double s = 0.0;
-            for (int t = 0; t < nnear; t++) s = s + s_p[t][k][j];
+            for (int t = 0; t < nnear; t++) {
+                const int64_t i = t < na ? a0 + t : b0 + (t - na);
+                const bool inA = (i >= ar0 && i < ar1), inB = (i >= br0 && i < br1);
+                s = s + ((inA && inB) ? s_p[t][k][j] : (inA ? s_p[t][k][j == 0 ? 0 : 1] : s_p[t][0][j]));
+            }
             s = s + (j == 0 ? s_ff[2] : s_ff[3]);
             if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
             else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
         }
         if (threadIdx.x == 0 && olast && ilast && value_out) {
             double s = 0.0;
-            for (int t = 0; t < nnear; t++) s = s + s_v[t][0];
+            for (int t = 0; t < nnear; t++) s = s + s_v[t];
             mstore(M, value_out, s + s_ff[0]);
         }
         __syncthreads();                                         // s_p / s_v / s_ff are rewritten by the next pair
