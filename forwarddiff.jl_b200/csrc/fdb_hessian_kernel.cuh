@@ -47,9 +47,12 @@ template <int N, bool NS> struct NearLoader {
 // evaluated once per block (phase 1) instead of once per pair -- at C5 that is 2047 four-lane evaluations per eight pairs, where
 // the first version spent three quarters of its FP64 instructions on them.  Terms inside the group's inner range are far for
 // some pairs and near for others: their four-lane contribution is computed once (phase 1b) and added per pair when the term is
-// not near that pair's window.  Every term of every pair is still evaluated exactly as the reference's nested duals would see it
-// (seeded lanes per inner lane k when near, the representative zero lanes when far: 0 * Inf still poisons), only the order of the
-// additions differs (a tree either way).
+// not near that pair's window.  Near terms that read only ONE of the two windows share lanes on the other level (inner window only:
+// all outer lanes are the same zero lane; outer window only: the inner partial is zero(Dual{N}) whatever the inner lane and pair),
+// and the pairs whose windows do not meet -- all but the few around the diagonal -- go through phases 2 and 3 as one batch of work
+// items with two barriers per block instead of two per pair.  Every term of every pair is still evaluated exactly as the reference's
+// nested duals would see it (seeded lanes where it reads a seeded position, representative zero lanes elsewhere: 0 * Inf still
+// poisons), only the order of the additions differs (a tree either way).
 constexpr int HESS_GROUP = 8;     // measured at C5: 16 gains another 2 %, 8 keeps more blocks in flight for small n
 
 template <class F, int N, bool NS, int THREADS>
@@ -60,17 +63,24 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
     typedef Dual<double, N, NS> DI;
     typedef Dual<DI, 1, NS> DG;
     typedef Dual<Dual<double, 1, NS>, 1, NS> DF;
-    constexpr int MAXNEAR = 2 * (N + F::HALO);
+    constexpr int NA = N + F::HALO;                 // terms reading one window
+    constexpr int MAXNEAR = 2 * NA;
     constexpr int MAXU = HESS_GROUP * N + F::HALO;
-    // per near term t: a term reading both windows fills s_p[t][k][0..N] = partials(y,k) as Dual{N} for every inner lane k; one reading
-    // only the inner window fills s_p[t][k][0..1] = (value, representative outer lane) of partials(y,k); one reading only the outer
-    // window fills s_p[t][0][0..N] = the (k-independent) partials(y,.) as Dual{N}
-    __shared__ double s_p[MAXNEAR][N][N + 1];
-    __shared__ double s_v[MAXNEAR];             // per near term: value(value(y))
+    // One buffer, two uses.  (1) pairs whose windows do not meet (all but the few around the diagonal), all at once:
+    //     sa(g,t,k,0..1) = (value, representative outer lane) of partials(y,k) for term t of pair g's inner range;
+    // (2) afterwards, pairs around the diagonal one at a time: sp(t,k,0..N) as described at phase 2 below.
+    constexpr int SA_DOUBLES = HESS_GROUP * NA * N * 2, SP_DOUBLES = MAXNEAR * N * (N + 1);
+    __shared__ double s_buf[SA_DOUBLES > SP_DOUBLES ? SA_DOUBLES : SP_DOUBLES];
+    __shared__ double s_v[MAXNEAR];             // diagonal pairs, per near term: value(value(y))
+    __shared__ double s_av[HESS_GROUP][NA];     // batched pairs, per inner-range term: value(value(y))
+    __shared__ double s_b[NA][N + 1];           // terms of the outer window's range, inner partial zero(Dual{N}): partials(y,.) as Dual{N}, for every k and pair
+    __shared__ double s_bv[NA];                 // ... their value(value(y))
     __shared__ double s_c4[MAXU][4];            // four shared lanes of every term of the group's inner range (zero for terms near the outer window)
     __shared__ double s_common[4];              // far from every window of the block
-    __shared__ double s_ff[4];                  // far sum of the current pair
+    __shared__ double s_ffg[HESS_GROUP][4];     // far sum of each pair
     __shared__ double s_red[THREADS / 32][4];
+    auto sa = [&](int g, int t, int k, int q) -> double& { return s_buf[((g * NA + t) * N + k) * 2 + q]; };
+    auto sp = [&](int t, int k, int j) -> double& { return s_buf[(t * N + k) * (N + 1) + j]; };
 
     const int64_t cg0 = (int64_t)blockIdx.x * HESS_GROUP, co = outer_lo + blockIdx.y;
     const int gcount = (int)((nchunks_total - cg0) < HESS_GROUP ? (nchunks_total - cg0) : HESS_GROUP);
@@ -80,13 +90,22 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
     const int64_t nt = F::nterms(n);
     auto inner_start = [&](int64_t ci) { return ci == nchunks_total - 1 ? n - lastchunksize : ci * N; };
     auto inner_size = [&](int64_t ci) { return ci == nchunks_total - 1 ? lastchunksize : N; };
+    // raw near range of inner chunk cg0 + g (terms reading a seeded position of its window)
+    auto a_range = [&](int g, int64_t& r0, int64_t& r1) {
+        const int64_t is = inner_start(cg0 + g);
+        r0 = is - F::HALO; r1 = is + inner_size(cg0 + g);
+        if (r0 < 0) r0 = 0; if (r1 > nt) r1 = nt; if (r1 < r0) r1 = r0;
+    };
 
     // raw near ranges: B for the outer window, U for the union of the group's inner windows
     int64_t br0 = ostart - F::HALO, br1 = ostart + ocs;
     if (br0 < 0) br0 = 0; if (br1 > nt) br1 = nt; if (br1 < br0) br1 = br0;
+    const int nbr = (int)(br1 - br0);
     int64_t u0 = inner_start(cg0) - F::HALO, u1 = inner_start(cg0 + gcount - 1) + inner_size(cg0 + gcount - 1);
     if (u0 < 0) u0 = 0; if (u1 > nt) u1 = nt; if (u1 < u0) u1 = u0;
     const int nu = (int)(u1 - u0);
+    // a pair is "diagonal" when its two ranges meet: only then can a term read both windows
+    auto diagonal = [&](int g) { int64_t r0, r1; a_range(g, r0, r1); return br0 <= r1 && r0 <= br1; };
 
     // ---- phase 1: terms far from every window of the block, four shared lanes ------------------------
     DF accff[1]; accff[0].v.v = 0.0; accff[0].v.p[0] = 0.0; accff[0].p[0].v = 0.0; accff[0].p[0].p[0] = 0.0;
@@ -111,6 +130,32 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
         if (!(i >= br0 && i < br1)) F::term(xf, i, n, a);            // near the outer window: never far, contributes nothing here
         s_c4[w][0] = a[0].v.v; s_c4[w][1] = a[0].v.p[0]; s_c4[w][2] = a[0].p[0].v; s_c4[w][3] = a[0].p[0].p[0];
     }
+    // ---- phase 1c: the terms of the outer window's range with the inner partial zero(Dual{N}) -- what they are for every inner lane
+    // of every pair whose inner window they do not read (threads from the top end: the low ones are busy with 1b) ----
+    for (int w = THREADS - 1 - (int)threadIdx.x; w < nbr; w += THREADS) {
+        NearLoader<N, NS> xn{x, ostart, ocs, 0, 0, 0};               // ics = 0: no inner lane is hot
+        DG acc[1];
+        acc[0].v.v = 0.0; acc[0].p[0].v = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++) { acc[0].v.p[j] = 0.0; acc[0].p[0].p[j] = 0.0; }
+        F::term(xn, br0 + w, n, acc);
+        s_b[w][0] = acc[0].p[0].v;
+#pragma unroll
+        for (int j = 0; j < N; j++) s_b[w][j + 1] = acc[0].p[0].p[j];
+        s_bv[w] = acc[0].v.v;
+    }
+    // ---- phase 2, pairs off the diagonal, all at once: one work item per (pair, term of its inner range, inner lane k).  Such a
+    // term reads no position of the outer window: all outer lanes of every intermediate are the same zero lane, Dual{Dual{1},1} ----
+    for (int w = threadIdx.x; w < gcount * NA * N; w += THREADS) {
+        const int g = w / (NA * N), r = w - g * (NA * N), t = r / N, k = r - t * N;
+        int64_t ar0, ar1; a_range(g, ar0, ar1);
+        if (t >= (int)(ar1 - ar0) || (br0 <= ar1 && ar0 <= br1)) continue;
+        NearInnerLoader<NS> xa{x, inner_start(cg0 + g), inner_size(cg0 + g), k};
+        DF a[1]; a[0].v.v = 0.0; a[0].v.p[0] = 0.0; a[0].p[0].v = 0.0; a[0].p[0].p[0] = 0.0;
+        F::term(xa, ar0 + t, n, a);
+        sa(g, t, k, 0) = a[0].p[0].v; sa(g, t, k, 1) = a[0].p[0].p[0];
+        if (k == 0) s_av[g][t] = a[0].v.v;
+    }
     __syncthreads();
     if (threadIdx.x < 4) {
         double s = 0.0;
@@ -118,34 +163,80 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
         s_common[threadIdx.x] = s;
     }
     __syncthreads();
+    // far sum of every pair: the block's common part + the inner-range terms outside the pair's own window
+    for (int g = threadIdx.x >> 5; g < gcount; g += THREADS / 32) {
+        const int l = threadIdx.x & 31;
+        int64_t ar0, ar1; a_range(g, ar0, ar1);
+        double r[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = l; w < nu; w += 32) {
+            const int64_t i = u0 + w;
+            if (i >= ar0 && i < ar1) continue;
+#pragma unroll
+            for (int q = 0; q < 4; q++) r[q] = r[q] + s_c4[w][q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) r[q] = r[q] + shfl_down_d(r[q], off);
+        }
+        if (l == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) s_ffg[g][q] = r[q] + s_common[q];
+        }
+    }
+    __syncthreads();
+    // ---- phase 3, pairs off the diagonal: fold and store (fused extract_gradient_chunk! + extract_jacobian_chunk!) ----
+    // far lanes: [0] = value.value, [1] = value.outer-partial, [2] = inner-partial.value, [3] = inner-partial.outer-partial
+    for (int e = threadIdx.x; e < gcount * N * (N + 1); e += THREADS) {
+        const int g = e / (N * (N + 1)), r = e - g * (N * (N + 1)), k = r / (N + 1), j = r - k * (N + 1);
+        int64_t ar0, ar1; a_range(g, ar0, ar1);
+        if (br0 <= ar1 && ar0 <= br1) continue;
+        const int64_t ci = cg0 + g, istart = inner_start(ci);
+        const int ics = inner_size(ci), na = (int)(ar1 - ar0);
+        if (k < ics) {
+            double s = 0.0;
+            if (ar0 < br0) {                                         // term order: the lower range first
+                for (int t = 0; t < na; t++) s = s + sa(g, t, k, j == 0 ? 0 : 1);
+                for (int t = 0; t < nbr; t++) s = s + s_b[t][j];
+            } else {
+                for (int t = 0; t < nbr; t++) s = s + s_b[t][j];
+                for (int t = 0; t < na; t++) s = s + sa(g, t, k, j == 0 ? 0 : 1);
+            }
+            s = s + (j == 0 ? s_ffg[g][2] : s_ffg[g][3]);
+            if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
+            else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
+        }
+        if (r == 0 && olast && ci == nchunks_total - 1 && value_out) {
+            double s = 0.0;
+            for (int t = 0; t < na; t++) s = s + s_av[g][t];
+            for (int t = 0; t < nbr; t++) s = s + s_bv[t];
+            mstore(M, value_out, s + s_ffg[g][0]);
+        }
+    }
 
+    // ---- pairs around the diagonal, one at a time (at most three per block row of the pair grid) ----
     for (int g = 0; g < gcount; g++) {
+        if (!diagonal(g)) continue;                              // block-uniform
+        __syncthreads();                                         // the buffer is free: the batched fold / the previous pair is done
         const int64_t ci = cg0 + g;
         const bool ilast = (ci == nchunks_total - 1);
         const int ics = ilast ? lastchunksize : N;
         const int64_t istart = ilast ? n - lastchunksize : ci * N;
-        // near-term ranges (terms reading a seeded position): A for the inner window, B for the outer
-        int64_t ar0 = istart - F::HALO, ar1 = istart + ics;
-        if (ar0 < 0) ar0 = 0; if (ar1 > nt) ar1 = nt; if (ar1 < ar0) ar1 = ar0;
+        int64_t ar0, ar1; a_range(g, ar0, ar1);
         int64_t a0 = ar0, a1 = ar1, b0 = br0, b1 = br1;
-        if (b0 <= a1 && a0 <= b1) { a0 = a0 < b0 ? a0 : b0; a1 = a1 > b1 ? a1 : b1; b0 = b1 = a1; }   // merge overlapping ranges
-        const int na = (int)(a1 - a0), nb = (int)(b1 - b0), nnear = na + nb;
-
-        // ---- phase 2: near terms.  Work items: (term, inner lane k) for the terms of the A range, one per term of the B range (after
-        // the merge above the B range holds terms that read the outer window only).  Three kinds of term:
-        //   both windows : Dual{Dual{N},1} per inner lane k (the full nested evaluation)
-        //   inner only   : Dual{Dual{1},1} per inner lane k (all outer lanes are the same zero lane)
-        //   outer only   : Dual{Dual{N},1} once (the inner partial is zero(Dual{N}) for every k)
-        for (int w = threadIdx.x; w < na * N + nb; w += THREADS) {
-            const bool arange = w < na * N;
-            const int t = arange ? w / N : na + (w - na * N), k = arange ? w - t * N : 0;
-            const int64_t i = t < na ? a0 + t : b0 + (t - na);
+        a0 = a0 < b0 ? a0 : b0; a1 = a1 > b1 ? a1 : b1; b0 = b1 = a1;      // the ranges meet: one merged range
+        const int na = (int)(a1 - a0), nnear = na;
+        // phase 2: (term, inner lane k).  A term reading both windows: Dual{Dual{N},1} per k (the full nested evaluation) -> sp(t,k,0..N);
+        // inner window only: Dual{Dual{1},1} per k -> sp(t,k,0..1); outer window only: Dual{Dual{N},1} once -> sp(t,0,0..N)
+        for (int w = threadIdx.x; w < na * N; w += THREADS) {
+            const int t = w / N, k = w - t * N;
+            const int64_t i = a0 + t;
             const bool inA = (i >= ar0 && i < ar1), inB = (i >= br0 && i < br1);
             if (inA && !inB) {
                 NearInnerLoader<NS> xa{x, istart, ics, k};
                 DF a[1]; a[0].v.v = 0.0; a[0].v.p[0] = 0.0; a[0].p[0].v = 0.0; a[0].p[0].p[0] = 0.0;
                 F::term(xa, i, n, a);
-                s_p[t][k][0] = a[0].p[0].v; s_p[t][k][1] = a[0].p[0].p[0];
+                sp(t, k, 0) = a[0].p[0].v; sp(t, k, 1) = a[0].p[0].p[0];
                 if (k == 0) s_v[t] = a[0].v.v;
             } else if (inA || k == 0) {
                 NearLoader<N, NS> xn{x, ostart, ocs, istart, ics, k};
@@ -154,55 +245,32 @@ FDB_DEV void hessian_sweep_body(const double* __restrict__ x, int64_t n, int64_t
 #pragma unroll
                 for (int j = 0; j < N; j++) { acc[0].v.p[j] = 0.0; acc[0].p[0].p[j] = 0.0; }
                 F::term(xn, i, n, acc);
-                s_p[t][k][0] = acc[0].p[0].v;
+                sp(t, k, 0) = acc[0].p[0].v;
 #pragma unroll
-                for (int j = 0; j < N; j++) s_p[t][k][j + 1] = acc[0].p[0].p[j];
+                for (int j = 0; j < N; j++) sp(t, k, j + 1) = acc[0].p[0].p[j];
                 if (k == 0) s_v[t] = acc[0].v.v;
             }
         }
-        // far sum of this pair: the block's common part + the inner-range terms outside this pair's window (by the last warp: it
-        // has the fewest near items)
-        if (threadIdx.x >= THREADS - 32) {
-            const int l = threadIdx.x - (THREADS - 32);
-            double r[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int w = l; w < nu; w += 32) {
-                const int64_t i = u0 + w;
-                if (i >= ar0 && i < ar1) continue;
-#pragma unroll
-                for (int q = 0; q < 4; q++) r[q] = r[q] + s_c4[w][q];
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) r[q] = r[q] + shfl_down_d(r[q], off);
-            }
-            if (l == 0) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) s_ff[q] = r[q] + s_common[q];
-            }
-        }
         __syncthreads();
-        // ---- phase 3: fold and store (fused extract_gradient_chunk! + extract_jacobian_chunk!) --------
-        // lanes: s_ff[0] = value.value, [1] = value.outer-partial, [2] = inner-partial.value, [3] = inner-partial.outer-partial
+        // phase 3
         for (int e = threadIdx.x; e < N * (N + 1); e += THREADS) {
             const int k = e / (N + 1), j = e - k * (N + 1);     // j = 0: value of partials(y,k); j >= 1: outer partial j
             if (k >= ics) continue;
             double s = 0.0;
             for (int t = 0; t < nnear; t++) {
-                const int64_t i = t < na ? a0 + t : b0 + (t - na);
+                const int64_t i = a0 + t;
                 const bool inA = (i >= ar0 && i < ar1), inB = (i >= br0 && i < br1);
-                s = s + ((inA && inB) ? s_p[t][k][j] : (inA ? s_p[t][k][j == 0 ? 0 : 1] : s_p[t][0][j]));
+                s = s + ((inA && inB) ? sp(t, k, j) : (inA ? sp(t, k, j == 0 ? 0 : 1) : sp(t, 0, j)));
             }
-            s = s + (j == 0 ? s_ff[2] : s_ff[3]);
+            s = s + (j == 0 ? s_ffg[g][2] : s_ffg[g][3]);
             if (j == 0) { if (olast && grad) mstore(M, &grad[istart + k], s); }
             else if (j - 1 < ocs && H) mstore(M, &H[(istart + k) + (ostart + j - 1) * ldH], s);
         }
         if (threadIdx.x == 0 && olast && ilast && value_out) {
             double s = 0.0;
             for (int t = 0; t < nnear; t++) s = s + s_v[t];
-            mstore(M, value_out, s + s_ff[0]);
+            mstore(M, value_out, s + s_ffg[g][0]);
         }
-        __syncthreads();                                         // s_p / s_v / s_ff are rewritten by the next pair
     }
 }
 
