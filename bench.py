@@ -40,7 +40,7 @@ DP_OPS_PER_TERM_FULL = 133          # all 12 lanes: 120 in the term + 13 accumul
 # FP64-pipe instructions (thread level) per element per chunk sweep / per term per chunk pair, measured with ncu on the C2 Ackley launch
 # and the C5 Hessian launch (profiles/r02_fp64_counts.md): sum of smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on / units
 ACKLEY_FP64_ISSUE_PER_TERM = 28.06   # (938.6 DADD + 1117.4 DMUL + 3161.3 DFMA) inst/cycle x 448.13e6 cycles / (1e6 x 83334)   [profiles/r02_ackley_sweep_raw.csv]
-HESSIAN_FP64_ISSUE_PER_TERM = 7.90   # (1353.1 DADD + 661.7 DMUL) inst/cycle x 5.25917e5 cycles / (2047 x 65536)                 [profiles/r02_hessian_c5_grouped_raw.csv]
+HESSIAN_FP64_ISSUE_PER_TERM = 7.19   # (2074.1 DADD + 988.2 DMUL) inst/cycle x 3.14919e5 cycles / (2047 x 65536)                  [profiles/r02_hessian_c5_grouped_raw.csv]
 #   (the first round-2 kernel, r02_hessian_c5_raw.csv, executed 52.88: every pair re-evaluated all far terms, every near term on all lanes)
 
 
@@ -701,7 +701,7 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
                                                  "algorithmic": f"{HESSIAN_FP64_ISSUE_PER_TERM} FP64 pipe instructions per term per (inner, outer) chunk pair "
                                                                 "(far terms on 4 shared lanes, evaluated once per block of 8 inner chunks; near terms that read one window only on shared lanes "
                                                                 "of the other level; ncu count of the launch / (2047 x 65536)) x 2047 terms x 256^2 pairs.  The kernel is latency-bound "
-                                                                "now (FP64 pipe 31 % active): 6.7x fewer instructions than the one-pair-per-block kernel bought 2x in time",
+                                                                "now (FP64 pipe 37 % active): 7.4x fewer instructions than the one-pair-per-block kernel bought 3.3x in time",
                                                  "peak_source": "fdb_measure_fp64_peak"}}
     # C3: tanh.(A*x .+ b) Jacobian n = m = 8192, Chunk{12} on the FP64 tensor cores
     m3 = 8192
