@@ -375,8 +375,8 @@ class ShardedHessian(_ShardedColumns):
 
     def __init__(self, ctx, f, xlen, cfg=None, group=None, exchange="auto", peer_stores="auto"):
         """peer_stores: "mirror" = the sweep kernel stores every entry into all peers (one launch), "push" = local stores, then one
-        streaming copy of the column block to the peers; "auto" = mirror up to four ranks, push beyond (measured mirror / push at C5:
-        0.300 / 0.336 ms at 2 ranks, 0.174 / 0.218 at 4, 0.171 / 0.166 at 8 -- see DESIGN.md section 6)."""
+        streaming copy of the column block to the peers; "auto" = mirror for two ranks, push beyond (measured mirror / push at C5:
+        0.110 / 0.140 ms at 2 ranks, 0.149 / 0.124 at 4, 0.173 / 0.112 at 8 -- see DESIGN.md section 6)."""
         self.f = f
         self.peer_stores = peer_stores
         self.cfg = cfg if cfg is not None else HessianConfig(f, np.empty(int(xlen)))
@@ -395,7 +395,7 @@ class ShardedHessian(_ShardedColumns):
         which cross NVLink at a fraction of the link rate (measured at 8 ranks: 0.169 ms with the stores mirrored from the sweep
         kernel, the 29 MB push runs at the link rate); same bits either way."""
         c = self.ctx
-        mode = self.peer_stores if self.peer_stores != "auto" else ("mirror" if self.world <= 4 else "push")
+        mode = self.peer_stores if self.peer_stores != "auto" else ("mirror" if self.world <= 2 else "push")
         if mode == "mirror":
             self._sweep_begin()
             try:
