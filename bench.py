@@ -604,6 +604,20 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
                                             "fp64_frac": DP_OPS_PER_TERM_FULL * (N_ELEMS - 1) * 8192 / (ms * 1e-3) / dp_peak,
                                             "verified": {"ok": bool(np.allclose(gh, closed[:8192 * CHUNK], rtol=1e-12, atol=1e-11)),
                                                          "against": "closed-form gradient, all 98304 entries of the timed chunk range"}}
+    # opt-in chunk grouping (fdb_set_chunk_grouping): a block sweeps G chunks and evaluates the terms far from all of them once.  NOT the
+    # headline: there the ceil(n/N) sweeps stay independent evaluations of f, as in the reference's loop.  Same gradient (checked).
+    grouped = {}
+    for G in (8, 32):
+        ctx.set_chunk_grouping(G)
+        ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["rosenbrock"], x.h, CHUNK, 0, -1, g.h, v.h)), reps=3)
+        ops = DP_OPS_PER_TERM * (N_ELEMS - 1) * -(-83334 // G)
+        grouped[f"group_{G}"] = {"evals_per_s": 1e3 / ms, "ms": ms, "far_fp64_frac": ops / (ms * 1e-3) / dp_peak,
+                                 "verified": {"ok": bool(np.array_equal(g.numpy(), closed) or np.allclose(g.numpy(), closed, rtol=1e-12, atol=1e-11)),
+                                              "against": "closed-form gradient, all entries"}}
+    ctx.set_chunk_grouping(1)
+    grouped["note"] = ("fdb_set_chunk_grouping(G): the far terms' Dual{1} evaluation is chunk-invariant and is shared by the G chunks of a block; "
+                       "far_fp64_frac counts only the shared far evaluations (20 ops x terms x ceil(chunks/G)) against the FP64 issue rate")
+    out["rosenbrock_gradient_c2_grouped_chunks"] = grouped
     # Ackley at C2's size.  Roofline: FP64 thread-level instructions of one launch, from the ncu capture of this kernel
     # (profiles/r02_ackley_sweep_raw.csv: smsp__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on.sum; libdevice sincos is
     # FP64 polynomial code, so they are all on the FP64 pipe), against the FP64 issue rate
@@ -809,7 +823,8 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
         del a, bb, oo, o1, xs
     out["generic_kernels"] = gk
     out["all_verified"] = bool(all(vv.get("verified", {}).get("ok", True) for vv in out.values() if isinstance(vv, dict)) and
-                               all(r["verified"]["ok"] for r in gk.values()))
+                               all(r["verified"]["ok"] for r in gk.values()) and
+                               all(r["verified"]["ok"] for r in out["rosenbrock_gradient_c2_grouped_chunks"].values() if isinstance(r, dict)))
     return out
 
 

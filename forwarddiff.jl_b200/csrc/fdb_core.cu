@@ -201,6 +201,11 @@ extern "C" int fdb_sync(fdb_ctx* ctx) {
 extern "C" int fdb_set_async(fdb_ctx* ctx, int async) { if (!ctx) return FDB_ERR_BADARG; ctx->async = async != 0; return FDB_OK; }
 extern "C" int fdb_set_nansafe(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->nansafe = en != 0; return FDB_OK; }
 extern "C" int fdb_set_lane_sharing(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->lane_sharing = en != 0; return FDB_OK; }
+extern "C" int fdb_set_chunk_grouping(fdb_ctx* ctx, int group) {
+    if (!ctx || group < 1 || group > 64) return fail(ctx, FDB_ERR_BADARG, "fdb_set_chunk_grouping: group must be 1..64");
+    ctx->grad_group = group;
+    return FDB_OK;
+}
 extern "C" int fdb_set_dmma(fdb_ctx* ctx, int en) { if (!ctx) return FDB_ERR_BADARG; ctx->use_dmma = en != 0; return FDB_OK; }
 extern "C" int fdb_set_dmma_tma_store(fdb_ctx* ctx, int mode) { if (!ctx || mode < 0 || mode > 3) return FDB_ERR_BADARG; ctx->dmma_tma_store = mode; return FDB_OK; }
 extern "C" int fdb_set_dmma_tile(fdb_ctx* ctx, int bn) {

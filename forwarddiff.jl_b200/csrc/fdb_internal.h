@@ -16,6 +16,7 @@ struct fdb_ctx {
     bool async = false;
     bool nansafe = false;
     bool lane_sharing = true;   // see fdb_sweep.cu (SHARE)
+    int grad_group = 1;         // chunks swept per block by the catalogue gradient kernel (fdb_set_chunk_grouping); 1 = independent sweeps
     bool use_dmma = true;       // tanh_affine: DMMA contraction (fdb_dmma.cu) vs CUDA-core kernel
     int dmma_tma_store = 1;     // 0 never, 1 when the result is mirrored to peers, 2 always -- fused DMMA epilogue: result blocks staged in shared memory and written by TMA tensor stores (fdb_set_dmma_tma_store)
     int dmma_bn = 0;            // column-tile width of the DMMA contraction: 0 = chosen per shape, or 16 / 32 / 64 (fdb_set_dmma_tile)

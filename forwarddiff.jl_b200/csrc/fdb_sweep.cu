@@ -28,7 +28,14 @@ static int gradient_launch(fdb_ctx* ctx, const fdb_array* x, int N, int64_t lo, 
     fdb_mirrors M;
     const fdb_array* outs[2] = {grad, value_dev};
     int rc = mirrors_for(ctx, &M, outs, 2, what); if (rc) return rc;
-    if (ctx->lane_sharing) {
+    if (ctx->lane_sharing && ctx->grad_group > 1 && hi - lo > 1) {
+        // opt-in (fdb_set_chunk_grouping): a block sweeps `group` chunks and evaluates the terms far from all of them once
+        const int group = ctx->grad_group;
+        const unsigned ggrid = (unsigned)cdiv(hi - lo, (int64_t)group);
+        FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
+            (gradient_sweep_group_kernel<F, NN, NS, THREADS><<<ggrid, THREADS, 0, ctx->stream>>>(x->data, x->n, lo, hi, nchunks, lastchunksize, group,
+                                                                                                 grad->data, vout, M))));
+    } else if (ctx->lane_sharing) {
         FDB_DISPATCH_N(N, FDB_DISPATCH_NS(ctx->nansafe,
             (gradient_sweep_kernel<F, NN, NS, THREADS, true><<<grid, THREADS, 0, ctx->stream>>>(x->data, x->n, lo, nchunks, lastchunksize,
                                                                                                  grad->data, vout, M))));

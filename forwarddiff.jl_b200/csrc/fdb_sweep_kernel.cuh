@@ -136,6 +136,75 @@ FDB_DEV void gradient_sweep_body(const double* __restrict__ x, int64_t n, int64_
     }
 }
 
+// Opt-in variant (fdb_set_chunk_grouping): a block sweeps `group` consecutive chunks.  A term that reads no seeded position of ANY
+// of them has the same Dual{1} result (value, representative zero lane) for every chunk of the group, so the far iterations are
+// evaluated once per block and folded into each chunk's accumulators; the iterations that hold the group's windows are evaluated
+// per chunk on all N lanes with that chunk's seeds, exactly as above.  The gradient is the same lane by lane (the far lanes are
+// really computed, 0 * Inf still poisons), the FP64 work drops by ~group.  The default stays one chunk per block: the ceil(n/N)
+// sweeps of src/gradient.jl:141-152 are then independent evaluations of f, which is what BASELINE.json's C2 number measures.
+template <class F, int N, bool NS, int THREADS>
+FDB_DEV void gradient_sweep_group_body(const double* __restrict__ x, int64_t n, int64_t chunk_lo, int64_t chunk_hi, int64_t nchunks_total,
+                                       int lastchunksize, int group, double* __restrict__ grad, double* __restrict__ value_out,
+                                       const fdb_mirrors& M) {
+    typedef Dual<double, N, NS> D;
+    typedef Dual<double, 1, NS> D1;
+    const int64_t c0 = chunk_lo + (int64_t)blockIdx.x * group;
+    const int gcount = (int)((chunk_hi - c0) < group ? (chunk_hi - c0) : group);
+    auto cstart = [&](int64_t c) { return c == nchunks_total - 1 ? n - lastchunksize : c * N; };
+    auto csize = [&](int64_t c) { return c == nchunks_total - 1 ? lastchunksize : N; };
+    const int64_t ustart = cstart(c0), uend = cstart(c0 + gcount - 1) + csize(c0 + gcount - 1);
+    const int64_t nt = F::nterms(n);
+    const int64_t nit = (nt + THREADS - 1) / THREADS;
+    int64_t itA = (ustart - F::HALO) / THREADS; if (itA < 0) itA = 0; if (itA > nit) itA = nit;
+    int64_t itB = (uend + THREADS - 1) / THREADS; if (itB > nit) itB = nit; if (itB < itA) itB = itA;
+    ZeroLoader<1, NS> xz{x};
+    D1 acc1[F::K];
+    D1 like1; like1.v = 0.0; like1.p[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < F::K; k++) acc1[k] = F::init(k, like1);
+    // iterations [0,itA) and [itB,nit) touch no seeded position of any chunk of the group
+    far_range<F, NS, THREADS>(x, n, 0, itA, acc1);
+    const int64_t full = nt / THREADS;
+    far_range<F, NS, THREADS>(x, n, itB, full, acc1);
+    for (int64_t it = (itB > full ? itB : full); it < nit; it++) {
+        const int64_t i = it * THREADS + threadIdx.x;
+        if (i < nt) F::term(xz, i, n, acc1);
+    }
+    D like; like.v = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) like.p[k] = 0.0;
+    for (int g = 0; g < gcount; g++) {
+        if (g) __syncthreads();                                    // block_combine's staging is reused
+        const int64_t c = c0 + g;
+        const bool last = (c == nchunks_total - 1);
+        const int chunksize = last ? lastchunksize : N;
+        const int64_t start = last ? (n - lastchunksize) : c * N;
+        SeedLoader<N, NS> xs{x, start, chunksize};
+        D acc[F::K];
+#pragma unroll
+        for (int k = 0; k < F::K; k++) acc[k] = F::init(k, like);
+        for (int64_t it = itA; it < itB; it++) {
+            const int64_t i = it * THREADS + threadIdx.x;
+            if (i < nt) F::term(xs, i, n, acc);
+        }
+#pragma unroll
+        for (int k = 0; k < F::K; k++) {
+            D e; e.v = acc1[k].v;
+#pragma unroll
+            for (int j = 0; j < N; j++) e.p[j] = acc1[k].p[0];
+            acc[k] = F::combine(k, acc[k], e);
+        }
+        block_combine<F, D, THREADS>(acc);
+        if (threadIdx.x == 0) {
+            D y = F::finalize(acc, n);
+#pragma unroll
+            for (int k = 0; k < N; k++)
+                if (k < chunksize) mstore(M, &grad[start + k], y.p[k]);
+            if (last && value_out) mstore(M, value_out, y.v);
+        }
+    }
+}
+
 // Two-pass form: f uses a reduced value inside a second broadcast -- sum((x .- mean(x)).^2), log(sum(exp.(x .- m))) ...
 // Pass 1 is the sweep above (lane sharing included) over the first-stage terms; thread 0 runs F::finalize1 on the reduced
 // Duals and publishes the resulting scalar Duals S (dense partials: every lane of the window contributes) in shared
@@ -270,6 +339,14 @@ __global__ void __launch_bounds__(THREADS) gradient_sweep_kernel(const double* _
                                                                  double* __restrict__ grad, double* __restrict__ value_out,
                                                                  const __grid_constant__ fdb_mirrors M) {
     gradient_sweep_body<F, N, NS, THREADS, SHARE>(x, n, chunk_lo, nchunks_total, lastchunksize, grad, value_out, M);
+}
+
+template <class F, int N, bool NS, int THREADS>
+__global__ void __launch_bounds__(THREADS) gradient_sweep_group_kernel(const double* __restrict__ x, int64_t n, int64_t chunk_lo, int64_t chunk_hi,
+                                                                       int64_t nchunks_total, int lastchunksize, int group,
+                                                                       double* __restrict__ grad, double* __restrict__ value_out,
+                                                                       const __grid_constant__ fdb_mirrors M) {
+    gradient_sweep_group_body<F, N, NS, THREADS>(x, n, chunk_lo, chunk_hi, nchunks_total, lastchunksize, group, grad, value_out, M);
 }
 
 }  // namespace fdb

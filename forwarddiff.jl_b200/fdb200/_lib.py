@@ -61,6 +61,7 @@ SIGNATURES = {
     "fdb_get_stream": (C.c_int, [c_ctx, C.POINTER(C.c_void_p)]),
     "fdb_set_nansafe": (C.c_int, [c_ctx, C.c_int]),
     "fdb_set_lane_sharing": (C.c_int, [c_ctx, C.c_int]),
+    "fdb_set_chunk_grouping": (C.c_int, [c_ctx, C.c_int]),
     "fdb_set_dmma": (C.c_int, [c_ctx, C.c_int]),
     "fdb_set_dmma_tile": (C.c_int, [c_ctx, C.c_int]),
     "fdb_set_dmma_tma_store": (C.c_int, [c_ctx, C.c_int]),

@@ -63,6 +63,10 @@ class Context:
     def set_lane_sharing(self, flag):
         self.check(self.lib.fdb_set_lane_sharing(self.h, int(flag)))
 
+    def set_chunk_grouping(self, group):
+        """Opt-in: the catalogue gradient kernel sweeps `group` chunks per block and shares the far terms between them (1 = off)."""
+        self.check(self.lib.fdb_set_chunk_grouping(self.h, int(group)))
+
     def set_jit(self, flag):
         """Run-time specialisation of the op-program kernels (fdb_jit.cu); False = per-thread interpreter."""
         self._jit = bool(flag)

@@ -102,6 +102,11 @@ int fdb_set_nansafe(fdb_ctx* ctx, int enabled);   /* `nansafe_mode` preference, 
 /* 1 (default): terms that touch no seeded position are evaluated on one representative
  * partial lane (bit-identical results; see fdb_sweep.cu).  0: all N lanes for every term. */
 int fdb_set_lane_sharing(fdb_ctx* ctx, int enabled);
+/* Opt-in for fdb_gradient_chunked / fdb_gradient_host on catalogue targets with lane sharing on: a thread block sweeps `group`
+ * consecutive chunks (1..64) and evaluates the terms that read no seeded position of any of them ONCE (their Dual{1} result is
+ * the same for every chunk of the group).  Same gradient lane by lane; the FP64 work drops by ~group.  Default 1: the ceil(n/N)
+ * chunk sweeps of src/gradient.jl:141-152 stay independent evaluations of f (what bench.py's headline measures). */
+int fdb_set_chunk_grouping(fdb_ctx* ctx, int group);
 /* 1 (default): A*xdual contractions run on FP64 tensor cores (DMMA) when shapes allow; 0: CUDA-core kernels */
 int fdb_set_dmma(fdb_ctx* ctx, int enabled);
 /* operand columns per thread-block tile of the DMMA contraction: 0 (default) = chosen per shape so that the equal-sized

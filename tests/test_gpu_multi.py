@@ -462,3 +462,46 @@ def test_readme_examples_run_and_agree_with_finite_differences(ctx):
     for i in range(95):
         Href[i, i] += 2 * ws[i]; Href[i + 1, i + 1] += 2 * ws[i]; Href[i, i + 1] -= 2 * ws[i]; Href[i + 1, i] -= 2 * ws[i]
     assert np.allclose(H, Href, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("group", [2, 8, 32])
+def test_grouped_gradient_sweep_matches_independent_chunk_sweeps(ctx, group):
+    """fdb_set_chunk_grouping: a block sweeps `group` chunks and evaluates the far terms once.  Same gradient as the independent
+    sweeps -- bit for bit where every lane has at most two non-zero addends (Rosenbrock, sum of squares), to reduction tolerance
+    otherwise -- for whole gradients, chunk sub-ranges, short last chunks, N = 1 and non-finite inputs (0 * Inf must still poison)."""
+    lib = ctx.lib
+    rng = np.random.default_rng(21)
+    FN = fdb200._lib.FN
+    try:
+        for n, N in ((1003, 12), (25, 12), (100_003, 12), (4099, 7), (300, 1), (12, 12), (13, 12)):
+            xs = rng.uniform(0.5, 1.5, n)
+            x = ctx.array(xs)
+            nchunks = 1 if n == N else fdb200.chunk_plan(n, N)["nchunks"]
+            for name in ("rosenbrock", "ackley", "sumsq", "prod"):
+                if name == "prod" and n > 2000:
+                    continue
+                for lo, hi in ((0, -1), (min(3, nchunks - 1), max(min(3, nchunks - 1) + 1, min(41, nchunks)))):
+                    out = []
+                    for g in (1, group):
+                        ctx.set_chunk_grouping(g)
+                        gr = ctx.array(np.full(n, -7.0)); v = ctx.array(np.array([-7.0]))
+                        ctx.check(lib.fdb_gradient_chunked(ctx.h, FN[name], x.h, N, lo, hi, gr.h, v.h))
+                        out.append((gr.numpy(), v.numpy()[0]))
+                    (g1, v1), (g2, v2) = out
+                    if name in ("rosenbrock", "sumsq"):
+                        assert np.array_equal(g1, g2), (name, n, N, lo, hi)
+                    else:
+                        assert np.allclose(g1, g2, rtol=1e-12, atol=1e-12 * np.max(np.abs(g1))), (name, n, N, lo, hi)
+                    assert v1 == v2 or abs(v1 - v2) <= 1e-12 * abs(v1), (name, n, N, v1, v2)
+        # a non-finite far term poisons every lane of every chunk in both forms (the representative zero lane is really computed)
+        xs = rng.uniform(0.5, 1.5, 500); xs[400] = np.inf
+        x = ctx.array(xs)
+        res = []
+        for g in (1, group):
+            ctx.set_chunk_grouping(g)
+            gr = ctx.zeros(500)
+            ctx.check(lib.fdb_gradient_chunked(ctx.h, FN["rosenbrock"], x.h, 12, 0, -1, gr.h, None))
+            res.append(gr.numpy())
+        assert np.array_equal(np.isnan(res[0]), np.isnan(res[1])) and np.isnan(res[0]).all()
+    finally:
+        ctx.set_chunk_grouping(1)

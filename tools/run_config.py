@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--no-dmma", action="store_true")
     ap.add_argument("--bn", type=int, default=0, help="DMMA column-tile width (0 = auto, 16, 32, 64)")
     ap.add_argument("--no-tma-store", action="store_true", help="fused DMMA epilogue: per-thread stores instead of TMA tensor stores")
+    ap.add_argument("--group", type=int, default=1, help="fdb_set_chunk_grouping: chunks per block of the catalogue gradient kernel")
     ap.add_argument("--store-mode", type=int, default=-1, help="fdb_set_dmma_tma_store mode 0..3")
     a = ap.parse_args()
     ctx = fdb200.Context(0)
@@ -30,6 +31,7 @@ def main():
     ctx.set_lane_sharing(not a.no_share)
     ctx.check(lib.fdb_set_dmma(ctx.h, 0 if a.no_dmma else 1))
     ctx.check(lib.fdb_set_dmma_tile(ctx.h, a.bn))
+    ctx.set_chunk_grouping(a.group)
     ctx.check(lib.fdb_set_dmma_tma_store(ctx.h, a.store_mode if a.store_mode >= 0 else (0 if a.no_tma_store else 2)))
     rng = np.random.default_rng(1)
     FN, JFN = fdb200._lib.FN, fdb200._lib.JFN
