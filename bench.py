@@ -610,7 +610,7 @@ def extras(ctx, torch, dev, flush, hbm_peak, dp_peak):
     for G in (8, 32):
         ctx.set_chunk_grouping(G)
         ms = t(lambda: ctx.check(lib.fdb_gradient_chunked(ctx.h, fid["rosenbrock"], x.h, CHUNK, 0, -1, g.h, v.h)), reps=3)
-        ops = DP_OPS_PER_TERM * (N_ELEMS - 1) * -(-83334 // G)
+        ops = DP_OPS_PER_TERM_SHARED * (N_ELEMS - 1) * -(-83334 // G)
         grouped[f"group_{G}"] = {"evals_per_s": 1e3 / ms, "ms": ms, "far_fp64_frac": ops / (ms * 1e-3) / dp_peak,
                                  "verified": {"ok": bool(np.array_equal(g.numpy(), closed) or np.allclose(g.numpy(), closed, rtol=1e-12, atol=1e-11)),
                                               "against": "closed-form gradient, all entries"}}
