@@ -400,6 +400,25 @@ function PeerExchange(ctx::Context, ndoubles::Integer, rank::Integer, world::Int
     check(ctx.h, ccall((:fdb_exchange_connect, libfdb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}), r[], all))
     return PeerExchange(r[], ctx)
 end
+# The same arena bound into an NVSwitch multicast object (csrc/fdb_multicast.cu): every result entry is stored once and the switch
+# replicates it into all ranks' arenas.  `allgather16` / `bcast16` move the 16-byte {pid, fd} handles (MPI.Allgather / MPI.Bcast!),
+# `hostbarrier()` is any barrier of the host transport (every device must be added before anyone binds, and every arena bound
+# before anyone stores).  Throws (FDB_ERR_UNSUPPORTED) where the box cannot do it: fall back to PeerExchange.
+function MulticastExchange(ctx::Context, ndoubles::Integer, rank::Integer, world::Integer, allgather16, bcast16, hostbarrier)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx.h, ccall((:fdb_exchange_create_multicast, libfdb200), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Ref{Ptr{Cvoid}}), ctx.h, ndoubles, rank, world, r))
+    mine = Vector{UInt8}(undef, 16); mc = zeros(UInt8, 16)
+    check(ctx.h, ccall((:fdb_exchange_share_handle, libfdb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}), r[], mine))
+    rank == 0 && check(ctx.h, ccall((:fdb_exchange_multicast_create, libfdb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}), r[], mc))
+    all = allgather16(mine); mc = bcast16(mc)
+    check(ctx.h, ccall((:fdb_exchange_connect_multicast, libfdb200), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{UInt8}), r[], all, mc))
+    hostbarrier()
+    check(ctx.h, ccall((:fdb_exchange_multicast_bind, libfdb200), Cint, (Ptr{Cvoid},), r[]))
+    hostbarrier()
+    return PeerExchange(r[], ctx)
+end
+# opt-in: the catalogue gradient kernel sweeps `group` chunks per block and shares the chunk-invariant far terms (1 = independent sweeps)
+set_chunk_grouping!(ctx::Context, group::Integer) = check(ctx.h, ccall((:fdb_set_chunk_grouping, libfdb200), Cint, (Ptr{Cvoid}, Cint), ctx.h, group))
 function arena_view(x::PeerExchange, offset::Integer, n::Integer, ld::Integer = n)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(x.ctx.h, ccall((:fdb_exchange_view, libfdb200), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ref{Ptr{Cvoid}}), x.h, offset, n, ld, r))

@@ -264,3 +264,36 @@ def test_julia_shim_is_consistent_with_the_c_abi():
                 assert a in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(a, ctypes._Pointer), (name, t, a)
             elif t in ctype_ok:
                 assert a in ctype_ok[t], (name, t, a)
+
+
+def test_handle_sizes_agree_between_header_and_binding():
+    """The byte sizes of the handles that travel through the host transport are part of the C ABI."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "fdb200.h")).read()
+    sizes = dict(re.findall(r"#define\s+(FDB_\w+_HANDLE_BYTES)\s+(\d+)", hdr))
+    assert int(sizes["FDB_IPC_HANDLE_BYTES"]) == fdb200._lib.IPC_HANDLE_BYTES == 64
+    assert int(sizes["FDB_SHARE_HANDLE_BYTES"]) == fdb200._lib.SHARE_HANDLE_BYTES == 16
+    # the multicast sequence is exported completely (a partial set would leave a caller stuck between two collective steps)
+    for name in ("fdb_multicast_supported", "fdb_exchange_create_multicast", "fdb_exchange_share_handle", "fdb_exchange_multicast_create",
+                 "fdb_exchange_connect_multicast", "fdb_exchange_multicast_bind", "fdb_exchange_set_multicast", "fdb_set_chunk_grouping"):
+        assert name in fdb200._lib.SIGNATURES and re.search(r"\b" + name + r"\s*\(", hdr), name
+
+
+def test_launch_list_tool_summarises_an_ncu_csv(tmp_path):
+    """tools/launch_list.py: per-kernel launches, average and share from the CSV that `ncu --csv --log-file` writes."""
+    import subprocess, sys
+    rows = ['==PROF== Connected to process 1', '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size",'
+            '"Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"']
+    def row(i, kernel, ns):
+        return f'"{i}","1","python","box","{kernel}","1","7","(256, 1, 1)","(100, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","ns","{ns}"'
+    rows += [row(0, "void fdb::gradient_sweep_kernel<Rosenbrock, 12, 0, 256, 1>(const double *, long)", "94,000,000"),
+             row(1, "void fdb::gradient_sweep_kernel<Rosenbrock, 12, 0, 256, 1>(const double *, long)", "96,000,000"),
+             row(2, "fdb::seed_kernel(double *)", "10,000,000")]
+    p = tmp_path / "launches.csv"
+    p.write_text("\n".join(rows) + "\n")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_list.py"), str(p), "--md"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("| `")]
+    assert lines[0].startswith("| `gradient_sweep_kernel<Rosenbrock, 12, 0, 256, 1>` | 2 | 95.0000 | 190.000 | 95.00 |"), lines[0]
+    assert lines[1].startswith("| `seed_kernel` | 1 | 10.0000 | 10.000 | 5.00 |"), lines[1]
+    assert "total listed GPU time: 200.000 ms over 3 launches" in out.stdout
