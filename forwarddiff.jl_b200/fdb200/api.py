@@ -793,7 +793,10 @@ def _loop_jacobian(ctx, result, out, f, x, cfg, y, lo, hi):
             state["J"] = out if isinstance(out, _DeviceArray) else B200Array.alloc(ctx, m * n)
             if state["J"].n != m * n:
                 raise DimensionMismatch(f"Jacobian result has {state['J'].n} entries, expected {m}x{n}")
-        ctx.check(lib.fdb_extract_jacobian_chunk(ctx.h, state["J"].h, state["m"], ydual.h, index, cs))
+        if index == 1 and cs == n:        # vector mode: extract_jacobian!, src/jacobian.jl:95-107 (all N partials of every row)
+            ctx.check(lib.fdb_extract_jacobian(ctx.h, state["J"].h, state["m"], ydual.h, n))
+        else:
+            ctx.check(lib.fdb_extract_jacobian_chunk(ctx.h, state["J"].h, state["m"], ydual.h, index, cs))
 
     if n == N:
         ctx.check(lib.fdb_seed(ctx.h, xdual.h, xd.h, 0, 0))

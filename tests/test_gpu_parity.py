@@ -132,6 +132,12 @@ def test_extract_bit_exact(ctx, oracle, N):
         oracle.extract_jacobian_chunk(Jh, m, ym, index, cs)
         ctx.check(ctx.lib.fdb_extract_jacobian_chunk(ctx.h, Jd.h, m, ydm.h, index, cs))
         assert np.array_equal(Jd.numpy().reshape((m, ncols), order="F"), Jh)
+    # extract_jacobian! (vector mode, src/jacobian.jl:95-107): all N partials of every row at once
+    J = rng.random((m, N)); Jh = np.asfortranarray(J.copy())
+    Jd = ctx.array(np.asfortranarray(J).ravel(order="F"))
+    oracle.extract_jacobian_chunk(Jh, m, ym, 1, N)
+    ctx.check(ctx.lib.fdb_extract_jacobian(ctx.h, Jd.h, m, ydm.h, N))
+    assert np.array_equal(Jd.numpy().reshape((m, N), order="F"), Jh)
     assert np.array_equal(ydm.values().numpy(), ym[:, 0])
     with pytest.raises(fdb200.DimensionMismatch):       # GRAD_ERROR: f(x) must be a real number
         res = ctx.zeros(n)
