@@ -344,7 +344,9 @@ def main():
                 # independent of the probe: SMs x 64 FP64 lanes x the SM clock sampled by nvidia-smi during the timed region
                 "peak_spec_crosscheck": (ctx_sm_count * 64 * (clocks or {}).get("sm_mhz", 0) * 1e6 / 1e12) if clocks and clocks.get("sm_mhz") else None,
                 "algorithmic": f"{DP_OPS_PER_TERM_SHARED} FP64 ops per term per chunk sweep x {N_ELEMS - 1} terms x {my_chunks} chunks "
-                               "(SURVEY.md 8d: implicit seeds => bound is FP64 issue, not HBM)",
+                               "(SURVEY.md 8d: implicit seeds => bound is FP64 issue, not HBM).  20 is the count of the CHOSEN algorithm: with lane "
+                               "sharing a term far from the seeded window is evaluated on the value lane and ONE representative zero lane, a 6.6x "
+                               "saving over the 133 ops of all 12 lanes (extra.rosenbrock_gradient_all_lanes times that form: 0.86 of the FP64 issue rate)",
                 "hbm_equivalent": {"achieved": 8.0 * (CHUNK + 1) * N_ELEMS * my_chunks / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                    "note": "materialised-dual bytes 8(N+1)n per chunk sweep that the reference would stream; "
                                            "this kernel builds seeds in registers and reads x (8 MB) from L2, so it is NOT DRAM traffic",
