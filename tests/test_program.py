@@ -867,3 +867,19 @@ def test_programs_beyond_the_interpreter_limits_run_specialised(ctx, N):
         ctx.set_jit(True)
     v60, g60 = program_ref.evaluate(trace.trace_scalar(_many_live_values, 60), x[:60])
     assert np.allclose(g2, g60, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("halo,N", [(4, 12), (3, 12), (4, 11), (2, 1)])
+def test_specialised_hessian_kernel_fits_static_shared_memory_at_the_largest_shapes(halo, N):
+    """hessian_sweep_body keeps its staging in static shared memory (48 KB): the buffer grows with N and the stencil reach, so the
+    largest supported shapes (N = 12, halo = PH_MAXHALO = 4) are compiled here -- NVRTC rejects a kernel that does not fit."""
+    import ctypes as C
+    from fdb200.api import _i32p
+    lib = fdb200._lib.load()
+    prog = trace.trace_scalar(lambda xd, h=halo: ((xd[h:] - xd[:-h]) ** 2 * xd[:-h]).sum(), 200)
+    assert prog.halo == halo
+    log = C.create_string_buffer(1 << 16); nbytes = C.c_int64()
+    rc = lib.fdb_jit_compile_check(2, _i32p(prog.term), len(prog.term), _i32p(prog.epi), len(prog.epi),
+                                   prog.consts.ctypes.data_as(C.POINTER(C.c_double)) if prog.consts.size else None, prog.consts.size, prog.n_acc,
+                                   prog.halo, prog.result_reg, len(prog.params), N, 0, 1, log, len(log), C.byref(nbytes))
+    assert rc == 0 and nbytes.value > 1000, log.value.decode()
